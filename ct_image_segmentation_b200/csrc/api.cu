@@ -1,0 +1,366 @@
+// extern "C" surface of libb200seg.so (see include/b200seg.h): argument validation, mapping of
+// layer descriptors onto the kernel families, error reporting.  No device allocation, no sync.
+#include <stdarg.h>
+#include <atomic>
+#include <string.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "tc_conv.h"
+
+namespace b200seg {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+int check_conv_desc(const b200seg_conv_desc* d, bool transposed_layer) {
+  B200SEG_CHECK_ARG(d != nullptr, "conv desc is NULL");
+  B200SEG_CHECK_ARG(d->n > 0 && d->cin > 0 && d->cout > 0, "conv desc: n/cin/cout must be positive");
+  B200SEG_CHECK_ARG(d->dtype == B200SEG_F32 || d->dtype == B200SEG_BF16, "conv desc: bad dtype %d", d->dtype);
+  const int k[3] = {d->kd, d->kh, d->kw}, s[3] = {d->sd, d->sh, d->sw}, p[3] = {d->pd, d->ph, d->pw};
+  const int in[3] = {d->in_d, d->in_h, d->in_w}, out[3] = {d->out_d, d->out_h, d->out_w};
+  for (int i = 0; i < 3; ++i) {
+    B200SEG_CHECK_ARG(k[i] == 1 || k[i] == 3, "conv desc: kernel extent must be 1 or 3, got %d", k[i]);
+    B200SEG_CHECK_ARG(s[i] == 1 || s[i] == 2, "conv desc: stride must be 1 or 2, got %d", s[i]);
+    B200SEG_CHECK_ARG(p[i] == (k[i] - 1) / 2, "conv desc: padding must be (k-1)/2");
+    B200SEG_CHECK_ARG(in[i] > 0 && out[i] > 0, "conv desc: non-positive extent");
+    if (!transposed_layer) {
+      B200SEG_CHECK_ARG(out[i] == (in[i] + 2 * p[i] - k[i]) / s[i] + 1,
+                        "conv desc: out extent %d inconsistent with in %d (k=%d s=%d p=%d)", out[i],
+                        in[i], k[i], s[i], p[i]);
+    } else {
+      // output_padding = s - 1  (MONAI Convolution)
+      B200SEG_CHECK_ARG(out[i] == (in[i] - 1) * s[i] - 2 * p[i] + k[i] + (s[i] - 1),
+                        "convtr desc: out extent %d inconsistent with in %d (k=%d s=%d p=%d)", out[i],
+                        in[i], k[i], s[i], p[i]);
+    }
+  }
+  B200SEG_CHECK_ARG(d->x_ld >= d->cin && d->y_ld >= d->cout, "conv desc: ld smaller than channel count");
+  return B200SEG_OK;
+}
+
+void fill_geom(GatherParams& g, const b200seg_conv_desc* d) {
+  g.n = d->n;
+  g.kd = d->kd; g.kh = d->kh; g.kw = d->kw;
+  g.sd = d->sd; g.sh = d->sh; g.sw = d->sw;
+  g.pd = d->pd; g.ph = d->ph; g.pw = d->pw;
+  g.accumulate = (d->flags & B200SEG_CONV_ACCUMULATE) ? 1 : 0;
+}
+
+}  // namespace
+}  // namespace b200seg
+
+using namespace b200seg;
+
+extern "C" {
+
+int b200seg_version(void) { return B200SEG_VERSION; }
+const char* b200seg_last_error(void) { return g_err; }
+long long b200seg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int b200seg_check_device(int device) {
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) {
+    set_error("cudaGetDeviceProperties(%d): %s", device, cudaGetErrorString(e));
+    return B200SEG_ERR_CUDA;
+  }
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; libb200seg is built for sm_100a only", device, prop.major, prop.minor);
+    return B200SEG_ERR_DEVICE;
+  }
+  return B200SEG_OK;
+}
+
+// ---- weights ---------------------------------------------------------------------------------
+size_t b200seg_packed_weight_bytes(const b200seg_conv_desc* d, int kind) {
+  if (!d) return 0;
+  (void)kind;
+  size_t esz = d->dtype == B200SEG_BF16 ? 2 : 4;
+  return (size_t)d->kd * d->kh * d->kw * d->cin * d->cout * esz;
+}
+
+int b200seg_pack_weight(const b200seg_conv_desc* d, int kind, const float* w_torch, void* w_packed,
+                        void* stream) {
+  B200SEG_CHECK_ARG(d && w_torch && w_packed, "pack_weight: NULL argument");
+  B200SEG_CHECK_ARG(kind >= 0 && kind <= 3, "pack_weight: bad kind %d", kind);
+  return launch_pack_weight(d->dtype, kind, w_torch, w_packed, d->kd * d->kh * d->kw, d->cin, d->cout,
+                            as_stream(stream));
+}
+
+// ---- conv ---------------------------------------------------------------------------------------
+int b200seg_conv_fprop(const b200seg_conv_desc* d, const void* x, const void* w_packed,
+                       const float* bias, const void* residual, void* y, void* stream) {
+  int rc = check_conv_desc(d, false);
+  if (rc) return rc;
+  B200SEG_CHECK_ARG(x && w_packed && y, "conv_fprop: NULL pointer");
+  if (tc_conv_supported(d, TC_CONV_FPROP)) return tc_conv_run(d, TC_CONV_FPROP, x, w_packed, bias, residual, y, as_stream(stream));
+  GatherParams g{};
+  fill_geom(g, d);
+  g.sD = d->in_d; g.sH = d->in_h; g.sW = d->in_w;
+  g.dD = d->out_d; g.dH = d->out_h; g.dW = d->out_w;
+  g.src_c = d->cin; g.dst_c = d->cout;
+  g.src_ld = d->x_ld; g.dst_ld = d->y_ld; g.res_ld = d->r_ld;
+  g.transposed = 0;
+  return launch_gather(g, d->dtype, x, w_packed, bias, residual, y, as_stream(stream));
+}
+
+int b200seg_conv_dgrad(const b200seg_conv_desc* d, const void* dy, const void* w_packed,
+                       const void* residual, void* dx, void* stream) {
+  int rc = check_conv_desc(d, false);
+  if (rc) return rc;
+  B200SEG_CHECK_ARG(dy && w_packed && dx, "conv_dgrad: NULL pointer");
+  if (tc_conv_supported(d, TC_CONV_DGRAD)) return tc_conv_run(d, TC_CONV_DGRAD, dy, w_packed, nullptr, residual, dx, as_stream(stream));
+  GatherParams g{};
+  fill_geom(g, d);
+  g.sD = d->out_d; g.sH = d->out_h; g.sW = d->out_w;
+  g.dD = d->in_d; g.dH = d->in_h; g.dW = d->in_w;
+  g.src_c = d->cout; g.dst_c = d->cin;
+  g.src_ld = d->y_ld; g.dst_ld = d->x_ld; g.res_ld = d->r_ld;
+  g.transposed = 1;
+  return launch_gather(g, d->dtype, dy, w_packed, nullptr, residual, dx, as_stream(stream));
+}
+
+static void conv_wgrad_params(const b200seg_conv_desc* d, WgradParams& w) {
+  w.n = d->n;
+  w.sD = d->in_d; w.sH = d->in_h; w.sW = d->in_w;
+  w.tD = d->out_d; w.tH = d->out_h; w.tW = d->out_w;
+  w.a_c = d->cin; w.b_c = d->cout;
+  w.kd = d->kd; w.kh = d->kh; w.kw = d->kw;
+  w.sd = d->sd; w.sh = d->sh; w.sw = d->sw;
+  w.pd = d->pd; w.ph = d->ph; w.pw = d->pw;
+  w.s_ld = d->x_ld; w.t_ld = d->y_ld;
+  wgrad_plan(w);
+}
+
+static void convtr_wgrad_params(const b200seg_conv_desc* d, WgradParams& w) {
+  // G[k][co][ci] = sum_i dy[i*s - p + k, co] * x[i, ci]  : S = dy (gathered), T = x
+  w.n = d->n;
+  w.sD = d->out_d; w.sH = d->out_h; w.sW = d->out_w;
+  w.tD = d->in_d; w.tH = d->in_h; w.tW = d->in_w;
+  w.a_c = d->cout; w.b_c = d->cin;
+  w.kd = d->kd; w.kh = d->kh; w.kw = d->kw;
+  w.sd = d->sd; w.sh = d->sh; w.sw = d->sw;
+  w.pd = d->pd; w.ph = d->ph; w.pw = d->pw;
+  w.s_ld = d->y_ld; w.t_ld = d->x_ld;
+  wgrad_plan(w);
+}
+
+static size_t wgrad_ws_bytes(const b200seg_conv_desc* d, const WgradParams& w) {
+  int64_t nvox_y = (int64_t)d->n * d->out_d * d->out_h * d->out_w;
+  size_t colsum = (size_t)colsum_blocks(nvox_y) * d->cout * sizeof(float);
+  return align_up(wgrad_partial_bytes(w), 256) + align_up(colsum, 256) + tc_wgrad_extra_workspace(d);
+}
+
+size_t b200seg_conv_wgrad_workspace_bytes(const b200seg_conv_desc* d) {
+  if (!d) return 0;
+  WgradParams w{};
+  conv_wgrad_params(d, w);
+  return wgrad_ws_bytes(d, w);
+}
+
+size_t b200seg_convtr_wgrad_workspace_bytes(const b200seg_conv_desc* d) {
+  if (!d) return 0;
+  WgradParams w{};
+  convtr_wgrad_params(d, w);
+  return wgrad_ws_bytes(d, w);
+}
+
+static int wgrad_common(const b200seg_conv_desc* d, const WgradParams& w, const void* S, const void* T,
+                        const void* dy, float* gw, float* gbias, void* ws, size_t ws_bytes, void* stream) {
+  B200SEG_CHECK_ARG(S && T && gw && ws, "wgrad: NULL pointer");
+  size_t need = wgrad_ws_bytes(d, w);
+  if (ws_bytes < need) {
+    set_error("wgrad: workspace %zu < required %zu bytes", ws_bytes, need);
+    return B200SEG_ERR_WORKSPACE;
+  }
+  float* partial = (float*)ws;
+  int rc = launch_wgrad(w, d->dtype, S, T, gw, partial, as_stream(stream));
+  if (rc) return rc;
+  if (gbias) {
+    float* cs = (float*)((char*)ws + align_up(wgrad_partial_bytes(w), 256));
+    int64_t nvox_y = (int64_t)d->n * d->out_d * d->out_h * d->out_w;
+    rc = launch_colsum(d->dtype, dy, nvox_y, d->cout, d->y_ld, gbias, cs, as_stream(stream));
+  }
+  return rc;
+}
+
+int b200seg_conv_wgrad(const b200seg_conv_desc* d, const void* x, const void* dy, float* gw,
+                       float* gbias, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_conv_desc(d, false);
+  if (rc) return rc;
+  WgradParams w{};
+  conv_wgrad_params(d, w);
+  return wgrad_common(d, w, x, dy, dy, gw, gbias, workspace, workspace_bytes, stream);
+}
+
+int b200seg_convtr_fprop(const b200seg_conv_desc* d, const void* x, const void* w_packed,
+                         const float* bias, const void* residual, void* y, void* stream) {
+  int rc = check_conv_desc(d, true);
+  if (rc) return rc;
+  B200SEG_CHECK_ARG(x && w_packed && y, "convtr_fprop: NULL pointer");
+  if (tc_conv_supported(d, TC_CONVTR_FPROP)) return tc_conv_run(d, TC_CONVTR_FPROP, x, w_packed, bias, residual, y, as_stream(stream));
+  GatherParams g{};
+  fill_geom(g, d);
+  g.sD = d->in_d; g.sH = d->in_h; g.sW = d->in_w;
+  g.dD = d->out_d; g.dH = d->out_h; g.dW = d->out_w;
+  g.src_c = d->cin; g.dst_c = d->cout;
+  g.src_ld = d->x_ld; g.dst_ld = d->y_ld; g.res_ld = d->r_ld;
+  g.transposed = 1;
+  return launch_gather(g, d->dtype, x, w_packed, bias, residual, y, as_stream(stream));
+}
+
+int b200seg_convtr_dgrad(const b200seg_conv_desc* d, const void* dy, const void* w_packed,
+                         const void* residual, void* dx, void* stream) {
+  int rc = check_conv_desc(d, true);
+  if (rc) return rc;
+  B200SEG_CHECK_ARG(dy && w_packed && dx, "convtr_dgrad: NULL pointer");
+  if (tc_conv_supported(d, TC_CONVTR_DGRAD)) return tc_conv_run(d, TC_CONVTR_DGRAD, dy, w_packed, nullptr, residual, dx, as_stream(stream));
+  GatherParams g{};
+  fill_geom(g, d);
+  g.sD = d->out_d; g.sH = d->out_h; g.sW = d->out_w;
+  g.dD = d->in_d; g.dH = d->in_h; g.dW = d->in_w;
+  g.src_c = d->cout; g.dst_c = d->cin;
+  g.src_ld = d->y_ld; g.dst_ld = d->x_ld; g.res_ld = d->r_ld;
+  g.transposed = 0;
+  return launch_gather(g, d->dtype, dy, w_packed, nullptr, residual, dx, as_stream(stream));
+}
+
+int b200seg_convtr_wgrad(const b200seg_conv_desc* d, const void* x, const void* dy, float* gw,
+                         float* gbias, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_conv_desc(d, true);
+  if (rc) return rc;
+  WgradParams w{};
+  convtr_wgrad_params(d, w);
+  return wgrad_common(d, w, dy, x, dy, gw, gbias, workspace, workspace_bytes, stream);
+}
+
+// ---- InstanceNorm + PReLU ---------------------------------------------------------------------------
+static int check_norm_desc(const b200seg_norm_desc* d) {
+  B200SEG_CHECK_ARG(d != nullptr, "norm desc is NULL");
+  B200SEG_CHECK_ARG(d->n > 0 && d->c > 0 && d->spatial > 0, "norm desc: n/c/spatial must be positive");
+  B200SEG_CHECK_ARG(d->dtype == B200SEG_F32 || d->dtype == B200SEG_BF16, "norm desc: bad dtype");
+  B200SEG_CHECK_ARG(d->x_ld >= d->c, "norm desc: x_ld smaller than channel count");
+  return B200SEG_OK;
+}
+
+size_t b200seg_instnorm_workspace_bytes(const b200seg_norm_desc* d) {
+  return d ? norm_workspace_bytes(*d) : 0;
+}
+
+int b200seg_instnorm_stats(const b200seg_norm_desc* d, const void* x, float* mean, float* rstd,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_norm_desc(d);
+  if (rc) return rc;
+  B200SEG_CHECK_ARG(x && mean && rstd && workspace, "instnorm_stats: NULL pointer");
+  if (workspace_bytes < norm_workspace_bytes(*d)) {
+    set_error("instnorm_stats: workspace %zu < required %zu", workspace_bytes, norm_workspace_bytes(*d));
+    return B200SEG_ERR_WORKSPACE;
+  }
+  return launch_instnorm_stats(*d, x, mean, rstd, workspace, as_stream(stream));
+}
+
+int b200seg_instnorm_prelu_fwd(const b200seg_norm_desc* d, const void* x, const float* mean,
+                               const float* rstd, const float* alpha, const void* residual, void* y,
+                               void* stream) {
+  int rc = check_norm_desc(d);
+  if (rc) return rc;
+  B200SEG_CHECK_ARG(x && mean && rstd && alpha && y, "instnorm_prelu_fwd: NULL pointer");
+  B200SEG_CHECK_ARG(d->y_ld >= d->c && (!residual || d->r_ld >= d->c), "instnorm_prelu_fwd: bad ld");
+  return launch_instnorm_prelu_fwd(*d, x, mean, rstd, alpha, residual, y, as_stream(stream));
+}
+
+int b200seg_instnorm_prelu_bwd(const b200seg_norm_desc* d, const void* x, const float* mean,
+                               const float* rstd, const float* alpha, const void* dy, void* dx,
+                               float* dalpha, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_norm_desc(d);
+  if (rc) return rc;
+  B200SEG_CHECK_ARG(x && mean && rstd && alpha && dy && dx && dalpha && workspace,
+                    "instnorm_prelu_bwd: NULL pointer");
+  B200SEG_CHECK_ARG(d->y_ld >= d->c && d->r_ld >= d->c, "instnorm_prelu_bwd: y_ld (dy) / r_ld (dx) too small");
+  if (workspace_bytes < norm_workspace_bytes(*d)) {
+    set_error("instnorm_prelu_bwd: workspace %zu < required %zu", workspace_bytes, norm_workspace_bytes(*d));
+    return B200SEG_ERR_WORKSPACE;
+  }
+  return launch_instnorm_prelu_bwd(*d, x, mean, rstd, alpha, dy, dx, dalpha, workspace, as_stream(stream));
+}
+
+// ---- softmax + Dice -------------------------------------------------------------------------------------
+static int check_dice_desc(const b200seg_dice_desc* d) {
+  B200SEG_CHECK_ARG(d != nullptr, "dice desc is NULL");
+  B200SEG_CHECK_ARG(d->n > 0 && d->c > 0 && d->spatial > 0, "dice desc: n/c/spatial must be positive");
+  B200SEG_CHECK_ARG(d->ld >= d->c, "dice desc: ld smaller than class count");
+  B200SEG_CHECK_ARG(d->dtype == B200SEG_F32 || d->dtype == B200SEG_BF16, "dice desc: bad dtype");
+  B200SEG_CHECK_ARG(d->label_dtype == B200SEG_LABEL_U8 || d->label_dtype == B200SEG_LABEL_I64,
+                    "dice desc: bad label dtype");
+  return B200SEG_OK;
+}
+
+size_t b200seg_softmax_dice_workspace_bytes(const b200seg_dice_desc* d) {
+  return d ? dice_workspace_bytes(*d) : 0;
+}
+
+int b200seg_softmax_dice_fwd(const b200seg_dice_desc* d, const void* logits, const void* labels,
+                             float* sums, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_dice_desc(d);
+  if (rc) return rc;
+  B200SEG_CHECK_ARG(logits && labels && sums && workspace, "softmax_dice_fwd: NULL pointer");
+  if (workspace_bytes < dice_workspace_bytes(*d)) {
+    set_error("softmax_dice_fwd: workspace %zu < required %zu", workspace_bytes, dice_workspace_bytes(*d));
+    return B200SEG_ERR_WORKSPACE;
+  }
+  return launch_softmax_dice_fwd(*d, logits, labels, sums, workspace, as_stream(stream));
+}
+
+int b200seg_softmax_dice_bwd(const b200seg_dice_desc* d, const void* logits, const void* labels,
+                             const float* gI, const float* gP, void* dlogits, void* stream) {
+  int rc = check_dice_desc(d);
+  if (rc) return rc;
+  B200SEG_CHECK_ARG(logits && labels && gI && gP && dlogits, "softmax_dice_bwd: NULL pointer");
+  return launch_softmax_dice_bwd(*d, logits, labels, gI, gP, dlogits, as_stream(stream));
+}
+
+int b200seg_argmax_dice_counts(const b200seg_dice_desc* d, const void* logits, const void* target,
+                               uint8_t* pred_out, int64_t* counts, void* stream) {
+  int rc = check_dice_desc(d);
+  if (rc) return rc;
+  B200SEG_CHECK_ARG(logits, "argmax_dice_counts: NULL logits");
+  B200SEG_CHECK_ARG(!target || counts, "argmax_dice_counts: target given but counts is NULL");
+  B200SEG_CHECK_ARG(target || pred_out, "argmax_dice_counts: nothing to produce");
+  return launch_argmax_dice_counts(*d, logits, target, pred_out, counts, as_stream(stream));
+}
+
+int b200seg_label_dice_counts(int32_t n, int64_t spatial, int32_t c, const uint8_t* pred,
+                              const void* target, int32_t target_dtype, int64_t* counts, void* stream) {
+  B200SEG_CHECK_ARG(n > 0 && spatial > 0 && c > 0 && pred && target && counts, "label_dice_counts: bad argument");
+  return launch_label_dice_counts(n, spatial, c, pred, target, target_dtype, counts, as_stream(stream));
+}
+
+int b200seg_squash_masks(int32_t n, int32_t n_struct, int64_t spatial, const uint8_t* masks,
+                         uint8_t* labels, void* stream) {
+  B200SEG_CHECK_ARG(n > 0 && n_struct > 0 && n_struct < 255 && spatial > 0 && masks && labels,
+                    "squash_masks: bad argument");
+  return launch_squash_masks(n, n_struct, spatial, masks, labels, as_stream(stream));
+}
+
+int b200seg_hu_window_norm(int64_t n_vox, int32_t n_windows, const int16_t* hu, const float* lo,
+                           const float* hi, const float* mean, const float* std_, void* out,
+                           int32_t out_ld, int32_t dtype, void* stream) {
+  B200SEG_CHECK_ARG(n_vox > 0 && n_windows >= 1 && n_windows <= 4 && hu && lo && hi && mean && std_ && out,
+                    "hu_window_norm: bad argument");
+  B200SEG_CHECK_ARG(out_ld >= n_windows, "hu_window_norm: out_ld < n_windows");
+  return launch_hu_window_norm(n_vox, n_windows, hu, lo, hi, mean, std_, out, out_ld, dtype, as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,382 @@
+// Bandwidth-bound voxel-wise kernels at the end of the network: fused softmax + Dice sums
+// (forward and backward), fused softmax-argmax + Dice-metric counts, mask squashing and HU
+// windowing.  One thread per voxel, channels-last logits (C <= 32), fp32 math.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200seg {
+
+namespace {
+
+constexpr int kDiceThreads = 256;
+
+inline int dice_blocks(int64_t spatial, int n) {
+  int64_t nb = cdiv64(spatial, kDiceThreads * 4);
+  int64_t cap = 1184 / (n > 0 ? n : 1);
+  if (cap < 1) cap = 1;
+  if (nb > cap) nb = cap;
+  if (nb < 1) nb = 1;
+  return (int)nb;
+}
+
+template <int LT>
+__device__ __forceinline__ int load_label(const void* labels, int64_t idx) {
+  if constexpr (LT == B200SEG_LABEL_U8) return (int)reinterpret_cast<const uint8_t*>(labels)[idx];
+  else return (int)reinterpret_cast<const long long*>(labels)[idx];
+}
+
+// softmax of one voxel: p[0..C) (entries >= C are 0).  Plain expf / division in fp32, i.e. the
+// arithmetic `torch.softmax` performs (max-subtracted exponentials over their sum).
+template <typename T, int CMAX>
+__device__ __forceinline__ void voxel_softmax(const T* z, int C, float (&p)[CMAX]) {
+  float mx = -INFINITY;
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    p[c] = c < C ? to_f<T>(z[c]) : -INFINITY;
+    mx = fmaxf(mx, p[c]);
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    p[c] = c < C ? expf(p[c] - mx) : 0.f;
+    s += p[c];
+  }
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) p[c] = p[c] / s;
+}
+
+}  // namespace
+
+size_t dice_workspace_bytes(const b200seg_dice_desc& d) {
+  return (size_t)d.n * dice_blocks(d.spatial, d.n) * d.c * 3 * sizeof(float) + 256;
+}
+
+// partial[n][blk][c][3] = { I, G, P }
+template <typename T, int CMAX, int LT>
+__global__ void __launch_bounds__(kDiceThreads)
+softmax_dice_fwd_kernel(const T* __restrict__ logits, const void* __restrict__ labels,
+                        int64_t spatial, int C, int ld, int64_t vox_per_block,
+                        float* __restrict__ partial) {
+  __shared__ float red[kDiceThreads / 32][CMAX * 3];
+  const int n = blockIdx.y;
+  const int64_t v_begin = (int64_t)blockIdx.x * vox_per_block;
+  const int64_t v_end = min(v_begin + vox_per_block, spatial);
+  float aI[CMAX], aG[CMAX], aP[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) aI[c] = aG[c] = aP[c] = 0.f;
+  for (int64_t v = v_begin + threadIdx.x; v < v_end; v += kDiceThreads) {
+    int64_t vox = (int64_t)n * spatial + v;
+    float p[CMAX];
+    voxel_softmax<T, CMAX>(logits + vox * ld, C, p);
+    int lab = load_label<LT>(labels, vox);
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      bool hit = (lab == c);
+      aI[c] += hit ? p[c] : 0.f;
+      aG[c] += hit ? 1.f : 0.f;
+      aP[c] += p[c];
+    }
+  }
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    float i_ = warp_sum(aI[c]), g_ = warp_sum(aG[c]), p_ = warp_sum(aP[c]);
+    if (lane == 0) {
+      red[warp][c * 3 + 0] = i_;
+      red[warp][c * 3 + 1] = g_;
+      red[warp][c * 3 + 2] = p_;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < C * 3) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kDiceThreads / 32; ++w) s += red[w][threadIdx.x];
+    partial[((int64_t)n * gridDim.x + blockIdx.x) * C * 3 + threadIdx.x] = s;
+  }
+}
+
+__global__ void dice_sums_final_kernel(const float* __restrict__ partial, int nblk, int per_n,
+                                       int total, float* __restrict__ sums) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (warp >= total) return;
+  int n = warp / per_n, j = warp % per_n;
+  double s = 0.0;
+  for (int b = lane; b < nblk; b += 32) s += (double)partial[((int64_t)n * nblk + b) * per_n + j];
+  s = warp_sum_d(s);
+  if (lane == 0) sums[warp] = (float)s;
+}
+
+template <typename T, int CMAX, int LT>
+__global__ void __launch_bounds__(kDiceThreads)
+softmax_dice_bwd_kernel(const T* __restrict__ logits, const void* __restrict__ labels,
+                        const float* __restrict__ gI, const float* __restrict__ gP,
+                        T* __restrict__ dlogits, int64_t spatial, int C, int ld) {
+  const int n = blockIdx.y;
+  float cI[CMAX], cP[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    cI[c] = c < C ? gI[n * C + c] : 0.f;
+    cP[c] = c < C ? gP[n * C + c] : 0.f;
+  }
+  for (int64_t v = (int64_t)blockIdx.x * kDiceThreads + threadIdx.x; v < spatial;
+       v += (int64_t)gridDim.x * kDiceThreads) {
+    int64_t vox = (int64_t)n * spatial + v;
+    float p[CMAX];
+    voxel_softmax<T, CMAX>(logits + vox * ld, C, p);
+    int lab = load_label<LT>(labels, vox);
+    float g[CMAX];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      g[c] = (lab == c ? cI[c] : 0.f) + cP[c];
+      dot = fmaf(g[c], p[c], dot);
+    }
+    T* o = dlogits + vox * ld;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      if (c < C) o[c] = from_f<T>(p[c] * (g[c] - dot));
+  }
+}
+
+// pred = argmax softmax (first maximum), optional counts[n][c][3] = {tp, |pred|, |target|}
+template <typename T, int CMAX, int LT>
+__global__ void __launch_bounds__(kDiceThreads)
+argmax_counts_kernel(const T* __restrict__ logits, const void* __restrict__ target,
+                     uint8_t* __restrict__ pred_out, unsigned long long* __restrict__ counts,
+                     int64_t spatial, int C, int ld) {
+  __shared__ unsigned int red[CMAX * 3];
+  const int n = blockIdx.y;
+  if (threadIdx.x < CMAX * 3) red[threadIdx.x] = 0u;
+  __syncthreads();
+  unsigned int tp[CMAX], np_[CMAX], nt[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) tp[c] = np_[c] = nt[c] = 0u;
+  for (int64_t v = (int64_t)blockIdx.x * kDiceThreads + threadIdx.x; v < spatial;
+       v += (int64_t)gridDim.x * kDiceThreads) {
+    int64_t vox = (int64_t)n * spatial + v;
+    float p[CMAX];
+    voxel_softmax<T, CMAX>(logits + vox * ld, C, p);
+    int best = 0;
+    float bv = p[0];
+#pragma unroll
+    for (int c = 1; c < CMAX; ++c)
+      if (c < C && p[c] > bv) { bv = p[c]; best = c; }
+    if (pred_out) pred_out[vox] = (uint8_t)best;
+    if (target) {
+      int lab = load_label<LT>(target, vox);
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        np_[c] += (best == c);
+        nt[c] += (lab == c);
+        tp[c] += (best == c && lab == c);
+      }
+    }
+  }
+  if (target) {
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      unsigned a = __reduce_add_sync(0xffffffffu, tp[c]);
+      unsigned b = __reduce_add_sync(0xffffffffu, np_[c]);
+      unsigned d = __reduce_add_sync(0xffffffffu, nt[c]);
+      if ((threadIdx.x % 32) == 0 && c < C) {
+        if (a) atomicAdd(&red[c * 3 + 0], a);
+        if (b) atomicAdd(&red[c * 3 + 1], b);
+        if (d) atomicAdd(&red[c * 3 + 2], d);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x < C * 3 && red[threadIdx.x])
+      atomicAdd(&counts[(int64_t)n * C * 3 + threadIdx.x], (unsigned long long)red[threadIdx.x]);
+  }
+}
+
+template <int LT>
+__global__ void __launch_bounds__(kDiceThreads)
+label_counts_kernel(const uint8_t* __restrict__ pred, const void* __restrict__ target,
+                    unsigned long long* __restrict__ counts, int64_t spatial, int C) {
+  constexpr int CMAX = 32;
+  __shared__ unsigned int red[CMAX * 3];
+  const int n = blockIdx.y;
+  if (threadIdx.x < CMAX * 3) red[threadIdx.x] = 0u;
+  __syncthreads();
+  for (int64_t v = (int64_t)blockIdx.x * kDiceThreads + threadIdx.x; v < spatial;
+       v += (int64_t)gridDim.x * kDiceThreads) {
+    int64_t vox = (int64_t)n * spatial + v;
+    int pr = pred[vox], lab = load_label<LT>(target, vox);
+    if (pr >= 0 && pr < C) atomicAdd(&red[pr * 3 + 1], 1u);
+    if (lab >= 0 && lab < C) atomicAdd(&red[lab * 3 + 2], 1u);
+    if (pr == lab && pr >= 0 && pr < C) atomicAdd(&red[pr * 3 + 0], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < C * 3 && red[threadIdx.x])
+    atomicAdd(&counts[(int64_t)n * C * 3 + threadIdx.x], (unsigned long long)red[threadIdx.x]);
+}
+
+// labels[n][v] = max_c masks[n][c][v] * (c+1)
+__global__ void squash_masks_kernel(const uint8_t* __restrict__ masks, uint8_t* __restrict__ labels,
+                                    int n_struct, int64_t spatial, int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t n = i / spatial, v = i % spatial;
+    const uint8_t* m = masks + (n * n_struct) * spatial + v;
+    int best = 0;
+    for (int c = 0; c < n_struct; ++c) {
+      int val = (int)m[(int64_t)c * spatial] * (c + 1);
+      best = val > best ? val : best;
+    }
+    labels[i] = (uint8_t)best;
+  }
+}
+
+struct WindowCfg {
+  float lo[4], hi[4], mean[4], std_[4];
+  int n;
+};
+
+template <typename T>
+__global__ void hu_window_norm_kernel(const int16_t* __restrict__ hu, T* __restrict__ out,
+                                      int64_t n_vox, int out_ld, WindowCfg w) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_vox;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    float x = (float)hu[i];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < w.n) {
+        // double, as numpy promotes int16 / float64 in apply_window; then float32 normalise
+        double c = fmin(fmax((double)x, (double)w.lo[k]), (double)w.hi[k]);
+        double s = (c - (double)w.lo[k]) / ((double)w.hi[k] - (double)w.lo[k] + 1e-8);
+        float f = (float)s;
+        f = (f - w.mean[k]) * (1.0f / w.std_[k]);
+        out[i * out_ld + k] = from_f<T>(f);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+#define DISPATCH_DICE(d, ...)                                                              \
+  do {                                                                                     \
+    if ((d).c > 32 || (d).c < 1) {                                                         \
+      set_error("softmax/dice kernels support 1..32 classes, got %d", (d).c);              \
+      return B200SEG_ERR_UNSUPPORTED;                                                      \
+    }                                                                                      \
+    const bool bf = (d).dtype == B200SEG_BF16, u8 = (d).label_dtype == B200SEG_LABEL_U8;   \
+    const bool small = (d).c <= 16;                                                        \
+    if (bf && u8 && small)        { using T = __nv_bfloat16; constexpr int CM = 16; constexpr int LT = B200SEG_LABEL_U8;  __VA_ARGS__; } \
+    else if (bf && u8)            { using T = __nv_bfloat16; constexpr int CM = 32; constexpr int LT = B200SEG_LABEL_U8;  __VA_ARGS__; } \
+    else if (bf && small)         { using T = __nv_bfloat16; constexpr int CM = 16; constexpr int LT = B200SEG_LABEL_I64; __VA_ARGS__; } \
+    else if (bf)                  { using T = __nv_bfloat16; constexpr int CM = 32; constexpr int LT = B200SEG_LABEL_I64; __VA_ARGS__; } \
+    else if (u8 && small)         { using T = float;         constexpr int CM = 16; constexpr int LT = B200SEG_LABEL_U8;  __VA_ARGS__; } \
+    else if (u8)                  { using T = float;         constexpr int CM = 32; constexpr int LT = B200SEG_LABEL_U8;  __VA_ARGS__; } \
+    else if (small)               { using T = float;         constexpr int CM = 16; constexpr int LT = B200SEG_LABEL_I64; __VA_ARGS__; } \
+    else                          { using T = float;         constexpr int CM = 32; constexpr int LT = B200SEG_LABEL_I64; __VA_ARGS__; } \
+  } while (0)
+
+int launch_softmax_dice_fwd(const b200seg_dice_desc& d, const void* logits, const void* labels,
+                            float* sums, void* ws, cudaStream_t st) {
+  int nb = dice_blocks(d.spatial, d.n);
+  int64_t per = cdiv64(d.spatial, nb);
+  dim3 grid(nb, d.n);
+  float* partial = (float*)ws;
+  DISPATCH_DICE(d, (softmax_dice_fwd_kernel<T, CM, LT><<<grid, kDiceThreads, 0, st>>>(
+                       (const T*)logits, labels, d.spatial, d.c, d.ld, per, partial)));
+  B200SEG_CHECK_LAUNCH("softmax_dice_fwd");
+  int total = d.n * d.c * 3;
+  dice_sums_final_kernel<<<(total * 32 + 255) / 256, 256, 0, st>>>(partial, nb, d.c * 3, total, sums);
+  B200SEG_CHECK_LAUNCH("dice_sums_final");
+  return B200SEG_OK;
+}
+
+int launch_softmax_dice_bwd(const b200seg_dice_desc& d, const void* logits, const void* labels,
+                            const float* gI, const float* gP, void* dlogits, cudaStream_t st) {
+  int64_t nb = cdiv64(d.spatial, kDiceThreads * 2);
+  int64_t cap = 4736 / (d.n > 0 ? d.n : 1);
+  if (cap < 1) cap = 1;
+  if (nb > cap) nb = cap;
+  dim3 grid((unsigned)nb, d.n);
+  DISPATCH_DICE(d, (softmax_dice_bwd_kernel<T, CM, LT><<<grid, kDiceThreads, 0, st>>>(
+                       (const T*)logits, labels, gI, gP, (T*)dlogits, d.spatial, d.c, d.ld)));
+  B200SEG_CHECK_LAUNCH("softmax_dice_bwd");
+  return B200SEG_OK;
+}
+
+int launch_argmax_dice_counts(const b200seg_dice_desc& d, const void* logits, const void* target,
+                              uint8_t* pred_out, int64_t* counts, cudaStream_t st) {
+  if (target) {
+    cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)d.n * d.c * 3 * sizeof(int64_t), st);
+    if (e != cudaSuccess) {
+      set_error("argmax_dice_counts: memset failed: %s", cudaGetErrorString(e));
+      return B200SEG_ERR_CUDA;
+    }
+  }
+  int64_t nb = cdiv64(d.spatial, kDiceThreads * 4);
+  int64_t cap = 2368 / (d.n > 0 ? d.n : 1);
+  if (cap < 1) cap = 1;
+  if (nb > cap) nb = cap;
+  dim3 grid((unsigned)nb, d.n);
+  DISPATCH_DICE(d, (argmax_counts_kernel<T, CM, LT><<<grid, kDiceThreads, 0, st>>>(
+                       (const T*)logits, target, pred_out, (unsigned long long*)counts, d.spatial,
+                       d.c, d.ld)));
+  B200SEG_CHECK_LAUNCH("argmax_counts");
+  return B200SEG_OK;
+}
+
+int launch_label_dice_counts(int n, int64_t spatial, int c, const uint8_t* pred, const void* target,
+                             int target_dtype, int64_t* counts, cudaStream_t st) {
+  if (c > 32 || c < 1) {
+    set_error("label_dice_counts supports 1..32 classes, got %d", c);
+    return B200SEG_ERR_UNSUPPORTED;
+  }
+  cudaError_t e = cudaMemsetAsync(counts, 0, (size_t)n * c * 3 * sizeof(int64_t), st);
+  if (e != cudaSuccess) {
+    set_error("label_dice_counts: memset failed: %s", cudaGetErrorString(e));
+    return B200SEG_ERR_CUDA;
+  }
+  int64_t nb = cdiv64(spatial, kDiceThreads * 8);
+  int64_t cap = 2368 / (n > 0 ? n : 1);
+  if (cap < 1) cap = 1;
+  if (nb > cap) nb = cap;
+  dim3 grid((unsigned)nb, n);
+  if (target_dtype == B200SEG_LABEL_U8)
+    label_counts_kernel<B200SEG_LABEL_U8><<<grid, kDiceThreads, 0, st>>>(pred, target, (unsigned long long*)counts, spatial, c);
+  else
+    label_counts_kernel<B200SEG_LABEL_I64><<<grid, kDiceThreads, 0, st>>>(pred, target, (unsigned long long*)counts, spatial, c);
+  B200SEG_CHECK_LAUNCH("label_counts");
+  return B200SEG_OK;
+}
+
+int launch_squash_masks(int n, int n_struct, int64_t spatial, const uint8_t* masks, uint8_t* labels,
+                        cudaStream_t st) {
+  int64_t total = (int64_t)n * spatial;
+  int64_t nb = cdiv64(total, 256 * 4);
+  if (nb > 148 * 16) nb = 148 * 16;
+  if (nb < 1) nb = 1;
+  squash_masks_kernel<<<(unsigned)nb, 256, 0, st>>>(masks, labels, n_struct, spatial, total);
+  B200SEG_CHECK_LAUNCH("squash_masks");
+  return B200SEG_OK;
+}
+
+int launch_hu_window_norm(int64_t n_vox, int n_windows, const int16_t* hu, const float* lo,
+                          const float* hi, const float* mean, const float* std_, void* out,
+                          int out_ld, int dtype, cudaStream_t st) {
+  WindowCfg w;
+  w.n = n_windows;
+  for (int k = 0; k < 4; ++k) {
+    w.lo[k] = k < n_windows ? lo[k] : 0.f;
+    w.hi[k] = k < n_windows ? hi[k] : 1.f;
+    w.mean[k] = k < n_windows ? mean[k] : 0.f;
+    w.std_[k] = k < n_windows ? std_[k] : 1.f;
+  }
+  int64_t nb = cdiv64(n_vox, 256 * 4);
+  if (nb > 148 * 16) nb = 148 * 16;
+  if (nb < 1) nb = 1;
+  if (dtype == B200SEG_BF16)
+    hu_window_norm_kernel<__nv_bfloat16><<<(unsigned)nb, 256, 0, st>>>(hu, (__nv_bfloat16*)out, n_vox, out_ld, w);
+  else
+    hu_window_norm_kernel<float><<<(unsigned)nb, 256, 0, st>>>(hu, (float*)out, n_vox, out_ld, w);
+  B200SEG_CHECK_LAUNCH("hu_window_norm");
+  return B200SEG_OK;
+}
+
+}  // namespace b200seg

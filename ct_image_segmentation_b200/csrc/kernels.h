@@ -1,0 +1,79 @@
+// Internal launch interfaces between api.cu and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200seg.h"
+
+namespace b200seg {
+
+struct GatherParams {
+  int n;
+  int sD, sH, sW;  // extent of the gathered (source) tensor
+  int dD, dH, dW;  // extent of the destination tensor
+  int src_c, dst_c;
+  int kd, kh, kw, sd, sh, sw, pd, ph, pw;
+  int src_ld, dst_ld, res_ld;
+  int transposed;  // 0: src = dst*s - p + k ; 1: src = (dst + p - k)/s
+  int accumulate;
+  // filled by launch_gather
+  int csd, csh, csw;  // parity classes per dim (stride for the transposed gather, else 1)
+  int cD, cH, cW;     // per-class grid
+  int64_t per_class;
+  int tiles_per_class;
+  int src_vec;
+};
+
+struct WgradParams {
+  int n;
+  int sD, sH, sW;  // extent of S (gathered operand)
+  int tD, tH, tW;  // extent of T (indexed by output position)
+  int a_c, b_c;    // channels of S and T
+  int kd, kh, kw, sd, sh, sw, pd, ph, pw;
+  int s_ld, t_ld;
+  // filled by wgrad_plan
+  int taps, tiles_a, tiles_b, splits;
+  int64_t vox_total, vox_per_split;
+};
+
+int launch_gather(GatherParams p, int dtype, const void* src, const void* w, const float* bias,
+                  const void* res, void* dst, cudaStream_t st);
+void wgrad_plan(WgradParams& p);
+size_t wgrad_partial_bytes(const WgradParams& p);
+int launch_wgrad(const WgradParams& p, int dtype, const void* S, const void* T, float* gw,
+                 float* partial, cudaStream_t st);
+int colsum_blocks(int64_t nvox);
+int launch_colsum(int dtype, const void* x, int64_t nvox, int c, int ld, float* out, float* partial,
+                  cudaStream_t st);
+int launch_pack_weight(int dtype, int kind, const float* w, void* packed, int taps, int cin,
+                       int cout, cudaStream_t st);
+
+// norm.cu
+int norm_blocks(const b200seg_norm_desc& d);
+size_t norm_workspace_bytes(const b200seg_norm_desc& d);
+int launch_instnorm_stats(const b200seg_norm_desc& d, const void* x, float* mean, float* rstd,
+                          void* ws, cudaStream_t st);
+int launch_instnorm_prelu_fwd(const b200seg_norm_desc& d, const void* x, const float* mean,
+                              const float* rstd, const float* alpha, const void* res, void* y,
+                              cudaStream_t st);
+int launch_instnorm_prelu_bwd(const b200seg_norm_desc& d, const void* x, const float* mean,
+                              const float* rstd, const float* alpha, const void* dy, void* dx,
+                              float* dalpha, void* ws, cudaStream_t st);
+
+// dice.cu
+size_t dice_workspace_bytes(const b200seg_dice_desc& d);
+int launch_softmax_dice_fwd(const b200seg_dice_desc& d, const void* logits, const void* labels,
+                            float* sums, void* ws, cudaStream_t st);
+int launch_softmax_dice_bwd(const b200seg_dice_desc& d, const void* logits, const void* labels,
+                            const float* gI, const float* gP, void* dlogits, cudaStream_t st);
+int launch_argmax_dice_counts(const b200seg_dice_desc& d, const void* logits, const void* target,
+                              uint8_t* pred_out, int64_t* counts, cudaStream_t st);
+int launch_label_dice_counts(int n, int64_t spatial, int c, const uint8_t* pred, const void* target,
+                             int target_dtype, int64_t* counts, cudaStream_t st);
+int launch_squash_masks(int n, int n_struct, int64_t spatial, const uint8_t* masks, uint8_t* labels,
+                        cudaStream_t st);
+int launch_hu_window_norm(int64_t n_vox, int n_windows, const int16_t* hu, const float* lo,
+                          const float* hi, const float* mean, const float* std_, void* out,
+                          int out_ld, int dtype, cudaStream_t st);
+
+}  // namespace b200seg

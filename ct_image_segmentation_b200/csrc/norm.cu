@@ -1,0 +1,405 @@
+// InstanceNorm (affine=False, biased variance, eps inside the sqrt) fused with PReLU (one shared
+// alpha) and the residual sum of the enclosing ResidualUnit.  Channels-last, bandwidth-bound:
+// vectorised coalesced access (up to 16 B per thread), fp32 statistics, deterministic two-stage
+// reductions (per-block partials, then a fixed-order finalisation in double).
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200seg {
+
+namespace {
+
+struct NormGeom {
+  int V;      // elements per thread access
+  int L;      // threads per voxel  (= C / V)
+  int VB;     // voxels per block iteration (= 256 / L)
+  int nblk;   // blocks per sample for the reduction kernels
+  int nblk_apply;
+};
+
+inline bool aligned(const void* p, size_t a) { return p == nullptr || ((uintptr_t)p % a) == 0; }
+
+// largest V in {8,4,2,1} with V*esz <= 16 that divides C and every ld and keeps 'ptrs' aligned
+int pick_vec(const b200seg_norm_desc& d, std::initializer_list<const void*> ptrs,
+             std::initializer_list<int> lds) {
+  size_t esz = d.dtype == B200SEG_BF16 ? 2 : 4;
+  for (int V = (int)(16 / esz); V > 1; V >>= 1) {
+    bool ok = (d.c % V) == 0;
+    for (int ld : lds) ok = ok && (ld % V) == 0;
+    for (const void* p : ptrs) ok = ok && aligned(p, V * esz);
+    if (ok) return V;
+  }
+  return 1;
+}
+
+}  // namespace
+
+int norm_blocks(const b200seg_norm_desc& d) {
+  int64_t nb = cdiv64(d.spatial, 1024);
+  int64_t cap = 1184 / (d.n > 0 ? d.n : 1);
+  if (cap < 1) cap = 1;
+  if (nb > cap) nb = cap;
+  if (nb < 1) nb = 1;
+  return (int)nb;
+}
+
+size_t norm_workspace_bytes(const b200seg_norm_desc& d) {
+  size_t nb = norm_blocks(d);
+  return ((size_t)d.n * nb * d.c * 3 + (size_t)d.n * d.c * 3) * sizeof(float) + 256;
+}
+
+// ------------------------------------------------------------------------------------------
+template <typename T, int V, int NACC, typename F>
+__device__ __forceinline__ void block_reduce_store(float (&acc)[NACC][V], int L, int VB, int vi,
+                                                   int l, float* red, float* out, int c, F) {
+  // red: [256][NACC*V] floats in shared memory
+  const int t = threadIdx.x;
+#pragma unroll
+  for (int a = 0; a < NACC; ++a)
+#pragma unroll
+    for (int i = 0; i < V; ++i) red[t * (NACC * V) + a * V + i] = acc[a][i];
+  __syncthreads();
+  int s = 1;
+  while (s < VB) s <<= 1;
+  for (s >>= 1; s >= 1; s >>= 1) {
+    if (vi < s && vi + s < VB) {
+#pragma unroll
+      for (int j = 0; j < NACC * V; ++j) red[t * (NACC * V) + j] += red[(t + s * L) * (NACC * V) + j];
+    }
+    __syncthreads();
+  }
+  if (vi == 0) {
+#pragma unroll
+    for (int a = 0; a < NACC; ++a)
+#pragma unroll
+      for (int i = 0; i < V; ++i) out[(l * V + i) * NACC + a] = red[t * (NACC * V) + a * V + i];
+  }
+}
+
+// partial[n][blk][c][2] = { sum x, sum x^2 }
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+instnorm_stats_partial_kernel(const T* __restrict__ x, int64_t spatial, int c, int ld, int L, int VB,
+                              int64_t vox_per_block, float* __restrict__ partial) {
+  extern __shared__ float red[];
+  const int t = threadIdx.x, vi = t / L, l = t % L;
+  const int n = blockIdx.y;
+  const int64_t v_begin = (int64_t)blockIdx.x * vox_per_block;
+  const int64_t v_end = min(v_begin + vox_per_block, spatial);
+  float acc[2][V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[0][i] = acc[1][i] = 0.f;
+  if (vi < VB) {
+    const T* base = x + ((int64_t)n * spatial) * ld + l * V;
+    for (int64_t v = v_begin + vi; v < v_end; v += VB) {
+      Vec<T, V> xv;
+      xv.load(base + v * ld);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        acc[0][i] += xv.v[i];
+        acc[1][i] = fmaf(xv.v[i], xv.v[i], acc[1][i]);
+      }
+    }
+  }
+  float* out = partial + ((int64_t)n * gridDim.x + blockIdx.x) * c * 2;
+  block_reduce_store<T, V, 2>(acc, L, VB, vi, l, red, out, c, 0);
+}
+
+// one warp per (n, c): mean, rstd from the block partials (double accumulation, fixed order)
+__global__ void instnorm_stats_final_kernel(const float* __restrict__ partial, int nblk, int c,
+                                            int nc_total, int64_t spatial, float eps,
+                                            float* __restrict__ mean, float* __restrict__ rstd) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (warp >= nc_total) return;
+  int n = warp / c, ch = warp % c;
+  double s1 = 0.0, s2 = 0.0;
+  for (int b = lane; b < nblk; b += 32) {
+    const float* p = partial + (((int64_t)n * nblk + b) * c + ch) * 2;
+    s1 += (double)p[0];
+    s2 += (double)p[1];
+  }
+  s1 = warp_sum_d(s1);
+  s2 = warp_sum_d(s2);
+  if (lane == 0) {
+    double m = s1 / (double)spatial;
+    double var = s2 / (double)spatial - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[warp] = (float)m;
+    rstd[warp] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+instnorm_prelu_fwd_kernel(const T* __restrict__ x, const float* __restrict__ mean,
+                          const float* __restrict__ rstd, const float* __restrict__ alpha,
+                          const T* __restrict__ res, T* __restrict__ y, int64_t spatial, int c,
+                          int x_ld, int y_ld, int r_ld, int L, int VB, int64_t vox_per_block) {
+  const int t = threadIdx.x, vi = t / L, l = t % L;
+  if (vi >= VB) return;
+  const int n = blockIdx.y;
+  const int64_t v_begin = (int64_t)blockIdx.x * vox_per_block;
+  const int64_t v_end = min(v_begin + vox_per_block, spatial);
+  float m[V], r[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    m[i] = mean[n * c + l * V + i];
+    r[i] = rstd[n * c + l * V + i];
+  }
+  const float a = alpha[0];
+  const int64_t vox0 = (int64_t)n * spatial;
+  for (int64_t v = v_begin + vi; v < v_end; v += VB) {
+    Vec<T, V> xv, ov;
+    xv.load(x + (vox0 + v) * x_ld + l * V);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float h = (xv.v[i] - m[i]) * r[i];
+      ov.v[i] = h > 0.f ? h : a * h;
+    }
+    if (res) {
+      Vec<T, V> rv;
+      rv.load(res + (vox0 + v) * r_ld + l * V);
+#pragma unroll
+      for (int i = 0; i < V; ++i) ov.v[i] += rv.v[i];
+    }
+    ov.store(y + (vox0 + v) * y_ld + l * V);
+  }
+}
+
+// partial[n][blk][c][3] = { sum g~, sum g~*xhat, sum dy*xhat*[xhat<=0] },  g~ = dy * prelu'(xhat)
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+instnorm_prelu_bwd_partial_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                  const float* __restrict__ mean, const float* __restrict__ rstd,
+                                  const float* __restrict__ alpha, int64_t spatial, int c, int x_ld,
+                                  int dy_ld, int L, int VB, int64_t vox_per_block,
+                                  float* __restrict__ partial) {
+  extern __shared__ float red[];
+  const int t = threadIdx.x, vi = t / L, l = t % L;
+  const int n = blockIdx.y;
+  const int64_t v_begin = (int64_t)blockIdx.x * vox_per_block;
+  const int64_t v_end = min(v_begin + vox_per_block, spatial);
+  float acc[3][V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[0][i] = acc[1][i] = acc[2][i] = 0.f;
+  if (vi < VB) {
+    float m[V], r[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      m[i] = mean[n * c + l * V + i];
+      r[i] = rstd[n * c + l * V + i];
+    }
+    const float a = alpha[0];
+    const int64_t vox0 = (int64_t)n * spatial;
+    for (int64_t v = v_begin + vi; v < v_end; v += VB) {
+      Vec<T, V> xv, gv;
+      xv.load(x + (vox0 + v) * x_ld + l * V);
+      gv.load(dy + (vox0 + v) * dy_ld + l * V);
+#pragma unroll
+      for (int i = 0; i < V; ++i) {
+        float h = (xv.v[i] - m[i]) * r[i];
+        bool pos = h > 0.f;
+        float g = pos ? gv.v[i] : a * gv.v[i];
+        acc[0][i] += g;
+        acc[1][i] = fmaf(g, h, acc[1][i]);
+        acc[2][i] += pos ? 0.f : gv.v[i] * h;
+      }
+    }
+  }
+  float* out = partial + ((int64_t)n * gridDim.x + blockIdx.x) * c * 3;
+  block_reduce_store<T, V, 3>(acc, L, VB, vi, l, red, out, c, 0);
+}
+
+// sums[nc][3] = { s1/S, s2/S, dalpha contribution }
+__global__ void instnorm_bwd_final_kernel(const float* __restrict__ partial, int nblk, int c,
+                                          int nc_total, int64_t spatial, float* __restrict__ sums) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (warp >= nc_total) return;
+  int n = warp / c, ch = warp % c;
+  double s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  for (int b = lane; b < nblk; b += 32) {
+    const float* p = partial + (((int64_t)n * nblk + b) * c + ch) * 3;
+    s1 += (double)p[0];
+    s2 += (double)p[1];
+    s3 += (double)p[2];
+  }
+  s1 = warp_sum_d(s1);
+  s2 = warp_sum_d(s2);
+  s3 = warp_sum_d(s3);
+  if (lane == 0) {
+    sums[warp * 3 + 0] = (float)(s1 / (double)spatial);
+    sums[warp * 3 + 1] = (float)(s2 / (double)spatial);
+    sums[warp * 3 + 2] = (float)s3;
+  }
+}
+
+// dalpha = sum over (n,c) of sums[.][2], one block, fixed order
+__global__ void dalpha_final_kernel(const float* __restrict__ sums, int nc_total,
+                                    float* __restrict__ dalpha) {
+  __shared__ double red[256];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nc_total; i += 256) s += (double)sums[i * 3 + 2];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) dalpha[0] = (float)red[0];
+}
+
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+instnorm_prelu_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy,
+                                const float* __restrict__ mean, const float* __restrict__ rstd,
+                                const float* __restrict__ alpha, const float* __restrict__ sums,
+                                T* __restrict__ dx, int64_t spatial, int c, int x_ld, int dy_ld,
+                                int dx_ld, int L, int VB, int64_t vox_per_block) {
+  const int t = threadIdx.x, vi = t / L, l = t % L;
+  if (vi >= VB) return;
+  const int n = blockIdx.y;
+  const int64_t v_begin = (int64_t)blockIdx.x * vox_per_block;
+  const int64_t v_end = min(v_begin + vox_per_block, spatial);
+  float m[V], r[V], s1[V], s2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    int idx = n * c + l * V + i;
+    m[i] = mean[idx];
+    r[i] = rstd[idx];
+    s1[i] = sums[idx * 3 + 0];
+    s2[i] = sums[idx * 3 + 1];
+  }
+  const float a = alpha[0];
+  const int64_t vox0 = (int64_t)n * spatial;
+  for (int64_t v = v_begin + vi; v < v_end; v += VB) {
+    Vec<T, V> xv, gv, ov;
+    xv.load(x + (vox0 + v) * x_ld + l * V);
+    gv.load(dy + (vox0 + v) * dy_ld + l * V);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float h = (xv.v[i] - m[i]) * r[i];
+      float g = h > 0.f ? gv.v[i] : a * gv.v[i];
+      ov.v[i] = r[i] * (g - s1[i] - h * s2[i]);
+    }
+    ov.store(dx + (vox0 + v) * dx_ld + l * V);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+namespace {
+
+int make_geom(const b200seg_norm_desc& d, int V, NormGeom& g) {
+  g.V = V;
+  g.L = d.c / V;
+  if (g.L > 256 || g.L < 1) {
+    set_error("instnorm: %d channels with vector width %d needs more than 256 threads per voxel",
+              d.c, V);
+    return B200SEG_ERR_UNSUPPORTED;
+  }
+  g.VB = 256 / g.L;
+  g.nblk = norm_blocks(d);
+  int64_t nb = cdiv64(d.spatial, (int64_t)g.VB * 8);
+  int64_t cap = 2368 / (d.n > 0 ? d.n : 1);
+  if (cap < 1) cap = 1;
+  if (nb > cap) nb = cap;
+  if (nb < 1) nb = 1;
+  g.nblk_apply = (int)nb;
+  return B200SEG_OK;
+}
+
+#define DISPATCH_TV(dtype, V, ...)                                                       \
+  do {                                                                                   \
+    if (dtype == B200SEG_BF16) {                                                         \
+      using T = __nv_bfloat16;                                                           \
+      switch (V) {                                                                       \
+        case 8: { constexpr int VV = 8; __VA_ARGS__; } break;                            \
+        case 4: { constexpr int VV = 4; __VA_ARGS__; } break;                            \
+        case 2: { constexpr int VV = 2; __VA_ARGS__; } break;                            \
+        default: { constexpr int VV = 1; __VA_ARGS__; } break;                           \
+      }                                                                                  \
+    } else {                                                                             \
+      using T = float;                                                                   \
+      switch (V) {                                                                       \
+        case 4: { constexpr int VV = 4; __VA_ARGS__; } break;                            \
+        case 2: { constexpr int VV = 2; __VA_ARGS__; } break;                            \
+        default: { constexpr int VV = 1; __VA_ARGS__; } break;                           \
+      }                                                                                  \
+    }                                                                                    \
+  } while (0)
+
+}  // namespace
+
+int launch_instnorm_stats(const b200seg_norm_desc& d, const void* x, float* mean, float* rstd,
+                          void* ws, cudaStream_t st) {
+  NormGeom g;
+  int V = pick_vec(d, {x}, {d.x_ld});
+  int rc = make_geom(d, V, g);
+  if (rc) return rc;
+  float* partial = (float*)ws;
+  int64_t per = cdiv64(d.spatial, g.nblk);
+  dim3 grid(g.nblk, d.n);
+  size_t smem = 256 * 2 * V * sizeof(float);
+  DISPATCH_TV(d.dtype, V,
+              (instnorm_stats_partial_kernel<T, VV><<<grid, 256, smem, st>>>(
+                  (const T*)x, d.spatial, d.c, d.x_ld, g.L, g.VB, per, partial)));
+  B200SEG_CHECK_LAUNCH("instnorm_stats_partial");
+  int nc = d.n * d.c;
+  instnorm_stats_final_kernel<<<(nc * 32 + 255) / 256, 256, 0, st>>>(partial, g.nblk, d.c, nc,
+                                                                     d.spatial, d.eps, mean, rstd);
+  B200SEG_CHECK_LAUNCH("instnorm_stats_final");
+  return B200SEG_OK;
+}
+
+int launch_instnorm_prelu_fwd(const b200seg_norm_desc& d, const void* x, const float* mean,
+                              const float* rstd, const float* alpha, const void* res, void* y,
+                              cudaStream_t st) {
+  NormGeom g;
+  int V = res ? pick_vec(d, {x, y, res}, {d.x_ld, d.y_ld, d.r_ld})
+              : pick_vec(d, {x, y}, {d.x_ld, d.y_ld});
+  int rc = make_geom(d, V, g);
+  if (rc) return rc;
+  int64_t per = cdiv64(d.spatial, g.nblk_apply);
+  dim3 grid(g.nblk_apply, d.n);
+  DISPATCH_TV(d.dtype, V,
+              (instnorm_prelu_fwd_kernel<T, VV><<<grid, 256, 0, st>>>(
+                  (const T*)x, mean, rstd, alpha, (const T*)res, (T*)y, d.spatial, d.c, d.x_ld,
+                  d.y_ld, d.r_ld, g.L, g.VB, per)));
+  B200SEG_CHECK_LAUNCH("instnorm_prelu_fwd");
+  return B200SEG_OK;
+}
+
+int launch_instnorm_prelu_bwd(const b200seg_norm_desc& d, const void* x, const float* mean,
+                              const float* rstd, const float* alpha, const void* dy, void* dx,
+                              float* dalpha, void* ws, cudaStream_t st) {
+  // descriptor roles in the backward: x_ld -> x, y_ld -> dy, r_ld -> dx
+  NormGeom g;
+  int V = pick_vec(d, {x, dy, dx}, {d.x_ld, d.y_ld, d.r_ld});
+  int rc = make_geom(d, V, g);
+  if (rc) return rc;
+  float* partial = (float*)ws;
+  float* sums = partial + (size_t)d.n * g.nblk * d.c * 3;
+  int64_t per = cdiv64(d.spatial, g.nblk);
+  dim3 grid(g.nblk, d.n);
+  size_t smem = 256 * 3 * V * sizeof(float);
+  DISPATCH_TV(d.dtype, V,
+              (instnorm_prelu_bwd_partial_kernel<T, VV><<<grid, 256, smem, st>>>(
+                  (const T*)x, (const T*)dy, mean, rstd, alpha, d.spatial, d.c, d.x_ld, d.y_ld,
+                  g.L, g.VB, per, partial)));
+  B200SEG_CHECK_LAUNCH("instnorm_prelu_bwd_partial");
+  int nc = d.n * d.c;
+  instnorm_bwd_final_kernel<<<(nc * 32 + 255) / 256, 256, 0, st>>>(partial, g.nblk, d.c, nc,
+                                                                   d.spatial, sums);
+  B200SEG_CHECK_LAUNCH("instnorm_bwd_final");
+  dalpha_final_kernel<<<1, 256, 0, st>>>(sums, nc, dalpha);
+  B200SEG_CHECK_LAUNCH("dalpha_final");
+  int64_t per2 = cdiv64(d.spatial, g.nblk_apply);
+  dim3 grid2(g.nblk_apply, d.n);
+  DISPATCH_TV(d.dtype, V,
+              (instnorm_prelu_bwd_apply_kernel<T, VV><<<grid2, 256, 0, st>>>(
+                  (const T*)x, (const T*)dy, mean, rstd, alpha, sums, (T*)dx, d.spatial, d.c,
+                  d.x_ld, d.y_ld, d.r_ld, g.L, g.VB, per2)));
+  B200SEG_CHECK_LAUNCH("instnorm_prelu_bwd_apply");
+  return B200SEG_OK;
+}
+
+}  // namespace b200seg

@@ -1,0 +1,18 @@
+// tcgen05 / TMEM / TMA implicit-GEMM convolution family (bf16, fp32 accumulation).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+
+#include "../../include/b200seg.h"
+
+namespace b200seg {
+
+enum TcConvOp { TC_CONV_FPROP = 0, TC_CONV_DGRAD = 1, TC_CONVTR_FPROP = 2, TC_CONVTR_DGRAD = 3 };
+
+// true when the tcgen05 kernel takes this layer/op (bf16, channel counts multiple of 16, ...)
+bool tc_conv_supported(const b200seg_conv_desc* d, int op);
+int tc_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_packed,
+                const float* bias, const void* residual, void* dst, cudaStream_t st);
+size_t tc_wgrad_extra_workspace(const b200seg_conv_desc* d);
+
+}  // namespace b200seg

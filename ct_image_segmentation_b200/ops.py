@@ -1,0 +1,359 @@
+"""Thin host-side wrappers: torch tensors in, C-ABI calls on the current CUDA stream.
+
+Activations are *channels-last* tensors of shape ``(N, D, H, W, C)`` (2-D data: ``D == 1``)
+whose last-dim stride is 1 and whose voxel stride ``ld >= C`` is uniform, i.e. either a
+contiguous tensor or a channel slice ``buf[..., c0:c1]`` of one (zero-copy concatenation).
+Nothing here falls back to PyTorch arithmetic: a missing library or a failed launch raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32, ConvDesc, DiceDesc, NormDesc
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def dtype_code(dt: torch.dtype) -> int:
+    try:
+        return _DT[dt]
+    except KeyError:
+        raise TypeError(f"b200seg kernels take float32 or bfloat16 activations, got {dt}") from None
+
+
+def cl_info(t: torch.Tensor) -> Tuple[int, int, int, int, int, int]:
+    """(n, d, h, w, c, ld) of a channels-last activation; raises if the layout is not usable."""
+    if t.dim() != 5:
+        raise ValueError(f"expected (N, D, H, W, C), got shape {tuple(t.shape)}")
+    n, d, h, w, c = t.shape
+    sn, sd, sh, sw, sc = t.stride()
+    ld = sw if w > 1 else (sh if h > 1 else (sd if d > 1 else (sn if n > 1 else c)))
+    ok = (sc == 1 or c == 1) and ld >= c
+    ok = ok and (w == 1 or sw == ld) and (h == 1 or sh == w * ld) and (d == 1 or sd == h * w * ld)
+    ok = ok and (n == 1 or sn == d * h * w * ld)
+    if not ok:
+        raise ValueError(f"tensor is not channels-last with a uniform voxel stride: shape "
+                         f"{tuple(t.shape)}, strides {t.stride()}")
+    if not t.is_cuda:
+        raise RuntimeError("b200seg ops need CUDA tensors (no CPU fallback)")
+    return n, d, h, w, c, ld
+
+
+def to_channels_last(x: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """(N, C, *S) logical tensor -> (N, D, H, W, C) channels-last (a view when already so)."""
+    if x.dim() == 4:
+        x = x.unsqueeze(2)
+    y = x.permute(0, 2, 3, 4, 1)
+    if dtype is not None and y.dtype != dtype:
+        y = y.to(dtype)
+    return y if y.is_contiguous() else y.contiguous()
+
+
+def from_channels_last(y: torch.Tensor, dims: int) -> torch.Tensor:
+    """(N, D, H, W, C) -> logical (N, C, D, H, W) / (N, C, H, W) view (no copy)."""
+    out = y.permute(0, 4, 1, 2, 3)
+    return out.squeeze(2) if dims == 2 else out
+
+
+# ----------------------------------------------------------------------------------------------
+# workspace (owned by the caller side of the ABI: a grow-only per-stream torch buffer)
+# ----------------------------------------------------------------------------------------------
+_workspaces = {}
+
+
+def workspace(nbytes: int, device: torch.device) -> torch.Tensor:
+    key = (device.index if device.index is not None else torch.cuda.current_device(), _stream())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+# ----------------------------------------------------------------------------------------------
+# convolution
+# ----------------------------------------------------------------------------------------------
+@dataclass(frozen=True)
+class ConvGeom:
+    """One Conv / ConvTranspose layer of the U-Net (kernel 1 or 3, stride 1 or 2, same padding)."""
+    dims: int          # 2 or 3
+    cin: int
+    cout: int
+    kernel: int        # 1 or 3
+    stride: int        # 1 or 2
+    transposed: bool
+
+    def out_spatial(self, d: int, h: int, w: int) -> Tuple[int, int, int]:
+        k, s, p = self.kernel, self.stride, (self.kernel - 1) // 2
+        if self.transposed:
+            f = lambda n: (n - 1) * s - 2 * p + k + (s - 1)
+        else:
+            f = lambda n: (n + 2 * p - k) // s + 1
+        return (d if self.dims == 2 else f(d)), f(h), f(w)
+
+    def desc(self, n, in_sp, out_sp, x_ld, y_ld, r_ld, dtype, flags=0) -> ConvDesc:
+        k, s, p = self.kernel, self.stride, (self.kernel - 1) // 2
+        kd, sd, pd = (1, 1, 0) if self.dims == 2 else (k, s, p)
+        return ConvDesc(n, self.cin, self.cout, *in_sp, *out_sp, kd, k, k, sd, s, s, pd, p, p,
+                        x_ld, y_ld, r_ld, dtype_code(dtype), flags)
+
+
+def pack_weight(geom: ConvGeom, kind: int, w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """fp32 PyTorch-layout parameter -> kernel layout for one data-path use."""
+    lib = _lib.load()
+    w = w.detach()
+    if w.dtype != torch.float32 or not w.is_contiguous():
+        w = w.float().contiguous()
+    d = geom.desc(1, (1, 1, 1), (1, 1, 1), geom.cin, geom.cout, 0, dtype)
+    nbytes = lib.b200seg_packed_weight_bytes(C.byref(d), kind)
+    out = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+    _lib.check(lib.b200seg_pack_weight(C.byref(d), kind, w.data_ptr(), out.data_ptr(), _stream()),
+               "b200seg_pack_weight")
+    return out
+
+
+def _conv_call(geom: ConvGeom, src, wp, bias, residual, dst, data_grad: bool, flags: int):
+    """Shared driver of the four data-path entry points.  ``src``/``dst`` are x/y for fprop and
+    dy/dx for dgrad; the descriptor is always written in the layer's own terms."""
+    lib = _lib.load()
+    n, sd_, sh_, sw_, sc, s_ld = cl_info(src)
+    n2, dd_, dh_, dw_, dc, d_ld = cl_info(dst)
+    if n != n2 or src.dtype != dst.dtype:
+        raise ValueError("conv: batch/dtype mismatch between source and destination")
+    r_ld = 0
+    if residual is not None:
+        rn, rd, rh, rw, rc, r_ld = cl_info(residual)
+        if (rn, rd, rh, rw, rc) != (n2, dd_, dh_, dw_, dc) or residual.dtype != dst.dtype:
+            raise ValueError("conv: residual must match the destination")
+    if not data_grad:
+        in_sp, out_sp, x_ld, y_ld = (sd_, sh_, sw_), (dd_, dh_, dw_), s_ld, d_ld
+        if (sc, dc) != (geom.cin, geom.cout):
+            raise ValueError(f"conv fprop: channels {(sc, dc)} != {(geom.cin, geom.cout)}")
+    else:
+        in_sp, out_sp, x_ld, y_ld = (dd_, dh_, dw_), (sd_, sh_, sw_), d_ld, s_ld
+        if (sc, dc) != (geom.cout, geom.cin):
+            raise ValueError(f"conv dgrad: channels {(sc, dc)} != {(geom.cout, geom.cin)}")
+    if geom.out_spatial(*in_sp) != tuple(out_sp):
+        raise ValueError(f"conv: spatial extents {in_sp} -> {out_sp} inconsistent with {geom}")
+    d = geom.desc(n, in_sp, out_sp, x_ld, y_ld, r_ld, src.dtype, flags)
+    name = ("b200seg_convtr_" if geom.transposed else "b200seg_conv_") + ("dgrad" if data_grad else "fprop")
+    fn = getattr(lib, name)
+    if data_grad:
+        rc = fn(C.byref(d), src.data_ptr(), wp.data_ptr(), _ptr(residual), dst.data_ptr(), _stream())
+    else:
+        if bias is not None and (bias.dtype != torch.float32 or not bias.is_contiguous()):
+            raise ValueError("conv: bias must be contiguous float32")
+        rc = fn(C.byref(d), src.data_ptr(), wp.data_ptr(), _ptr(bias), _ptr(residual), dst.data_ptr(),
+                _stream())
+    _lib.check(rc, name)
+    return dst
+
+
+def conv_fprop(geom, x, wp, bias, y, residual=None, flags=0):
+    """y = conv(x) [+ bias] [+ residual]  (Conv or ConvTranspose per ``geom``)."""
+    return _conv_call(geom, x, wp, bias, residual, y, False, flags)
+
+
+def conv_dgrad(geom, dy, wp, dx, residual=None, accumulate=False, flags=0):
+    """dx = conv^T(dy) [+ residual] [+ dx]."""
+    if accumulate:
+        flags |= _lib.CONV_ACCUMULATE
+    return _conv_call(geom, dy, wp, None, residual, dx, True, flags)
+
+
+def conv_wgrad(geom: ConvGeom, x, dy, want_bias: bool = True, flags=0):
+    """(gw, gbias): fp32 gradients in PyTorch parameter layout."""
+    lib = _lib.load()
+    n, xd, xh, xw, xc, x_ld = cl_info(x)
+    n2, yd, yh, yw, yc, y_ld = cl_info(dy)
+    if n != n2 or (xc, yc) != (geom.cin, geom.cout) or x.dtype != dy.dtype:
+        raise ValueError("conv wgrad: shape/dtype mismatch")
+    d = geom.desc(n, (xd, xh, xw), (yd, yh, yw), x_ld, y_ld, 0, x.dtype, flags)
+    k = geom.kernel
+    ks = (k, k) if geom.dims == 2 else (k, k, k)
+    shape = (geom.cin, geom.cout, *ks) if geom.transposed else (geom.cout, geom.cin, *ks)
+    gw = torch.empty(shape, dtype=torch.float32, device=x.device)
+    gb = torch.empty(geom.cout, dtype=torch.float32, device=x.device) if want_bias else None
+    pre = "b200seg_convtr_wgrad" if geom.transposed else "b200seg_conv_wgrad"
+    nbytes = getattr(lib, pre + "_workspace_bytes")(C.byref(d))
+    ws = workspace(nbytes, x.device)
+    rc = getattr(lib, pre)(C.byref(d), x.data_ptr(), dy.data_ptr(), gw.data_ptr(), _ptr(gb),
+                           ws.data_ptr(), ws.numel(), _stream())
+    _lib.check(rc, pre)
+    return gw, gb
+
+
+# ----------------------------------------------------------------------------------------------
+# InstanceNorm + PReLU
+# ----------------------------------------------------------------------------------------------
+def _norm_desc(x, y_ld, r_ld, eps):
+    n, d, h, w, c, x_ld = cl_info(x)
+    return NormDesc(n, c, d * h * w, x_ld, y_ld, r_ld, dtype_code(x.dtype), eps), (n, c)
+
+
+def instnorm_stats(x, eps: float = 1e-5):
+    lib = _lib.load()
+    d, (n, c) = _norm_desc(x, 0, 0, eps)
+    mean = torch.empty(n * c, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(n * c, dtype=torch.float32, device=x.device)
+    nbytes = lib.b200seg_instnorm_workspace_bytes(C.byref(d))
+    ws = workspace(nbytes, x.device)
+    _lib.check(lib.b200seg_instnorm_stats(C.byref(d), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                          ws.data_ptr(), ws.numel(), _stream()), "b200seg_instnorm_stats")
+    return mean, rstd
+
+
+def instnorm_prelu_fwd(x, mean, rstd, alpha, y, residual=None, eps: float = 1e-5):
+    lib = _lib.load()
+    y_ld = cl_info(y)[5]
+    r_ld = cl_info(residual)[5] if residual is not None else 0
+    if y.shape != x.shape or (residual is not None and residual.shape != x.shape):
+        raise ValueError("instnorm_prelu_fwd: shape mismatch")
+    d, _ = _norm_desc(x, y_ld, r_ld, eps)
+    _lib.check(lib.b200seg_instnorm_prelu_fwd(C.byref(d), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                              alpha.data_ptr(), _ptr(residual), y.data_ptr(), _stream()),
+               "b200seg_instnorm_prelu_fwd")
+    return y
+
+
+def instnorm_prelu_bwd(x, mean, rstd, alpha, dy, dx, eps: float = 1e-5):
+    """Writes dx; returns dalpha (1-element fp32 tensor)."""
+    lib = _lib.load()
+    if dy.shape != x.shape or dx.shape != x.shape:
+        raise ValueError("instnorm_prelu_bwd: shape mismatch")
+    d, _ = _norm_desc(x, cl_info(dy)[5], cl_info(dx)[5], eps)
+    dalpha = torch.empty(1, dtype=torch.float32, device=x.device)
+    nbytes = lib.b200seg_instnorm_workspace_bytes(C.byref(d))
+    ws = workspace(nbytes, x.device)
+    _lib.check(lib.b200seg_instnorm_prelu_bwd(C.byref(d), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                              alpha.data_ptr(), dy.data_ptr(), dx.data_ptr(),
+                                              dalpha.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+               "b200seg_instnorm_prelu_bwd")
+    return dalpha
+
+
+# ----------------------------------------------------------------------------------------------
+# softmax + Dice, label maps
+# ----------------------------------------------------------------------------------------------
+def _labels(labels: torch.Tensor, n: int, spatial: int):
+    if labels.dtype == torch.uint8:
+        code = _lib.LABEL_U8
+    else:
+        if labels.dtype != torch.int64:
+            labels = labels.long()  # MONAI does target.long()
+        code = _lib.LABEL_I64
+    if not labels.is_contiguous():
+        labels = labels.contiguous()
+    if labels.numel() != n * spatial:
+        raise ValueError(f"labels have {labels.numel()} elements, expected {n * spatial}")
+    return labels, code
+
+
+def _dice_desc(logits, label_code, include_background=False):
+    n, d, h, w, c, ld = cl_info(logits)
+    return DiceDesc(n, c, d * h * w, ld, dtype_code(logits.dtype), label_code, int(include_background))
+
+
+def softmax_dice_sums(logits, labels) -> torch.Tensor:
+    """(N, C, 3) fp32: I = sum p*t, G = sum t, P = sum p per sample and class."""
+    lib = _lib.load()
+    n, d, h, w, c, ld = cl_info(logits)
+    labels, code = _labels(labels, n, d * h * w)
+    desc = _dice_desc(logits, code)
+    sums = torch.empty(n, c, 3, dtype=torch.float32, device=logits.device)
+    nbytes = lib.b200seg_softmax_dice_workspace_bytes(C.byref(desc))
+    ws = workspace(nbytes, logits.device)
+    _lib.check(lib.b200seg_softmax_dice_fwd(C.byref(desc), logits.data_ptr(), labels.data_ptr(),
+                                            sums.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+               "b200seg_softmax_dice_fwd")
+    return sums
+
+
+def softmax_dice_bwd(logits, labels, g_i, g_p, dlogits=None) -> torch.Tensor:
+    lib = _lib.load()
+    n, d, h, w, c, ld = cl_info(logits)
+    labels, code = _labels(labels, n, d * h * w)
+    if dlogits is None:
+        dlogits = torch.empty_like(logits) if logits.is_contiguous() else \
+            torch.empty(logits.shape, dtype=logits.dtype, device=logits.device)
+    if cl_info(dlogits)[5] != ld:
+        raise ValueError("softmax_dice_bwd: dlogits must share the logits' voxel stride")
+    g_i = g_i.contiguous().float()
+    g_p = g_p.contiguous().float()
+    desc = _dice_desc(logits, code)
+    _lib.check(lib.b200seg_softmax_dice_bwd(C.byref(desc), logits.data_ptr(), labels.data_ptr(),
+                                            g_i.data_ptr(), g_p.data_ptr(), dlogits.data_ptr(), _stream()),
+               "b200seg_softmax_dice_bwd")
+    return dlogits
+
+
+def argmax_dice_counts(logits, target=None, want_pred=True):
+    """(pred uint8 (N, D, H, W) or None, counts int64 (N, C, 3) or None)."""
+    lib = _lib.load()
+    n, d, h, w, c, ld = cl_info(logits)
+    code, tptr, counts = _lib.LABEL_U8, None, None
+    if target is not None:
+        target, code = _labels(target, n, d * h * w)
+        tptr = target.data_ptr()
+        counts = torch.empty(n, c, 3, dtype=torch.int64, device=logits.device)
+    pred = torch.empty(n, d, h, w, dtype=torch.uint8, device=logits.device) if want_pred else None
+    desc = _dice_desc(logits, code)
+    _lib.check(lib.b200seg_argmax_dice_counts(C.byref(desc), logits.data_ptr(), tptr, _ptr(pred),
+                                              _ptr(counts), _stream()), "b200seg_argmax_dice_counts")
+    return pred, counts
+
+
+def label_dice_counts(pred, target, n_classes: int) -> torch.Tensor:
+    lib = _lib.load()
+    n = pred.shape[0]
+    spatial = pred.numel() // n
+    if pred.dtype != torch.uint8:
+        pred = pred.to(torch.uint8)
+    pred = pred.contiguous()
+    target, code = _labels(target, n, spatial)
+    counts = torch.empty(n, n_classes, 3, dtype=torch.int64, device=pred.device)
+    _lib.check(lib.b200seg_label_dice_counts(n, spatial, n_classes, pred.data_ptr(), target.data_ptr(),
+                                             code, counts.data_ptr(), _stream()), "b200seg_label_dice_counts")
+    return counts
+
+
+def squash_masks(masks: torch.Tensor) -> torch.Tensor:
+    """(N, S, *spatial) uint8 binary masks -> (N, *spatial) uint8 label map."""
+    lib = _lib.load()
+    if masks.dtype != torch.uint8:
+        masks = masks.to(torch.uint8)
+    masks = masks.contiguous()
+    n, s = masks.shape[:2]
+    spatial = masks[0, 0].numel()
+    out = torch.empty((n,) + tuple(masks.shape[2:]), dtype=torch.uint8, device=masks.device)
+    _lib.check(lib.b200seg_squash_masks(n, s, spatial, masks.data_ptr(), out.data_ptr(), _stream()),
+               "b200seg_squash_masks")
+    return out
+
+
+def hu_window_norm(hu: torch.Tensor, lo, hi, mean, std, dtype=torch.float32) -> torch.Tensor:
+    """int16 HU (any shape) -> (*shape, n_windows) windowed + normalised channels-last tensor."""
+    lib = _lib.load()
+    if hu.dtype != torch.int16:
+        raise TypeError("hu_window_norm takes int16 Hounsfield units")
+    hu = hu.contiguous()
+    k = len(lo)
+    out = torch.empty(tuple(hu.shape) + (k,), dtype=dtype, device=hu.device)
+    arr = lambda v: (C.c_float * k)(*[float(a) for a in v])
+    _lib.check(lib.b200seg_hu_window_norm(hu.numel(), k, hu.data_ptr(), arr(lo), arr(hi), arr(mean),
+                                          arr(std), out.data_ptr(), k, dtype_code(dtype), _stream()),
+               "b200seg_hu_window_norm")
+    return out

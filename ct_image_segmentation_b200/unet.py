@@ -1,0 +1,374 @@
+"""B200-native drop-in for ``monai.networks.nets.UNet`` as the reference uses it.
+
+Reference seam: ``capstone/models/__init__.py:3`` re-exports ``monai.networks.nets.UNet``; it
+is built at ``capstone/volumetric/base_trainer.py:65-72`` / ``capstone/training/base_trainer.py:72-79``
+and called at ``capstone/volumetric/base_trainer.py:74-78``.
+
+The module tree (names, parameter shapes, PyTorch weight layouts) is the MONAI-0.3 tree of
+SURVEY.md Appendix A, so ``state_dict()`` / ``load_state_dict()`` / attribute paths such as
+``unet.model[2][1].conv.unit0.conv`` (``capstone/interpretability.py:88``) keep working.  The leaf
+``torch.nn`` modules only *hold* the parameters: the arithmetic never goes through them.
+``forward`` runs an explicit forward plan on hand-written sm_100a kernels through the C ABI
+(``include/b200seg.h``) and registers ONE autograd node whose backward runs the explicit reverse
+plan (dgrad / wgrad / InstanceNorm+PReLU backward, in-place gradient fan-in, zero-copy skip
+concatenation in both directions).
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from .ops import ConvGeom
+
+_CONV = {2: nn.Conv2d, 3: nn.Conv3d}
+_CONVT = {2: nn.ConvTranspose2d, 3: nn.ConvTranspose3d}
+_INORM = {2: nn.InstanceNorm2d, 3: nn.InstanceNorm3d}
+
+
+class Convolution(nn.Sequential):
+    """Parameter holder for MONAI ``Convolution``: ``conv`` [-> ``norm`` -> ``act``] (A.2)."""
+
+    def __init__(self, dimensions, in_channels, out_channels, strides=1, kernel_size=3,
+                 conv_only=False, is_transposed=False):
+        super().__init__()
+        pad = (kernel_size - 1) // 2
+        if is_transposed:
+            conv = _CONVT[dimensions](in_channels, out_channels, kernel_size, stride=strides,
+                                      padding=pad, output_padding=strides - 1, bias=True)
+        else:
+            conv = _CONV[dimensions](in_channels, out_channels, kernel_size, stride=strides,
+                                     padding=pad, bias=True)
+        self.add_module("conv", conv)
+        self.conv_only = conv_only
+        if not conv_only:
+            self.add_module("norm", _INORM[dimensions](out_channels))
+            self.add_module("act", nn.PReLU())
+        self.geom = ConvGeom(dimensions, in_channels, out_channels, kernel_size, strides, is_transposed)
+
+    def forward(self, x):  # pragma: no cover - the engine never calls leaf modules
+        raise RuntimeError("b200seg blocks are executed by UNet.forward, not called directly")
+
+
+class ResidualUnit(nn.Module):
+    """Parameter holder for MONAI ``ResidualUnit``: ``conv(x) + residual(x)`` (A.3)."""
+
+    def __init__(self, dimensions, in_channels, out_channels, strides=1, kernel_size=3, subunits=2,
+                 last_conv_only=False):
+        super().__init__()
+        self.conv = nn.Sequential()
+        self.residual = nn.Identity()
+        self.res_geom: Optional[ConvGeom] = None
+        subunits = max(1, subunits)
+        sc, ss = in_channels, strides
+        for su in range(subunits):
+            self.conv.add_module(
+                f"unit{su:d}",
+                Convolution(dimensions, sc, out_channels, strides=ss, kernel_size=kernel_size,
+                            conv_only=last_conv_only and su == subunits - 1))
+            sc, ss = out_channels, 1
+        if strides != 1 or in_channels != out_channels:
+            rk = kernel_size if strides != 1 else 1
+            self.residual = _CONV[dimensions](in_channels, out_channels, rk, strides, (rk - 1) // 2,
+                                              bias=True)
+            self.res_geom = ConvGeom(dimensions, in_channels, out_channels, rk, strides, False)
+        self.out_channels = out_channels
+
+    def forward(self, x):  # pragma: no cover
+        raise RuntimeError("b200seg blocks are executed by UNet.forward, not called directly")
+
+
+class SkipConnection(nn.Module):
+    """``cat([x, submodule(x)], 1)`` -- realised zero-copy by the engine (A.3)."""
+
+    def __init__(self, submodule):
+        super().__init__()
+        self.submodule = submodule
+
+    def forward(self, x):  # pragma: no cover
+        raise RuntimeError("b200seg blocks are executed by UNet.forward, not called directly")
+
+
+class _Level(nn.Sequential):
+    """(down, SkipConnection(sub), up) triple of one U-Net level."""
+
+
+def _out_channels(layer) -> int:
+    if isinstance(layer, ResidualUnit):
+        return layer.out_channels
+    if isinstance(layer, Convolution):
+        return layer.geom.cout
+    if isinstance(layer, _Level):
+        return _out_channels(layer[2])
+    return _out_channels(layer[-1])  # Sequential(conv, residual unit)
+
+
+class UNet(nn.Module):
+    """``UNet(dimensions, in_channels, out_channels, channels, strides, kernel_size=3,
+    up_kernel_size=3, num_res_units=0, act="PRELU", norm="INSTANCE", dropout=0)``.
+
+    Extra keyword (build-specific): ``dtype`` -- ``torch.bfloat16`` (production: bf16 storage,
+    fp32 accumulation) or ``torch.float32`` (check mode).
+    """
+
+    def __init__(self, dimensions: int, in_channels: int, out_channels: int, channels: Sequence[int],
+                 strides: Sequence[int], kernel_size=3, up_kernel_size=3, num_res_units: int = 0,
+                 act="PRELU", norm="INSTANCE", dropout=0, dtype: torch.dtype = torch.bfloat16):
+        super().__init__()
+        if dimensions not in (2, 3):
+            raise NotImplementedError("b200seg UNet supports dimensions 2 and 3")
+        if kernel_size != 3 or up_kernel_size != 3:
+            raise NotImplementedError("b200seg UNet supports kernel_size = up_kernel_size = 3")
+        if str(act).upper() not in ("PRELU", "ACT.PRELU") or str(norm).upper() not in ("INSTANCE", "NORM.INSTANCE"):
+            raise NotImplementedError("b200seg UNet supports act=PRELU, norm=INSTANCE")
+        if dropout:
+            raise NotImplementedError("b200seg UNet supports dropout=0")
+        if len(channels) < 2 or len(strides) != len(channels) - 1:
+            raise ValueError("need len(channels) >= 2 and len(strides) == len(channels) - 1")
+        if any(s not in (1, 2) for s in strides):
+            raise NotImplementedError("b200seg UNet supports strides 1 and 2")
+        if dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError("dtype must be torch.float32 or torch.bfloat16")
+        self.dimensions = dimensions
+        self.in_channels = in_channels
+        self.out_channels = out_channels
+        self.channels = list(channels)
+        self.strides = list(strides)
+        self.kernel_size = kernel_size
+        self.up_kernel_size = up_kernel_size
+        self.num_res_units = num_res_units
+        self.compute_dtype = dtype
+        self._packed: Dict = {}
+
+        def level(inc, outc, chans, strds, is_top):
+            c, s = chans[0], strds[0]
+            if len(chans) > 2:
+                sub, upc = level(c, c, chans[1:], strds[1:], False), 2 * c
+            else:
+                sub, upc = self._down(c, chans[1], 1), c + chans[1]
+            return _Level(self._down(inc, c, s), SkipConnection(sub), self._up(upc, outc, s, is_top))
+
+        self.model = level(in_channels, out_channels, self.channels, self.strides, True)
+
+    # ---- tree construction ---------------------------------------------------------------
+    def _down(self, inc, outc, s):
+        if self.num_res_units > 0:
+            return ResidualUnit(self.dimensions, inc, outc, strides=s, kernel_size=self.kernel_size,
+                                subunits=self.num_res_units)
+        return Convolution(self.dimensions, inc, outc, strides=s, kernel_size=self.kernel_size)
+
+    def _up(self, inc, outc, s, is_top):
+        conv = Convolution(self.dimensions, inc, outc, strides=s, kernel_size=self.up_kernel_size,
+                           conv_only=is_top and self.num_res_units == 0, is_transposed=True)
+        if self.num_res_units > 0:
+            return nn.Sequential(conv, ResidualUnit(self.dimensions, outc, outc, strides=1,
+                                                    kernel_size=self.kernel_size, subunits=1,
+                                                    last_conv_only=is_top))
+        return conv
+
+    # ---- public forward ------------------------------------------------------------------
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if x.dim() != self.dimensions + 2 or x.shape[1] != self.in_channels:
+            raise ValueError(f"expected input (B, {self.in_channels}, *spatial[{self.dimensions}]), "
+                             f"got {tuple(x.shape)}")
+        if not x.is_cuda:
+            raise RuntimeError("b200seg UNet runs on a CUDA (sm_100a) device only; there is no CPU path")
+        div = 1
+        for s in self.strides:
+            div *= s
+        if any(int(n) % div for n in x.shape[2:]):
+            raise ValueError(f"spatial extents {tuple(x.shape[2:])} must be divisible by {div}")
+        params = list(self.parameters())
+        return _UNetFunction.apply(self, x, *params)
+
+    def forward_debug(self, x: torch.Tensor) -> Dict[str, torch.Tensor]:
+        """Per-layer outputs as fp32 NC[D]HW tensors keyed by module path (parity tests)."""
+        with torch.no_grad():
+            saved: Dict = {}
+            out = self._run_forward(ops.to_channels_last(x, self.compute_dtype), saved, keep_all=True)
+        names = {m: n for n, m in self.named_modules()}
+        taps = {"": ops.from_channels_last(out, self.dimensions).float()}
+        for m, s in saved.items():
+            if isinstance(m, Convolution):
+                if s.get("c") is not None:
+                    taps[names[m] + ".conv"] = ops.from_channels_last(s["c"], self.dimensions).float()
+                taps[names[m]] = ops.from_channels_last(s["out"], self.dimensions).float()
+        return taps
+
+    # ---- weights ---------------------------------------------------------------------------
+    def _pack(self, param: torch.Tensor, geom: ConvGeom, kind: int) -> torch.Tensor:
+        key = (id(param), kind, self.compute_dtype)
+        hit = self._packed.get(key)
+        ver = (param._version, param.data_ptr())
+        if hit is None or hit[0] != ver:
+            hit = (ver, ops.pack_weight(geom, kind, param, self.compute_dtype))
+            self._packed[key] = hit
+        return hit[1]
+
+    def _w_fprop(self, conv: nn.Module, geom: ConvGeom):
+        kind = _lib.W_CONVTR_FPROP if geom.transposed else _lib.W_CONV_FPROP
+        return self._pack(conv.weight, geom, kind)
+
+    def _w_dgrad(self, conv: nn.Module, geom: ConvGeom):
+        kind = _lib.W_CONVTR_DGRAD if geom.transposed else _lib.W_CONV_DGRAD
+        return self._pack(conv.weight, geom, kind)
+
+    # ---- forward plan ----------------------------------------------------------------------
+    def _new(self, like: torch.Tensor, spatial, c: int) -> torch.Tensor:
+        return torch.empty((like.shape[0], *spatial, c), dtype=self.compute_dtype, device=like.device)
+
+    def _run_forward(self, x_cl: torch.Tensor, saved: Dict, keep_all: bool = False) -> torch.Tensor:
+        return self._fwd_level(self.model, x_cl, saved, None, keep_all)
+
+    def _fwd_level(self, lvl: _Level, x, saved, dst, keep):
+        down, skip, up = lvl[0], lvl[1], lvl[2]
+        sub = skip.submodule
+        c_x, c_sub = _out_channels(down), _out_channels(sub)
+        sp = self._down_geom(down).out_spatial(*x.shape[1:4])
+        cat = self._new(x, sp, c_x + c_sub)  # skip concatenation buffer: [x | sub(x)]
+        xd = self._fwd_layer(down, x, saved, cat[..., :c_x], keep)
+        if isinstance(sub, _Level):
+            self._fwd_level(sub, xd, saved, cat[..., c_x:], keep)
+        else:
+            self._fwd_layer(sub, xd, saved, cat[..., c_x:], keep)
+        saved[lvl] = {"c_x": c_x}
+        return self._fwd_layer(up, cat, saved, dst, keep)
+
+    @staticmethod
+    def _down_geom(down) -> ConvGeom:
+        return down.conv.unit0.geom if isinstance(down, ResidualUnit) else down.geom
+
+    def _fwd_layer(self, layer, x, saved, dst, keep):
+        if isinstance(layer, ResidualUnit):
+            return self._fwd_resunit(layer, x, saved, dst, keep)
+        if isinstance(layer, Convolution):
+            return self._fwd_convolution(layer, x, saved, dst, None, keep)
+        h = self._fwd_convolution(layer[0], x, saved, None, None, keep)  # up: ConvTranspose block
+        return self._fwd_resunit(layer[1], h, saved, dst, keep)
+
+    def _fwd_convolution(self, m: Convolution, x, saved, dst, residual, keep):
+        g = m.geom
+        sp = g.out_spatial(*x.shape[1:4])
+        wp = self._w_fprop(m.conv, g)
+        bias = m.conv.bias.detach()
+        if m.conv_only:
+            y = dst if dst is not None else self._new(x, sp, g.cout)
+            ops.conv_fprop(g, x, wp, bias, y, residual)
+            saved[m] = {"x": x, "c": None, "out": y if keep else None}
+            return y
+        c = self._new(x, sp, g.cout)
+        ops.conv_fprop(g, x, wp, bias, c)
+        mean, rstd = ops.instnorm_stats(c, m.norm.eps)
+        a = dst if dst is not None else self._new(x, sp, g.cout)
+        ops.instnorm_prelu_fwd(c, mean, rstd, m.act.weight.detach(), a, residual, m.norm.eps)
+        saved[m] = {"x": x, "c": c, "mean": mean, "rstd": rstd, "out": a if keep else None}
+        return a
+
+    def _fwd_resunit(self, ru: ResidualUnit, x, saved, dst, keep):
+        units = list(ru.conv.children())
+        if ru.res_geom is not None:
+            rg = ru.res_geom
+            r = self._new(x, rg.out_spatial(*x.shape[1:4]), rg.cout)
+            ops.conv_fprop(rg, x, self._w_fprop(ru.residual, rg), ru.residual.bias.detach(), r)
+        else:
+            r = x
+        h = x
+        for i, u in enumerate(units):
+            last = i == len(units) - 1
+            h = self._fwd_convolution(u, h, saved, dst if last else None, r if last else None, keep)
+        saved[ru] = {"x": x}
+        return h
+
+    # ---- backward plan -------------------------------------------------------------------------
+    def _run_backward(self, saved: Dict, g_out: torch.Tensor, need_gx: bool):
+        grads: Dict[torch.Tensor, torch.Tensor] = {}
+        gx = self._bwd_level(self.model, g_out, saved, grads, need_gx, None, False)
+        return grads, gx
+
+    def _bwd_level(self, lvl: _Level, g_out, saved, grads, need_gx, gx_dst, gx_accum):
+        down, skip, up = lvl[0], lvl[1], lvl[2]
+        sub = skip.submodule
+        c_x = saved.pop(lvl)["c_x"]
+        g_cat = self._bwd_layer(up, g_out, saved, grads, True, None, False)
+        g_x, g_sub = g_cat[..., :c_x], g_cat[..., c_x:]
+        # the sub-network's input gradient is accumulated in place into the skip half of g_cat
+        if isinstance(sub, _Level):
+            self._bwd_level(sub, g_sub, saved, grads, True, g_x, True)
+        else:
+            self._bwd_layer(sub, g_sub, saved, grads, True, g_x, True)
+        return self._bwd_layer(down, g_x, saved, grads, need_gx, gx_dst, gx_accum)
+
+    def _bwd_layer(self, layer, g_out, saved, grads, need_gx, gx_dst, gx_accum):
+        if isinstance(layer, ResidualUnit):
+            return self._bwd_resunit(layer, g_out, saved, grads, need_gx, gx_dst, gx_accum)
+        if isinstance(layer, Convolution):
+            return self._bwd_convolution(layer, g_out, saved, grads, need_gx, gx_dst, gx_accum, None)
+        g_h = self._bwd_resunit(layer[1], g_out, saved, grads, True, None, False)
+        return self._bwd_convolution(layer[0], g_h, saved, grads, need_gx, gx_dst, gx_accum, None)
+
+    def _bwd_convolution(self, m: Convolution, g_out, saved, grads, need_gx, gx_dst, gx_accum,
+                         gx_residual):
+        s = saved.pop(m)
+        g, x = m.geom, s["x"]
+        if m.conv_only:
+            g_c = g_out
+        else:
+            c = s["c"]
+            g_c = torch.empty(c.shape, dtype=c.dtype, device=c.device)
+            grads[m.act.weight] = ops.instnorm_prelu_bwd(c, s["mean"], s["rstd"], m.act.weight.detach(),
+                                                         g_out, g_c, m.norm.eps)
+        gw, gb = ops.conv_wgrad(g, x, g_c)
+        grads[m.conv.weight], grads[m.conv.bias] = gw, gb
+        if not need_gx:
+            return None
+        gx = gx_dst if gx_dst is not None else torch.empty(x.shape, dtype=x.dtype, device=x.device)
+        ops.conv_dgrad(g, g_c, self._w_dgrad(m.conv, g), gx, residual=gx_residual, accumulate=gx_accum)
+        return gx
+
+    def _bwd_resunit(self, ru: ResidualUnit, g_out, saved, grads, need_gx, gx_dst, gx_accum):
+        units = list(ru.conv.children())
+        x = saved.pop(ru)["x"]
+        g = g_out
+        for i in range(len(units) - 1, 0, -1):
+            g = self._bwd_convolution(units[i], g, saved, grads, True, None, False, None)
+        if ru.res_geom is None:
+            # identity residual: d/dx = dgrad(unit0) + g_out, fused as the dgrad epilogue addend
+            return self._bwd_convolution(units[0], g, saved, grads, need_gx, gx_dst, gx_accum, g_out)
+        gx = self._bwd_convolution(units[0], g, saved, grads, need_gx, gx_dst, gx_accum, None)
+        rg = ru.res_geom
+        gw, gb = ops.conv_wgrad(rg, x, g_out)
+        grads[ru.residual.weight], grads[ru.residual.bias] = gw, gb
+        if need_gx:
+            ops.conv_dgrad(rg, g_out, self._w_dgrad(ru.residual, rg), gx, accumulate=True)
+        return gx
+
+
+class _UNetFunction(torch.autograd.Function):
+    """One autograd node for the whole network: explicit forward and reverse plans."""
+
+    @staticmethod
+    def forward(ctx, net: UNet, x: torch.Tensor, *params):
+        x_cl = ops.to_channels_last(x.detach(), net.compute_dtype)
+        saved: Dict = {}
+        out = net._run_forward(x_cl, saved)
+        need = any(ctx.needs_input_grad[1:])
+        ctx.net = net
+        ctx.saved = saved if need else None
+        ctx.params = params
+        ctx.x_dtype = x.dtype
+        return ops.from_channels_last(out, net.dimensions)
+
+    @staticmethod
+    def backward(ctx, g: torch.Tensor):
+        net = ctx.net
+        if ctx.saved is None:
+            raise RuntimeError("UNet backward called but the forward did not record activations")
+        g_cl = ops.to_channels_last(g, net.compute_dtype)
+        saved, ctx.saved = ctx.saved, None
+        grads, gx = net._run_backward(saved, g_cl, ctx.needs_input_grad[1])
+        gx_out = None
+        if gx is not None:
+            gx_out = ops.from_channels_last(gx, net.dimensions).to(ctx.x_dtype)
+        return (None, gx_out, *[grads.get(p) for p in ctx.params])

@@ -1,0 +1,211 @@
+/*
+ * b200seg.h -- C ABI of the B200-native U-Net + Dice hot path.
+ *
+ * One shared library (libb200seg.so), built for sm_100a only.  Plain pointers,
+ * sizes and POD descriptors; no C++ or torch types cross this boundary.
+ *
+ * The reference (MrinalJain17/CT-image-segmentation) is pure Python and has no
+ * native interface of its own: its hot path bottoms out in torch/MONAI calls.
+ * Each entry point therefore cites the reference CALL SITE whose arithmetic it
+ * replaces (file:line relative to the reference repository root); the Python
+ * binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *  - Activations are channels-last ("NDHWC"): element (n, d, h, w, c) of a
+ *    tensor lives at  base[((((n*D + d)*H + h)*W + w) * ld) + c]  where `ld`
+ *    (>= C) is the voxel stride in ELEMENTS.  ld > C addresses a channel slice
+ *    of a wider buffer (zero-copy skip concatenation).  2-D data is D = 1.
+ *  - dtype selects the storage type of activations and packed weights:
+ *    B200SEG_BF16 (production; fp32 accumulation) or B200SEG_F32 (check mode).
+ *  - All device memory, including workspaces, is owned by the caller.  The
+ *    library never allocates or frees device memory and never synchronises;
+ *    every launch is asynchronous on the `stream` argument (a cudaStream_t
+ *    passed as void*).
+ *  - Return value: 0 on success, negative on error; b200seg_last_error()
+ *    returns a thread-local message.  No exceptions, no abort, no CPU fallback.
+ */
+#ifndef B200SEG_H_
+#define B200SEG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200SEG_VERSION 100 /* 0.1.0 */
+
+enum b200seg_status {
+  B200SEG_OK = 0,
+  B200SEG_ERR_ARG = -1,         /* bad argument / shape / alignment */
+  B200SEG_ERR_UNSUPPORTED = -2, /* configuration not implemented */
+  B200SEG_ERR_WORKSPACE = -3,   /* workspace too small */
+  B200SEG_ERR_CUDA = -4,        /* CUDA launch / runtime error */
+  B200SEG_ERR_DEVICE = -5       /* not an sm_100 device */
+};
+
+enum b200seg_dtype { B200SEG_F32 = 0, B200SEG_BF16 = 1 };
+enum b200seg_label_dtype { B200SEG_LABEL_U8 = 0, B200SEG_LABEL_I64 = 1 };
+
+/* which of the four data-path GEMMs a packed weight feeds */
+enum b200seg_weight_kind {
+  B200SEG_W_CONV_FPROP = 0,
+  B200SEG_W_CONV_DGRAD = 1,
+  B200SEG_W_CONVTR_FPROP = 2,
+  B200SEG_W_CONVTR_DGRAD = 3
+};
+
+enum b200seg_conv_flags {
+  B200SEG_CONV_ACCUMULATE = 1,   /* destination += result (gradient fan-in) */
+  B200SEG_CONV_FORCE_GENERIC = 2 /* use the CUDA-core kernel even where a tcgen05 kernel exists */
+};
+
+/*
+ * Geometry of one Conv{2,3}d / ConvTranspose{2,3}d layer, in the layer's own
+ * terms: x is the layer INPUT (cin channels, in_* extent), y its OUTPUT (cout
+ * channels, out_* extent).  Conv:  out = floor((in + 2p - k)/s) + 1.
+ * ConvTranspose: out = (in - 1)s - 2p + k + output_padding (= s*in here).
+ */
+typedef struct b200seg_conv_desc {
+  int32_t n, cin, cout;
+  int32_t in_d, in_h, in_w;
+  int32_t out_d, out_h, out_w;
+  int32_t kd, kh, kw; /* 1 or 3 */
+  int32_t sd, sh, sw; /* 1 or 2 */
+  int32_t pd, ph, pw;
+  int32_t x_ld, y_ld, r_ld; /* voxel strides (elements) of x-shaped, y-shaped, residual tensors */
+  int32_t dtype;            /* enum b200seg_dtype */
+  int32_t flags;            /* enum b200seg_conv_flags */
+} b200seg_conv_desc;
+
+typedef struct b200seg_norm_desc {
+  int32_t n, c;
+  int64_t spatial;          /* D*H*W */
+  int32_t x_ld, y_ld, r_ld; /* voxel strides (elements) */
+  int32_t dtype;
+  float eps;
+} b200seg_norm_desc;
+
+typedef struct b200seg_dice_desc {
+  int32_t n, c;
+  int64_t spatial;
+  int32_t ld;               /* voxel stride of logits / dlogits (elements) */
+  int32_t dtype;            /* logits dtype */
+  int32_t label_dtype;      /* enum b200seg_label_dtype */
+  int32_t include_background;
+} b200seg_dice_desc;
+
+/* ---- library ------------------------------------------------------------ */
+int b200seg_version(void);
+const char* b200seg_last_error(void);
+/* number of CUDA kernels this library has launched in the process so far (all threads) */
+long long b200seg_launch_count(void);
+/* 0 if `device` is an sm_100 part this library can run on */
+int b200seg_check_device(int device);
+
+/* ---- weights -------------------------------------------------------------
+ * Repack an fp32 PyTorch-layout parameter (Conv: (cout,cin,kd,kh,kw);
+ * ConvTranspose: (cin,cout,kd,kh,kw); reference state_dict)
+ * into the kernel layout for one of the four data-path uses. */
+size_t b200seg_packed_weight_bytes(const b200seg_conv_desc* d, int kind);
+int b200seg_pack_weight(const b200seg_conv_desc* d, int kind, const float* w_torch,
+                        void* w_packed, void* stream);
+
+/* ---- convolutions ---------------------------------------------------------
+ * Replace torch.nn.Conv{2,3}d / ConvTranspose{2,3}d forward + autograd as called
+ * by monai.networks.nets.UNet, which the reference instantiates at
+ * capstone/volumetric/base_trainer.py:65-72 and capstone/training/base_trainer.py:72-79
+ * and calls at capstone/volumetric/base_trainer.py:74-78 (forward) / PL backward.
+ *
+ * fprop:  y = conv(x, w) [+ bias] [+ residual]          (residual is y-shaped, voxel stride r_ld)
+ * dgrad:  dx = conv^T(dy, w) [+ residual] [+ dx if ACCUMULATE]   (residual is x-shaped)
+ * wgrad:  gw (fp32, PyTorch layout) = d loss / d w ; gbias (fp32, may be NULL) = sum dy
+ */
+int b200seg_conv_fprop(const b200seg_conv_desc* d, const void* x, const void* w_packed,
+                       const float* bias, const void* residual, void* y, void* stream);
+int b200seg_conv_dgrad(const b200seg_conv_desc* d, const void* dy, const void* w_packed,
+                       const void* residual, void* dx, void* stream);
+size_t b200seg_conv_wgrad_workspace_bytes(const b200seg_conv_desc* d);
+int b200seg_conv_wgrad(const b200seg_conv_desc* d, const void* x, const void* dy, float* gw,
+                       float* gbias, void* workspace, size_t workspace_bytes, void* stream);
+
+int b200seg_convtr_fprop(const b200seg_conv_desc* d, const void* x, const void* w_packed,
+                         const float* bias, const void* residual, void* y, void* stream);
+int b200seg_convtr_dgrad(const b200seg_conv_desc* d, const void* dy, const void* w_packed,
+                         const void* residual, void* dx, void* stream);
+size_t b200seg_convtr_wgrad_workspace_bytes(const b200seg_conv_desc* d);
+int b200seg_convtr_wgrad(const b200seg_conv_desc* d, const void* x, const void* dy, float* gw,
+                         float* gbias, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- InstanceNorm(affine=False, eps, biased var) + PReLU(one shared alpha) ---
+ * Replace the `norm` and `act` children of monai Convolution and the
+ * residual sum of monai ResidualUnit (A.3), reached from the same call sites as above.
+ *
+ * stats:  mean[n*c], rstd[n*c]   (fp32)
+ * fwd:    y = prelu((x - mean) * rstd, alpha) [+ residual]
+ * bwd:    dx = d loss / d x  given dy = d loss / d y ;  dalpha[0] = d loss / d alpha
+ * alpha / dalpha are DEVICE pointers to one float.
+ */
+size_t b200seg_instnorm_workspace_bytes(const b200seg_norm_desc* d);
+int b200seg_instnorm_stats(const b200seg_norm_desc* d, const void* x, float* mean, float* rstd,
+                           void* workspace, size_t workspace_bytes, void* stream);
+int b200seg_instnorm_prelu_fwd(const b200seg_norm_desc* d, const void* x, const float* mean,
+                               const float* rstd, const float* alpha, const void* residual,
+                               void* y, void* stream);
+int b200seg_instnorm_prelu_bwd(const b200seg_norm_desc* d, const void* x, const float* mean,
+                               const float* rstd, const float* alpha, const void* dy, void* dx,
+                               float* dalpha, void* workspace, size_t workspace_bytes,
+                               void* stream);
+
+/* ---- softmax + Dice ---------------------------------------------------------
+ * Replace monai.losses.DiceLoss(include_background=False, to_onehot_y=True, softmax=True)
+ * as built at capstone/models/losses.py:78-85 and capstone/volumetric/losses.py:70-77
+ * (formula identical to the in-tree capstone/models/temp.py:137-157 with uniform weights).
+ *
+ * fwd:  sums[n][c][3] (fp32) = { I = sum_v p*t, G = sum_v t, P = sum_v p }, p = softmax(logits),
+ *       t = one_hot(labels).  (With include_background == 0 the c = 0 row is still produced.)
+ * bwd:  dlogits given gI[n][c] = d loss / d I and gP[n][c] = d loss / d P (fp32; rows of
+ *       excluded classes must be 0):  g_c = gI*t_c + gP ;  dz_c = p_c (g_c - sum_k g_k p_k).
+ * The per-(n,c) epilogue  f = 1 - (2I + s)/(G + P + s), its reduction and the
+ * missing-annotation weighting (capstone/models/losses.py:206-221) operate on n*c numbers and
+ * stay in host-side PyTorch.
+ */
+size_t b200seg_softmax_dice_workspace_bytes(const b200seg_dice_desc* d);
+int b200seg_softmax_dice_fwd(const b200seg_dice_desc* d, const void* logits, const void* labels,
+                             float* sums, void* workspace, size_t workspace_bytes, void* stream);
+int b200seg_softmax_dice_bwd(const b200seg_dice_desc* d, const void* logits, const void* labels,
+                             const float* gI, const float* gP, void* dlogits, void* stream);
+
+/* ---- label maps and the Dice metric -------------------------------------------
+ * argmax:  pred[v] = argmax_c softmax(logits)[c], first maximum wins
+ *          (capstone/training/utils.py:19-20 `_squash_predictions`).
+ * counts:  counts[n][c][3] (int64) = { |pred==c & target==c|, |pred==c|, |target==c| }, the
+ *          integer form of compute_meandice's sums (capstone/models/temp.py:173-214), used by
+ *          DiceMetricWrapper (capstone/models/metrics.py:15-21).  `pred_out` (uint8) may be NULL;
+ *          `target` may be NULL (then only the label map is produced and counts is untouched).
+ * squash:  labels[v] = max_c masks[c][v] * (c+1)  (capstone/volumetric/utils.py:4-7,
+ *          capstone/training/utils.py:13-16); masks are (n, n_struct, spatial) uint8, NCDHW.
+ */
+int b200seg_argmax_dice_counts(const b200seg_dice_desc* d, const void* logits, const void* target,
+                               uint8_t* pred_out, int64_t* counts, void* stream);
+int b200seg_label_dice_counts(int32_t n, int64_t spatial, int32_t c, const uint8_t* pred,
+                              const void* target, int32_t target_dtype, int64_t* counts,
+                              void* stream);
+int b200seg_squash_masks(int32_t n, int32_t n_struct, int64_t spatial, const uint8_t* masks,
+                         uint8_t* labels, void* stream);
+
+/* ---- HU windowing + normalisation ------------------------------------------------
+ * out[v][k] = ((clip(hu[v], lo_k, hi_k) - lo_k) / (hi_k - lo_k + 1e-8) - mean_k) / std_k
+ * (capstone/transforms/transforms_2d.py:97-107 `apply_window`, then albumentations Normalize
+ * with the constants of capstone/transforms/predefined.py:5-29).  hu: int16; out: channels-last
+ * `dtype`, voxel stride out_ld.  lo/hi/mean/std are HOST arrays of n_windows (<= 4) floats.
+ */
+int b200seg_hu_window_norm(int64_t n_vox, int32_t n_windows, const int16_t* hu, const float* lo,
+                           const float* hi, const float* mean, const float* std_, void* out,
+                           int32_t out_ld, int32_t dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200SEG_H_ */

