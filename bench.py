@@ -73,7 +73,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:  # noqa: BLE001
@@ -81,13 +81,21 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def mark(self):
+        """Start of the timed region: only samples taken after this call are reported."""
+        self.t0 = time.time()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        t1 = time.time()
+        time.sleep(0.1)
         self.proc.terminate()
+        t0 = getattr(self, "t0", 0.0)
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.1] or [r for _, r in self.rows[-3:]]
+        self.rows = rows
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -206,10 +214,12 @@ def run_b200(args, rank, world, local):
             ms = t.item()
         return ms, (last if from_host else last.item())
 
-    timed(args.warmup, False)
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    timed(args.warmup, False)
+    if sampler:
+        sampler.mark()
     l0 = lib.b200seg_launch_count()
     ms_dev, loss_val = timed(args.steps, False)
     launches = lib.b200seg_launch_count() - l0

@@ -194,7 +194,8 @@ class UNet(nn.Module):
             if isinstance(m, Convolution):
                 if s.get("c") is not None:
                     taps[names[m] + ".conv"] = ops.from_channels_last(s["c"], self.dimensions).float()
-                taps[names[m]] = ops.from_channels_last(s["out"], self.dimensions).float()
+                if s.get("out") is not None:
+                    taps[names[m]] = ops.from_channels_last(s["out"], self.dimensions).float()
         return taps
 
     # ---- weights ---------------------------------------------------------------------------
@@ -256,7 +257,8 @@ class UNet(nn.Module):
         if m.conv_only:
             y = dst if dst is not None else self._new(x, sp, g.cout)
             ops.conv_fprop(g, x, wp, bias, y, residual)
-            saved[m] = {"x": x, "c": None, "out": y if keep else None}
+            # with a fused residual the module's own output is never materialised: no tap
+            saved[m] = {"x": x, "c": None, "out": y if (keep and residual is None) else None}
             return y
         c = self._new(x, sp, g.cout)
         ops.conv_fprop(g, x, wp, bias, c)

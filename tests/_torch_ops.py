@@ -31,7 +31,7 @@ def _cl(t, dims):
 
 
 def pack_weight(geom, kind, w, dtype):
-    return w.detach().to(torch.float32)
+    return w.detach().to(dtype).to(torch.float32)  # weights are stored in the compute dtype
 
 
 def _conv(geom, x, w, bias=None):
