@@ -265,7 +265,8 @@ class UNet(nn.Module):
         mean, rstd = ops.instnorm_stats(c, m.norm.eps)
         a = dst if dst is not None else self._new(x, sp, g.cout)
         ops.instnorm_prelu_fwd(c, mean, rstd, m.act.weight.detach(), a, residual, m.norm.eps)
-        saved[m] = {"x": x, "c": c, "mean": mean, "rstd": rstd, "out": a if keep else None}
+        saved[m] = {"x": x, "c": c, "mean": mean, "rstd": rstd,
+                    "out": a if (keep and residual is None) else None}
         return a
 
     def _fwd_resunit(self, ru: ResidualUnit, x, saved, dst, keep):
@@ -284,8 +285,11 @@ class UNet(nn.Module):
         return h
 
     # ---- backward plan -------------------------------------------------------------------------
-    def _run_backward(self, saved: Dict, g_out: torch.Tensor, need_gx: bool):
+    def _run_backward(self, saved: Dict, g_out: torch.Tensor, need_gx: bool, taps: Optional[Dict] = None):
+        """Reverse plan.  ``taps`` (tests only) receives the local inputs/outputs of every
+        Convolution's backward (g_out, g_c, x, c, mean, rstd)."""
         grads: Dict[torch.Tensor, torch.Tensor] = {}
+        self._bwd_taps = taps
         gx = self._bwd_level(self.model, g_out, saved, grads, need_gx, None, False)
         return grads, gx
 
@@ -321,6 +325,9 @@ class UNet(nn.Module):
             g_c = torch.empty(c.shape, dtype=c.dtype, device=c.device)
             grads[m.act.weight] = ops.instnorm_prelu_bwd(c, s["mean"], s["rstd"], m.act.weight.detach(),
                                                          g_out, g_c, m.norm.eps)
+        if getattr(self, "_bwd_taps", None) is not None:
+            self._bwd_taps[m] = {"g_out": g_out, "g_c": g_c, "x": x, "c": s.get("c"),
+                                 "mean": s.get("mean"), "rstd": s.get("rstd")}
         gw, gb = ops.conv_wgrad(g, x, g_c)
         grads[m.conv.weight], grads[m.conv.bias] = gw, gb
         if not need_gx:

