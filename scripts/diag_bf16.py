@@ -57,7 +57,7 @@ for m_e, s in fw_e.items():
 print("--- backward taps d/d conv-out, in backward order")
 for m_e, t in taps_e.items():
     n = names_e[m_e]
-    tg = taps_g[mods_g[n]]
+    tg = taps_g[mods_g[n]]['g_c']; t = t['g_c']
     pe = dict(emu.named_parameters()); pg = dict(net.named_parameters())
     we = rel(grads_g[pg[n + '.conv.weight']], grads_e[pe[n + '.conv.weight']])
     print(f"{n:70s} g_c {rel(tg, t):.2e}  |g_c| {t.float().abs().mean().item():.2e} mean/absmean {abs(t.float().mean().item())/t.float().abs().mean().item():.2e} gw {we:.2e}")
