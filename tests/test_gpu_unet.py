@@ -114,7 +114,8 @@ def test_unet_dice_parity(dims, inc, ch, st, res, shape, dtype):
                 bad.append((name, "dead-bias abs"))
             continue
         e = rel(p.grad, rg)
-        if e >= (tol if fp32 else 5e-2):
+        # PReLU slope gradients are one scalar = a sum of cancelling terms over the whole tensor
+        if e >= (1e-3 if name.endswith("act.weight") else tol):
             bad.append((name, e))
     assert not bad, f"parameter gradients out of tolerance: {bad}"
 
