@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libb200seg.so")
 F32, BF16 = 0, 1
 LABEL_U8, LABEL_I64 = 0, 1
 W_CONV_FPROP, W_CONV_DGRAD, W_CONVTR_FPROP, W_CONVTR_DGRAD = 0, 1, 2, 3
-CONV_ACCUMULATE, CONV_FORCE_GENERIC = 1, 2
+CONV_ACCUMULATE, CONV_FORCE_GENERIC, CONV_PADDED_CHANNELS = 1, 2, 4
 
 
 class ConvDesc(C.Structure):
@@ -44,6 +44,7 @@ SIGNATURES = {
     "b200seg_version": (C.c_int, []),
     "b200seg_last_error": (C.c_char_p, []),
     "b200seg_launch_count": (C.c_longlong, []),
+    "b200seg_tc_launch_count": (C.c_longlong, []),
     "b200seg_check_device": (C.c_int, [C.c_int]),
     "b200seg_packed_weight_bytes": (C.c_size_t, [_CD, C.c_int]),
     "b200seg_pack_weight": (C.c_int, [_CD, C.c_int, _P, _P, _P]),

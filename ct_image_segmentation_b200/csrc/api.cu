@@ -13,7 +13,9 @@ namespace b200seg {
 static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 
+static std::atomic<long long> g_tc_launches{0};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void count_tc_launch() { g_tc_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -68,6 +70,7 @@ extern "C" {
 int b200seg_version(void) { return B200SEG_VERSION; }
 const char* b200seg_last_error(void) { return g_err; }
 long long b200seg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+long long b200seg_tc_launch_count(void) { return g_tc_launches.load(std::memory_order_relaxed); }
 
 int b200seg_check_device(int device) {
   cudaDeviceProp prop;
@@ -84,19 +87,29 @@ int b200seg_check_device(int device) {
 }
 
 // ---- weights ---------------------------------------------------------------------------------
+static size_t generic_weight_bytes(const b200seg_conv_desc* d) {
+  size_t esz = d->dtype == B200SEG_BF16 ? 2 : 4;
+  return align_up((size_t)d->kd * d->kh * d->kw * d->cin * d->cout * esz, 256);
+}
+static const void* tc_weights(const b200seg_conv_desc* d, const void* w_packed) {
+  return (const char*)w_packed + generic_weight_bytes(d);
+}
+
+// packed buffer = [ generic layout [tap][src][dst] | tcgen05 layout (bf16 only) ]
 size_t b200seg_packed_weight_bytes(const b200seg_conv_desc* d, int kind) {
   if (!d) return 0;
   (void)kind;
-  size_t esz = d->dtype == B200SEG_BF16 ? 2 : 4;
-  return (size_t)d->kd * d->kh * d->kw * d->cin * d->cout * esz;
+  return generic_weight_bytes(d) + tc_packed_weight_bytes(d);
 }
 
 int b200seg_pack_weight(const b200seg_conv_desc* d, int kind, const float* w_torch, void* w_packed,
                         void* stream) {
   B200SEG_CHECK_ARG(d && w_torch && w_packed, "pack_weight: NULL argument");
   B200SEG_CHECK_ARG(kind >= 0 && kind <= 3, "pack_weight: bad kind %d", kind);
-  return launch_pack_weight(d->dtype, kind, w_torch, w_packed, d->kd * d->kh * d->kw, d->cin, d->cout,
-                            as_stream(stream));
+  int rc = launch_pack_weight(d->dtype, kind, w_torch, w_packed, d->kd * d->kh * d->kw, d->cin, d->cout,
+                              as_stream(stream));
+  if (rc || d->dtype != B200SEG_BF16) return rc;
+  return tc_pack_weight(d, kind, w_torch, (char*)w_packed + generic_weight_bytes(d), as_stream(stream));
 }
 
 // ---- conv ---------------------------------------------------------------------------------------
@@ -105,7 +118,7 @@ int b200seg_conv_fprop(const b200seg_conv_desc* d, const void* x, const void* w_
   int rc = check_conv_desc(d, false);
   if (rc) return rc;
   B200SEG_CHECK_ARG(x && w_packed && y, "conv_fprop: NULL pointer");
-  if (tc_conv_supported(d, TC_CONV_FPROP)) return tc_conv_run(d, TC_CONV_FPROP, x, w_packed, bias, residual, y, as_stream(stream));
+  if (tc_conv_supported(d, TC_CONV_FPROP, x, y, residual)) return tc_conv_run(d, TC_CONV_FPROP, x, tc_weights(d, w_packed), bias, residual, y, as_stream(stream));
   GatherParams g{};
   fill_geom(g, d);
   g.sD = d->in_d; g.sH = d->in_h; g.sW = d->in_w;
@@ -121,7 +134,7 @@ int b200seg_conv_dgrad(const b200seg_conv_desc* d, const void* dy, const void* w
   int rc = check_conv_desc(d, false);
   if (rc) return rc;
   B200SEG_CHECK_ARG(dy && w_packed && dx, "conv_dgrad: NULL pointer");
-  if (tc_conv_supported(d, TC_CONV_DGRAD)) return tc_conv_run(d, TC_CONV_DGRAD, dy, w_packed, nullptr, residual, dx, as_stream(stream));
+  if (tc_conv_supported(d, TC_CONV_DGRAD, dy, dx, residual)) return tc_conv_run(d, TC_CONV_DGRAD, dy, tc_weights(d, w_packed), nullptr, residual, dx, as_stream(stream));
   GatherParams g{};
   fill_geom(g, d);
   g.sD = d->out_d; g.sH = d->out_h; g.sW = d->out_w;
@@ -210,7 +223,7 @@ int b200seg_convtr_fprop(const b200seg_conv_desc* d, const void* x, const void* 
   int rc = check_conv_desc(d, true);
   if (rc) return rc;
   B200SEG_CHECK_ARG(x && w_packed && y, "convtr_fprop: NULL pointer");
-  if (tc_conv_supported(d, TC_CONVTR_FPROP)) return tc_conv_run(d, TC_CONVTR_FPROP, x, w_packed, bias, residual, y, as_stream(stream));
+  if (tc_conv_supported(d, TC_CONVTR_FPROP, x, y, residual)) return tc_conv_run(d, TC_CONVTR_FPROP, x, tc_weights(d, w_packed), bias, residual, y, as_stream(stream));
   GatherParams g{};
   fill_geom(g, d);
   g.sD = d->in_d; g.sH = d->in_h; g.sW = d->in_w;
@@ -226,7 +239,7 @@ int b200seg_convtr_dgrad(const b200seg_conv_desc* d, const void* dy, const void*
   int rc = check_conv_desc(d, true);
   if (rc) return rc;
   B200SEG_CHECK_ARG(dy && w_packed && dx, "convtr_dgrad: NULL pointer");
-  if (tc_conv_supported(d, TC_CONVTR_DGRAD)) return tc_conv_run(d, TC_CONVTR_DGRAD, dy, w_packed, nullptr, residual, dx, as_stream(stream));
+  if (tc_conv_supported(d, TC_CONVTR_DGRAD, dy, dx, residual)) return tc_conv_run(d, TC_CONVTR_DGRAD, dy, tc_weights(d, w_packed), nullptr, residual, dx, as_stream(stream));
   GatherParams g{};
   fill_geom(g, d);
   g.sD = d->out_d; g.sH = d->out_h; g.sW = d->out_w;

@@ -11,6 +11,7 @@ namespace b200seg {
 
 void set_error(const char* fmt, ...);
 void count_launch();
+void count_tc_launch();
 
 #define B200SEG_CHECK_ARG(cond, ...)      \
   do {                                    \

@@ -9,10 +9,13 @@ namespace b200seg {
 
 enum TcConvOp { TC_CONV_FPROP = 0, TC_CONV_DGRAD = 1, TC_CONVTR_FPROP = 2, TC_CONVTR_DGRAD = 3 };
 
-// true when the tcgen05 kernel takes this layer/op (bf16, channel counts multiple of 16, ...)
-bool tc_conv_supported(const b200seg_conv_desc* d, int op);
-int tc_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_packed,
-                const float* bias, const void* residual, void* dst, cudaStream_t st);
+// true when the tcgen05 kernel takes this layer/op (bf16, channel counts multiple of 16 or
+// zero-padded to it, 16-byte aligned pointers, ...)
+bool tc_conv_supported(const b200seg_conv_desc* d, int op, const void* src, const void* dst, const void* res);
+int tc_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,
+                const void* residual, void* dst, cudaStream_t st);
+size_t tc_packed_weight_bytes(const b200seg_conv_desc* d);
+int tc_pack_weight(const b200seg_conv_desc* d, int kind, const float* w, void* out, cudaStream_t st);
 size_t tc_wgrad_extra_workspace(const b200seg_conv_desc* d);
 
 }  // namespace b200seg

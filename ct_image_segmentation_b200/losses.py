@@ -32,7 +32,11 @@ def _as_cl(input: torch.Tensor) -> torch.Tensor:
     if x.dim() != 5:
         raise ValueError(f"expected (B, C, H, W[, D]) logits, got {tuple(input.shape)}")
     cl = x.permute(0, 2, 3, 4, 1)
-    return cl if cl.is_contiguous() else cl.contiguous()
+    try:
+        ops.cl_info(cl)  # any uniform-stride channels-last layout (incl. padded buffers) is used as is
+        return cl
+    except ValueError:
+        return cl.contiguous()
 
 
 class _SoftmaxDiceSums(torch.autograd.Function):

@@ -59,7 +59,13 @@ def to_channels_last(x: torch.Tensor, dtype: Optional[torch.dtype] = None) -> to
     y = x.permute(0, 2, 3, 4, 1)
     if dtype is not None and y.dtype != dtype:
         y = y.to(dtype)
-    return y if y.is_contiguous() else y.contiguous()
+    if y.is_contiguous():
+        return y
+    try:
+        cl_info(y)  # uniform voxel stride (e.g. a zero-padded buffer): usable without a copy
+        return y
+    except (ValueError, RuntimeError):
+        return y.contiguous()
 
 
 def from_channels_last(y: torch.Tensor, dims: int) -> torch.Tensor:
@@ -125,6 +131,37 @@ def pack_weight(geom: ConvGeom, kind: int, w: torch.Tensor, dtype: torch.dtype) 
     return out
 
 
+def alloc_activation(n: int, spatial, c: int, dtype: torch.dtype, device) -> torch.Tensor:
+    """(N, *spatial, C) activation buffer.  For bf16 and C not a multiple of 16 (the 10-class
+    layers) the buffer is zero-padded to the next multiple of 16 channels and marked, so the
+    tcgen05 kernels can take it (B200SEG_CONV_PADDED_CHANNELS)."""
+    if dtype == torch.bfloat16 and c % 16 != 0 and c >= 8:
+        cp = (c + 15) // 16 * 16
+        return torch.zeros((n, *spatial, cp), dtype=dtype, device=device)[..., :c]
+    return torch.empty((n, *spatial, c), dtype=dtype, device=device)
+
+
+def alloc_like(t: torch.Tensor) -> torch.Tensor:
+    return alloc_activation(t.shape[0], tuple(t.shape[1:4]), t.shape[4], t.dtype, t.device)
+
+
+def _pad_safe(t: Optional[torch.Tensor]) -> bool:
+    """True if the tcgen05 kernels may treat channels [C, round_up(C, 16)) of ``t`` as its own zero
+    padding: C is a multiple of 16, or ``t`` is the leading-channel slice of a whole standalone
+    buffer with exactly round_up(C, 16) channels (what ``alloc_activation`` hands out; every kernel
+    keeps that padding zero).  A channel slice of a wider buffer never qualifies."""
+    if t is None or t.shape[-1] % 16 == 0:
+        return True
+    n, d, h, w, c = t.shape
+    cp = (c + 15) // 16 * 16
+    try:
+        ld = cl_info(t)[5]
+    except (ValueError, RuntimeError):
+        return False
+    return (ld == cp and t.storage_offset() == 0
+            and t.untyped_storage().nbytes() == n * d * h * w * cp * t.element_size())
+
+
 def _conv_call(geom: ConvGeom, src, wp, bias, residual, dst, data_grad: bool, flags: int):
     """Shared driver of the four data-path entry points.  ``src``/``dst`` are x/y for fprop and
     dy/dx for dgrad; the descriptor is always written in the layer's own terms."""
@@ -148,6 +185,8 @@ def _conv_call(geom: ConvGeom, src, wp, bias, residual, dst, data_grad: bool, fl
             raise ValueError(f"conv dgrad: channels {(sc, dc)} != {(geom.cout, geom.cin)}")
     if geom.out_spatial(*in_sp) != tuple(out_sp):
         raise ValueError(f"conv: spatial extents {in_sp} -> {out_sp} inconsistent with {geom}")
+    if _pad_safe(src) and _pad_safe(dst) and _pad_safe(residual):
+        flags |= _lib.CONV_PADDED_CHANNELS
     d = geom.desc(n, in_sp, out_sp, x_ld, y_ld, r_ld, src.dtype, flags)
     name = ("b200seg_convtr_" if geom.transposed else "b200seg_conv_") + ("dgrad" if data_grad else "fprop")
     fn = getattr(lib, name)
@@ -287,8 +326,11 @@ def softmax_dice_bwd(logits, labels, g_i, g_p, dlogits=None) -> torch.Tensor:
     n, d, h, w, c, ld = cl_info(logits)
     labels, code = _labels(labels, n, d * h * w)
     if dlogits is None:
-        dlogits = torch.empty_like(logits) if logits.is_contiguous() else \
-            torch.empty(logits.shape, dtype=logits.dtype, device=logits.device)
+        if ld > c:  # keep the (zero) channel padding of the logits buffer
+            full = torch.zeros((n, d, h, w, ld), dtype=logits.dtype, device=logits.device)
+            dlogits = full[..., :c]
+        else:
+            dlogits = torch.empty(logits.shape, dtype=logits.dtype, device=logits.device)
     if cl_info(dlogits)[5] != ld:
         raise ValueError("softmax_dice_bwd: dlogits must share the logits' voxel stride")
     g_i = g_i.contiguous().float()

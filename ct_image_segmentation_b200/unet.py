@@ -218,7 +218,7 @@ class UNet(nn.Module):
 
     # ---- forward plan ----------------------------------------------------------------------
     def _new(self, like: torch.Tensor, spatial, c: int) -> torch.Tensor:
-        return torch.empty((like.shape[0], *spatial, c), dtype=self.compute_dtype, device=like.device)
+        return ops.alloc_activation(like.shape[0], tuple(spatial), c, self.compute_dtype, like.device)
 
     def _run_forward(self, x_cl: torch.Tensor, saved: Dict, keep_all: bool = False) -> torch.Tensor:
         return self._fwd_level(self.model, x_cl, saved, None, keep_all)
@@ -322,7 +322,7 @@ class UNet(nn.Module):
             g_c = g_out
         else:
             c = s["c"]
-            g_c = torch.empty(c.shape, dtype=c.dtype, device=c.device)
+            g_c = ops.alloc_like(c)
             grads[m.act.weight] = ops.instnorm_prelu_bwd(c, s["mean"], s["rstd"], m.act.weight.detach(),
                                                          g_out, g_c, m.norm.eps)
         if getattr(self, "_bwd_taps", None) is not None:
@@ -332,7 +332,7 @@ class UNet(nn.Module):
         grads[m.conv.weight], grads[m.conv.bias] = gw, gb
         if not need_gx:
             return None
-        gx = gx_dst if gx_dst is not None else torch.empty(x.shape, dtype=x.dtype, device=x.device)
+        gx = gx_dst if gx_dst is not None else ops.alloc_like(x)
         ops.conv_dgrad(g, g_c, self._w_dgrad(m.conv, g), gx, residual=gx_residual, accumulate=gx_accum)
         return gx
 

@@ -58,7 +58,11 @@ enum b200seg_weight_kind {
 
 enum b200seg_conv_flags {
   B200SEG_CONV_ACCUMULATE = 1,   /* destination += result (gradient fan-in) */
-  B200SEG_CONV_FORCE_GENERIC = 2 /* use the CUDA-core kernel even where a tcgen05 kernel exists */
+  B200SEG_CONV_FORCE_GENERIC = 2, /* use the CUDA-core kernel even where a tcgen05 kernel exists */
+  /* x-, y- and residual-shaped tensors whose channel count C is not a multiple of 16 carry
+   * ZERO padding in channels [C, round_up(C,16)) (so ld >= round_up(C,16)); kernels may read the
+   * padding and rewrite it with zeros.  Lets the tcgen05 kernels take the 10-class layers. */
+  B200SEG_CONV_PADDED_CHANNELS = 4
 };
 
 /*
@@ -101,6 +105,8 @@ int b200seg_version(void);
 const char* b200seg_last_error(void);
 /* number of CUDA kernels this library has launched in the process so far (all threads) */
 long long b200seg_launch_count(void);
+/* ... of which tcgen05 (tensor-core) kernels */
+long long b200seg_tc_launch_count(void);
 /* 0 if `device` is an sm_100 part this library can run on */
 int b200seg_check_device(int device);
 

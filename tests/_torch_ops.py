@@ -10,6 +10,14 @@ import torch.nn.functional as F
 from ct_image_segmentation_b200.ops import ConvGeom, from_channels_last  # noqa: F401
 
 
+def alloc_activation(n, spatial, c, dtype, device):
+    return torch.empty((n, *spatial, c), dtype=dtype, device=device)
+
+
+def alloc_like(t):
+    return torch.empty(t.shape, dtype=t.dtype, device=t.device)
+
+
 def to_channels_last(x, dtype=None):
     if x.dim() == 4:
         x = x.unsqueeze(2)

@@ -93,15 +93,18 @@ def test_conv_fprop_dgrad_wgrad(dims, cin, cout, k, s, tr, sp, dtype):
     wdev = w.detach().to(DEV)
     x_cl = cl_dev(x.detach(), dtype, pad_c=8, c_off=8)           # strided source
     res_cl = cl_dev(res, dtype)
-    y_buf = torch.zeros(res_cl.shape[:-1] + (cout + 6,), dtype=dtype, device=DEV)
-    y_cl = y_buf[..., 3:3 + cout] if dtype == torch.float32 else y_buf[..., 2:2 + cout]
+    # fp32: odd channel offset (unaligned scalar path); bf16: 16-byte aligned slice (tcgen05 path)
+    off = 3 if dtype == torch.float32 else 8
+    y_buf = torch.zeros(res_cl.shape[:-1] + (cout + 16,), dtype=dtype, device=DEV)
+    y_cl = y_buf[..., off:off + cout]
     kind_f = _lib.W_CONVTR_FPROP if tr else _lib.W_CONV_FPROP
     kind_d = _lib.W_CONVTR_DGRAD if tr else _lib.W_CONV_DGRAD
     ops.conv_fprop(g, x_cl, ops.pack_weight(g, kind_f, wdev, dtype), b.to(DEV), y_cl, res_cl)
     tol = TOL[dtype]
     e = rel(nc_cpu(y_cl, dims), (y_ref + res).detach())
     assert e < tol, f"fprop rel err {e}"
-    assert float(y_buf[..., :2].abs().max()) == 0.0  # neighbours of the slice untouched
+    assert float(y_buf[..., :off].abs().max()) == 0.0  # neighbours of the slice untouched
+    assert float(y_buf[..., off + cout:].abs().max()) == 0.0
 
     # dgrad: plain, then accumulate + residual
     dy_cl = cl_dev(dy, dtype, pad_c=8, c_off=0)
@@ -122,6 +125,81 @@ def test_conv_fprop_dgrad_wgrad(dims, cin, cout, k, s, tr, sp, dtype):
     assert e < tol, f"wgrad rel err {e}"
     e = rel(gb, dy.sum(dim=[0] + list(range(2, 2 + dims))))
     assert e < tol, f"bias grad rel err {e}"
+
+
+TC_GEOMS = [
+    # dims, cin, cout, k, stride, transposed, n, spatial  -- shapes the tcgen05 kernels take
+    (3, 16, 16, 3, 1, False, 2, (16, 16, 16)),
+    (3, 16, 32, 3, 2, False, 2, (16, 24, 16)),
+    (3, 32, 32, 3, 1, False, 1, (8, 12, 20)),
+    (3, 64, 16, 3, 2, True, 1, (6, 8, 8)),
+    (3, 32, 10, 3, 2, True, 1, (8, 8, 8)),       # 10 classes: zero-padded to 16 channels
+    (3, 10, 10, 3, 1, False, 1, (16, 16, 16)),
+    (3, 128, 256, 3, 1, False, 2, (6, 6, 6)),    # 2 K blocks, 2 N tiles, ragged tiles
+    (3, 128, 256, 1, 1, False, 1, (8, 8, 8)),    # 1x1x1 residual conv
+    (3, 384, 64, 3, 2, True, 1, (4, 4, 4)),
+    (3, 256, 256, 3, 1, False, 1, (8, 8, 8)),
+    (2, 64, 128, 3, 2, False, 2, (32, 48)),
+    (2, 128, 64, 3, 2, True, 1, (16, 24)),
+    (2, 16, 16, 3, 1, False, 1, (40, 56)),
+]
+
+
+@pytest.mark.parametrize("dims,cin,cout,k,s,tr,n,sp", TC_GEOMS)
+def test_tcgen05_conv_vs_torch_and_generic(dims, cin, cout, k, s, tr, n, sp):
+    """bf16 tcgen05 kernels (fprop + dgrad, with residual / accumulate) against torch fp32 on the
+    same bf16-rounded inputs (1e-2) and against the CUDA-core kernel through the same ABI."""
+    lib = _lib.load()
+    dtype = torch.bfloat16
+    torch.manual_seed(4242)
+    g = ConvGeom(dims, cin, cout, k, s, tr)
+    ks = (k,) * dims
+    w = q(torch.randn((cin, cout, *ks) if tr else (cout, cin, *ks)) * (2.0 / (cin * k ** dims)) ** 0.5, dtype)
+    b = torch.randn(cout)
+    x = q(torch.randn(n, cin, *sp), dtype).requires_grad_(True)
+    y_ref = ref_conv(g, x, w, b)
+    res = q(torch.randn_like(y_ref), dtype)
+    dy = q(torch.randn_like(y_ref), dtype)
+    (y_ref + res).backward(dy)
+
+    def dev(t_nc):  # padded, pad-safe channels-last device tensor
+        if t_nc.dim() == 4:
+            t_nc = t_nc.unsqueeze(2)
+        out = ops.alloc_activation(t_nc.shape[0], tuple(t_nc.shape[2:]), t_nc.shape[1], dtype, DEV)
+        out.copy_(t_nc.permute(0, 2, 3, 4, 1))
+        return out
+
+    wdev = w.detach().to(DEV)
+    kind_f = _lib.W_CONVTR_FPROP if tr else _lib.W_CONV_FPROP
+    kind_d = _lib.W_CONVTR_DGRAD if tr else _lib.W_CONV_DGRAD
+    x_cl, res_cl, dy_cl = dev(x.detach()), dev(res), dev(dy)
+    y_cl = ops.alloc_like(res_cl)
+    t0 = lib.b200seg_tc_launch_count()
+    ops.conv_fprop(g, x_cl, ops.pack_weight(g, kind_f, wdev, dtype), b.to(DEV), y_cl, res_cl)
+    assert lib.b200seg_tc_launch_count() == t0 + 1, "tcgen05 kernel was not used"
+    e = rel(nc_cpu(y_cl, dims), (y_ref + res).detach())
+    assert e < 1e-2, f"tc fprop rel err {e}"
+    y_gen = ops.alloc_like(res_cl)
+    ops.conv_fprop(g, x_cl, ops.pack_weight(g, kind_f, wdev, dtype), b.to(DEV), y_gen, res_cl,
+                   flags=_lib.CONV_FORCE_GENERIC)
+    assert lib.b200seg_tc_launch_count() == t0 + 1
+    assert rel(y_cl, y_gen) < 6e-3, "tc vs generic fprop"
+
+    wp_d = ops.pack_weight(g, kind_d, wdev, dtype)
+    dx_cl = ops.alloc_like(x_cl)
+    ops.conv_dgrad(g, dy_cl, wp_d, dx_cl)
+    assert lib.b200seg_tc_launch_count() == t0 + 2, "tcgen05 dgrad kernel was not used"
+    e = rel(nc_cpu(dx_cl, dims), x.grad)
+    assert e < 1e-2, f"tc dgrad rel err {e}"
+    addend = q(torch.randn_like(x.grad), dtype)
+    base = q(torch.randn_like(x.grad), dtype)
+    dx2 = dev(base)
+    ops.conv_dgrad(g, dy_cl, wp_d, dx2, residual=dev(addend), accumulate=True)
+    e = rel(nc_cpu(dx2, dims), x.grad + addend + base)
+    assert e < 2e-2, f"tc dgrad accumulate rel err {e}"
+    if cout % 16:  # channel padding of the destination stays zero
+        full = y_cl.as_strided(y_cl.shape[:-1] + ((cout + 15) // 16 * 16,), y_cl.stride())
+        assert float(full[..., cout:].abs().max()) == 0.0
 
 
 NORM_CASES = [(2, 16, (6, 8, 10)), (1, 10, (8, 8, 12)), (2, 64, (4, 4, 4)), (3, 32, (1, 12, 20)),
