@@ -190,8 +190,9 @@ size_t b200seg_convtr_wgrad_workspace_bytes(const b200seg_conv_desc* d) {
   return wgrad_ws_bytes(d, w);
 }
 
-static int wgrad_common(const b200seg_conv_desc* d, const WgradParams& w, const void* S, const void* T,
-                        const void* dy, float* gw, float* gbias, void* ws, size_t ws_bytes, void* stream) {
+static int wgrad_common(const b200seg_conv_desc* d, bool transposed_layer, const WgradParams& w, const void* S,
+                        const void* T, const void* x, const void* dy, float* gw, float* gbias, void* ws,
+                        size_t ws_bytes, void* stream) {
   B200SEG_CHECK_ARG(S && T && gw && ws, "wgrad: NULL pointer");
   size_t need = wgrad_ws_bytes(d, w);
   if (ws_bytes < need) {
@@ -199,7 +200,15 @@ static int wgrad_common(const b200seg_conv_desc* d, const WgradParams& w, const 
     return B200SEG_ERR_WORKSPACE;
   }
   float* partial = (float*)ws;
-  int rc = launch_wgrad(w, d->dtype, S, T, gw, partial, as_stream(stream));
+  int rc;
+  if (tc_wgrad_supported(d, transposed_layer, x, dy)) {
+    int64_t nvox_y = (int64_t)d->n * d->out_d * d->out_h * d->out_w;
+    size_t colsum = (size_t)colsum_blocks(nvox_y) * d->cout * sizeof(float);
+    float* g32 = (float*)((char*)ws + align_up(wgrad_partial_bytes(w), 256) + align_up(colsum, 256));
+    rc = tc_wgrad_run(d, transposed_layer, x, dy, gw, g32, as_stream(stream));
+  } else {
+    rc = launch_wgrad(w, d->dtype, S, T, gw, partial, as_stream(stream));
+  }
   if (rc) return rc;
   if (gbias) {
     float* cs = (float*)((char*)ws + align_up(wgrad_partial_bytes(w), 256));
@@ -215,7 +224,7 @@ int b200seg_conv_wgrad(const b200seg_conv_desc* d, const void* x, const void* dy
   if (rc) return rc;
   WgradParams w{};
   conv_wgrad_params(d, w);
-  return wgrad_common(d, w, x, dy, dy, gw, gbias, workspace, workspace_bytes, stream);
+  return wgrad_common(d, false, w, x, dy, x, dy, gw, gbias, workspace, workspace_bytes, stream);
 }
 
 int b200seg_convtr_fprop(const b200seg_conv_desc* d, const void* x, const void* w_packed,
@@ -256,7 +265,7 @@ int b200seg_convtr_wgrad(const b200seg_conv_desc* d, const void* x, const void* 
   if (rc) return rc;
   WgradParams w{};
   convtr_wgrad_params(d, w);
-  return wgrad_common(d, w, dy, x, dy, gw, gbias, workspace, workspace_bytes, stream);
+  return wgrad_common(d, true, w, dy, x, x, dy, gw, gbias, workspace, workspace_bytes, stream);
 }
 
 // ---- InstanceNorm + PReLU ---------------------------------------------------------------------------

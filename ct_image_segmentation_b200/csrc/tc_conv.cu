@@ -528,6 +528,9 @@ int tc_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void*
   return B200SEG_ERR_UNSUPPORTED;
 }
 
-size_t tc_wgrad_extra_workspace(const b200seg_conv_desc*) { return 0; }
+int tc_make_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                const uint32_t* box, int row_bytes) {
+  return make_map(out, base, rank, dims, strides, box, row_bytes);
+}
 
 }  // namespace b200seg

@@ -17,5 +17,9 @@ int tc_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void*
 size_t tc_packed_weight_bytes(const b200seg_conv_desc* d);
 int tc_pack_weight(const b200seg_conv_desc* d, int kind, const float* w, void* out, cudaStream_t st);
 size_t tc_wgrad_extra_workspace(const b200seg_conv_desc* d);
+// weight gradient on tcgen05: x / dy in the layer's own terms, gw in PyTorch layout, G32 = fp32 scratch
+bool tc_wgrad_supported(const b200seg_conv_desc* d, bool transposed_layer, const void* x, const void* dy);
+int tc_wgrad_run(const b200seg_conv_desc* d, bool transposed_layer, const void* x, const void* dy, float* gw,
+                 float* G32, cudaStream_t st);
 
 }  // namespace b200seg

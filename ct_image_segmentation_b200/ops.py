@@ -8,6 +8,7 @@ Nothing here falls back to PyTorch arithmetic: a missing library or a failed lau
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from dataclasses import dataclass
 from typing import Optional, Tuple
 
@@ -131,13 +132,20 @@ def pack_weight(geom: ConvGeom, kind: int, w: torch.Tensor, dtype: torch.dtype) 
     return out
 
 
+_PADDED = set()  # (storage pointer, C) of live zero-padded buffers handed out by alloc_activation
+
+
 def alloc_activation(n: int, spatial, c: int, dtype: torch.dtype, device) -> torch.Tensor:
     """(N, *spatial, C) activation buffer.  For bf16 and C not a multiple of 16 (the 10-class
     layers) the buffer is zero-padded to the next multiple of 16 channels and marked, so the
     tcgen05 kernels can take it (B200SEG_CONV_PADDED_CHANNELS)."""
     if dtype == torch.bfloat16 and c % 16 != 0 and c >= 8:
         cp = (c + 15) // 16 * 16
-        return torch.zeros((n, *spatial, cp), dtype=dtype, device=device)[..., :c]
+        full = torch.zeros((n, *spatial, cp), dtype=dtype, device=device)
+        key = (full.untyped_storage().data_ptr(), c)
+        _PADDED.add(key)
+        weakref.finalize(full, _PADDED.discard, key)  # views keep `full` alive through ._base
+        return full[..., :c]
     return torch.empty((n, *spatial, c), dtype=dtype, device=device)
 
 
@@ -147,9 +155,9 @@ def alloc_like(t: torch.Tensor) -> torch.Tensor:
 
 def _pad_safe(t: Optional[torch.Tensor]) -> bool:
     """True if the tcgen05 kernels may treat channels [C, round_up(C, 16)) of ``t`` as its own zero
-    padding: C is a multiple of 16, or ``t`` is the leading-channel slice of a whole standalone
-    buffer with exactly round_up(C, 16) channels (what ``alloc_activation`` hands out; every kernel
-    keeps that padding zero).  A channel slice of a wider buffer never qualifies."""
+    padding: C is a multiple of 16, or ``t`` views a live buffer that ``alloc_activation`` created
+    zero-padded for exactly C channels (every kernel keeps that padding zero).  A channel slice of
+    a concatenation buffer never qualifies."""
     if t is None or t.shape[-1] % 16 == 0:
         return True
     n, d, h, w, c = t.shape
@@ -159,7 +167,7 @@ def _pad_safe(t: Optional[torch.Tensor]) -> bool:
     except (ValueError, RuntimeError):
         return False
     return (ld == cp and t.storage_offset() == 0
-            and t.untyped_storage().nbytes() == n * d * h * w * cp * t.element_size())
+            and (t.untyped_storage().data_ptr(), c) in _PADDED)
 
 
 def _conv_call(geom: ConvGeom, src, wp, bias, residual, dst, data_grad: bool, flags: int):
@@ -220,6 +228,8 @@ def conv_wgrad(geom: ConvGeom, x, dy, want_bias: bool = True, flags=0):
     n2, yd, yh, yw, yc, y_ld = cl_info(dy)
     if n != n2 or (xc, yc) != (geom.cin, geom.cout) or x.dtype != dy.dtype:
         raise ValueError("conv wgrad: shape/dtype mismatch")
+    if _pad_safe(x) and _pad_safe(dy):
+        flags |= _lib.CONV_PADDED_CHANNELS
     d = geom.desc(n, (xd, xh, xw), (yd, yh, yw), x_ld, y_ld, 0, x.dtype, flags)
     k = geom.kernel
     ks = (k, k) if geom.dims == 2 else (k, k, k)
@@ -327,8 +337,9 @@ def softmax_dice_bwd(logits, labels, g_i, g_p, dlogits=None) -> torch.Tensor:
     labels, code = _labels(labels, n, d * h * w)
     if dlogits is None:
         if ld > c:  # keep the (zero) channel padding of the logits buffer
-            full = torch.zeros((n, d, h, w, ld), dtype=logits.dtype, device=logits.device)
-            dlogits = full[..., :c]
+            dlogits = alloc_activation(n, (d, h, w), c, logits.dtype, logits.device)
+            if cl_info(dlogits)[5] != ld:
+                dlogits = torch.zeros((n, d, h, w, ld), dtype=logits.dtype, device=logits.device)[..., :c]
         else:
             dlogits = torch.empty(logits.shape, dtype=logits.dtype, device=logits.device)
     if cl_info(dlogits)[5] != ld:

@@ -201,6 +201,16 @@ def test_tcgen05_conv_vs_torch_and_generic(dims, cin, cout, k, s, tr, n, sp):
         full = y_cl.as_strided(y_cl.shape[:-1] + ((cout + 15) // 16 * 16,), y_cl.stride())
         assert float(full[..., cout:].abs().max()) == 0.0
 
+    # weight gradient on tcgen05 (MN-major operands, split-K) vs torch fp32 and vs the CUDA-core kernel
+    t1 = lib.b200seg_tc_launch_count()
+    gw, gb = ops.conv_wgrad(g, x_cl, dy_cl)
+    assert lib.b200seg_tc_launch_count() == t1 + 1, "tcgen05 wgrad kernel was not used"
+    e = rel(gw, w.grad)
+    assert e < 1e-2, f"tc wgrad rel err {e}"
+    gw2, _ = ops.conv_wgrad(g, x_cl, dy_cl, flags=_lib.CONV_FORCE_GENERIC)
+    assert rel(gw, gw2) < 1e-4, "tc vs generic wgrad"
+    assert rel(gb, dy.sum(dim=[0] + list(range(2, 2 + dims)))) < 1e-2
+
 
 NORM_CASES = [(2, 16, (6, 8, 10)), (1, 10, (8, 8, 12)), (2, 64, (4, 4, 4)), (3, 32, (1, 12, 20)),
               (1, 256, (2, 3, 4)), (2, 7, (3, 5, 7))]
