@@ -157,6 +157,7 @@ def test_tcgen05_conv_vs_torch_and_generic(dims, cin, cout, k, s, tr, n, sp):
     w = q(torch.randn((cin, cout, *ks) if tr else (cout, cin, *ks)) * (2.0 / (cin * k ** dims)) ** 0.5, dtype)
     b = torch.randn(cout)
     x = q(torch.randn(n, cin, *sp), dtype).requires_grad_(True)
+    w.requires_grad_(True)
     y_ref = ref_conv(g, x, w, b)
     res = q(torch.randn_like(y_ref), dtype)
     dy = q(torch.randn_like(y_ref), dtype)
