@@ -119,6 +119,7 @@ int b200seg_conv_fprop(const b200seg_conv_desc* d, const void* x, const void* w_
   if (rc) return rc;
   B200SEG_CHECK_ARG(x && w_packed && y, "conv_fprop: NULL pointer");
   if (tc_conv_supported(d, TC_CONV_FPROP, x, y, residual)) return tc_conv_run(d, TC_CONV_FPROP, x, tc_weights(d, w_packed), bias, residual, y, as_stream(stream));
+  if (small_cin_supported(d)) return launch_small_cin_fprop(d, x, w_packed, bias, residual, y, as_stream(stream));
   GatherParams g{};
   fill_geom(g, d);
   g.sD = d->in_d; g.sH = d->in_h; g.sW = d->in_w;
@@ -170,10 +171,16 @@ static void convtr_wgrad_params(const b200seg_conv_desc* d, WgradParams& w) {
   wgrad_plan(w);
 }
 
-static size_t wgrad_ws_bytes(const b200seg_conv_desc* d, const WgradParams& w) {
+static size_t wgrad_main_bytes(const b200seg_conv_desc* d, const WgradParams& w) {
+  size_t a = wgrad_partial_bytes(w), b = small_cin_wgrad_workspace(d);
+  return align_up(a > b ? a : b, 256);
+}
+static size_t wgrad_colsum_bytes(const b200seg_conv_desc* d) {
   int64_t nvox_y = (int64_t)d->n * d->out_d * d->out_h * d->out_w;
-  size_t colsum = (size_t)colsum_blocks(nvox_y) * d->cout * sizeof(float);
-  return align_up(wgrad_partial_bytes(w), 256) + align_up(colsum, 256) + tc_wgrad_extra_workspace(d);
+  return align_up(colsum_workspace_bytes(nvox_y, d->cout), 256);
+}
+static size_t wgrad_ws_bytes(const b200seg_conv_desc* d, const WgradParams& w) {
+  return wgrad_main_bytes(d, w) + wgrad_colsum_bytes(d) + tc_wgrad_extra_workspace(d);
 }
 
 size_t b200seg_conv_wgrad_workspace_bytes(const b200seg_conv_desc* d) {
@@ -202,16 +209,16 @@ static int wgrad_common(const b200seg_conv_desc* d, bool transposed_layer, const
   float* partial = (float*)ws;
   int rc;
   if (tc_wgrad_supported(d, transposed_layer, x, dy)) {
-    int64_t nvox_y = (int64_t)d->n * d->out_d * d->out_h * d->out_w;
-    size_t colsum = (size_t)colsum_blocks(nvox_y) * d->cout * sizeof(float);
-    float* g32 = (float*)((char*)ws + align_up(wgrad_partial_bytes(w), 256) + align_up(colsum, 256));
+    float* g32 = (float*)((char*)ws + wgrad_main_bytes(d, w) + wgrad_colsum_bytes(d));
     rc = tc_wgrad_run(d, transposed_layer, x, dy, gw, g32, as_stream(stream));
+  } else if (!transposed_layer && small_cin_supported(d)) {
+    rc = launch_small_cin_wgrad(d, x, dy, gw, partial, as_stream(stream));
   } else {
     rc = launch_wgrad(w, d->dtype, S, T, gw, partial, as_stream(stream));
   }
   if (rc) return rc;
   if (gbias) {
-    float* cs = (float*)((char*)ws + align_up(wgrad_partial_bytes(w), 256));
+    float* cs = (float*)((char*)ws + wgrad_main_bytes(d, w));
     int64_t nvox_y = (int64_t)d->n * d->out_d * d->out_h * d->out_w;
     rc = launch_colsum(d->dtype, dy, nvox_y, d->cout, d->y_ld, gbias, cs, as_stream(stream));
   }

@@ -349,65 +349,6 @@ int launch_wgrad(const WgradParams& p, int dtype, const void* S, const void* T, 
 }
 
 // ------------------------------------------------------------------------------------------
-// column sums (bias gradient):  out[c] = sum_v x[v*ld + c]
-// ------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(256)
-colsum_partial_kernel(const T* __restrict__ x, int64_t nvox, int c, int ld, int64_t vox_per_block,
-                      float* __restrict__ partial) {
-  __shared__ float red[256];
-  const int L = c < 256 ? c : 256;
-  const int VB = 256 / L;
-  const int l = threadIdx.x % L, vi = threadIdx.x / L;
-  const int64_t v_begin = (int64_t)blockIdx.x * vox_per_block;
-  const int64_t v_end = min(v_begin + vox_per_block, nvox);
-  for (int cb = 0; cb < c; cb += L) {
-    int ch = cb + l;
-    float s = 0.f;
-    if (vi < VB && ch < c)
-      for (int64_t v = v_begin + vi; v < v_end; v += VB) s += to_f<T>(x[v * ld + ch]);
-    red[threadIdx.x] = s;
-    __syncthreads();
-    if (vi == 0 && ch < c) {
-      float tot = 0.f;
-      for (int j = 0; j < VB; ++j) tot += red[j * L + l];
-      partial[(int64_t)blockIdx.x * c + ch] = tot;
-    }
-    __syncthreads();
-  }
-}
-
-__global__ void colsum_final_kernel(const float* __restrict__ partial, int nblocks, int c,
-                                    float* __restrict__ out) {
-  int ch = blockIdx.x * blockDim.x + threadIdx.x;
-  if (ch >= c) return;
-  double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += (double)partial[(int64_t)b * c + ch];
-  out[ch] = (float)s;
-}
-
-int colsum_blocks(int64_t nvox) {
-  int64_t b = cdiv64(nvox, 2048);
-  if (b > 1024) b = 1024;
-  if (b < 1) b = 1;
-  return (int)b;
-}
-
-int launch_colsum(int dtype, const void* x, int64_t nvox, int c, int ld, float* out, float* partial,
-                  cudaStream_t st) {
-  int nb = colsum_blocks(nvox);
-  int64_t per = cdiv64(nvox, nb);
-  if (dtype == B200SEG_BF16)
-    colsum_partial_kernel<__nv_bfloat16><<<nb, 256, 0, st>>>((const __nv_bfloat16*)x, nvox, c, ld, per, partial);
-  else
-    colsum_partial_kernel<float><<<nb, 256, 0, st>>>((const float*)x, nvox, c, ld, per, partial);
-  B200SEG_CHECK_LAUNCH("colsum_partial");
-  colsum_final_kernel<<<(c + 127) / 128, 128, 0, st>>>(partial, nb, c, out);
-  B200SEG_CHECK_LAUNCH("colsum_final");
-  return B200SEG_OK;
-}
-
-// ------------------------------------------------------------------------------------------
 // weight packing:  packed[tap][s][t]  from the fp32 PyTorch parameter
 // ------------------------------------------------------------------------------------------
 template <typename T>

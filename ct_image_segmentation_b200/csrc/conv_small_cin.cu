@@ -1,0 +1,237 @@
+// Direct (CUDA-core) kernels for the network's first convolutions, Cin <= 4 (CT volumes have one
+// channel; the 2-D windowed input has three).  27*Cin multiply-adds per output value: these layers
+// are bandwidth-bound (AI ~ 18 FLOP/B), a tensor-core tile would be > 90 %
+// zero padding.  fprop: one thread per output voxel and 16 output channels.  wgrad: the gathered
+// inputs of a voxel chunk (an im2col row of 27*Cin values per voxel) and the output gradients are
+// staged in shared memory, every thread owns a few (tap, ci, co) sums; per-block partials are
+// reduced in a fixed order (deterministic).  No dgrad: the network input needs no gradient.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace b200seg {
+
+struct SmallCinParams {
+  int n, cin, cout;
+  int iD, iH, iW, oD, oH, oW;
+  int kd, kh, kw, sd, sh, sw, pd, ph, pw;
+  int x_ld, y_ld, r_ld;
+  int64_t nvox;  // n*oD*oH*oW
+};
+
+// y[v][co] = bias[co] + sum_{tap,ci} x[in(v,tap)][ci] * w[tap][ci][co]   (+ residual)
+template <typename T>
+__global__ void __launch_bounds__(128)
+conv_small_cin_fprop_kernel(SmallCinParams p, const T* __restrict__ x, const T* __restrict__ w,
+                            const float* __restrict__ bias, const T* __restrict__ res, T* __restrict__ y) {
+  extern __shared__ float ws[];  // [taps*cin][16] weights of this channel group
+  const int taps = p.kd * p.kh * p.kw;
+  const int J = taps * p.cin;
+  const int co0 = blockIdx.y * 16;
+  for (int i = threadIdx.x; i < J * 16; i += blockDim.x) {
+    int j = i / 16, c = i % 16;
+    ws[i] = (co0 + c < p.cout) ? to_f<T>(w[(int64_t)j * p.cout + co0 + c]) : 0.f;
+  }
+  __syncthreads();
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= p.nvox) return;
+  int64_t r = v;
+  const int ow = (int)(r % p.oW); r /= p.oW;
+  const int oh = (int)(r % p.oH); r /= p.oH;
+  const int od = (int)(r % p.oD); r /= p.oD;
+  const int n = (int)r;
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = (bias && co0 + c < p.cout) ? bias[co0 + c] : 0.f;
+  int j = 0;
+  for (int kd = 0; kd < p.kd; ++kd) {
+    const int id = od * p.sd - p.pd + kd;
+    for (int kh = 0; kh < p.kh; ++kh) {
+      const int ih = oh * p.sh - p.ph + kh;
+      for (int kw = 0; kw < p.kw; ++kw) {
+        const int iw = ow * p.sw - p.pw + kw;
+        const bool in = id >= 0 && id < p.iD && ih >= 0 && ih < p.iH && iw >= 0 && iw < p.iW;
+        const T* xp = x + ((((int64_t)n * p.iD + id) * p.iH + ih) * p.iW + iw) * (int64_t)p.x_ld;
+        for (int ci = 0; ci < p.cin; ++ci, ++j) {
+          const float xv = in ? to_f<T>(xp[ci]) : 0.f;
+          const float* wr = ws + j * 16;
+#pragma unroll
+          for (int c = 0; c < 16; ++c) acc[c] = fmaf(xv, wr[c], acc[c]);
+        }
+      }
+    }
+  }
+  T* yp = y + v * (int64_t)p.y_ld + co0;
+  const T* rp = res ? res + v * (int64_t)p.r_ld + co0 : nullptr;
+  const bool vec = (co0 + 16 <= p.cout) && (((uintptr_t)yp % (8 * sizeof(T))) == 0) &&
+                   (!rp || ((uintptr_t)rp % (8 * sizeof(T))) == 0);
+  if (vec) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      Vec<T, 8> o;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o.v[i] = acc[h * 8 + i];
+      if (rp) {
+        Vec<T, 8> rv;
+        rv.load(rp + h * 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o.v[i] += rv.v[i];
+      }
+      o.store(yp + h * 8);
+    }
+  } else {
+    for (int c = 0; c < 16 && co0 + c < p.cout; ++c) {
+      float o = acc[c];
+      if (rp) o += to_f<T>(rp[c]);
+      yp[c] = from_f<T>(o);
+    }
+  }
+}
+
+// partial[blk][j][co] = sum over the block's voxels of x[in(v,tap)][ci] * dy[v][co],  j = tap*cin+ci
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv_small_cin_wgrad_kernel(SmallCinParams p, const T* __restrict__ x, const T* __restrict__ dy,
+                            float* __restrict__ partial, int64_t vox_per_block) {
+  constexpr int VC = 32;             // voxels per chunk
+  extern __shared__ float sm[];      // X[VC][J] | DY[VC][cout]
+  const int taps = p.kd * p.kh * p.kw;
+  const int J = taps * p.cin;
+  const int CO = p.cout;
+  float* Xs = sm;
+  float* Ds = sm + VC * J;
+  const int nout = J * CO;
+  constexpr int R = 8;  // outputs per thread (J*CO <= 256*R)
+  float acc[R];
+  int oj[R], oc[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    acc[r] = 0.f;
+    int o = threadIdx.x + r * 256;
+    oj[r] = o < nout ? o / CO : 0;
+    oc[r] = o < nout ? o % CO : 0;
+  }
+  const int64_t v_begin = (int64_t)blockIdx.x * vox_per_block;
+  const int64_t v_end = min(v_begin + vox_per_block, p.nvox);
+  for (int64_t v0 = v_begin; v0 < v_end; v0 += VC) {
+    // gather X
+    for (int i = threadIdx.x; i < VC * J; i += 256) {
+      const int lv = i / J, j = i % J;
+      const int64_t v = v0 + lv;
+      float val = 0.f;
+      if (v < v_end) {
+        int64_t r = v;
+        const int ow = (int)(r % p.oW); r /= p.oW;
+        const int oh = (int)(r % p.oH); r /= p.oH;
+        const int od = (int)(r % p.oD); r /= p.oD;
+        const int n = (int)r;
+        const int tap = j / p.cin, ci = j % p.cin;
+        const int kw = tap % p.kw, kh = (tap / p.kw) % p.kh, kd = tap / (p.kw * p.kh);
+        const int id = od * p.sd - p.pd + kd, ih = oh * p.sh - p.ph + kh, iw = ow * p.sw - p.pw + kw;
+        if (id >= 0 && id < p.iD && ih >= 0 && ih < p.iH && iw >= 0 && iw < p.iW)
+          val = to_f<T>(x[((((int64_t)n * p.iD + id) * p.iH + ih) * p.iW + iw) * (int64_t)p.x_ld + ci]);
+      }
+      Xs[i] = val;
+    }
+    for (int i = threadIdx.x; i < VC * CO; i += 256) {
+      const int lv = i / CO, c = i % CO;
+      const int64_t v = v0 + lv;
+      Ds[i] = v < v_end ? to_f<T>(dy[v * (int64_t)p.y_ld + c]) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int lv = 0; lv < VC; ++lv) {
+      const float* xr = Xs + lv * J;
+      const float* dr = Ds + lv * CO;
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = fmaf(xr[oj[r]], dr[oc[r]], acc[r]);
+    }
+    __syncthreads();
+  }
+  float* out = partial + (int64_t)blockIdx.x * nout;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    int o = threadIdx.x + r * 256;
+    if (o < nout) out[o] = acc[r];
+  }
+}
+
+// gw[co][ci][tap] = sum_blk partial[blk][tap*cin+ci][co]
+__global__ void conv_small_cin_wgrad_final_kernel(const float* __restrict__ partial, int nblk, int taps,
+                                                  int cin, int cout, float* __restrict__ gw) {
+  const int nout = taps * cin * cout;
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= nout) return;
+  double s = 0.0;
+  for (int b = 0; b < nblk; ++b) s += (double)partial[(int64_t)b * nout + o];
+  const int co = o % cout, j = o / cout;
+  const int tap = j / cin, ci = j % cin;
+  gw[((int64_t)co * cin + ci) * taps + tap] = (float)s;
+}
+
+namespace {
+void fill(SmallCinParams& p, const b200seg_conv_desc* d) {
+  p.n = d->n; p.cin = d->cin; p.cout = d->cout;
+  p.iD = d->in_d; p.iH = d->in_h; p.iW = d->in_w; p.oD = d->out_d; p.oH = d->out_h; p.oW = d->out_w;
+  p.kd = d->kd; p.kh = d->kh; p.kw = d->kw; p.sd = d->sd; p.sh = d->sh; p.sw = d->sw;
+  p.pd = d->pd; p.ph = d->ph; p.pw = d->pw;
+  p.x_ld = d->x_ld; p.y_ld = d->y_ld; p.r_ld = d->r_ld;
+  p.nvox = (int64_t)d->n * d->out_d * d->out_h * d->out_w;
+}
+}  // namespace
+
+bool small_cin_supported(const b200seg_conv_desc* d) {
+  const int J = d->kd * d->kh * d->kw * d->cin;
+  return d->cin <= 4 && J * d->cout <= 2048 && !(d->flags & B200SEG_CONV_FORCE_GENERIC);
+}
+
+int small_cin_wgrad_blocks(const b200seg_conv_desc* d) {
+  int64_t nvox = (int64_t)d->n * d->out_d * d->out_h * d->out_w;
+  int64_t nb = cdiv64(nvox, 256);
+  if (nb > 592) nb = 592;
+  if (nb < 1) nb = 1;
+  return (int)nb;
+}
+
+size_t small_cin_wgrad_workspace(const b200seg_conv_desc* d) {
+  if (!small_cin_supported(d)) return 0;
+  return (size_t)small_cin_wgrad_blocks(d) * d->kd * d->kh * d->kw * d->cin * d->cout * sizeof(float);
+}
+
+int launch_small_cin_fprop(const b200seg_conv_desc* d, const void* x, const void* w, const float* bias,
+                           const void* res, void* y, cudaStream_t st) {
+  SmallCinParams p;
+  fill(p, d);
+  const int J = d->kd * d->kh * d->kw * d->cin;
+  dim3 grid((unsigned)cdiv64(p.nvox, 128), (unsigned)((d->cout + 15) / 16));
+  size_t smem = (size_t)J * 16 * sizeof(float);
+  if (d->dtype == B200SEG_BF16)
+    conv_small_cin_fprop_kernel<__nv_bfloat16><<<grid, 128, smem, st>>>(
+        p, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, bias, (const __nv_bfloat16*)res, (__nv_bfloat16*)y);
+  else
+    conv_small_cin_fprop_kernel<float><<<grid, 128, smem, st>>>(p, (const float*)x, (const float*)w, bias,
+                                                                (const float*)res, (float*)y);
+  B200SEG_CHECK_LAUNCH("conv_small_cin_fprop");
+  return B200SEG_OK;
+}
+
+int launch_small_cin_wgrad(const b200seg_conv_desc* d, const void* x, const void* dy, float* gw, float* partial,
+                           cudaStream_t st) {
+  SmallCinParams p;
+  fill(p, d);
+  const int taps = d->kd * d->kh * d->kw, J = taps * d->cin;
+  const int nb = small_cin_wgrad_blocks(d);
+  int64_t per = cdiv64(cdiv64(p.nvox, nb), 32) * 32;
+  size_t smem = (size_t)32 * (J + d->cout) * sizeof(float);
+  if (d->dtype == B200SEG_BF16)
+    conv_small_cin_wgrad_kernel<__nv_bfloat16><<<nb, 256, smem, st>>>(p, (const __nv_bfloat16*)x,
+                                                                      (const __nv_bfloat16*)dy, partial, per);
+  else
+    conv_small_cin_wgrad_kernel<float><<<nb, 256, smem, st>>>(p, (const float*)x, (const float*)dy, partial, per);
+  B200SEG_CHECK_LAUNCH("conv_small_cin_wgrad");
+  const int nout = J * d->cout;
+  conv_small_cin_wgrad_final_kernel<<<(nout + 127) / 128, 128, 0, st>>>(partial, nb, taps, d->cin, d->cout, gw);
+  B200SEG_CHECK_LAUNCH("conv_small_cin_wgrad_final");
+  return B200SEG_OK;
+}
+
+}  // namespace b200seg

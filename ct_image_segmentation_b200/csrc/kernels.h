@@ -42,11 +42,19 @@ void wgrad_plan(WgradParams& p);
 size_t wgrad_partial_bytes(const WgradParams& p);
 int launch_wgrad(const WgradParams& p, int dtype, const void* S, const void* T, float* gw,
                  float* partial, cudaStream_t st);
-int colsum_blocks(int64_t nvox);
+size_t colsum_workspace_bytes(int64_t nvox, int c);
 int launch_colsum(int dtype, const void* x, int64_t nvox, int c, int ld, float* out, float* partial,
                   cudaStream_t st);
 int launch_pack_weight(int dtype, int kind, const float* w, void* packed, int taps, int cin,
                        int cout, cudaStream_t st);
+
+// conv_small_cin.cu  (Cin <= 4 first-layer convolutions)
+bool small_cin_supported(const b200seg_conv_desc* d);
+size_t small_cin_wgrad_workspace(const b200seg_conv_desc* d);
+int launch_small_cin_fprop(const b200seg_conv_desc* d, const void* x, const void* w, const float* bias,
+                           const void* res, void* y, cudaStream_t st);
+int launch_small_cin_wgrad(const b200seg_conv_desc* d, const void* x, const void* dy, float* gw, float* partial,
+                           cudaStream_t st);
 
 // norm.cu
 int norm_blocks(const b200seg_norm_desc& d);

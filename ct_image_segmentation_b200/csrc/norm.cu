@@ -402,4 +402,48 @@ int launch_instnorm_prelu_bwd(const b200seg_norm_desc& d, const void* x, const f
   return B200SEG_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// column sums (bias gradient):  out[c] = sum_v x[v*ld + c]   -- the statistics kernel with the
+// batch folded into the voxel axis; per-block partials, fixed-order finalisation in double
+// ------------------------------------------------------------------------------------------
+__global__ void colsum_final_kernel(const float* __restrict__ partial, int nblk, int c,
+                                    float* __restrict__ out) {
+  int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (warp >= c) return;
+  double s = 0.0;
+  for (int b = lane; b < nblk; b += 32) s += (double)partial[((int64_t)b * c + warp) * 2];
+  s = warp_sum_d(s);
+  if (lane == 0) out[warp] = (float)s;
+}
+
+static b200seg_norm_desc colsum_desc(int dtype, int64_t nvox, int c, int ld) {
+  b200seg_norm_desc d;
+  d.n = 1; d.c = c; d.spatial = nvox; d.x_ld = ld; d.y_ld = ld; d.r_ld = ld; d.dtype = dtype; d.eps = 0.f;
+  return d;
+}
+
+size_t colsum_workspace_bytes(int64_t nvox, int c) {
+  b200seg_norm_desc d = colsum_desc(B200SEG_F32, nvox, c, c);
+  return (size_t)norm_blocks(d) * c * 2 * sizeof(float) + 256;
+}
+
+int launch_colsum(int dtype, const void* x, int64_t nvox, int c, int ld, float* out, float* partial,
+                  cudaStream_t st) {
+  b200seg_norm_desc d = colsum_desc(dtype, nvox, c, ld);
+  NormGeom g;
+  int V = pick_vec(d, {x}, {ld});
+  int rc = make_geom(d, V, g);
+  if (rc) return rc;
+  int64_t per = cdiv64(nvox, g.nblk);
+  dim3 grid(g.nblk, 1);
+  size_t smem = 256 * 2 * V * sizeof(float);
+  DISPATCH_TV(dtype, V,
+              (instnorm_stats_partial_kernel<T, VV><<<grid, 256, smem, st>>>((const T*)x, nvox, c, ld, g.L,
+                                                                            g.VB, per, partial)));
+  B200SEG_CHECK_LAUNCH("colsum_partial");
+  colsum_final_kernel<<<(c * 32 + 255) / 256, 256, 0, st>>>(partial, g.nblk, c, out);
+  B200SEG_CHECK_LAUNCH("colsum_final");
+  return B200SEG_OK;
+}
+
 }  // namespace b200seg

@@ -328,8 +328,12 @@ class UNet(nn.Module):
         if getattr(self, "_bwd_taps", None) is not None:
             self._bwd_taps[m] = {"g_out": g_out, "g_c": g_c, "x": x, "c": s.get("c"),
                                  "mean": s.get("mean"), "rstd": s.get("rstd")}
-        gw, gb = ops.conv_wgrad(g, x, g_c)
-        grads[m.conv.weight], grads[m.conv.bias] = gw, gb
+        # A bias in front of an affine-less InstanceNorm is cancelled by the mean subtraction: its
+        # gradient is identically zero (sum_v g_c = 0 analytically; the reference holds rounding noise
+        # there).  Only live biases (conv-only head) get a column sum.
+        gw, gb = ops.conv_wgrad(g, x, g_c, want_bias=m.conv_only)
+        grads[m.conv.weight] = gw
+        grads[m.conv.bias] = gb if gb is not None else torch.zeros_like(m.conv.bias)
         if not need_gx:
             return None
         gx = gx_dst if gx_dst is not None else ops.alloc_like(x)
