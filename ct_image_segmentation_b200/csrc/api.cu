@@ -112,13 +112,21 @@ int b200seg_pack_weight(const b200seg_conv_desc* d, int kind, const float* w_tor
   return tc_pack_weight(d, kind, w_torch, (char*)w_packed + generic_weight_bytes(d), as_stream(stream));
 }
 
+// tcgen05 dispatch: sliding-window kernel where it applies, else the streaming kernel
+static int tc_dispatch(const b200seg_conv_desc* d, int op, const void* src, const void* w_packed,
+                       const float* bias, const void* residual, void* dst, void* stream) {
+  if (!(d->flags & B200SEG_CONV_NO_SLIDE) && tc_slide_conv_supported(d, op))
+    return tc_slide_conv_run(d, op, src, tc_weights(d, w_packed), bias, residual, dst, as_stream(stream));
+  return tc_conv_run(d, op, src, tc_weights(d, w_packed), bias, residual, dst, as_stream(stream));
+}
+
 // ---- conv ---------------------------------------------------------------------------------------
 int b200seg_conv_fprop(const b200seg_conv_desc* d, const void* x, const void* w_packed,
                        const float* bias, const void* residual, void* y, void* stream) {
   int rc = check_conv_desc(d, false);
   if (rc) return rc;
   B200SEG_CHECK_ARG(x && w_packed && y, "conv_fprop: NULL pointer");
-  if (tc_conv_supported(d, TC_CONV_FPROP, x, y, residual)) return tc_conv_run(d, TC_CONV_FPROP, x, tc_weights(d, w_packed), bias, residual, y, as_stream(stream));
+  if (tc_conv_supported(d, TC_CONV_FPROP, x, y, residual)) return tc_dispatch(d, TC_CONV_FPROP, x, w_packed, bias, residual, y, stream);
   if (small_cin_supported(d)) return launch_small_cin_fprop(d, x, w_packed, bias, residual, y, as_stream(stream));
   GatherParams g{};
   fill_geom(g, d);
@@ -135,7 +143,7 @@ int b200seg_conv_dgrad(const b200seg_conv_desc* d, const void* dy, const void* w
   int rc = check_conv_desc(d, false);
   if (rc) return rc;
   B200SEG_CHECK_ARG(dy && w_packed && dx, "conv_dgrad: NULL pointer");
-  if (tc_conv_supported(d, TC_CONV_DGRAD, dy, dx, residual)) return tc_conv_run(d, TC_CONV_DGRAD, dy, tc_weights(d, w_packed), nullptr, residual, dx, as_stream(stream));
+  if (tc_conv_supported(d, TC_CONV_DGRAD, dy, dx, residual)) return tc_dispatch(d, TC_CONV_DGRAD, dy, w_packed, nullptr, residual, dx, stream);
   GatherParams g{};
   fill_geom(g, d);
   g.sD = d->out_d; g.sH = d->out_h; g.sW = d->out_w;
@@ -239,7 +247,7 @@ int b200seg_convtr_fprop(const b200seg_conv_desc* d, const void* x, const void* 
   int rc = check_conv_desc(d, true);
   if (rc) return rc;
   B200SEG_CHECK_ARG(x && w_packed && y, "convtr_fprop: NULL pointer");
-  if (tc_conv_supported(d, TC_CONVTR_FPROP, x, y, residual)) return tc_conv_run(d, TC_CONVTR_FPROP, x, tc_weights(d, w_packed), bias, residual, y, as_stream(stream));
+  if (tc_conv_supported(d, TC_CONVTR_FPROP, x, y, residual)) return tc_dispatch(d, TC_CONVTR_FPROP, x, w_packed, bias, residual, y, stream);
   GatherParams g{};
   fill_geom(g, d);
   g.sD = d->in_d; g.sH = d->in_h; g.sW = d->in_w;
@@ -255,7 +263,7 @@ int b200seg_convtr_dgrad(const b200seg_conv_desc* d, const void* dy, const void*
   int rc = check_conv_desc(d, true);
   if (rc) return rc;
   B200SEG_CHECK_ARG(dy && w_packed && dx, "convtr_dgrad: NULL pointer");
-  if (tc_conv_supported(d, TC_CONVTR_DGRAD, dy, dx, residual)) return tc_conv_run(d, TC_CONVTR_DGRAD, dy, tc_weights(d, w_packed), nullptr, residual, dx, as_stream(stream));
+  if (tc_conv_supported(d, TC_CONVTR_DGRAD, dy, dx, residual)) return tc_dispatch(d, TC_CONVTR_DGRAD, dy, w_packed, nullptr, residual, dx, stream);
   GatherParams g{};
   fill_geom(g, d);
   g.sD = d->out_d; g.sH = d->out_h; g.sW = d->out_w;

@@ -14,6 +14,10 @@ enum TcConvOp { TC_CONV_FPROP = 0, TC_CONV_DGRAD = 1, TC_CONVTR_FPROP = 2, TC_CO
 bool tc_conv_supported(const b200seg_conv_desc* d, int op, const void* src, const void* dst, const void* res);
 int tc_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,
                 const void* residual, void* dst, cudaStream_t st);
+// sliding-window variant for small-channel, high-resolution 3x3x3 stride-1 layers (tc_slide.cu)
+bool tc_slide_conv_supported(const b200seg_conv_desc* d, int op);
+int tc_slide_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,
+                      const void* residual, void* dst, cudaStream_t st);
 size_t tc_packed_weight_bytes(const b200seg_conv_desc* d);
 int tc_pack_weight(const b200seg_conv_desc* d, int kind, const float* w, void* out, cudaStream_t st);
 size_t tc_wgrad_extra_workspace(const b200seg_conv_desc* d);

@@ -1,0 +1,314 @@
+// Sliding-window tcgen05 kernels for the small-channel / high-resolution 3x3x3 stride-1 layers
+// (head 10->10 at full resolution, 16->16 at 1/2, 32->32 at 1/4): the layers that dominate the
+// network's time and whose arithmetic intensity is too low to re-read the source once per tap.
+//
+// A CTA owns a column of the volume: TH=16 lines x 8 voxels in (h, w), and sweeps along d.  For
+// every source slab it TMA-loads three w-shifted copies of the (TH+2) x 8 halo tile into a
+// shared-memory ring (box rows of exactly 8 voxels = one swizzle atom, so a shift by whole lines
+// (kh) or whole slabs (kd) is an atom-aligned descriptor offset and the w shift (kw) selects the
+// copy).  Each source voxel is therefore read 3 x 18/16 = 3.4 times from L2 instead of 27 times.
+//   conv (fprop / dgrad): per output slab 27 x (KC/16) tcgen05.mma of M=128 (16 lines x 8 voxels),
+//     N=Cout, K=16 against the 27 weight tiles resident in shared memory; two TMEM accumulator
+//     buffers so the epilogue of slab d overlaps the MMAs of slab d+1.
+//   wgrad: see tc_slide_wgrad_kernel below.
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tc_conv.h"
+
+namespace b200seg {
+
+using bf16 = __nv_bfloat16;
+
+int tc_make_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                const uint32_t* box, int row_bytes);
+
+namespace {
+constexpr int TH = 16;      // lines per tile
+constexpr int TWV = 8;      // voxels per line (one swizzle atom of rows)
+constexpr int RING = 4;     // source slabs in flight
+inline int round16(int c) { return (c + 15) / 16 * 16; }
+}  // namespace
+
+struct alignas(64) TcSlideConvParams {
+  CUtensorMap tmA;
+  CUtensorMap tmB;
+  int n, D, H, W;
+  int tilesH, tilesW, dseg, nseg;
+  int cout, dst_ld, res_ld, accumulate, flip;
+  const float* bias;
+  const bf16* res;
+  bf16* dst;
+};
+
+template <int BN, int KC>
+__global__ void __launch_bounds__(192)
+tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
+  constexpr int PITCH = KC * 2;                          // bytes per voxel row
+  constexpr int COPY_BYTES = (TH + 2) * TWV * PITCH;     // one w-shifted halo tile
+  constexpr int SLAB_BYTES = 3 * COPY_BYTES;
+  constexpr int WT_BYTES = BN * PITCH;                   // one weight tile (tap)
+  constexpr int W_BYTES = (27 * WT_BYTES + 1023) / 1024 * 1024;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* wsm = smem;
+  uint8_t* ring = smem + W_BYTES;
+  uint64_t* full = reinterpret_cast<uint64_t*>(ring + RING * SLAB_BYTES);
+  uint64_t* empty = full + RING;
+  uint64_t* acc_full = empty + RING;   // [2]
+  uint64_t* acc_empty = acc_full + 2;  // [2]
+  uint64_t* wbar = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int bx = blockIdx.x;
+  const int seg = bx % p.nseg; bx /= p.nseg;
+  const int tw_i = bx % p.tilesW; bx /= p.tilesW;
+  const int th_i = bx % p.tilesH; bx /= p.tilesH;
+  const int n = bx;
+  const int h0 = th_i * TH, w0 = tw_i * TWV;
+  const int d_begin = seg * p.dseg;
+  const int nd = min(p.dseg, p.D - d_begin);  // output slabs of this CTA
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < RING; ++i) {
+      tc::mbar_init(&full[i], 1);
+      tc::mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      tc::mbar_init(&acc_full[i], 1);
+      tc::mbar_init(&acc_empty[i], 4);
+    }
+    tc::mbar_init(wbar, 1);
+    tc::fence_barrier_init();
+    tc::prefetch_tmap(&p.tmA);
+    tc::prefetch_tmap(&p.tmB);
+  }
+  if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tc::mbar_expect_tx(wbar, 27 * WT_BYTES);
+      for (int t = 0; t < 27; ++t) tc::tma_load_2d(wsm + t * WT_BYTES, &p.tmB, wbar, 0, t * BN);
+      uint32_t ph = 0;
+      for (int s = 0; s < nd + 2; ++s) {
+        const int slot = s % RING;
+        if (s > 0 && slot == 0) ph ^= 1u;
+        tc::mbar_wait(&empty[slot], ph ^ 1u);
+        uint8_t* dst = ring + slot * SLAB_BYTES;
+        tc::mbar_expect_tx(&full[slot], SLAB_BYTES);
+        const int ds = d_begin - 1 + s;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+          tc::tma_load_5d(dst + kw * COPY_BYTES, &p.tmA, &full[slot], 0, w0 + kw - 1, h0 - 1, ds, n);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN, false, false);
+      constexpr uint64_t layout = tc::layout_for_row_bytes(PITCH);
+      const uint32_t w_addr = tc::smem_u32(wsm), r_addr = tc::smem_u32(ring);
+      tc::mbar_wait(wbar, 0);
+      int waited = 0;
+      for (int j = 0; j < nd; ++j) {
+        const int buf = j & 1;
+        tc::mbar_wait(&acc_empty[buf], (((uint32_t)j >> 1) & 1u) ^ 1u);
+        while (waited <= j + 2) {
+          tc::mbar_wait(&full[waited % RING], ((uint32_t)(waited / RING)) & 1u);
+          ++waited;
+        }
+        tc::tc_fence_after();
+        uint32_t first = 1;
+#pragma unroll 1
+        for (int id = 0; id < 3; ++id) {
+          const uint32_t slab = r_addr + ((j + id) % RING) * SLAB_BYTES;
+#pragma unroll
+          for (int ih = 0; ih < 3; ++ih)
+#pragma unroll
+            for (int iw = 0; iw < 3; ++iw) {
+              const int wt = p.flip ? ((2 - id) * 3 + (2 - ih)) * 3 + (2 - iw) : (id * 3 + ih) * 3 + iw;
+              const uint32_t a = slab + iw * COPY_BYTES + ih * (TWV * PITCH);
+              const uint32_t b = w_addr + wt * WT_BYTES;
+#pragma unroll
+              for (int k = 0; k < KC / 16; ++k) {
+                tc::umma_bf16(tmem_acc + buf * BN, tc::make_smem_desc(a + k * 32, 16, 8 * PITCH, layout),
+                              tc::make_smem_desc(b + k * 32, 16, 8 * PITCH, layout), idesc, first ? 0u : 1u);
+                first = 0;
+              }
+            }
+        }
+        tc::umma_commit(&acc_full[buf]);
+        tc::umma_commit(&empty[j % RING]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int oh = h0 + row / TWV, ow = w0 + row % TWV;
+    const bool valid = oh < p.H && ow < p.W;
+    for (int j = 0; j < nd; ++j) {
+      const int buf = j & 1;
+      tc::mbar_wait(&acc_full[buf], ((uint32_t)j >> 1) & 1u);
+      tc::tc_fence_after();
+      const int od = d_begin + j;
+      const int64_t lin = (((int64_t)n * p.D + od) * p.H + oh) * p.W + ow;
+#pragma unroll
+      for (int ch = 0; ch < BN / 16; ++ch) {
+        uint32_t v[16];
+        tc::tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + buf * BN + ch * 16, v);
+        tc::tmem_ld_wait();
+        if (valid) {
+          const int c0 = ch * 16;
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+          if (p.bias) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+              if (c0 + i < p.cout) f[i] += p.bias[c0 + i];
+          }
+          if (p.res) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.res + lin * p.res_ld + c0);
+            uint4 r0 = rp[0], r1 = rp[1];
+            const __nv_bfloat162* g0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+            const __nv_bfloat162* g1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float2 a = __bfloat1622float2(g0[i]), b = __bfloat1622float2(g1[i]);
+              f[2 * i] += a.x; f[2 * i + 1] += a.y;
+              f[8 + 2 * i] += b.x; f[8 + 2 * i + 1] += b.y;
+            }
+          }
+          uint4* op = reinterpret_cast<uint4*>(p.dst + lin * p.dst_ld + c0);
+          if (p.accumulate) {
+            uint4 r0 = op[0], r1 = op[1];
+            const __nv_bfloat162* g0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+            const __nv_bfloat162* g1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float2 a = __bfloat1622float2(g0[i]), b = __bfloat1622float2(g1[i]);
+              f[2 * i] += a.x; f[2 * i + 1] += a.y;
+              f[8 + 2 * i] += b.x; f[8 + 2 * i + 1] += b.y;
+            }
+          }
+          uint4 o0, o1;
+          __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+          __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            q0[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+            q1[i] = __floats2bfloat162_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
+          }
+          op[0] = o0;
+          op[1] = o1;
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<TMEM_COLS>(tmem_acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct SlideGeom {
+  int n, D, H, W, src_c, dst_c, src_ld, dst_ld;
+};
+
+bool slide_geom(const b200seg_conv_desc* d, int op, SlideGeom& g) {
+  if (op != TC_CONV_FPROP && op != TC_CONV_DGRAD) return false;
+  if (d->kd != 3 || d->kh != 3 || d->kw != 3 || d->sd != 1 || d->sh != 1 || d->sw != 1) return false;
+  g.n = d->n; g.D = d->in_d; g.H = d->in_h; g.W = d->in_w;
+  if (op == TC_CONV_FPROP) { g.src_c = d->cin; g.dst_c = d->cout; g.src_ld = d->x_ld; g.dst_ld = d->y_ld; }
+  else { g.src_c = d->cout; g.dst_c = d->cin; g.src_ld = d->y_ld; g.dst_ld = d->x_ld; }
+  return true;
+}
+
+template <int BN, int KC>
+int launch_slide(const TcSlideConvParams& p, unsigned grid, cudaStream_t st) {
+  constexpr int PITCH = KC * 2;
+  constexpr int SLAB = 3 * (TH + 2) * TWV * PITCH;
+  constexpr int WB = (27 * BN * PITCH + 1023) / 1024 * 1024;
+  const size_t smem = 1024 + WB + RING * SLAB + 8 * PITCH * 8 + 16 * 8 + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(tc_slide_conv_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr_set = true;
+  }
+  tc_slide_conv_kernel<BN, KC><<<grid, 192, smem, st>>>(p);
+  B200SEG_CHECK_LAUNCH("tc_slide_conv");
+  count_tc_launch();
+  return B200SEG_OK;
+}
+
+}  // namespace
+
+// Layers the sliding kernel takes (on top of tc_conv_supported): 3-D, 3x3x3, stride 1, source and
+// destination channel counts (padded) in {16, 32}, and a volume large enough to amortise the sweep.
+bool tc_slide_conv_supported(const b200seg_conv_desc* d, int op) {
+  SlideGeom g;
+  if (!slide_geom(d, op, g)) return false;
+  const int sp = round16(g.src_c), dp = round16(g.dst_c);
+  if ((sp != 16 && sp != 32) || (dp != 16 && dp != 32)) return false;
+  if (g.D < 8 || (int64_t)g.H * g.W < 512) return false;
+  return true;
+}
+
+int tc_slide_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,
+                      const void* residual, void* dst, cudaStream_t st) {
+  SlideGeom g;
+  slide_geom(d, op, g);
+  TcSlideConvParams p;
+  memset(&p, 0, sizeof(p));
+  const int KC = round16(g.src_c), BN = round16(g.dst_c);
+  p.n = g.n; p.D = g.D; p.H = g.H; p.W = g.W;
+  p.tilesH = (g.H + TH - 1) / TH; p.tilesW = (g.W + TWV - 1) / TWV;
+  // d segments: enough CTAs for ~4 per SM, at least 8 slabs each
+  const int64_t cols = (int64_t)g.n * p.tilesH * p.tilesW;
+  int nseg = (int)((148 * 4 + cols - 1) / cols);
+  if (nseg < 1) nseg = 1;
+  int dseg = (g.D + nseg - 1) / nseg;
+  if (dseg < 8) dseg = 8;
+  if (dseg > g.D) dseg = g.D;
+  p.dseg = dseg; p.nseg = (g.D + dseg - 1) / dseg;
+  p.cout = g.dst_c; p.dst_ld = g.dst_ld; p.res_ld = d->r_ld;
+  p.accumulate = (d->flags & B200SEG_CONV_ACCUMULATE) ? 1 : 0;
+  p.flip = (op == TC_CONV_DGRAD) ? 1 : 0;
+  p.bias = bias; p.res = (const bf16*)residual; p.dst = (bf16*)dst;
+  {
+    uint64_t dims[5] = {(uint64_t)KC, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.D, (uint64_t)g.n};
+    uint64_t strides[4] = {(uint64_t)g.src_ld * 2, (uint64_t)g.W * g.src_ld * 2, (uint64_t)g.H * g.W * g.src_ld * 2,
+                           (uint64_t)g.D * g.H * g.W * g.src_ld * 2};
+    uint32_t box[5] = {(uint32_t)KC, (uint32_t)TWV, (uint32_t)(TH + 2), 1, 1};
+    int rc = tc_make_map(&p.tmA, src, 5, dims, strides, box, KC * 2);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)KC, (uint64_t)27 * BN};
+    uint64_t strides[1] = {(uint64_t)KC * 2};
+    uint32_t box[2] = {(uint32_t)KC, (uint32_t)BN};
+    int rc = tc_make_map(&p.tmB, w_tc, 2, dims, strides, box, KC * 2);
+    if (rc) return rc;
+  }
+  const int64_t grid = cols * p.nseg;
+  if (grid > 0x7fffffffLL) { set_error("tc_slide_conv: grid too large"); return B200SEG_ERR_ARG; }
+  if (BN == 16 && KC == 16) return launch_slide<16, 16>(p, (unsigned)grid, st);
+  if (BN == 16 && KC == 32) return launch_slide<16, 32>(p, (unsigned)grid, st);
+  if (BN == 32 && KC == 16) return launch_slide<32, 16>(p, (unsigned)grid, st);
+  if (BN == 32 && KC == 32) return launch_slide<32, 32>(p, (unsigned)grid, st);
+  set_error("tc_slide_conv: no kernel for BN=%d KC=%d", BN, KC);
+  return B200SEG_ERR_UNSUPPORTED;
+}
+
+}  // namespace b200seg

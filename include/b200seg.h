@@ -62,7 +62,8 @@ enum b200seg_conv_flags {
   /* x-, y- and residual-shaped tensors whose channel count C is not a multiple of 16 carry
    * ZERO padding in channels [C, round_up(C,16)) (so ld >= round_up(C,16)); kernels may read the
    * padding and rewrite it with zeros.  Lets the tcgen05 kernels take the 10-class layers. */
-  B200SEG_CONV_PADDED_CHANNELS = 4
+  B200SEG_CONV_PADDED_CHANNELS = 4,
+  B200SEG_CONV_NO_SLIDE = 8 /* tcgen05 streaming kernel even where the sliding-window kernel applies (tests) */
 };
 
 /*

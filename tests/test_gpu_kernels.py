@@ -142,6 +142,12 @@ TC_GEOMS = [
     (2, 64, 128, 3, 2, False, 2, (32, 48)),
     (2, 128, 64, 3, 2, True, 1, (16, 24)),
     (2, 16, 16, 3, 1, False, 1, (40, 56)),
+    # sliding-window kernels (3x3x3 stride 1, 16/32 channels, larger volumes, ragged tiles, d segments)
+    (3, 16, 16, 3, 1, False, 1, (12, 40, 24)),
+    (3, 32, 32, 3, 1, False, 2, (8, 32, 32)),
+    (3, 10, 10, 3, 1, False, 1, (20, 32, 40)),
+    (3, 16, 32, 3, 1, False, 1, (9, 48, 16)),
+    (3, 32, 16, 3, 1, False, 1, (16, 24, 32)),
 ]
 
 
