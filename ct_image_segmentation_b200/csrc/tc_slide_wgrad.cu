@@ -1,0 +1,257 @@
+// Sliding-window tcgen05 weight gradient for the small-channel / high-resolution 3x3x3 stride-1
+// conv layers:   G[tap][a][b] = sum_v S[v + tap - 1][a] * T[v][b]      (S = x, T = dy)
+//
+// Same column sweep and 3-copy source-slab ring as tc_slide.cu (each S voxel is read 3.4x from L2
+// instead of 27x); T is loaded once per slab.  Voxels are the K dimension, so both operands are
+// MN-major exactly as TMA delivers them.  One tcgen05.mma covers a (kd, kw) pair: its 128 M rows
+// are 128/CA "slots" = consecutive LINE offsets into the S copy (leading-dimension byte offset =
+// one line = one swizzle atom); the first three slots are the taps kh = 0, 1, 2, the other rows are
+// never read back.  The 9 (kd, kw) accumulators x N columns stay in TMEM for the whole sweep and are
+// added to the fp32 result with red.global.add.f32 at the end.
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tc_conv.h"
+
+namespace b200seg {
+
+using bf16 = __nv_bfloat16;
+
+int tc_make_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides,
+                const uint32_t* box, int row_bytes);
+
+namespace {
+constexpr int TH = 16;
+constexpr int TWV = 8;
+constexpr int RING = 4;
+constexpr int RT = 3;
+inline int round16(int c) { return (c + 15) / 16 * 16; }
+}  // namespace
+
+struct alignas(64) TcSlideWgradParams {
+  CUtensorMap tmS;
+  CUtensorMap tmT;
+  int n, D, H, W;
+  int tilesH, tilesW, dseg, nseg;
+  int a_pad, b_pad;
+  float* out;  // [27][a_pad][b_pad]
+};
+
+template <int CA, int CB>
+__global__ void __launch_bounds__(192)
+tc_slide_wgrad_kernel(const __grid_constant__ TcSlideWgradParams p) {
+  constexpr int PA = CA * 2, PB = CB * 2;
+  constexpr int COPY_BYTES = (TH + 2) * TWV * PA;
+  constexpr int SLAB_BYTES = 3 * COPY_BYTES;
+  constexpr int TSLAB_BYTES = TH * TWV * PB;
+  constexpr uint32_t TMEM_COLS = 9 * CB <= 256 ? 256 : 512;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = smem;
+  uint8_t* tring = smem + RING * SLAB_BYTES;  // doubles as the read slack behind the last S copy
+  uint64_t* fullS = reinterpret_cast<uint64_t*>(tring + RT * TSLAB_BYTES);
+  uint64_t* emptyS = fullS + RING;
+  uint64_t* fullT = emptyS + RING;
+  uint64_t* emptyT = fullT + RT;
+  uint64_t* acc_full = emptyT + RT;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int bx = blockIdx.x;
+  const int seg = bx % p.nseg; bx /= p.nseg;
+  const int tw_i = bx % p.tilesW; bx /= p.tilesW;
+  const int th_i = bx % p.tilesH; bx /= p.tilesH;
+  const int n = bx;
+  const int h0 = th_i * TH, w0 = tw_i * TWV;
+  const int d_begin = seg * p.dseg;
+  const int nd = min(p.dseg, p.D - d_begin);
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < RING; ++i) { tc::mbar_init(&fullS[i], 1); tc::mbar_init(&emptyS[i], 1); }
+    for (int i = 0; i < RT; ++i) { tc::mbar_init(&fullT[i], 1); tc::mbar_init(&emptyT[i], 1); }
+    tc::mbar_init(acc_full, 1);
+    tc::fence_barrier_init();
+    tc::prefetch_tmap(&p.tmS);
+    tc::prefetch_tmap(&p.tmT);
+  }
+  if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int s = 0; s < nd + 2; ++s) {
+        const int slot = s % RING;
+        tc::mbar_wait(&emptyS[slot], (((uint32_t)(s / RING)) & 1u) ^ 1u);
+        uint8_t* dst = ring + slot * SLAB_BYTES;
+        tc::mbar_expect_tx(&fullS[slot], SLAB_BYTES);
+        const int ds = d_begin - 1 + s;
+#pragma unroll
+        for (int kw = 0; kw < 3; ++kw)
+          tc::tma_load_5d(dst + kw * COPY_BYTES, &p.tmS, &fullS[slot], 0, w0 + kw - 1, h0 - 1, ds, n);
+        if (s >= 2) {
+          const int j = s - 2, ts = j % RT;
+          tc::mbar_wait(&emptyT[ts], (((uint32_t)(j / RT)) & 1u) ^ 1u);
+          tc::mbar_expect_tx(&fullT[ts], TSLAB_BYTES);
+          tc::tma_load_5d(tring + ts * TSLAB_BYTES, &p.tmT, &fullT[ts], 0, w0, h0, d_begin + j, n);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = tc::make_idesc_bf16(128, CB, true, true);
+      constexpr uint64_t layA = tc::layout_for_row_bytes(PA), layB = tc::layout_for_row_bytes(PB);
+      const uint32_t r_addr = tc::smem_u32(ring), t_addr = tc::smem_u32(tring);
+      int waited = 0;
+      for (int j = 0; j < nd; ++j) {
+        while (waited <= j + 2) {
+          tc::mbar_wait(&fullS[waited % RING], ((uint32_t)(waited / RING)) & 1u);
+          ++waited;
+        }
+        tc::mbar_wait(&fullT[j % RT], ((uint32_t)(j / RT)) & 1u);
+        tc::tc_fence_after();
+        const uint32_t tb = t_addr + (j % RT) * TSLAB_BYTES;
+#pragma unroll 1
+        for (int id = 0; id < 3; ++id) {
+          const uint32_t slab = r_addr + ((j + id) % RING) * SLAB_BYTES;
+#pragma unroll
+          for (int iw = 0; iw < 3; ++iw) {
+            const uint32_t acc = tmem_acc + (id * 3 + iw) * CB;
+#pragma unroll
+            for (int t = 0; t < TH / 2; ++t) {
+              // K step t = output lines 2t, 2t+1; slot i of A starts at S line 2t + i
+              const uint64_t ad = tc::make_smem_desc(slab + iw * COPY_BYTES + (2 * t) * (TWV * PA), TWV * PA,
+                                                     TWV * PA, layA);
+              const uint64_t bd = tc::make_smem_desc(tb + (2 * t) * (TWV * PB), 16, TWV * PB, layB);
+              tc::umma_bf16(acc, ad, bd, idesc, (j > 0 || t > 0) ? 1u : 0u);
+            }
+          }
+        }
+        tc::umma_commit(&emptyS[j % RING]);
+        tc::umma_commit(&emptyT[j % RT]);
+      }
+      tc::umma_commit(acc_full);
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int ih = row / CA, a = row % CA;
+    const bool valid = ih < 3;
+    tc::mbar_wait(acc_full, 0);
+    tc::tc_fence_after();
+    if (q * 32 < 3 * CA) {  // warp-uniform: only the first 3*CA accumulator rows are taps
+      for (int acc = 0; acc < 9; ++acc) {
+        const int id = acc / 3, iw = acc % 3;
+        const int tap = (id * 3 + (valid ? ih : 0)) * 3 + iw;
+        float* orow = p.out + ((int64_t)tap * p.a_pad + a) * p.b_pad;
+#pragma unroll
+        for (int ch = 0; ch < CB / 16; ++ch) {
+          uint32_t v[16];
+          tc::tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + acc * CB + ch * 16, v);
+          tc::tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) atomicAdd(orow + ch * 16 + i, __uint_as_float(v[i]));
+          }
+        }
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tc::tmem_dealloc<TMEM_COLS>(tmem_acc);
+}
+
+__global__ void tc_slide_wgrad_unpack_kernel(const float* __restrict__ G, float* __restrict__ gw, int taps, int a_c,
+                                             int b_c, int a_pad, int b_pad) {
+  int64_t total = (int64_t)taps * a_c * b_c;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  int b = (int)(idx % b_c);
+  int64_t r = idx / b_c;
+  int a = (int)(r % a_c);
+  int tap = (int)(r / a_c);
+  gw[((int64_t)b * a_c + a) * taps + tap] = G[((int64_t)tap * a_pad + a) * b_pad + b];
+}
+
+namespace {
+template <int CA, int CB>
+int launch_slide_wgrad(const TcSlideWgradParams& p, unsigned grid, cudaStream_t st) {
+  constexpr int SLAB = 3 * (TH + 2) * TWV * CA * 2;
+  constexpr int TSLAB = TH * TWV * CB * 2;
+  const size_t smem = 1024 + RING * SLAB + RT * TSLAB + 32 * 8 + 64;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(tc_slide_wgrad_kernel<CA, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    attr_set = true;
+  }
+  tc_slide_wgrad_kernel<CA, CB><<<grid, 192, smem, st>>>(p);
+  B200SEG_CHECK_LAUNCH("tc_slide_wgrad");
+  count_tc_launch();
+  return B200SEG_OK;
+}
+}  // namespace
+
+// conv layers only (S = x, T = dy): 3-D 3x3x3 stride 1, padded channel counts in {16, 32}
+bool tc_slide_wgrad_supported(const b200seg_conv_desc* d, bool transposed_layer) {
+  if (transposed_layer || (d->flags & B200SEG_CONV_NO_SLIDE)) return false;
+  if (d->kd != 3 || d->kh != 3 || d->kw != 3 || d->sd != 1 || d->sh != 1 || d->sw != 1) return false;
+  const int ap = round16(d->cin), bp = round16(d->cout);
+  if ((ap != 16 && ap != 32) || (bp != 16 && bp != 32)) return false;
+  if (d->in_d < 8 || (int64_t)d->in_h * d->in_w < 512) return false;
+  return true;
+}
+
+int tc_slide_wgrad_run(const b200seg_conv_desc* d, const void* x, const void* dy, float* gw, float* G32,
+                       cudaStream_t st) {
+  TcSlideWgradParams p;
+  memset(&p, 0, sizeof(p));
+  const int CA = round16(d->cin), CB = round16(d->cout);
+  p.n = d->n; p.D = d->in_d; p.H = d->in_h; p.W = d->in_w;
+  p.tilesH = (p.H + TH - 1) / TH; p.tilesW = (p.W + TWV - 1) / TWV;
+  const int64_t cols = (int64_t)p.n * p.tilesH * p.tilesW;
+  int nseg = (int)((148 * 3 + cols - 1) / cols);
+  if (nseg < 1) nseg = 1;
+  int dseg = (p.D + nseg - 1) / nseg;
+  if (dseg < 8) dseg = 8;
+  if (dseg > p.D) dseg = p.D;
+  p.dseg = dseg; p.nseg = (p.D + dseg - 1) / dseg;
+  p.a_pad = CA; p.b_pad = CB; p.out = G32;
+  {
+    uint64_t dims[5] = {(uint64_t)CA, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.D, (uint64_t)p.n};
+    uint64_t strides[4] = {(uint64_t)d->x_ld * 2, (uint64_t)p.W * d->x_ld * 2, (uint64_t)p.H * p.W * d->x_ld * 2,
+                           (uint64_t)p.D * p.H * p.W * d->x_ld * 2};
+    uint32_t box[5] = {(uint32_t)CA, (uint32_t)TWV, (uint32_t)(TH + 2), 1, 1};
+    int rc = tc_make_map(&p.tmS, x, 5, dims, strides, box, CA * 2);
+    if (rc) return rc;
+  }
+  {
+    uint64_t dims[5] = {(uint64_t)CB, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.D, (uint64_t)p.n};
+    uint64_t strides[4] = {(uint64_t)d->y_ld * 2, (uint64_t)p.W * d->y_ld * 2, (uint64_t)p.H * p.W * d->y_ld * 2,
+                           (uint64_t)p.D * p.H * p.W * d->y_ld * 2};
+    uint32_t box[5] = {(uint32_t)CB, (uint32_t)TWV, (uint32_t)TH, 1, 1};
+    int rc = tc_make_map(&p.tmT, dy, 5, dims, strides, box, CB * 2);
+    if (rc) return rc;
+  }
+  cudaError_t e = cudaMemsetAsync(G32, 0, (size_t)27 * CA * CB * sizeof(float), st);
+  if (e != cudaSuccess) {
+    set_error("tc_slide_wgrad: memset failed: %s", cudaGetErrorString(e));
+    return B200SEG_ERR_CUDA;
+  }
+  const int64_t grid = cols * p.nseg;
+  int rc;
+  if (CA == 16 && CB == 16) rc = launch_slide_wgrad<16, 16>(p, (unsigned)grid, st);
+  else if (CA == 16 && CB == 32) rc = launch_slide_wgrad<16, 32>(p, (unsigned)grid, st);
+  else if (CA == 32 && CB == 16) rc = launch_slide_wgrad<32, 16>(p, (unsigned)grid, st);
+  else rc = launch_slide_wgrad<32, 32>(p, (unsigned)grid, st);
+  if (rc) return rc;
+  const int64_t total = (int64_t)27 * d->cin * d->cout;
+  tc_slide_wgrad_unpack_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(G32, gw, 27, d->cin, d->cout, CA, CB);
+  B200SEG_CHECK_LAUNCH("tc_slide_wgrad_unpack");
+  return B200SEG_OK;
+}
+
+}  // namespace b200seg
