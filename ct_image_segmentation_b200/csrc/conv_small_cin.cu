@@ -92,13 +92,22 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 conv_small_cin_wgrad_kernel(SmallCinParams p, const T* __restrict__ x, const T* __restrict__ dy,
                             float* __restrict__ partial, int64_t vox_per_block) {
-  constexpr int VC = 32;             // voxels per chunk
-  extern __shared__ float sm[];      // X[VC][J] | DY[VC][cout]
+  constexpr int VC = 64;             // voxels per chunk
+  extern __shared__ float sm[];      // X[J][VC] | DY[VC][cout] | per-voxel base offsets | tap table
   const int taps = p.kd * p.kh * p.kw;
   const int J = taps * p.cin;
   const int CO = p.cout;
-  float* Xs = sm;
-  float* Ds = sm + VC * J;
+  float* Xs = sm;                    // [J][VC]
+  float* Ds = sm + (VC + 1) * J;     // [VC][CO]
+  int* vbase = reinterpret_cast<int*>(Ds + VC * CO);   // [VC][4]: n, id0, ih0, iw0 (n < 0: no voxel)
+  int* jtab = vbase + VC * 4;        // [J][4]: kd, kh, kw, ci
+  for (int j = threadIdx.x; j < J; j += 256) {
+    const int tap = j / p.cin;
+    jtab[j * 4 + 0] = tap / (p.kw * p.kh);
+    jtab[j * 4 + 1] = (tap / p.kw) % p.kh;
+    jtab[j * 4 + 2] = tap % p.kw;
+    jtab[j * 4 + 3] = j % p.cin;
+  }
   const int nout = J * CO;
   constexpr int R = 8;  // outputs per thread (J*CO <= 256*R)
   float acc[R];
@@ -107,30 +116,39 @@ conv_small_cin_wgrad_kernel(SmallCinParams p, const T* __restrict__ x, const T* 
   for (int r = 0; r < R; ++r) {
     acc[r] = 0.f;
     int o = threadIdx.x + r * 256;
-    oj[r] = o < nout ? o / CO : 0;
+    oj[r] = o < nout ? (o / CO) * (VC + 1) : 0;
     oc[r] = o < nout ? o % CO : 0;
   }
   const int64_t v_begin = (int64_t)blockIdx.x * vox_per_block;
   const int64_t v_end = min(v_begin + vox_per_block, p.nvox);
   for (int64_t v0 = v_begin; v0 < v_end; v0 += VC) {
-    // gather X
-    for (int i = threadIdx.x; i < VC * J; i += 256) {
-      const int lv = i / J, j = i % J;
-      const int64_t v = v0 + lv;
-      float val = 0.f;
+    __syncthreads();
+    if (threadIdx.x < VC) {
+      const int64_t v = v0 + threadIdx.x;
+      int nn = -1, id0 = 0, ih0 = 0, iw0 = 0;
       if (v < v_end) {
         int64_t r = v;
         const int ow = (int)(r % p.oW); r /= p.oW;
         const int oh = (int)(r % p.oH); r /= p.oH;
         const int od = (int)(r % p.oD); r /= p.oD;
-        const int n = (int)r;
-        const int tap = j / p.cin, ci = j % p.cin;
-        const int kw = tap % p.kw, kh = (tap / p.kw) % p.kh, kd = tap / (p.kw * p.kh);
-        const int id = od * p.sd - p.pd + kd, ih = oh * p.sh - p.ph + kh, iw = ow * p.sw - p.pw + kw;
-        if (id >= 0 && id < p.iD && ih >= 0 && ih < p.iH && iw >= 0 && iw < p.iW)
-          val = to_f<T>(x[((((int64_t)n * p.iD + id) * p.iH + ih) * p.iW + iw) * (int64_t)p.x_ld + ci]);
+        nn = (int)r;
+        id0 = od * p.sd - p.pd; ih0 = oh * p.sh - p.ph; iw0 = ow * p.sw - p.pw;
       }
-      Xs[i] = val;
+      vbase[threadIdx.x * 4 + 0] = nn; vbase[threadIdx.x * 4 + 1] = id0;
+      vbase[threadIdx.x * 4 + 2] = ih0; vbase[threadIdx.x * 4 + 3] = iw0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < VC * J; i += 256) {
+      const int lv = i % VC, j = i / VC;  // consecutive threads -> consecutive voxels
+      const int nn = vbase[lv * 4];
+      float val = 0.f;
+      if (nn >= 0) {
+        const int id = vbase[lv * 4 + 1] + jtab[j * 4], ih = vbase[lv * 4 + 2] + jtab[j * 4 + 1],
+                  iw = vbase[lv * 4 + 3] + jtab[j * 4 + 2];
+        if (id >= 0 && id < p.iD && ih >= 0 && ih < p.iH && iw >= 0 && iw < p.iW)
+          val = to_f<T>(x[((((int64_t)nn * p.iD + id) * p.iH + ih) * p.iW + iw) * (int64_t)p.x_ld + jtab[j * 4 + 3]]);
+      }
+      Xs[j * (VC + 1) + lv] = val;  // Xs[j][lv], padded rows: conflict-free column reads
     }
     for (int i = threadIdx.x; i < VC * CO; i += 256) {
       const int lv = i / CO, c = i % CO;
@@ -140,12 +158,10 @@ conv_small_cin_wgrad_kernel(SmallCinParams p, const T* __restrict__ x, const T* 
     __syncthreads();
 #pragma unroll 4
     for (int lv = 0; lv < VC; ++lv) {
-      const float* xr = Xs + lv * J;
       const float* dr = Ds + lv * CO;
 #pragma unroll
-      for (int r = 0; r < R; ++r) acc[r] = fmaf(xr[oj[r]], dr[oc[r]], acc[r]);
+      for (int r = 0; r < R; ++r) acc[r] = fmaf(Xs[oj[r] + lv], dr[oc[r]], acc[r]);
     }
-    __syncthreads();
   }
   float* out = partial + (int64_t)blockIdx.x * nout;
 #pragma unroll
@@ -155,17 +171,20 @@ conv_small_cin_wgrad_kernel(SmallCinParams p, const T* __restrict__ x, const T* 
   }
 }
 
-// gw[co][ci][tap] = sum_blk partial[blk][tap*cin+ci][co]
+// gw[co][ci][tap] = sum_blk partial[blk][tap*cin+ci][co]; one warp per output, fixed order
 __global__ void conv_small_cin_wgrad_final_kernel(const float* __restrict__ partial, int nblk, int taps,
                                                   int cin, int cout, float* __restrict__ gw) {
   const int nout = taps * cin * cout;
-  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  const int o = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
   if (o >= nout) return;
   double s = 0.0;
-  for (int b = 0; b < nblk; ++b) s += (double)partial[(int64_t)b * nout + o];
-  const int co = o % cout, j = o / cout;
-  const int tap = j / cin, ci = j % cin;
-  gw[((int64_t)co * cin + ci) * taps + tap] = (float)s;
+  for (int b = lane; b < nblk; b += 32) s += (double)partial[(int64_t)b * nout + o];
+  s = warp_sum_d(s);
+  if (lane == 0) {
+    const int co = o % cout, j = o / cout;
+    const int tap = j / cin, ci = j % cin;
+    gw[((int64_t)co * cin + ci) * taps + tap] = (float)s;
+  }
 }
 
 namespace {
@@ -220,8 +239,8 @@ int launch_small_cin_wgrad(const b200seg_conv_desc* d, const void* x, const void
   fill(p, d);
   const int taps = d->kd * d->kh * d->kw, J = taps * d->cin;
   const int nb = small_cin_wgrad_blocks(d);
-  int64_t per = cdiv64(cdiv64(p.nvox, nb), 32) * 32;
-  size_t smem = (size_t)32 * (J + d->cout) * sizeof(float);
+  int64_t per = cdiv64(cdiv64(p.nvox, nb), 64) * 64;
+  size_t smem = (size_t)(65 * J + 64 * d->cout) * sizeof(float) + (size_t)(64 * 4 + J * 4) * sizeof(int);
   if (d->dtype == B200SEG_BF16)
     conv_small_cin_wgrad_kernel<__nv_bfloat16><<<nb, 256, smem, st>>>(p, (const __nv_bfloat16*)x,
                                                                       (const __nv_bfloat16*)dy, partial, per);
@@ -229,7 +248,7 @@ int launch_small_cin_wgrad(const b200seg_conv_desc* d, const void* x, const void
     conv_small_cin_wgrad_kernel<float><<<nb, 256, smem, st>>>(p, (const float*)x, (const float*)dy, partial, per);
   B200SEG_CHECK_LAUNCH("conv_small_cin_wgrad");
   const int nout = J * d->cout;
-  conv_small_cin_wgrad_final_kernel<<<(nout + 127) / 128, 128, 0, st>>>(partial, nb, taps, d->cin, d->cout, gw);
+  conv_small_cin_wgrad_final_kernel<<<(nout * 32 + 255) / 256, 256, 0, st>>>(partial, nb, taps, d->cin, d->cout, gw);
   B200SEG_CHECK_LAUNCH("conv_small_cin_wgrad_final");
   return B200SEG_OK;
 }

@@ -27,13 +27,34 @@ __device__ __forceinline__ int load_label(const void* labels, int64_t idx) {
 
 // softmax of one voxel: p[0..C) (entries >= C are 0).  Plain expf / division in fp32, i.e. the
 // arithmetic `torch.softmax` performs (max-subtracted exponentials over their sum).
+// vec16: the voxel row is 16 bf16 (32 B, 16-byte aligned): two 128-bit loads instead of C scalar ones
 template <typename T, int CMAX>
-__device__ __forceinline__ void voxel_softmax(const T* z, int C, float (&p)[CMAX]) {
+__device__ __forceinline__ void voxel_softmax(const T* z, int C, float (&p)[CMAX], bool vec16 = false) {
   float mx = -INFINITY;
+  if constexpr (sizeof(T) == 2 && CMAX == 16) {
+    if (vec16) {
+      const uint4* zp = reinterpret_cast<const uint4*>(z);
+      uint4 r0 = zp[0], r1 = zp[1];
+      const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+      const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
 #pragma unroll
-  for (int c = 0; c < CMAX; ++c) {
-    p[c] = c < C ? to_f<T>(z[c]) : -INFINITY;
-    mx = fmaxf(mx, p[c]);
+      for (int i = 0; i < 4; ++i) {
+        float2 a = __bfloat1622float2(h0[i]), b = __bfloat1622float2(h1[i]);
+        p[2 * i] = a.x; p[2 * i + 1] = a.y; p[8 + 2 * i] = b.x; p[8 + 2 * i + 1] = b.y;
+      }
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c) {
+        p[c] = c < C ? p[c] : -INFINITY;
+        mx = fmaxf(mx, p[c]);
+      }
+    }
+  }
+  if (mx == -INFINITY) {
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      p[c] = c < C ? to_f<T>(z[c]) : -INFINITY;
+      mx = fmaxf(mx, p[c]);
+    }
   }
   float s = 0.f;
 #pragma unroll
@@ -47,6 +68,13 @@ __device__ __forceinline__ void voxel_softmax(const T* z, int C, float (&p)[CMAX
 
 }  // namespace
 
+// bf16 logits stored as 16-channel rows (10 classes zero-padded, B200SEG padded buffers): the row
+// can be moved with two 128-bit accesses; a destination row may be fully rewritten (padding = 0)
+static bool vec16_ok(const b200seg_dice_desc& d, const void* a, const void* b) {
+  return d.dtype == B200SEG_BF16 && d.ld == 16 && d.c <= 16 && ((uintptr_t)a % 16) == 0 &&
+         ((uintptr_t)b % 16) == 0;
+}
+
 size_t dice_workspace_bytes(const b200seg_dice_desc& d) {
   return (size_t)d.n * dice_blocks(d.spatial, d.n) * d.c * 3 * sizeof(float) + 256;
 }
@@ -56,7 +84,7 @@ template <typename T, int CMAX, int LT>
 __global__ void __launch_bounds__(kDiceThreads)
 softmax_dice_fwd_kernel(const T* __restrict__ logits, const void* __restrict__ labels,
                         int64_t spatial, int C, int ld, int64_t vox_per_block,
-                        float* __restrict__ partial) {
+                        float* __restrict__ partial, bool vec16) {
   __shared__ float red[kDiceThreads / 32][CMAX * 3];
   const int n = blockIdx.y;
   const int64_t v_begin = (int64_t)blockIdx.x * vox_per_block;
@@ -67,7 +95,7 @@ softmax_dice_fwd_kernel(const T* __restrict__ logits, const void* __restrict__ l
   for (int64_t v = v_begin + threadIdx.x; v < v_end; v += kDiceThreads) {
     int64_t vox = (int64_t)n * spatial + v;
     float p[CMAX];
-    voxel_softmax<T, CMAX>(logits + vox * ld, C, p);
+    voxel_softmax<T, CMAX>(logits + vox * ld, C, p, vec16);
     int lab = load_label<LT>(labels, vox);
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
@@ -111,7 +139,7 @@ template <typename T, int CMAX, int LT>
 __global__ void __launch_bounds__(kDiceThreads)
 softmax_dice_bwd_kernel(const T* __restrict__ logits, const void* __restrict__ labels,
                         const float* __restrict__ gI, const float* __restrict__ gP,
-                        T* __restrict__ dlogits, int64_t spatial, int C, int ld) {
+                        T* __restrict__ dlogits, int64_t spatial, int C, int ld, bool vec16) {
   const int n = blockIdx.y;
   float cI[CMAX], cP[CMAX];
 #pragma unroll
@@ -123,7 +151,7 @@ softmax_dice_bwd_kernel(const T* __restrict__ logits, const void* __restrict__ l
        v += (int64_t)gridDim.x * kDiceThreads) {
     int64_t vox = (int64_t)n * spatial + v;
     float p[CMAX];
-    voxel_softmax<T, CMAX>(logits + vox * ld, C, p);
+    voxel_softmax<T, CMAX>(logits + vox * ld, C, p, vec16);
     int lab = load_label<LT>(labels, vox);
     float g[CMAX];
     float dot = 0.f;
@@ -133,9 +161,30 @@ softmax_dice_bwd_kernel(const T* __restrict__ logits, const void* __restrict__ l
       dot = fmaf(g[c], p[c], dot);
     }
     T* o = dlogits + vox * ld;
+    bool done = false;
+    if constexpr (sizeof(T) == 2 && CMAX == 16) {
+      if (vec16) {  // 16-channel padded row: write all 16 (padding = 0) with two 128-bit stores
+        uint4 o0, o1;
+        __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+        __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+        float dz[16];
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c)
-      if (c < C) o[c] = from_f<T>(p[c] * (g[c] - dot));
+        for (int c = 0; c < 16; ++c) dz[c] = c < C ? p[c] * (g[c] - dot) : 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          q0[i] = __floats2bfloat162_rn(dz[2 * i], dz[2 * i + 1]);
+          q1[i] = __floats2bfloat162_rn(dz[8 + 2 * i], dz[8 + 2 * i + 1]);
+        }
+        reinterpret_cast<uint4*>(o)[0] = o0;
+        reinterpret_cast<uint4*>(o)[1] = o1;
+        done = true;
+      }
+    }
+    if (!done) {
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) o[c] = from_f<T>(p[c] * (g[c] - dot));
+    }
   }
 }
 
@@ -144,7 +193,7 @@ template <typename T, int CMAX, int LT>
 __global__ void __launch_bounds__(kDiceThreads)
 argmax_counts_kernel(const T* __restrict__ logits, const void* __restrict__ target,
                      uint8_t* __restrict__ pred_out, unsigned long long* __restrict__ counts,
-                     int64_t spatial, int C, int ld) {
+                     int64_t spatial, int C, int ld, bool vec16) {
   __shared__ unsigned int red[CMAX * 3];
   const int n = blockIdx.y;
   if (threadIdx.x < CMAX * 3) red[threadIdx.x] = 0u;
@@ -156,7 +205,7 @@ argmax_counts_kernel(const T* __restrict__ logits, const void* __restrict__ targ
        v += (int64_t)gridDim.x * kDiceThreads) {
     int64_t vox = (int64_t)n * spatial + v;
     float p[CMAX];
-    voxel_softmax<T, CMAX>(logits + vox * ld, C, p);
+    voxel_softmax<T, CMAX>(logits + vox * ld, C, p, vec16);
     int best = 0;
     float bv = p[0];
 #pragma unroll
@@ -280,7 +329,7 @@ int launch_softmax_dice_fwd(const b200seg_dice_desc& d, const void* logits, cons
   dim3 grid(nb, d.n);
   float* partial = (float*)ws;
   DISPATCH_DICE(d, (softmax_dice_fwd_kernel<T, CM, LT><<<grid, kDiceThreads, 0, st>>>(
-                       (const T*)logits, labels, d.spatial, d.c, d.ld, per, partial)));
+                       (const T*)logits, labels, d.spatial, d.c, d.ld, per, partial, vec16_ok(d, logits, nullptr))));
   B200SEG_CHECK_LAUNCH("softmax_dice_fwd");
   int total = d.n * d.c * 3;
   dice_sums_final_kernel<<<(total * 32 + 255) / 256, 256, 0, st>>>(partial, nb, d.c * 3, total, sums);
@@ -296,7 +345,8 @@ int launch_softmax_dice_bwd(const b200seg_dice_desc& d, const void* logits, cons
   if (nb > cap) nb = cap;
   dim3 grid((unsigned)nb, d.n);
   DISPATCH_DICE(d, (softmax_dice_bwd_kernel<T, CM, LT><<<grid, kDiceThreads, 0, st>>>(
-                       (const T*)logits, labels, gI, gP, (T*)dlogits, d.spatial, d.c, d.ld)));
+                       (const T*)logits, labels, gI, gP, (T*)dlogits, d.spatial, d.c, d.ld,
+                       vec16_ok(d, logits, dlogits))));
   B200SEG_CHECK_LAUNCH("softmax_dice_bwd");
   return B200SEG_OK;
 }
@@ -317,7 +367,7 @@ int launch_argmax_dice_counts(const b200seg_dice_desc& d, const void* logits, co
   dim3 grid((unsigned)nb, d.n);
   DISPATCH_DICE(d, (argmax_counts_kernel<T, CM, LT><<<grid, kDiceThreads, 0, st>>>(
                        (const T*)logits, target, pred_out, (unsigned long long*)counts, d.spatial,
-                       d.c, d.ld)));
+                       d.c, d.ld, vec16_ok(d, logits, nullptr))));
   B200SEG_CHECK_LAUNCH("argmax_counts");
   return B200SEG_OK;
 }

@@ -365,6 +365,11 @@ int tc_wgrad_run(const b200seg_conv_desc* d, bool transposed_layer, const void* 
   int64_t max_split = (p.total_tiles + 3) / 4;
   if (max_split < 1) max_split = 1;
   int64_t splits = want < max_split ? want : max_split;
+  // every split adds taps*a_pad*b_pad fp32 red.global.add: keep that below ~4 M per launch
+  const int64_t g_elems = (int64_t)taps * a_pad * b_pad;
+  int64_t atomic_cap = (4 << 20) / g_elems;
+  if (atomic_cap < 1) atomic_cap = 1;
+  if (splits > atomic_cap) splits = atomic_cap;
   if (splits < 1) splits = 1;
   p.tiles_per_cta = (int)((p.total_tiles + splits - 1) / splits);
   splits = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;

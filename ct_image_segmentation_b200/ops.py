@@ -248,6 +248,30 @@ def conv_wgrad(geom: ConvGeom, x, dy, want_bias: bool = True, flags=0):
 # ----------------------------------------------------------------------------------------------
 # InstanceNorm + PReLU
 # ----------------------------------------------------------------------------------------------
+def _expand_pad(t: Optional[torch.Tensor]):
+    """Zero-padded buffer (see ``alloc_activation``) viewed with its padding channels included, so
+    the bandwidth-bound kernels run their 16-byte vector path on e.g. the 10-class tensors.  The
+    padding stays zero under InstanceNorm + PReLU (x = 0 -> mean 0, xhat 0, output 0, gradient 0)."""
+    if t is None or t.shape[-1] % 16 == 0 or not _pad_safe(t):
+        return None
+    cp = (t.shape[-1] + 15) // 16 * 16
+    return t.as_strided(tuple(t.shape[:-1]) + (cp,), t.stride())
+
+
+def _expand_all(*ts):
+    """All given (non-None) tensors expanded, or None if any of them cannot be."""
+    out = []
+    for t in ts:
+        if t is None:
+            out.append(None)
+            continue
+        e = _expand_pad(t)
+        if e is None:
+            return None
+        out.append(e)
+    return out
+
+
 def _norm_desc(x, y_ld, r_ld, eps):
     n, d, h, w, c, x_ld = cl_info(x)
     return NormDesc(n, c, d * h * w, x_ld, y_ld, r_ld, dtype_code(x.dtype), eps), (n, c)
@@ -255,6 +279,9 @@ def _norm_desc(x, y_ld, r_ld, eps):
 
 def instnorm_stats(x, eps: float = 1e-5):
     lib = _lib.load()
+    ex = _expand_pad(x)
+    if ex is not None:
+        x = ex  # statistics for C_pad channels; fwd / bwd recognise that from mean.numel()
     d, (n, c) = _norm_desc(x, 0, 0, eps)
     mean = torch.empty(n * c, dtype=torch.float32, device=x.device)
     rstd = torch.empty(n * c, dtype=torch.float32, device=x.device)
@@ -265,8 +292,21 @@ def instnorm_stats(x, eps: float = 1e-5):
     return mean, rstd
 
 
+def _match_stats(mean, what, x, *others):
+    """Statistics were taken over the zero-padded channel count: expand every operand the same way."""
+    n, c = x.shape[0], x.shape[-1]
+    if mean.numel() == n * c:
+        return (x, *others)
+    ex = _expand_all(x, *others)
+    if ex is None or mean.numel() != n * ex[0].shape[-1]:
+        raise ValueError(f"{what}: statistics for {mean.numel() // n} channels do not match the operands")
+    return tuple(ex)
+
+
 def instnorm_prelu_fwd(x, mean, rstd, alpha, y, residual=None, eps: float = 1e-5):
     lib = _lib.load()
+    y_out = y
+    x, y, residual = _match_stats(mean, "instnorm_prelu_fwd", x, y, residual)
     y_ld = cl_info(y)[5]
     r_ld = cl_info(residual)[5] if residual is not None else 0
     if y.shape != x.shape or (residual is not None and residual.shape != x.shape):
@@ -275,7 +315,7 @@ def instnorm_prelu_fwd(x, mean, rstd, alpha, y, residual=None, eps: float = 1e-5
     _lib.check(lib.b200seg_instnorm_prelu_fwd(C.byref(d), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
                                               alpha.data_ptr(), _ptr(residual), y.data_ptr(), _stream()),
                "b200seg_instnorm_prelu_fwd")
-    return y
+    return y_out
 
 
 def instnorm_prelu_bwd(x, mean, rstd, alpha, dy, dx, eps: float = 1e-5):
@@ -283,6 +323,7 @@ def instnorm_prelu_bwd(x, mean, rstd, alpha, dy, dx, eps: float = 1e-5):
     lib = _lib.load()
     if dy.shape != x.shape or dx.shape != x.shape:
         raise ValueError("instnorm_prelu_bwd: shape mismatch")
+    x, dy, dx = _match_stats(mean, "instnorm_prelu_bwd", x, dy, dx)
     d, _ = _norm_desc(x, cl_info(dy)[5], cl_info(dx)[5], eps)
     dalpha = torch.empty(1, dtype=torch.float32, device=x.device)
     nbytes = lib.b200seg_instnorm_workspace_bytes(C.byref(d))

@@ -53,7 +53,7 @@ for m_e, s in fw_e.items():
     if not isinstance(m_e, U.Convolution): continue
     sg = fw_g[mods_g[n]]
     if s.get("c") is not None:
-        print(f"{n:70s} c {rel(sg['c'], s['c']):.2e} mean {rel(sg['mean'], s['mean']):.2e} rstd {rel(sg['rstd'], s['rstd']):.2e}")
+        print(f"{n:70s} c {rel(sg['c'], s['c']):.2e} ")
 print("--- backward taps d/d conv-out, in backward order")
 for m_e, t in taps_e.items():
     n = names_e[m_e]
