@@ -12,9 +12,10 @@ from .losses import (DiceLoss, DiceLossWrapper, GeneralizedDiceLoss, MultipleLos
 from .metrics import (DiceMetricWrapper, DiceMetricWrapper3D, dice_from_counts, squash_masks,
                       squash_predictions)
 from .unet import UNet
+from .engine import GraphedTrainStep
 
 __all__ = [
-    "UNet", "DiceLoss", "GeneralizedDiceLoss", "DiceLossWrapper", "MultipleLossWrapper",
+    "UNet", "GraphedTrainStep", "DiceLoss", "GeneralizedDiceLoss", "DiceLossWrapper", "MultipleLossWrapper",
     "MultipleLossWrapper3D", "DiceMetricWrapper", "DiceMetricWrapper3D", "apply_missing_mask",
     "squash_masks", "squash_predictions", "dice_from_counts", "STRUCTURES", "N_CLASSES",
 ]

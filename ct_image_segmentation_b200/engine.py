@@ -1,0 +1,91 @@
+"""Whole-step CUDA-graph execution: forward + loss + backward captured once, replayed per step.
+
+A training step of the 16-256 U-Net is ~250 kernel launches of a few microseconds each; issued
+eagerly from Python they are host-bound ("Scaling >= 7x").  All b200seg
+launches go to the current stream, allocate nothing themselves and never synchronise, so the
+step can be captured into one CUDA graph (activations live in the graph's private pool, TMA
+descriptors are encoded at capture time for those fixed addresses).  The packed weights are
+refreshed INSIDE the graph (the pack kernels are captured), so optimiser updates between
+replays are picked up.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional
+
+import torch
+import torch.distributed as dist
+
+from .parallel import GradientBucket
+from .unet import UNet
+
+
+class GraphedTrainStep:
+    """``step(images, labels) -> loss`` with forward + loss + backward replayed from a CUDA graph,
+    then (eagerly) one flat gradient all-reduce over the data-parallel group and the optimiser.
+
+    ``images`` / ``labels`` may live on the host (pinned) or on the device; they are copied into
+    the graph's static input buffers.  The returned loss is a device scalar (no host sync).
+    """
+
+    def __init__(self, net: UNet, loss_fn: Callable, optimizer: Optional[torch.optim.Optimizer],
+                 images: torch.Tensor, labels: torch.Tensor, warmup: int = 2, use_graph: bool = True):
+        self.net, self.loss_fn, self.optimizer = net, loss_fn, optimizer
+        dev = next(net.parameters()).device
+        self.static_images = torch.empty(images.shape, dtype=images.dtype, device=dev)
+        self.static_labels = torch.empty(labels.shape, dtype=labels.dtype, device=dev)
+        self.static_images.copy_(images)
+        self.static_labels.copy_(labels)
+        self.bucket = GradientBucket(net.parameters())
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.loss: Optional[torch.Tensor] = None
+        self.use_graph = use_graph
+        if use_graph:
+            self._capture(warmup)
+
+    def _fwd_bwd(self):
+        loss = self.loss_fn(self.net(self.static_images), self.static_labels.unsqueeze(1))
+        loss.backward()
+        return loss
+
+    def _capture(self, warmup: int):
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # warm-up off the default stream, as graph capture requires
+            for _ in range(max(1, warmup)):
+                for p in self.bucket.params:
+                    p.grad = None
+                self._fwd_bwd()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        for p in self.bucket.params:
+            p.grad = None
+        self.net.reset_packed_cache()  # the weight-repack kernels must be part of the graph
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.loss = self._fwd_bwd()
+            grads = [p.grad for p in self.bucket.params]
+            torch._foreach_copy_(self.bucket.views, grads)
+        for p, v in zip(self.bucket.params, self.bucket.views):
+            p.grad = v  # the optimiser reads the (all-reduced) bucket
+
+    def __call__(self, images: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None):
+        if images is not None:
+            self.static_images.copy_(images, non_blocking=True)
+        if labels is not None:
+            self.static_labels.copy_(labels, non_blocking=True)
+        if self.graph is not None:
+            self.graph.replay()
+            loss = self.loss
+        else:
+            for p in self.bucket.params:
+                p.grad = None
+            loss = self._fwd_bwd()
+            torch._foreach_copy_(self.bucket.views, [p.grad for p in self.bucket.params])
+            for p, v in zip(self.bucket.params, self.bucket.views):
+                p.grad = v
+        if dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.SUM)
+            self.bucket.flat.mul_(1.0 / dist.get_world_size())
+        if self.optimizer is not None:
+            self.optimizer.step()
+        return loss

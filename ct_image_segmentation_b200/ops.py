@@ -292,21 +292,25 @@ def instnorm_stats(x, eps: float = 1e-5):
     return mean, rstd
 
 
-def _match_stats(mean, what, x, *others):
-    """Statistics were taken over the zero-padded channel count: expand every operand the same way."""
+def _match_stats(mean, rstd, what, x, *others):
+    """Statistics may have been taken over the zero-padded channel count: expand every operand the
+    same way, or (if one of them is a concat slice) cut the statistics back to C channels."""
     n, c = x.shape[0], x.shape[-1]
     if mean.numel() == n * c:
-        return (x, *others)
+        return (mean, rstd, x, *others)
     ex = _expand_all(x, *others)
-    if ex is None or mean.numel() != n * ex[0].shape[-1]:
-        raise ValueError(f"{what}: statistics for {mean.numel() // n} channels do not match the operands")
-    return tuple(ex)
+    if ex is not None and mean.numel() == n * ex[0].shape[-1]:
+        return (mean, rstd, *ex)
+    cs = mean.numel() // n  # some operand is a concat slice: run on C channels with sliced statistics
+    if cs < c:
+        raise ValueError(f"{what}: statistics for {cs} channels do not match the operands")
+    return (mean.view(n, cs)[:, :c].contiguous(), rstd.view(n, cs)[:, :c].contiguous(), x, *others)
 
 
 def instnorm_prelu_fwd(x, mean, rstd, alpha, y, residual=None, eps: float = 1e-5):
     lib = _lib.load()
     y_out = y
-    x, y, residual = _match_stats(mean, "instnorm_prelu_fwd", x, y, residual)
+    mean, rstd, x, y, residual = _match_stats(mean, rstd, "instnorm_prelu_fwd", x, y, residual)
     y_ld = cl_info(y)[5]
     r_ld = cl_info(residual)[5] if residual is not None else 0
     if y.shape != x.shape or (residual is not None and residual.shape != x.shape):
@@ -323,7 +327,7 @@ def instnorm_prelu_bwd(x, mean, rstd, alpha, dy, dx, eps: float = 1e-5):
     lib = _lib.load()
     if dy.shape != x.shape or dx.shape != x.shape:
         raise ValueError("instnorm_prelu_bwd: shape mismatch")
-    x, dy, dx = _match_stats(mean, "instnorm_prelu_bwd", x, dy, dx)
+    mean, rstd, x, dy, dx = _match_stats(mean, rstd, "instnorm_prelu_bwd", x, dy, dx)
     d, _ = _norm_desc(x, cl_info(dy)[5], cl_info(dx)[5], eps)
     dalpha = torch.empty(1, dtype=torch.float32, device=x.device)
     nbytes = lib.b200seg_instnorm_workspace_bytes(C.byref(d))

@@ -199,6 +199,11 @@ class UNet(nn.Module):
         return taps
 
     # ---- weights ---------------------------------------------------------------------------
+    def reset_packed_cache(self) -> None:
+        """Forget the packed weights so that the next forward re-packs every layer (needed right
+        before CUDA-graph capture: the pack kernels must be recorded into the graph)."""
+        self._packed.clear()
+
     def _pack(self, param: torch.Tensor, geom: ConvGeom, kind: int) -> torch.Tensor:
         key = (id(param), kind, self.compute_dtype)
         hit = self._packed.get(key)
