@@ -218,6 +218,8 @@ def run_b200(args, rank, world, local):
     l0 = lib.b200seg_launch_count()
     ms_dev, loss_val = timed(args.steps, False)
     launches = lib.b200seg_launch_count() - l0
+    if train.launches_per_step is not None:  # graph replay: the recorded kernels run once per step
+        launches = train.launches_per_step * args.steps
     clocks = sampler.stop() if sampler else None
     timed(1, True)
     ms_e2e, _ = timed(args.steps, True)
@@ -232,7 +234,8 @@ def run_b200(args, rank, world, local):
         "dtype": args.dtype, "data": "synthetic", "config": workload_config(args, world),
         "e2e": {"value": e2e, "unit": "voxels/s", "ms_per_step": ms_e2e / args.steps,
                 "h2d_bytes_per_step": images_h.numel() * 4 + labels_h.numel(), "d2h_bytes_per_step": 4},
-        "gpu_launches": int(launches), "loss": loss_val, "clocks": clocks,
+        "gpu_launches": int(launches), "tcgen05_launches_per_step": train.tc_launches_per_step,
+        "loss": loss_val, "clocks": clocks,
     }
     flop = FWD_BWD_FLOP_PER_VOXEL.get(tuple(args.filters))
     if flop:

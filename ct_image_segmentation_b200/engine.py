@@ -39,6 +39,7 @@ class GraphedTrainStep:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.loss: Optional[torch.Tensor] = None
         self.use_graph = use_graph
+        self.launches_per_step = self.tc_launches_per_step = None
         if use_graph:
             self._capture(warmup)
 
@@ -60,11 +61,17 @@ class GraphedTrainStep:
         for p in self.bucket.params:
             p.grad = None
         self.net.reset_packed_cache()  # the weight-repack kernels must be part of the graph
+        from . import _lib
+        lib = _lib.load()
+        before = (lib.b200seg_launch_count(), lib.b200seg_tc_launch_count())
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = self._fwd_bwd()
             grads = [p.grad for p in self.bucket.params]
             torch._foreach_copy_(self.bucket.views, grads)
+        # b200seg kernels recorded into the graph = launched again on every replay
+        self.launches_per_step = lib.b200seg_launch_count() - before[0]
+        self.tc_launches_per_step = lib.b200seg_tc_launch_count() - before[1]
         for p, v in zip(self.bucket.params, self.bucket.views):
             p.grad = v  # the optimiser reads the (all-reduced) bucket
 
