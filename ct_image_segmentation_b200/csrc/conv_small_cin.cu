@@ -88,7 +88,7 @@ conv_small_cin_fprop_kernel(SmallCinParams p, const T* __restrict__ x, const T* 
 }
 
 // partial[blk][j][co] = sum over the block's voxels of x[in(v,tap)][ci] * dy[v][co],  j = tap*cin+ci
-template <typename T>
+template <typename T, int R>
 __global__ void __launch_bounds__(256)
 conv_small_cin_wgrad_kernel(SmallCinParams p, const T* __restrict__ x, const T* __restrict__ dy,
                             float* __restrict__ partial, int64_t vox_per_block) {
@@ -109,7 +109,7 @@ conv_small_cin_wgrad_kernel(SmallCinParams p, const T* __restrict__ x, const T* 
     jtab[j * 4 + 3] = j % p.cin;
   }
   const int nout = J * CO;
-  constexpr int R = 8;  // outputs per thread (J*CO <= 256*R)
+  // R = outputs per thread (J*CO <= 256*R)
   float acc[R];
   int oj[R], oc[R];
 #pragma unroll
@@ -241,11 +241,19 @@ int launch_small_cin_wgrad(const b200seg_conv_desc* d, const void* x, const void
   const int nb = small_cin_wgrad_blocks(d);
   int64_t per = cdiv64(cdiv64(p.nvox, nb), 64) * 64;
   size_t smem = (size_t)(65 * J + 64 * d->cout) * sizeof(float) + (size_t)(64 * 4 + J * 4) * sizeof(int);
-  if (d->dtype == B200SEG_BF16)
-    conv_small_cin_wgrad_kernel<__nv_bfloat16><<<nb, 256, smem, st>>>(p, (const __nv_bfloat16*)x,
-                                                                      (const __nv_bfloat16*)dy, partial, per);
-  else
-    conv_small_cin_wgrad_kernel<float><<<nb, 256, smem, st>>>(p, (const float*)x, (const float*)dy, partial, per);
+  const int nout_ = J * d->cout;
+#define SMALL_CIN_WGRAD(TT, RR) \
+  conv_small_cin_wgrad_kernel<TT, RR><<<nb, 256, smem, st>>>(p, (const TT*)x, (const TT*)dy, partial, per)
+  if (d->dtype == B200SEG_BF16) {
+    if (nout_ <= 512) SMALL_CIN_WGRAD(__nv_bfloat16, 2);
+    else if (nout_ <= 1024) SMALL_CIN_WGRAD(__nv_bfloat16, 4);
+    else SMALL_CIN_WGRAD(__nv_bfloat16, 8);
+  } else {
+    if (nout_ <= 512) SMALL_CIN_WGRAD(float, 2);
+    else if (nout_ <= 1024) SMALL_CIN_WGRAD(float, 4);
+    else SMALL_CIN_WGRAD(float, 8);
+  }
+#undef SMALL_CIN_WGRAD
   B200SEG_CHECK_LAUNCH("conv_small_cin_wgrad");
   const int nout = J * d->cout;
   conv_small_cin_wgrad_final_kernel<<<(nout * 32 + 255) / 256, 256, 0, st>>>(partial, nb, taps, d->cin, d->cout, gw);

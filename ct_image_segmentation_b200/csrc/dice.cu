@@ -57,13 +57,25 @@ __device__ __forceinline__ void voxel_softmax(const T* z, int C, float (&p)[CMAX
     }
   }
   float s = 0.f;
+  if constexpr (sizeof(T) == 2) {
+    // bf16 logits carry 8 significant bits: ex2.approx and one reciprocal are far below that
 #pragma unroll
-  for (int c = 0; c < CMAX; ++c) {
-    p[c] = c < C ? expf(p[c] - mx) : 0.f;
-    s += p[c];
+    for (int c = 0; c < CMAX; ++c) {
+      p[c] = c < C ? exp2f((p[c] - mx) * 1.4426950408889634f) : 0.f;
+      s += p[c];
+    }
+    const float inv = __frcp_rn(s);
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) p[c] *= inv;
+  } else {
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      p[c] = c < C ? expf(p[c] - mx) : 0.f;
+      s += p[c];
+    }
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) p[c] = p[c] / s;
   }
-#pragma unroll
-  for (int c = 0; c < CMAX; ++c) p[c] = p[c] / s;
 }
 
 }  // namespace

@@ -46,6 +46,10 @@ tc_slide_wgrad_kernel(const __grid_constant__ TcSlideWgradParams p) {
   constexpr int SLAB_BYTES = 3 * COPY_BYTES;
   constexpr int TSLAB_BYTES = TH * TWV * PB;
   constexpr uint32_t TMEM_COLS = 9 * CB <= 256 ? 256 : 512;
+  // CA = 16: an M = 64 instruction holds 4 line slots (3 taps) and reads half the A bytes of M = 128
+  // from shared memory -- these small-N MMAs are bound by the A-operand read, not by the math.
+  // M = 64 accumulator rows live in lanes 0..15 of each 32-lane TMEM quarter: quarter = slot (kh).
+  constexpr int MM = CA == 16 ? 64 : 128;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = smem;
@@ -102,7 +106,7 @@ tc_slide_wgrad_kernel(const __grid_constant__ TcSlideWgradParams p) {
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_bf16(128, CB, true, true);
+      constexpr uint32_t idesc = tc::make_idesc_bf16(MM, CB, true, true);
       constexpr uint64_t layA = tc::layout_for_row_bytes(PA), layB = tc::layout_for_row_bytes(PB);
       const uint32_t r_addr = tc::smem_u32(ring), t_addr = tc::smem_u32(tring);
       int waited = 0;
@@ -138,11 +142,12 @@ tc_slide_wgrad_kernel(const __grid_constant__ TcSlideWgradParams p) {
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int ih = row / CA, a = row % CA;
-    const bool valid = ih < 3;
+    const int ih = MM == 64 ? q : row / CA;
+    const int a = MM == 64 ? (lane & 15) : row % CA;
+    const bool valid = MM == 64 ? (q < 3 && lane < 16) : (ih < 3);
     tc::mbar_wait(acc_full, 0);
     tc::tc_fence_after();
-    if (q * 32 < 3 * CA) {  // warp-uniform: only the first 3*CA accumulator rows are taps
+    if (MM == 64 ? (q < 3) : (q * 32 < 3 * CA)) {  // warp-uniform: only rows that are taps
       for (int acc = 0; acc < 9; ++acc) {
         const int id = acc / 3, iw = acc % 3;
         const int tap = (id * 3 + (valid ? ih : 0)) * 3 + iw;
