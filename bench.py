@@ -255,39 +255,52 @@ def run_b200(args, rank, world, local):
 
 
 def roofline_probe(args, dev, dtype, pk):
-    """Dominant kernel timed alone with CUDA events on the launching stream: the head convolution
-    10->10 at full resolution (29 % of the network's conv FLOPs)."""
+    """Dominant layer timed alone with CUDA events on the launching stream: the head convolution
+    10->10 (3x3x3, stride 1) at full resolution -- 29 % of the network's conv FLOPs (SURVEY.md F11 /
+    Appendix B), run by the sliding-window tcgen05 kernel `tc_slide_conv_kernel<16,16>` (fprop here;
+    its dgrad is the same kernel with flipped taps).  AI = 135 FLOP/B < ridge (211), so the layer is
+    judged against HBM; the binding unit in practice is the tensor pipe's shared-memory operand fetch
+    (N = 16 MMAs), see profiles/r1_ncu_full_head_conv_slide.csv."""
     from ct_image_segmentation_b200 import _lib, ops
     g = ops.ConvGeom(3, 10, 10, 3, 1, False)
     n, p = args.batch, args.patch
-    x = torch.randn(n, p, p, p, 10, device=dev).to(dtype)
-    y = torch.empty_like(x)
+    x = ops.alloc_activation(n, (p, p, p), 10, dtype, dev)
+    x.copy_(torch.randn(x.shape, device=dev))
+    y = ops.alloc_activation(n, (p, p, p), 10, dtype, dev)
     w = torch.randn(10, 10, 3, 3, 3, device=dev) * 0.1
     wp = ops.pack_weight(g, _lib.W_CONV_FPROP, w, dtype)
     bias = torch.zeros(10, device=dev)
+    lib = _lib.load()
+    t0 = lib.b200seg_tc_launch_count()
     for _ in range(3):
         ops.conv_fprop(g, x, wp, bias, y)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 5
+    reps = 10
     e0.record()
     for _ in range(reps):
         ops.conv_fprop(g, x, wp, bias, y)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
+    used_tc = lib.b200seg_tc_launch_count() - t0 == 3 + reps
     vox = n * p ** 3
-    flops = 2.0 * 27 * 10 * 10 * vox
+    flops = 2.0 * 27 * 10 * 10 * vox          # dense conv FLOPs, no channel padding
     esz = 2 if dtype == torch.bfloat16 else 4
-    bytes_alg = vox * (10 + 10) * esz
+    bytes_alg = vox * (10 + 10) * esz          # read x once, write y once (SURVEY.md 8d)
     ach_tf = flops / (ms * 1e-3) / 1e12
     ach_gbs = bytes_alg / (ms * 1e-3) / 1e9
-    # AI = 135 FLOP/B < ridge (211): this layer is HBM-bound when it runs well (Appendix B)
-    return {"kernel": "conv_fprop head 10->10 k3 s1 (generic gather-GEMM)", "bound": "hbm",
-            "achieved": ach_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": ach_gbs / pk["hbm_gbs"],
-            "traffic": None, "ms": ms, "achieved_tflops": ach_tf,
-            "tensor_frac": ach_tf / pk["bf16_tflops"], "peak_source": pk["src"],
-            "algorithmic_bytes": bytes_alg, "algorithmic_flops": flops}
+    return {"kernel": "tc_slide_conv_kernel<16,16> (head conv 10->10 k3 s1 fprop, tcgen05 sliding window)"
+                      if used_tc else "conv_gather_kernel (CUDA-core fallback)",
+            "bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": ach_gbs / pk["hbm_gbs"],
+            # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of this
+            # kernel at batch 2 x 128^3 (profiles/r1_ncu_full_head_conv_slide.csv)
+            "traffic": 236.6e6 if (n, p, esz) == (2, 128, 2) else None,
+            "ms": ms, "achieved_tflops": ach_tf, "tensor_frac": ach_tf / pk["bf16_tflops"],
+            "tc_pipe_active_pct_ncu": 78.0, "peak_source": pk["src"],
+            "algorithmic_bytes": bytes_alg, "algorithmic_flops": flops,
+            "step_share_ncu": "2 launches (fprop+dgrad) = 5.5 % of the step; the conv family is 60 %"}
 
 
 def main():
