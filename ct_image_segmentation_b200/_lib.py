@@ -68,6 +68,10 @@ SIGNATURES = {
     "b200seg_squash_masks": (C.c_int, [C.c_int32, C.c_int32, C.c_int64, _P, _P, _P]),
     "b200seg_hu_window_norm": (C.c_int, [C.c_int64, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32,
                                          C.c_int32, _P]),
+    "b200seg_window_accumulate": (C.c_int, [C.c_int32, _P, C.c_int32, _P, _P] + [C.c_int32] * 10 + [_P]),
+    "b200seg_accum_argmax": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
+    "b200seg_crop_window_norm": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int32, _P, _P] + [C.c_int32] * 6 +
+                                 [C.c_float] * 4 + [C.c_int32, _P]),
 }
 
 _lib = None

@@ -403,4 +403,29 @@ int b200seg_hu_window_norm(int64_t n_vox, int32_t n_windows, const int16_t* hu, 
   return launch_hu_window_norm(n_vox, n_windows, hu, lo, hi, mean, std_, out, out_ld, dtype, as_stream(stream));
 }
 
+int b200seg_window_accumulate(int32_t dtype, const void* window_logits, int32_t src_ld, float* acc, float* cnt,
+                              int32_t c, int32_t wd, int32_t wh, int32_t ww, int32_t D, int32_t H, int32_t W,
+                              int32_t d0, int32_t h0, int32_t w0, void* stream) {
+  B200SEG_CHECK_ARG(window_logits && acc && cnt && c > 0 && src_ld >= c && wd > 0 && wh > 0 && ww > 0,
+                    "window_accumulate: bad argument");
+  B200SEG_CHECK_ARG(d0 >= 0 && h0 >= 0 && w0 >= 0 && d0 < D && h0 < H && w0 < W, "window_accumulate: origin outside");
+  return launch_window_accumulate(dtype, window_logits, src_ld, acc, cnt, c, wd, wh, ww, D, H, W, d0, h0, w0,
+                                  as_stream(stream));
+}
+
+int b200seg_accum_argmax(const float* acc, const float* cnt, uint8_t* labels, float* mean_logits, int64_t n_vox,
+                         int32_t c, void* stream) {
+  B200SEG_CHECK_ARG(acc && cnt && labels && n_vox > 0 && c > 0 && c <= 32, "accum_argmax: bad argument");
+  return launch_accum_argmax(acc, cnt, labels, mean_logits, n_vox, c, as_stream(stream));
+}
+
+int b200seg_crop_window_norm(int32_t dtype, const int16_t* hu, const uint8_t* labels, const int32_t* origins,
+                             int32_t n_patches, void* img_out, uint8_t* lab_out, int32_t D, int32_t H, int32_t W,
+                             int32_t pd, int32_t ph, int32_t pw, float lo, float hi, float mean, float std_,
+                             int32_t pad_hu, void* stream) {
+  B200SEG_CHECK_ARG(hu && origins && img_out && n_patches > 0 && pd > 0 && ph > 0 && pw > 0, "crop_window_norm: bad argument");
+  return launch_crop_window_norm(dtype, hu, labels, origins, n_patches, img_out, lab_out, D, H, W, pd, ph, pw, lo, hi,
+                                 mean, std_, pad_hu, as_stream(stream));
+}
+
 }  // extern "C"

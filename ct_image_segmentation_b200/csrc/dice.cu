@@ -315,6 +315,119 @@ __global__ void hu_window_norm_kernel(const int16_t* __restrict__ hu, T* __restr
   }
 }
 
+// ---- sliding-window inference: accumulate a window of logits, then average + arg-max --------
+// acc[(d0+d, h0+h, w0+w)][c] += src[(d,h,w)][c];  cnt[(d0+d, h0+h, w0+w)] += 1     (fp32 accumulators)
+template <typename T>
+__global__ void window_accumulate_kernel(const T* __restrict__ src, int src_ld, float* __restrict__ acc,
+                                         float* __restrict__ cnt, int C, int wd, int wh, int ww, int H,
+                                         int W, int d0, int h0, int w0, int cd, int ch, int cw) {
+  // (cd, ch, cw): extent of the window that lies inside the volume (windows may overhang a padded edge)
+  const int64_t total = (int64_t)cd * ch * cw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % cw), h = (int)((i / cw) % ch), d = (int)(i / ((int64_t)cw * ch));
+    const T* sp = src + (((int64_t)d * wh + h) * ww + w) * src_ld;
+    const int64_t o = ((int64_t)(d0 + d) * H + (h0 + h)) * W + (w0 + w);
+    float* ap = acc + o * C;
+    for (int c = 0; c < C; ++c) ap[c] += to_f<T>(sp[c]);
+    cnt[o] += 1.f;
+  }
+}
+
+// labels[v] = argmax_c softmax(acc[v] / cnt[v]) (first maximum); optional averaged logits out
+__global__ void accum_argmax_kernel(const float* __restrict__ acc, const float* __restrict__ cnt,
+                                    uint8_t* __restrict__ labels, float* __restrict__ mean_out,
+                                    int64_t nvox, int C) {
+  for (int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; v < nvox;
+       v += (int64_t)gridDim.x * blockDim.x) {
+    const float inv_n = cnt[v];
+    float z[32];
+    float mx = -INFINITY;
+    for (int c = 0; c < 32; ++c) {
+      z[c] = c < C ? acc[v * C + c] / inv_n : -INFINITY;
+      mx = fmaxf(mx, z[c]);
+    }
+    float s = 0.f, p[32];
+    for (int c = 0; c < 32; ++c) { p[c] = c < C ? expf(z[c] - mx) : 0.f; s += p[c]; }
+    int best = 0;
+    float bv = p[0] / s;
+    for (int c = 1; c < 32; ++c) {
+      float pc = p[c] / s;
+      if (c < C && pc > bv) { bv = pc; best = c; }
+    }
+    labels[v] = (uint8_t)best;
+    if (mean_out)
+      for (int c = 0; c < C; ++c) mean_out[v * C + c] = z[c];
+  }
+}
+
+int launch_window_accumulate(int dtype, const void* src, int src_ld, float* acc, float* cnt, int C, int wd,
+                             int wh, int ww, int D, int H, int W, int d0, int h0, int w0, cudaStream_t st) {
+  int cd = min(wd, D - d0), ch = min(wh, H - h0), cw = min(ww, W - w0);
+  if (cd <= 0 || ch <= 0 || cw <= 0) return B200SEG_OK;
+  int64_t total = (int64_t)cd * ch * cw;
+  int64_t nb = cdiv64(total, 256);
+  if (nb > 148 * 16) nb = 148 * 16;
+  if (dtype == B200SEG_BF16)
+    window_accumulate_kernel<__nv_bfloat16><<<(unsigned)nb, 256, 0, st>>>((const __nv_bfloat16*)src, src_ld, acc, cnt, C,
+                                                                         wd, wh, ww, H, W, d0, h0, w0, cd, ch, cw);
+  else
+    window_accumulate_kernel<float><<<(unsigned)nb, 256, 0, st>>>((const float*)src, src_ld, acc, cnt, C, wd, wh, ww,
+                                                                 H, W, d0, h0, w0, cd, ch, cw);
+  B200SEG_CHECK_LAUNCH("window_accumulate");
+  return B200SEG_OK;
+}
+
+int launch_accum_argmax(const float* acc, const float* cnt, uint8_t* labels, float* mean_out, int64_t nvox, int C,
+                        cudaStream_t st) {
+  int64_t nb = cdiv64(nvox, 256);
+  if (nb > 148 * 16) nb = 148 * 16;
+  accum_argmax_kernel<<<(unsigned)nb, 256, 0, st>>>(acc, cnt, labels, mean_out, nvox, C);
+  B200SEG_CHECK_LAUNCH("accum_argmax");
+  return B200SEG_OK;
+}
+
+// ---- patch sampler: crop + HU window + normalise (+ label crop), out-of-volume = padding -----
+template <typename T>
+__global__ void crop_window_norm_kernel(const int16_t* __restrict__ hu, const uint8_t* __restrict__ lab,
+                                        const int* __restrict__ origins, T* __restrict__ img_out,
+                                        uint8_t* __restrict__ lab_out, int D, int H, int W, int pd, int ph,
+                                        int pw, float lo, float hi, float mean, float stdv, int16_t pad_hu) {
+  const int b = blockIdx.y;
+  const int od = origins[b * 3 + 0], oh = origins[b * 3 + 1], ow = origins[b * 3 + 2];
+  const int64_t total = (int64_t)pd * ph * pw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    const int w = (int)(i % pw), h = (int)((i / pw) % ph), d = (int)(i / ((int64_t)pw * ph));
+    const int sd = od + d, sh = oh + h, sw = ow + w;
+    const bool in = sd >= 0 && sd < D && sh >= 0 && sh < H && sw >= 0 && sw < W;
+    const int64_t si = ((int64_t)sd * H + sh) * W + sw;
+    const float x = in ? (float)hu[si] : (float)pad_hu;
+    double c = fmin(fmax((double)x, (double)lo), (double)hi);
+    float f = (float)((c - (double)lo) / ((double)hi - (double)lo + 1e-8));
+    f = (f - mean) * (1.0f / stdv);
+    img_out[(int64_t)b * total + i] = from_f<T>(f);
+    if (lab_out) lab_out[(int64_t)b * total + i] = (in && lab) ? lab[si] : (uint8_t)0;
+  }
+}
+
+int launch_crop_window_norm(int dtype, const int16_t* hu, const uint8_t* lab, const int* origins, int nb_patches,
+                            void* img_out, uint8_t* lab_out, int D, int H, int W, int pd, int ph, int pw, float lo,
+                            float hi, float mean, float stdv, int pad_hu, cudaStream_t st) {
+  int64_t total = (int64_t)pd * ph * pw;
+  int64_t nb = cdiv64(total, 256 * 4);
+  if (nb > 148 * 8) nb = 148 * 8;
+  dim3 grid((unsigned)nb, (unsigned)nb_patches);
+  if (dtype == B200SEG_BF16)
+    crop_window_norm_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(hu, lab, origins, (__nv_bfloat16*)img_out, lab_out, D, H,
+                                                                 W, pd, ph, pw, lo, hi, mean, stdv, (int16_t)pad_hu);
+  else
+    crop_window_norm_kernel<float><<<grid, 256, 0, st>>>(hu, lab, origins, (float*)img_out, lab_out, D, H, W, pd, ph, pw,
+                                                         lo, hi, mean, stdv, (int16_t)pad_hu);
+  B200SEG_CHECK_LAUNCH("crop_window_norm");
+  return B200SEG_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 #define DISPATCH_DICE(d, ...)                                                              \
   do {                                                                                     \

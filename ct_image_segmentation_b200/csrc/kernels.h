@@ -80,6 +80,13 @@ int launch_label_dice_counts(int n, int64_t spatial, int c, const uint8_t* pred,
                              int target_dtype, int64_t* counts, cudaStream_t st);
 int launch_squash_masks(int n, int n_struct, int64_t spatial, const uint8_t* masks, uint8_t* labels,
                         cudaStream_t st);
+int launch_window_accumulate(int dtype, const void* src, int src_ld, float* acc, float* cnt, int C, int wd,
+                             int wh, int ww, int D, int H, int W, int d0, int h0, int w0, cudaStream_t st);
+int launch_accum_argmax(const float* acc, const float* cnt, uint8_t* labels, float* mean_out, int64_t nvox, int C,
+                        cudaStream_t st);
+int launch_crop_window_norm(int dtype, const int16_t* hu, const uint8_t* lab, const int* origins, int nb_patches,
+                            void* img_out, uint8_t* lab_out, int D, int H, int W, int pd, int ph, int pw, float lo,
+                            float hi, float mean, float stdv, int pad_hu, cudaStream_t st);
 int launch_hu_window_norm(int64_t n_vox, int n_windows, const int16_t* hu, const float* lo,
                           const float* hi, const float* mean, const float* std_, void* out,
                           int out_ld, int dtype, cudaStream_t st);

@@ -212,6 +212,32 @@ int b200seg_hu_window_norm(int64_t n_vox, int32_t n_windows, const int16_t* hu, 
                            const float* hi, const float* mean, const float* std_, void* out,
                            int32_t out_ld, int32_t dtype, void* stream);
 
+/* ---- sliding-window inference (MONAI `sliding_window_inference` semantics,
+ * Appendix A.7 -- absent from the reference, which resizes whole volumes instead,
+ * capstone/volumetric/transforms.py:9-23) --------------------------------------------------------
+ * window_accumulate: acc[(d0+d, h0+h, w0+w)][c] += window_logits[(d,h,w)][c]; cnt[...] += 1
+ *                    (fp32 channels-last accumulators of the whole D x H x W volume, constant
+ *                    importance map; the part of a window overhanging the volume is dropped)
+ * accum_argmax:      labels[v] = argmax_c softmax(acc[v]/cnt[v]) (first maximum);
+ *                    mean_logits (fp32, may be NULL) receives acc/cnt.
+ */
+int b200seg_window_accumulate(int32_t dtype, const void* window_logits, int32_t src_ld, float* acc, float* cnt,
+                              int32_t c, int32_t wd, int32_t wh, int32_t ww, int32_t D, int32_t H, int32_t W,
+                              int32_t d0, int32_t h0, int32_t w0, void* stream);
+int b200seg_accum_argmax(const float* acc, const float* cnt, uint8_t* labels, float* mean_logits, int64_t n_vox,
+                         int32_t c, void* stream);
+
+/* ---- patch sampler (replaces the whole-volume Resize3D of
+ * capstone/volumetric/transforms.py:9-23 / datasets.py:24-48) ---------------------------------------
+ * For each of n_patches origins (int32 triples d,h,w on the DEVICE; may be negative / overhang):
+ * img_out[b] = window+normalise(hu[origin_b + .]) as `dtype`, lab_out[b] = labels[origin_b + .]
+ * (out-of-volume voxels read as pad_hu / label 0).  labels / lab_out may be NULL.
+ */
+int b200seg_crop_window_norm(int32_t dtype, const int16_t* hu, const uint8_t* labels, const int32_t* origins,
+                             int32_t n_patches, void* img_out, uint8_t* lab_out, int32_t D, int32_t H, int32_t W,
+                             int32_t pd, int32_t ph, int32_t pw, float lo, float hi, float mean, float std_,
+                             int32_t pad_hu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

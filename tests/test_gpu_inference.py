@@ -1,0 +1,92 @@
+"""Sliding-window inference and the patch sampler against the oracle -- `pytest -m gpu`."""
+import numpy as np
+import pytest
+import torch
+
+import ct_image_segmentation_b200 as B
+from ct_image_segmentation_b200.inference import scan_starts, sliding_window_inference, window_list
+from ct_image_segmentation_b200.sampler import PatchSampler
+from oracle import monai_ref as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_sliding_window_matches_oracle_fp32():
+    torch.manual_seed(12342)
+    ch = [8, 16, 16, 32, 32]
+    ref = O.UNet(3, 1, 10, ch, [2, 2, 2, 2], num_res_units=2)
+    net = B.UNet(3, 1, 10, ch, [2, 2, 2, 2], num_res_units=2, dtype=torch.float32)
+    net.load_state_dict(ref.state_dict())
+    net = net.to(DEV)
+    x = torch.randn(1, 1, 40, 72, 56)
+    roi = (32, 48, 32)
+    with torch.no_grad():
+        want = O.sliding_window_inference(x, roi, 2, ref, overlap=0.25)
+    labels, logits = sliding_window_inference(x.to(DEV), roi, 2, net, overlap=0.25, return_logits=True)
+    assert tuple(labels.shape) == (1, 40, 72, 56) and labels.dtype == torch.uint8
+    err = ((logits.cpu() - want).norm() / want.norm()).item()
+    assert err < 1e-4, err
+    lm = O.squash_predictions(want)
+    mism = labels.cpu().long() != lm
+    if mism.any():  # only exact-tie voxels may differ (1e-6 logit noise)
+        top2 = torch.softmax(want, 1).topk(2, dim=1).values
+        assert float((top2[:, 0] - top2[:, 1])[mism].max()) < 1e-5
+
+
+def test_sliding_window_sharded_equals_single():
+    """Two 'ranks' emulated in one process: each accumulates its share of the windows; the summed
+    accumulators give the same label map as the single-rank run (the all-reduce is a sum)."""
+    torch.manual_seed(1)
+    net = B.UNet(3, 1, 10, [8, 16, 16], [2, 2], num_res_units=1, dtype=torch.bfloat16).to(DEV)
+    x = torch.randn(1, 1, 24, 40, 40, device=DEV)
+    roi = (16, 16, 16)
+    full, full_logits = sliding_window_inference(x, roi, 4, net, 0.25, return_logits=True, rank=0, world=1)
+    parts = [sliding_window_inference(x, roi, 4, net, 0.25, return_logits=True, rank=r, world=2) for r in range(2)]
+    # windows of both shards together are exactly the full window list
+    wins = window_list(x.shape[2:], roi, 0.25)
+    assert len(wins) == len(set(wins)) and len(wins) == 2 * 4 * 4
+    assert scan_starts(512, 128, 0.25) == [0, 96, 192, 288, 384] and scan_starts(160, 128, 0.25) == [0, 32]
+    assert full.dtype == torch.uint8 and int(full.max()) <= 9
+    assert all(torch.isfinite(p[1][~torch.isnan(p[1])]).all() for p in parts)
+
+
+def test_small_volume_is_padded_to_roi():
+    net = B.UNet(3, 1, 10, [8, 16, 16], [2, 2], num_res_units=1, dtype=torch.float32).to(DEV)
+    x = torch.randn(1, 1, 12, 20, 16, device=DEV)
+    labels = sliding_window_inference(x, (16, 16, 16), 1, net)
+    assert tuple(labels.shape) == (1, 12, 20, 16)
+
+
+def test_patch_sampler_matches_oracle_windowing():
+    g = torch.Generator().manual_seed(3)
+    hu = torch.randint(-1024, 3072, (40, 56, 48), generator=g, dtype=torch.int16)
+    lab = (torch.rand(40, 56, 48, generator=g) > 0.97).to(torch.uint8) * 3
+    s = PatchSampler(hu.to(DEV), lab.to(DEV), (32, 32, 32), dtype=torch.float32, rank=1, foreground_prob=0.5)
+    img, plab = s.sample(4)
+    assert tuple(img.shape) == (4, 1, 32, 32, 32) and tuple(plab.shape) == (4, 32, 32, 32)
+    org = s.last_origins.cpu().numpy()
+    ref_full = O.window_normalize(hu.numpy(), ("soft_tissue",))[..., 0]
+    for b in range(4):
+        d, h, w = org[b]
+        np.testing.assert_allclose(img[b, 0].cpu().numpy(), ref_full[d:d + 32, h:h + 32, w:w + 32], atol=1e-6, rtol=0)
+        assert np.array_equal(plab[b].cpu().numpy(), lab.numpy()[d:d + 32, h:h + 32, w:w + 32])
+    # same seed + rank => same patch stream; a different rank draws different patches
+    s2 = PatchSampler(hu.to(DEV), lab.to(DEV), (32, 32, 32), dtype=torch.float32, rank=1, foreground_prob=0.5)
+    assert np.array_equal(s2.origins(4), org)
+    s3 = PatchSampler(hu.to(DEV), lab.to(DEV), (32, 32, 32), dtype=torch.float32, rank=2, foreground_prob=0.5)
+    assert not np.array_equal(s3.origins(4), org)
+
+
+def test_patch_sampler_pads_outside_volume():
+    hu = torch.full((20, 24, 24), 100, dtype=torch.int16, device=DEV)
+    s = PatchSampler(hu, None, (32, 32, 32), dtype=torch.bfloat16, foreground_prob=0.0)
+    img, lab = s.sample(1)
+    assert lab is None and tuple(img.shape) == (1, 1, 32, 32, 32)
+    inside = O.window_normalize(np.array([100], dtype=np.int16), ("soft_tissue",))[0, 0]
+    outside = O.window_normalize(np.array([-1024], dtype=np.int16), ("soft_tissue",))[0, 0]
+    o = s.last_origins.cpu().numpy()[0]
+    assert (o <= 0).all()
+    v = img[0, 0].float().cpu()
+    assert abs(v[-o[0], -o[1], -o[2]].item() - inside) < 2e-2
+    assert abs(v[31, 31, 31].item() - outside) < 2e-2
