@@ -194,12 +194,26 @@ def run_b200(args, rank, world, local):
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        last = None
+        last = pending = None
         for _ in range(n_steps):
             if from_host:
-                last = step(images_h, labels_h).item()  # H2D of the inputs + D2H read of the loss
+                # every step: H2D of its inputs (pinned host memory, copy stream) and a D2H read of a
+                # step result; the read is of the PREVIOUS step's loss so that the host can enqueue
+                # step k+1's transfer while step k computes (software pipelining, nothing skipped)
+                loss = step(images_h, labels_h)
+                host_loss = torch.empty((), dtype=loss.dtype, pin_memory=True)
+                host_loss.copy_(loss, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                if pending is not None:
+                    pending[1].synchronize()
+                    last = pending[0].item()
+                pending = (host_loss, ev)
             else:
                 last = step(None, None)  # inputs already resident in the graph's input buffers
+        if from_host and pending is not None:
+            pending[1].synchronize()
+            last = pending[0].item()
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)

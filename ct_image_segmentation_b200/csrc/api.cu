@@ -106,10 +106,10 @@ int b200seg_pack_weight(const b200seg_conv_desc* d, int kind, const float* w_tor
                         void* stream) {
   B200SEG_CHECK_ARG(d && w_torch && w_packed, "pack_weight: NULL argument");
   B200SEG_CHECK_ARG(kind >= 0 && kind <= 3, "pack_weight: bad kind %d", kind);
-  int rc = launch_pack_weight(d->dtype, kind, w_torch, w_packed, d->kd * d->kh * d->kw, d->cin, d->cout,
-                              as_stream(stream));
-  if (rc || d->dtype != B200SEG_BF16) return rc;
-  return tc_pack_weight(d, kind, w_torch, (char*)w_packed + generic_weight_bytes(d), as_stream(stream));
+  if (d->dtype == B200SEG_BF16)  // both layouts in one launch
+    return tc_pack_weight(d, kind, w_torch, (char*)w_packed + generic_weight_bytes(d), w_packed, as_stream(stream));
+  return launch_pack_weight(d->dtype, kind, w_torch, w_packed, d->kd * d->kh * d->kw, d->cin, d->cout,
+                            as_stream(stream));
 }
 
 // tcgen05 dispatch: sliding-window kernel where it applies, else the streaming kernel

@@ -349,10 +349,25 @@ size_t tc_packed_weight_bytes(const b200seg_conv_desc* d) {
 }
 
 // Wt[((tap * kblocks + kb) * dst_pad + t) * KC + kc] = W(src = kb*KC + kc, dst = t, tap)
-__global__ void pack_weight_tc_kernel(const float* __restrict__ w, bf16* __restrict__ out, int taps, int src_c,
-                                      int dst_c, int src_pad, int dst_pad, int KC, int cin, int cout, int kind) {
+// and, in the same launch, the generic layout  gen[tap][src][dst]  (bf16)
+__global__ void pack_weight_tc_kernel(const float* __restrict__ w, bf16* __restrict__ out, bf16* __restrict__ gen,
+                                      int taps, int src_c, int dst_c, int src_pad, int dst_pad, int KC, int cin,
+                                      int cout, int kind) {
   int64_t total = (int64_t)taps * src_pad * dst_pad;
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gen && idx < (int64_t)taps * src_c * dst_c) {
+    int t = (int)(idx % dst_c);
+    int64_t r = idx / dst_c;
+    int s = (int)(r % src_c), tap = (int)(r / src_c);
+    int64_t wi;
+    switch (kind) {
+      case B200SEG_W_CONV_FPROP:   wi = ((int64_t)t * cin + s) * taps + tap; break;
+      case B200SEG_W_CONV_DGRAD:   wi = ((int64_t)s * cin + t) * taps + tap; break;
+      case B200SEG_W_CONVTR_FPROP: wi = ((int64_t)s * cout + t) * taps + tap; break;
+      default:                     wi = ((int64_t)t * cout + s) * taps + tap; break;
+    }
+    gen[idx] = __float2bfloat16_rn(w[wi]);
+  }
   if (idx >= total) return;
   int kc = (int)(idx % KC);
   int64_t r = idx / KC;
@@ -375,14 +390,15 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, bf16* __restr
   out[idx] = __float2bfloat16_rn(v);
 }
 
-int tc_pack_weight(const b200seg_conv_desc* d, int kind, const float* w, void* out, cudaStream_t st) {
+int tc_pack_weight(const b200seg_conv_desc* d, int kind, const float* w, void* out, void* gen, cudaStream_t st) {
   bool src_is_cin = (kind == B200SEG_W_CONV_FPROP || kind == B200SEG_W_CONVTR_FPROP);
   int src_c = src_is_cin ? d->cin : d->cout, dst_c = src_is_cin ? d->cout : d->cin;
   int src_pad = round16(src_c), dst_pad = round16(dst_c);
   int taps = d->kd * d->kh * d->kw;
   int64_t total = (int64_t)taps * src_pad * dst_pad;
-  pack_weight_tc_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(w, (bf16*)out, taps, src_c, dst_c, src_pad,
-                                                                      dst_pad, kc_for(src_pad), d->cin, d->cout, kind);
+  pack_weight_tc_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(w, (bf16*)out, (bf16*)gen, taps, src_c, dst_c,
+                                                                      src_pad, dst_pad, kc_for(src_pad), d->cin,
+                                                                      d->cout, kind);
   B200SEG_CHECK_LAUNCH("pack_weight_tc");
   return B200SEG_OK;
 }

@@ -40,6 +40,15 @@ class GraphedTrainStep:
         self.loss: Optional[torch.Tensor] = None
         self.use_graph = use_graph
         self.launches_per_step = self.tc_launches_per_step = None
+        # host inputs: double-buffered staging filled on a copy stream, so the H2D transfer of step
+        # k+1 overlaps the compute of step k (the static inputs are live for the whole step: the
+        # first-layer wgrad reads them at the very end of the backward)
+        self._copy_stream = torch.cuda.Stream(device=dev)
+        self._stage = [(torch.empty_like(self.static_images), torch.empty_like(self.static_labels))
+                       for _ in range(2)]
+        self._ready = [torch.cuda.Event() for _ in range(2)]
+        self._consumed = [torch.cuda.Event() for _ in range(2)]
+        self._k = 0
         if use_graph:
             self._capture(warmup)
 
@@ -76,10 +85,26 @@ class GraphedTrainStep:
             p.grad = v  # the optimiser reads the (all-reduced) bucket
 
     def __call__(self, images: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None):
-        if images is not None:
-            self.static_images.copy_(images, non_blocking=True)
-        if labels is not None:
-            self.static_labels.copy_(labels, non_blocking=True)
+        if images is not None and not images.is_cuda:
+            i = self._k & 1
+            self._k += 1
+            main = torch.cuda.current_stream()
+            with torch.cuda.stream(self._copy_stream):
+                self._copy_stream.wait_event(self._consumed[i])
+                self._stage[i][0].copy_(images, non_blocking=True)
+                if labels is not None:
+                    self._stage[i][1].copy_(labels, non_blocking=True)
+                self._ready[i].record(self._copy_stream)
+            main.wait_event(self._ready[i])
+            self.static_images.copy_(self._stage[i][0], non_blocking=True)
+            if labels is not None:
+                self.static_labels.copy_(self._stage[i][1], non_blocking=True)
+            self._consumed[i].record(main)
+        else:
+            if images is not None:
+                self.static_images.copy_(images, non_blocking=True)
+            if labels is not None:
+                self.static_labels.copy_(labels, non_blocking=True)
         if self.graph is not None:
             self.graph.replay()
             loss = self.loss

@@ -41,7 +41,7 @@ def window_list(dims: Sequence[int], roi: Sequence[int], overlap: float) -> List
 def sliding_window_inference(inputs: torch.Tensor, roi_size: Sequence[int], sw_batch_size: int,
                              predictor: Callable[[torch.Tensor], torch.Tensor], overlap: float = 0.25,
                              return_logits: bool = False, rank: Optional[int] = None,
-                             world: Optional[int] = None):
+                             world: Optional[int] = None, partial_only: bool = False):
     """``inputs`` (1, Cin, D, H, W) on the GPU -> uint8 label map (1, D, H, W) (and, with
     ``return_logits``, the averaged fp32 logits (1, C, D, H, W))."""
     if inputs.dim() != 5 or inputs.shape[0] != 1:
@@ -84,9 +84,20 @@ def sliding_window_inference(inputs: torch.Tensor, roi_size: Sequence[int], sw_b
         n_classes = probe.shape[1]
         acc = torch.zeros(pd, ph, pw, n_classes, dtype=torch.float32, device=x.device)
         cnt = torch.zeros(pd, ph, pw, dtype=torch.float32, device=x.device)
+    if partial_only:  # caller combines the shards itself (tests; custom reductions)
+        return acc, cnt
     if world > 1:
         dist.all_reduce(acc, op=dist.ReduceOp.SUM)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    return _finalize(acc, cnt, dims, roi_size, return_logits)
+
+
+def _finalize(acc, cnt, dims, roi_size, return_logits):
+    """Average + arg-max of the (summed) accumulators, cropped back to the unpadded volume."""
+    lib = _lib.load()
+    pd, ph, pw, n_classes = acc.shape
+    stream = torch.cuda.current_stream().cuda_stream
+    x = acc
     labels = torch.empty(pd, ph, pw, dtype=torch.uint8, device=x.device)
     mean = torch.empty_like(acc) if return_logits else None
     _lib.check(lib.b200seg_accum_argmax(acc.data_ptr(), cnt.data_ptr(), labels.data_ptr(),

@@ -41,14 +41,19 @@ def test_sliding_window_sharded_equals_single():
     net = B.UNet(3, 1, 10, [8, 16, 16], [2, 2], num_res_units=1, dtype=torch.bfloat16).to(DEV)
     x = torch.randn(1, 1, 24, 40, 40, device=DEV)
     roi = (16, 16, 16)
+    from ct_image_segmentation_b200.inference import _finalize
     full, full_logits = sliding_window_inference(x, roi, 4, net, 0.25, return_logits=True, rank=0, world=1)
-    parts = [sliding_window_inference(x, roi, 4, net, 0.25, return_logits=True, rank=r, world=2) for r in range(2)]
+    parts = [sliding_window_inference(x, roi, 4, net, 0.25, rank=r, world=2, partial_only=True) for r in range(2)]
+    acc, cnt = parts[0][0] + parts[1][0], parts[0][1] + parts[1][1]      # what the all-reduce computes
+    lab2, logits2 = _finalize(acc, cnt, tuple(x.shape[2:]), roi, True)
+    assert float(cnt.min()) >= 1.0
+    assert ((logits2 - full_logits).norm() / full_logits.norm()).item() < 1e-5
+    assert (lab2 != full).float().mean().item() < 1e-4
     # windows of both shards together are exactly the full window list
     wins = window_list(x.shape[2:], roi, 0.25)
-    assert len(wins) == len(set(wins)) and len(wins) == 2 * 4 * 4
+    assert len(wins) == len(set(wins)) and len(wins) == 2 * 3 * 3
     assert scan_starts(512, 128, 0.25) == [0, 96, 192, 288, 384] and scan_starts(160, 128, 0.25) == [0, 32]
     assert full.dtype == torch.uint8 and int(full.max()) <= 9
-    assert all(torch.isfinite(p[1][~torch.isnan(p[1])]).all() for p in parts)
 
 
 def test_small_volume_is_padded_to_roi():
