@@ -19,6 +19,7 @@ bool tc_slide_conv_supported(const b200seg_conv_desc* d, int op);
 int tc_slide_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,
                       const void* residual, void* dst, cudaStream_t st);
 bool tc_slide_wgrad_supported(const b200seg_conv_desc* d, bool transposed_layer);
+size_t tc_slide_wgrad_workspace(const b200seg_conv_desc* d);
 int tc_slide_wgrad_run(const b200seg_conv_desc* d, const void* x, const void* dy, float* gw, float* G32,
                        cudaStream_t st);
 size_t tc_packed_weight_bytes(const b200seg_conv_desc* d);

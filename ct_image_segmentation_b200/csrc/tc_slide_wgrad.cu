@@ -35,7 +35,7 @@ struct alignas(64) TcSlideWgradParams {
   int n, D, H, W;
   int tilesH, tilesW, dseg, nseg;
   int a_pad, b_pad;
-  float* out;  // [27][a_pad][b_pad]
+  float* out;  // [CTA][27][a_pad][b_pad] fp32 partial sums
 };
 
 template <int CA, int CB>
@@ -151,15 +151,18 @@ tc_slide_wgrad_kernel(const __grid_constant__ TcSlideWgradParams p) {
       for (int acc = 0; acc < 9; ++acc) {
         const int id = acc / 3, iw = acc % 3;
         const int tap = (id * 3 + (valid ? ih : 0)) * 3 + iw;
-        float* orow = p.out + ((int64_t)tap * p.a_pad + a) * p.b_pad;
+        float* orow = p.out + (int64_t)blockIdx.x * 27 * p.a_pad * p.b_pad + ((int64_t)tap * p.a_pad + a) * p.b_pad;
 #pragma unroll
         for (int ch = 0; ch < CB / 16; ++ch) {
           uint32_t v[16];
           tc::tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + acc * CB + ch * 16, v);
           tc::tmem_ld_wait();
           if (valid) {
+            float4* o4 = reinterpret_cast<float4*>(orow + ch * 16);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) atomicAdd(orow + ch * 16 + i, __uint_as_float(v[i]));
+            for (int i = 0; i < 4; ++i)
+              o4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                  __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
           }
         }
       }
@@ -170,16 +173,23 @@ tc_slide_wgrad_kernel(const __grid_constant__ TcSlideWgradParams p) {
   if (warp == 1) tc::tmem_dealloc<TMEM_COLS>(tmem_acc);
 }
 
+// gw[b][a][tap] = sum_cta G[cta][tap][a][b]: one warp per output element, fixed order (deterministic)
 __global__ void tc_slide_wgrad_unpack_kernel(const float* __restrict__ G, float* __restrict__ gw, int taps, int a_c,
-                                             int b_c, int a_pad, int b_pad) {
+                                             int b_c, int a_pad, int b_pad, int nparts) {
   int64_t total = (int64_t)taps * a_c * b_c;
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
+  const int lane = threadIdx.x % 32;
   if (idx >= total) return;
   int b = (int)(idx % b_c);
   int64_t r = idx / b_c;
   int a = (int)(r % a_c);
   int tap = (int)(r / a_c);
-  gw[((int64_t)b * a_c + a) * taps + tap] = G[((int64_t)tap * a_pad + a) * b_pad + b];
+  const int64_t g_elems = (int64_t)taps * a_pad * b_pad;
+  const float* gp = G + ((int64_t)tap * a_pad + a) * b_pad + b;
+  float s = 0.f;
+  for (int i = lane; i < nparts; i += 32) s += gp[(int64_t)i * g_elems];
+  s = warp_sum(s);
+  if (lane == 0) gw[((int64_t)b * a_c + a) * taps + tap] = s;
 }
 
 namespace {
@@ -200,6 +210,29 @@ int launch_slide_wgrad(const TcSlideWgradParams& p, unsigned grid, cudaStream_t 
 }
 }  // namespace
 
+namespace {
+// column / d-segment decomposition shared by the launcher and the workspace query
+void slide_wgrad_grid(const b200seg_conv_desc* d, int& tilesH, int& tilesW, int& dseg, int& nseg, int64_t& grid) {
+  tilesH = (d->in_h + TH - 1) / TH;
+  tilesW = (d->in_w + TWV - 1) / TWV;
+  const int64_t cols = (int64_t)d->n * tilesH * tilesW;
+  int ns = (int)((148 * 3 + cols - 1) / cols);
+  if (ns < 1) ns = 1;
+  dseg = (d->in_d + ns - 1) / ns;
+  if (dseg < 8) dseg = 8;
+  if (dseg > d->in_d) dseg = d->in_d;
+  nseg = (d->in_d + dseg - 1) / dseg;
+  grid = cols * nseg;
+}
+}  // namespace
+
+size_t tc_slide_wgrad_workspace(const b200seg_conv_desc* d) {
+  int th, tw, dseg, nseg;
+  int64_t grid;
+  slide_wgrad_grid(d, th, tw, dseg, nseg, grid);
+  return (size_t)grid * 27 * round16(d->cin) * round16(d->cout) * sizeof(float);
+}
+
 // conv layers only (S = x, T = dy): 3-D 3x3x3 stride 1, padded channel counts in {16, 32}
 bool tc_slide_wgrad_supported(const b200seg_conv_desc* d, bool transposed_layer) {
   if (transposed_layer || (d->flags & B200SEG_CONV_NO_SLIDE)) return false;
@@ -207,6 +240,7 @@ bool tc_slide_wgrad_supported(const b200seg_conv_desc* d, bool transposed_layer)
   const int ap = round16(d->cin), bp = round16(d->cout);
   if ((ap != 16 && ap != 32) || (bp != 16 && bp != 32)) return false;
   if (d->in_d < 8 || (int64_t)d->in_h * d->in_w < 512) return false;
+  if (tc_slide_wgrad_workspace(d) > (size_t)256 << 20) return false;  // partial tiles: one per CTA
   return true;
 }
 
@@ -216,14 +250,8 @@ int tc_slide_wgrad_run(const b200seg_conv_desc* d, const void* x, const void* dy
   memset(&p, 0, sizeof(p));
   const int CA = round16(d->cin), CB = round16(d->cout);
   p.n = d->n; p.D = d->in_d; p.H = d->in_h; p.W = d->in_w;
-  p.tilesH = (p.H + TH - 1) / TH; p.tilesW = (p.W + TWV - 1) / TWV;
-  const int64_t cols = (int64_t)p.n * p.tilesH * p.tilesW;
-  int nseg = (int)((148 * 3 + cols - 1) / cols);
-  if (nseg < 1) nseg = 1;
-  int dseg = (p.D + nseg - 1) / nseg;
-  if (dseg < 8) dseg = 8;
-  if (dseg > p.D) dseg = p.D;
-  p.dseg = dseg; p.nseg = (p.D + dseg - 1) / dseg;
+  int64_t grid;
+  slide_wgrad_grid(d, p.tilesH, p.tilesW, p.dseg, p.nseg, grid);
   p.a_pad = CA; p.b_pad = CB; p.out = G32;
   {
     uint64_t dims[5] = {(uint64_t)CA, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.D, (uint64_t)p.n};
@@ -241,12 +269,7 @@ int tc_slide_wgrad_run(const b200seg_conv_desc* d, const void* x, const void* dy
     int rc = tc_make_map(&p.tmT, dy, 5, dims, strides, box, CB * 2);
     if (rc) return rc;
   }
-  cudaError_t e = cudaMemsetAsync(G32, 0, (size_t)27 * CA * CB * sizeof(float), st);
-  if (e != cudaSuccess) {
-    set_error("tc_slide_wgrad: memset failed: %s", cudaGetErrorString(e));
-    return B200SEG_ERR_CUDA;
-  }
-  const int64_t grid = cols * p.nseg;
+
   int rc;
   if (CA == 16 && CB == 16) rc = launch_slide_wgrad<16, 16>(p, (unsigned)grid, st);
   else if (CA == 16 && CB == 32) rc = launch_slide_wgrad<16, 32>(p, (unsigned)grid, st);
@@ -254,7 +277,8 @@ int tc_slide_wgrad_run(const b200seg_conv_desc* d, const void* x, const void* dy
   else rc = launch_slide_wgrad<32, 32>(p, (unsigned)grid, st);
   if (rc) return rc;
   const int64_t total = (int64_t)27 * d->cin * d->cout;
-  tc_slide_wgrad_unpack_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(G32, gw, 27, d->cin, d->cout, CA, CB);
+  tc_slide_wgrad_unpack_kernel<<<(unsigned)cdiv64(total * 32, 256), 256, 0, st>>>(G32, gw, 27, d->cin, d->cout, CA, CB,
+                                                                                 (int)grid);
   B200SEG_CHECK_LAUNCH("tc_slide_wgrad_unpack");
   return B200SEG_OK;
 }

@@ -50,7 +50,7 @@ struct alignas(64) TcWgradParams {
   int tiles_per_cta;
   int stages;
   int a_pad, b_pad;
-  float* out;            // [taps][a_pad][b_pad] fp32, zeroed
+  float* out;            // [splits][taps][a_pad][b_pad] fp32 partial sums (plain stores, no atomics)
 };
 
 __device__ __forceinline__ void tmem_alloc_dyn(uint32_t* dst_smem, uint32_t ncols) {
@@ -167,14 +167,18 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
           tap = sl.tap;
           a = sl.chan + row % p.CA;
         }
-        float* orow = p.out + ((int64_t)tap * p.a_pad + a) * p.b_pad + n0;
+        const int64_t g_elems = (int64_t)(p.nslots / (p.a_pad / p.CA)) * p.a_pad * p.b_pad;
+        float* orow = p.out + (int64_t)blockIdx.x * g_elems + ((int64_t)tap * p.a_pad + a) * p.b_pad + n0;
         for (int ch = 0; ch < p.N / 16; ++ch) {
           uint32_t v[16];
           tc::tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + mt * p.N + ch * 16, v);
           tc::tmem_ld_wait();
           if (valid) {
+            float4* o4 = reinterpret_cast<float4*>(orow + ch * 16);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) atomicAdd(orow + ch * 16 + i, __uint_as_float(v[i]));
+            for (int i = 0; i < 4; ++i)
+              o4[i] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]),
+                                  __uint_as_float(v[4 * i + 2]), __uint_as_float(v[4 * i + 3]));
           }
         }
       }
@@ -185,9 +189,9 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
   if (warp == 1) tmem_dealloc_dyn(tmem_acc, 512);
 }
 
-// gw[b][a][tap] = G[tap][a][b] for the real channels
+// gw[b][a][tap] = sum_split G[split][tap][a][b] for the real channels (fixed order: deterministic)
 __global__ void tc_wgrad_unpack_kernel(const float* __restrict__ G, float* __restrict__ gw, int taps, int a_c,
-                                       int b_c, int a_pad, int b_pad) {
+                                       int b_c, int a_pad, int b_pad, int splits) {
   int64_t total = (int64_t)taps * a_c * b_c;
   int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
@@ -195,7 +199,11 @@ __global__ void tc_wgrad_unpack_kernel(const float* __restrict__ G, float* __res
   int64_t r = idx / b_c;
   int a = (int)(r % a_c);
   int tap = (int)(r / a_c);
-  gw[((int64_t)b * a_c + a) * taps + tap] = G[((int64_t)tap * a_pad + a) * b_pad + b];
+  const int64_t g_elems = (int64_t)taps * a_pad * b_pad;
+  const float* gp = G + ((int64_t)tap * a_pad + a) * b_pad + b;
+  float s = 0.f;
+  for (int i = 0; i < splits; ++i) s += gp[(int64_t)i * g_elems];
+  gw[((int64_t)b * a_c + a) * taps + tap] = s;
 }
 
 namespace {
@@ -235,9 +243,14 @@ int n_tile_for(int b_pad) {
 
 }  // namespace
 
+// split-K partial tiles: at most ~4 M fp32 per launch (see the split heuristic) plus one tile; the
+// sliding-window kernels need one tile per CTA (<= 2048 CTAs of 27*32*32)
 size_t tc_wgrad_extra_workspace(const b200seg_conv_desc* d) {
   if (d->dtype != B200SEG_BF16) return 0;
-  return align_up((size_t)d->kd * d->kh * d->kw * round16(d->cin) * round16(d->cout) * sizeof(float), 256);
+  const size_t g = (size_t)d->kd * d->kh * d->kw * round16(d->cin) * round16(d->cout);
+  size_t streaming = (g + (4u << 20)) * sizeof(float);
+  size_t sliding = tc_slide_wgrad_supported(d, false) ? tc_slide_wgrad_workspace(d) : 0;
+  return align_up(streaming > sliding ? streaming : sliding, 256);
 }
 
 bool tc_wgrad_supported(const b200seg_conv_desc* d, bool transposed_layer, const void* x, const void* dy) {
@@ -374,12 +387,6 @@ int tc_wgrad_run(const b200seg_conv_desc* d, bool transposed_layer, const void* 
   p.tiles_per_cta = (int)((p.total_tiles + splits - 1) / splits);
   splits = (p.total_tiles + p.tiles_per_cta - 1) / p.tiles_per_cta;
 
-  const size_t g_bytes = (size_t)taps * a_pad * b_pad * sizeof(float);
-  cudaError_t e = cudaMemsetAsync(G32, 0, g_bytes, st);
-  if (e != cudaSuccess) {
-    set_error("tc_wgrad: memset failed: %s", cudaGetErrorString(e));
-    return B200SEG_ERR_CUDA;
-  }
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -391,7 +398,8 @@ int tc_wgrad_run(const b200seg_conv_desc* d, bool transposed_layer, const void* 
   B200SEG_CHECK_LAUNCH("tc_wgrad");
   count_tc_launch();
   const int64_t total = (int64_t)taps * g.a_c * g.b_c;
-  tc_wgrad_unpack_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(G32, gw, taps, g.a_c, g.b_c, a_pad, b_pad);
+  tc_wgrad_unpack_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(G32, gw, taps, g.a_c, g.b_c, a_pad, b_pad,
+                                                                       (int)splits);
   B200SEG_CHECK_LAUNCH("tc_wgrad_unpack");
   return B200SEG_OK;
 }
