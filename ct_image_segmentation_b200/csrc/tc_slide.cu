@@ -114,6 +114,10 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
       constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN, false, false);
       constexpr uint64_t layout = tc::layout_for_row_bytes(PITCH);
       const uint32_t w_addr = tc::smem_u32(wsm), r_addr = tc::smem_u32(ring);
+      // descriptor template: only the 14-bit start-address field varies (keeps the issue loop short;
+      // one thread feeds the tensor pipe, every instruction on its path counts)
+      const uint64_t tmpl = tc::make_smem_desc(0, 16, 8 * PITCH, layout);
+      const uint64_t w_desc = tmpl + (w_addr >> 4);
       tc::mbar_wait(wbar, 0);
       int waited = 0;
       for (int j = 0; j < nd; ++j) {
@@ -127,18 +131,20 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
         uint32_t first = 1;
 #pragma unroll 1
         for (int id = 0; id < 3; ++id) {
-          const uint32_t slab = r_addr + ((j + id) % RING) * SLAB_BYTES;
+          const uint64_t slab = tmpl + ((r_addr + ((j + id) % RING) * SLAB_BYTES) >> 4);
+          const uint64_t wd = w_desc + (((p.flip ? (2 - id) : id) * 9 * WT_BYTES) >> 4);
 #pragma unroll
           for (int ih = 0; ih < 3; ++ih)
 #pragma unroll
             for (int iw = 0; iw < 3; ++iw) {
-              const int wt = p.flip ? ((2 - id) * 3 + (2 - ih)) * 3 + (2 - iw) : (id * 3 + ih) * 3 + iw;
-              const uint32_t a = slab + iw * COPY_BYTES + ih * (TWV * PITCH);
-              const uint32_t b = w_addr + wt * WT_BYTES;
+              // weight tile (id, ih, iw) for fprop, the mirrored tap for dgrad (constant offsets)
+              const uint64_t a = slab + ((iw * COPY_BYTES + ih * (TWV * PITCH)) >> 4);
+              const uint64_t bf = wd + (((ih * 3 + iw) * WT_BYTES) >> 4);
+              const uint64_t bb = wd + ((((2 - ih) * 3 + (2 - iw)) * WT_BYTES) >> 4);
+              const uint64_t b = p.flip ? bb : bf;
 #pragma unroll
               for (int k = 0; k < KC / 16; ++k) {
-                tc::umma_bf16(tmem_acc + buf * BN, tc::make_smem_desc(a + k * 32, 16, 8 * PITCH, layout),
-                              tc::make_smem_desc(b + k * 32, 16, 8 * PITCH, layout), idesc, first ? 0u : 1u);
+                tc::umma_bf16(tmem_acc + buf * BN, a + 2 * k, b + 2 * k, idesc, first ? 0u : 1u);
                 first = 0;
               }
             }

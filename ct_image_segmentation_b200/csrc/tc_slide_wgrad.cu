@@ -24,7 +24,6 @@ int tc_make_map(CUtensorMap* out, const void* base, int rank, const uint64_t* di
 namespace {
 constexpr int TH = 16;
 constexpr int TWV = 8;
-constexpr int RING = 4;
 constexpr int RT = 3;
 inline int round16(int c) { return (c + 15) / 16 * 16; }
 }  // namespace
@@ -41,6 +40,7 @@ struct alignas(64) TcSlideWgradParams {
 template <int CA, int CB>
 __global__ void __launch_bounds__(192)
 tc_slide_wgrad_kernel(const __grid_constant__ TcSlideWgradParams p) {
+  constexpr int RING = 6;  // source slabs in flight: deep enough to hide the TMA latency
   constexpr int PA = CA * 2, PB = CB * 2;
   constexpr int COPY_BYTES = (TH + 2) * TWV * PA;
   constexpr int SLAB_BYTES = 3 * COPY_BYTES;
@@ -72,9 +72,10 @@ tc_slide_wgrad_kernel(const __grid_constant__ TcSlideWgradParams p) {
   const int nd = min(p.dseg, p.D - d_begin);
 
   if (warp == 0 && lane == 0) {
-    for (int i = 0; i < RING; ++i) { tc::mbar_init(&fullS[i], 1); tc::mbar_init(&emptyS[i], 1); }
-    for (int i = 0; i < RT; ++i) { tc::mbar_init(&fullT[i], 1); tc::mbar_init(&emptyT[i], 1); }
-    tc::mbar_init(acc_full, 1);
+    // three MMA-issuing threads (one per kd): a stage is free / the result complete after all three
+    for (int i = 0; i < RING; ++i) { tc::mbar_init(&fullS[i], 1); tc::mbar_init(&emptyS[i], 3); }
+    for (int i = 0; i < RT; ++i) { tc::mbar_init(&fullT[i], 1); tc::mbar_init(&emptyT[i], 3); }
+    tc::mbar_init(acc_full, 3);
     tc::fence_barrier_init();
     tc::prefetch_tmap(&p.tmS);
     tc::prefetch_tmap(&p.tmT);
@@ -104,42 +105,44 @@ tc_slide_wgrad_kernel(const __grid_constant__ TcSlideWgradParams p) {
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_bf16(MM, CB, true, true);
-      constexpr uint64_t layA = tc::layout_for_row_bytes(PA), layB = tc::layout_for_row_bytes(PB);
-      const uint32_t r_addr = tc::smem_u32(ring), t_addr = tc::smem_u32(tring);
-      int waited = 0;
-      for (int j = 0; j < nd; ++j) {
-        while (waited <= j + 2) {
-          tc::mbar_wait(&fullS[waited % RING], ((uint32_t)(waited / RING)) & 1u);
-          ++waited;
-        }
-        tc::mbar_wait(&fullT[j % RT], ((uint32_t)(j / RT)) & 1u);
-        tc::tc_fence_after();
-        const uint32_t tb = t_addr + (j % RT) * TSLAB_BYTES;
-#pragma unroll 1
-        for (int id = 0; id < 3; ++id) {
-          const uint32_t slab = r_addr + ((j + id) % RING) * SLAB_BYTES;
-#pragma unroll
-          for (int iw = 0; iw < 3; ++iw) {
-            const uint32_t acc = tmem_acc + (id * 3 + iw) * CB;
-#pragma unroll
-            for (int t = 0; t < TH / 2; ++t) {
-              // K step t = output lines 2t, 2t+1; slot i of A starts at S line 2t + i
-              const uint64_t ad = tc::make_smem_desc(slab + iw * COPY_BYTES + (2 * t) * (TWV * PA), TWV * PA,
-                                                     TWV * PA, layA);
-              const uint64_t bd = tc::make_smem_desc(tb + (2 * t) * (TWV * PB), 16, TWV * PB, layB);
-              tc::umma_bf16(acc, ad, bd, idesc, (j > 0 || t > 0) ? 1u : 0u);
-            }
-          }
-        }
-        tc::umma_commit(&emptyS[j % RING]);
-        tc::umma_commit(&emptyT[j % RT]);
+  }
+  // ---- MMA issue: warps 1, 2, 3 each own one kd (three accumulators); a single thread can only
+  // issue ~1 MMA per 50-100 cycles (descriptor arithmetic + issue), which starves the tensor pipe
+  // when every MMA is this small, so the 72 MMAs per slab are spread over three issuing threads.
+  if (warp >= 1 && warp <= 3 && lane == 0) {
+    constexpr uint32_t idesc = tc::make_idesc_bf16(MM, CB, true, true);
+    constexpr uint64_t layA = tc::layout_for_row_bytes(PA), layB = tc::layout_for_row_bytes(PB);
+    const int id = warp - 1;
+    const uint32_t r_addr = tc::smem_u32(ring), t_addr = tc::smem_u32(tring);
+    // descriptor templates: only the 14-bit start-address field changes below
+    const uint64_t a_tmpl = tc::make_smem_desc(0, TWV * PA, TWV * PA, layA);
+    const uint64_t b_tmpl = tc::make_smem_desc(0, 16, TWV * PB, layB);
+    int waited = 0;
+    for (int j = 0; j < nd; ++j) {
+      while (waited <= j + 2) {
+        tc::mbar_wait(&fullS[waited % RING], ((uint32_t)(waited / RING)) & 1u);
+        ++waited;
       }
-      tc::umma_commit(acc_full);
+      tc::mbar_wait(&fullT[j % RT], ((uint32_t)(j / RT)) & 1u);
+      tc::tc_fence_after();
+      const uint64_t tb = b_tmpl + ((t_addr + (j % RT) * TSLAB_BYTES) >> 4);
+      const uint64_t sa = a_tmpl + ((r_addr + ((j + id) % RING) * SLAB_BYTES) >> 4);
+#pragma unroll
+      for (int iw = 0; iw < 3; ++iw) {
+        const uint32_t acc = tmem_acc + (id * 3 + iw) * CB;
+#pragma unroll
+        for (int t = 0; t < TH / 2; ++t) {
+          // K step t = output lines 2t, 2t+1; slot i of A starts at S line 2t + i
+          tc::umma_bf16(acc, sa + ((iw * COPY_BYTES + (2 * t) * (TWV * PA)) >> 4),
+                        tb + (((2 * t) * (TWV * PB)) >> 4), idesc, (j > 0 || t > 0) ? 1u : 0u);
+        }
+      }
+      tc::umma_commit(&emptyS[j % RING]);
+      tc::umma_commit(&emptyT[j % RT]);
     }
-  } else {
+    tc::umma_commit(acc_full);
+  }
+  if (warp >= 2) {
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int ih = MM == 64 ? q : row / CA;
@@ -195,9 +198,10 @@ __global__ void tc_slide_wgrad_unpack_kernel(const float* __restrict__ G, float*
 namespace {
 template <int CA, int CB>
 int launch_slide_wgrad(const TcSlideWgradParams& p, unsigned grid, cudaStream_t st) {
+  constexpr int RING = 6;
   constexpr int SLAB = 3 * (TH + 2) * TWV * CA * 2;
   constexpr int TSLAB = TH * TWV * CB * 2;
-  const size_t smem = 1024 + RING * SLAB + RT * TSLAB + 32 * 8 + 64;
+  const size_t smem = 1024 + RING * SLAB + RT * TSLAB + 40 * 8 + 64;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(tc_slide_wgrad_kernel<CA, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);

@@ -88,12 +88,15 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
   const int64_t tile_end = min(tile_begin + p.tiles_per_cta, p.total_tiles);
   const int ntiles = (int)(tile_end - tile_begin);
 
+  // up to three MMA-issuing threads (warps 1..3), each owning the M tiles mt = i, i+3, ... (distinct
+  // accumulators): one thread cannot issue these small MMAs fast enough to keep the tensor pipe busy
+  const int nissue = mtiles < 3 ? mtiles : 3;
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < stages; ++i) {
       tc::mbar_init(&full[i], 1);
-      tc::mbar_init(&empty[i], 1);
+      tc::mbar_init(&empty[i], nissue);
     }
-    tc::mbar_init(acc_full, 1);
+    tc::mbar_init(acc_full, nissue);
     tc::fence_barrier_init();
     tc::prefetch_tmap(&p.tmT);
   }
@@ -129,31 +132,33 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
           if (++st == stages) { st = 0; ph ^= 1u; }
         }
       }
-    } else if (warp == 1) {
-      if (lane == 0) {
-        const uint32_t idesc = tc::make_idesc_bf16(128, p.N, true, true);
-        const uint64_t layA = tc::layout_for_row_bytes(pitchA), layB = tc::layout_for_row_bytes(pitchB);
-        int st = 0;
-        uint32_t ph = 0;
-        for (int it = 0; it < ntiles; ++it) {
-          tc::mbar_wait(&full[st], ph);
-          tc::tc_fence_after();
-          const uint32_t b_addr = tc::smem_u32(smem + (size_t)st * stage_bytes);
-          const uint32_t a_addr = b_addr + p.nb * tileB;
-          for (int mt = 0; mt < mtiles; ++mt) {
-            for (int j = 0; j < p.kv / 16; ++j) {
-              const uint64_t ad = tc::make_smem_desc(a_addr + mt * p.spm * tileA + j * 16 * pitchA, tileA,
-                                                     8 * pitchA, layA);
-              const uint64_t bd = tc::make_smem_desc(b_addr + j * 16 * pitchB, tileB, 8 * pitchB, layB);
-              tc::umma_bf16(tmem_acc + mt * p.N, ad, bd, idesc, (it > 0 || j > 0) ? 1u : 0u);
-            }
-          }
-          tc::umma_commit(&empty[st]);
-          if (++st == stages) { st = 0; ph ^= 1u; }
+    }
+    if (warp >= 1 && warp <= nissue && lane == 0) {
+      const uint32_t idesc = tc::make_idesc_bf16(128, p.N, true, true);
+      const uint64_t layA = tc::layout_for_row_bytes(pitchA), layB = tc::layout_for_row_bytes(pitchB);
+      const uint64_t a_tmpl = tc::make_smem_desc(0, tileA, 8 * pitchA, layA);
+      const uint64_t b_tmpl = tc::make_smem_desc(0, tileB, 8 * pitchB, layB);
+      const int ksteps = p.kv / 16;
+      const uint32_t a_kstep = (16 * pitchA) >> 4, b_kstep = (16 * pitchB) >> 4;
+      int st = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < ntiles; ++it) {
+        tc::mbar_wait(&full[st], ph);
+        tc::tc_fence_after();
+        const uint32_t b_addr = tc::smem_u32(smem + (size_t)st * stage_bytes);
+        const uint64_t bd0 = b_tmpl + (b_addr >> 4);
+        for (int mt = warp - 1; mt < mtiles; mt += nissue) {
+          const uint64_t ad0 = a_tmpl + ((b_addr + p.nb * tileB + mt * p.spm * tileA) >> 4);
+          const uint32_t acc = tmem_acc + mt * p.N;
+          for (int j = 0; j < ksteps; ++j)
+            tc::umma_bf16(acc, ad0 + j * a_kstep, bd0 + j * b_kstep, idesc, (it > 0 || j > 0) ? 1u : 0u);
         }
-        tc::umma_commit(acc_full);
+        tc::umma_commit(&empty[st]);
+        if (++st == stages) { st = 0; ph ^= 1u; }
       }
-    } else {
+      tc::umma_commit(acc_full);
+    }
+    if (warp >= 2) {
       const int q = warp & 3;
       const int row = q * 32 + lane;
       tc::mbar_wait(acc_full, 0);
