@@ -24,6 +24,11 @@ class ConvDesc(C.Structure):
         "x_ld", "y_ld", "r_ld", "dtype", "flags")]
 
 
+class PackEntry(C.Structure):
+    _fields_ = [("w", C.c_uint64), ("packed", C.c_uint64), ("tc_offset", C.c_uint64),
+                ("taps", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32), ("kind", C.c_int32)]
+
+
 class NormDesc(C.Structure):
     _fields_ = [("n", C.c_int32), ("c", C.c_int32), ("spatial", C.c_int64),
                 ("x_ld", C.c_int32), ("y_ld", C.c_int32), ("r_ld", C.c_int32),
@@ -48,6 +53,8 @@ SIGNATURES = {
     "b200seg_check_device": (C.c_int, [C.c_int]),
     "b200seg_packed_weight_bytes": (C.c_size_t, [_CD, C.c_int]),
     "b200seg_pack_weight": (C.c_int, [_CD, C.c_int, _P, _P, _P]),
+    "b200seg_packed_weight_tc_offset": (C.c_size_t, [_CD, C.c_int]),
+    "b200seg_pack_weights_batched": (C.c_int, [_P, C.c_int32, _P]),
     "b200seg_conv_fprop": (C.c_int, [_CD, _P, _P, _P, _P, _P, _P]),
     "b200seg_conv_dgrad": (C.c_int, [_CD, _P, _P, _P, _P, _P]),
     "b200seg_conv_wgrad_workspace_bytes": (C.c_size_t, [_CD]),

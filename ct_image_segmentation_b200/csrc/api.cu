@@ -112,6 +112,16 @@ int b200seg_pack_weight(const b200seg_conv_desc* d, int kind, const float* w_tor
                             as_stream(stream));
 }
 
+extern "C" size_t b200seg_packed_weight_tc_offset(const b200seg_conv_desc* d, int kind) {
+  (void)kind;
+  return d ? generic_weight_bytes(d) : 0;
+}
+
+extern "C" int b200seg_pack_weights_batched(const b200seg_pack_entry* table, int32_t n_entries, void* stream) {
+  B200SEG_CHECK_ARG(table && n_entries > 0 && n_entries < 65536, "pack_weights_batched: bad argument");
+  return tc_pack_weights_batched(table, n_entries, as_stream(stream));
+}
+
 // tcgen05 dispatch: sliding-window kernel where it applies, else the streaming kernel
 static int tc_dispatch(const b200seg_conv_desc* d, int op, const void* src, const void* w_packed,
                        const float* bias, const void* residual, void* dst, void* stream) {

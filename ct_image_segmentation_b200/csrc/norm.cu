@@ -254,8 +254,22 @@ instnorm_prelu_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ d
                                 const float* __restrict__ mean, const float* __restrict__ rstd,
                                 const float* __restrict__ alpha, const float* __restrict__ sums,
                                 T* __restrict__ dx, int64_t spatial, int c, int x_ld, int dy_ld,
-                                int dx_ld, int L, int VB, int64_t vox_per_block) {
+                                int dx_ld, int L, int VB, int64_t vox_per_block, int nc_total,
+                                float* __restrict__ dalpha) {
   const int t = threadIdx.x, vi = t / L, l = t % L;
+  if (blockIdx.x == 0 && blockIdx.y == 0) {
+    // d loss / d alpha = sum over (n, c) of the per-instance terms: one block, fixed order
+    __shared__ double red[256];
+    double s = 0.0;
+    for (int i = t; i < nc_total; i += 256) s += (double)sums[i * 3 + 2];
+    red[t] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+      if (t < o) red[t] += red[t + o];
+      __syncthreads();
+    }
+    if (t == 0) dalpha[0] = (float)red[0];
+  }
   if (vi >= VB) return;
   const int n = blockIdx.y;
   const int64_t v_begin = (int64_t)blockIdx.x * vox_per_block;
@@ -390,14 +404,12 @@ int launch_instnorm_prelu_bwd(const b200seg_norm_desc& d, const void* x, const f
   instnorm_bwd_final_kernel<<<(nc * 32 + 255) / 256, 256, 0, st>>>(partial, g.nblk, d.c, nc,
                                                                    d.spatial, sums);
   B200SEG_CHECK_LAUNCH("instnorm_bwd_final");
-  dalpha_final_kernel<<<1, 256, 0, st>>>(sums, nc, dalpha);
-  B200SEG_CHECK_LAUNCH("dalpha_final");
   int64_t per2 = cdiv64(d.spatial, g.nblk_apply);
   dim3 grid2(g.nblk_apply, d.n);
   DISPATCH_TV(d.dtype, V,
               (instnorm_prelu_bwd_apply_kernel<T, VV><<<grid2, 256, 0, st>>>(
                   (const T*)x, (const T*)dy, mean, rstd, alpha, sums, (T*)dx, d.spatial, d.c,
-                  d.x_ld, d.y_ld, d.r_ld, g.L, g.VB, per2)));
+                  d.x_ld, d.y_ld, d.r_ld, g.L, g.VB, per2, nc, dalpha)));
   B200SEG_CHECK_LAUNCH("instnorm_prelu_bwd_apply");
   return B200SEG_OK;
 }

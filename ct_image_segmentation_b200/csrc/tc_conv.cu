@@ -390,6 +390,62 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, bf16* __restr
   out[idx] = __float2bfloat16_rn(v);
 }
 
+// ---- all layers in one launch: table of b200seg_pack_entry in device memory, blockIdx.y = entry ----
+__global__ void pack_weights_batched_kernel(const b200seg_pack_entry* __restrict__ table) {
+  const b200seg_pack_entry e = table[blockIdx.y];
+  const int taps = e.taps, cin = e.cin, cout = e.cout, kind = e.kind;
+  const bool src_is_cin = (kind == B200SEG_W_CONV_FPROP || kind == B200SEG_W_CONVTR_FPROP);
+  const int src_c = src_is_cin ? cin : cout, dst_c = src_is_cin ? cout : cin;
+  const int src_pad = (src_c + 15) / 16 * 16, dst_pad = (dst_c + 15) / 16 * 16;
+  const int KC = src_pad % 64 == 0 ? 64 : (src_pad % 32 == 0 ? 32 : 16);
+  const int kblocks = src_pad / KC;
+  const int64_t total = (int64_t)taps * src_pad * dst_pad, gen_total = (int64_t)taps * src_c * dst_c;
+  const float* w = reinterpret_cast<const float*>(e.w);
+  bf16* gen = reinterpret_cast<bf16*>(e.packed);
+  bf16* out = reinterpret_cast<bf16*>(e.packed + e.tc_offset);
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    if (idx < gen_total) {
+      int t = (int)(idx % dst_c);
+      int64_t r = idx / dst_c;
+      int sc = (int)(r % src_c), tap = (int)(r / src_c);
+      int64_t wi;
+      switch (kind) {
+        case B200SEG_W_CONV_FPROP:   wi = ((int64_t)t * cin + sc) * taps + tap; break;
+        case B200SEG_W_CONV_DGRAD:   wi = ((int64_t)sc * cin + t) * taps + tap; break;
+        case B200SEG_W_CONVTR_FPROP: wi = ((int64_t)sc * cout + t) * taps + tap; break;
+        default:                     wi = ((int64_t)t * cout + sc) * taps + tap; break;
+      }
+      gen[idx] = __float2bfloat16_rn(w[wi]);
+    }
+    int kc = (int)(idx % KC);
+    int64_t r = idx / KC;
+    int t = (int)(r % dst_pad); r /= dst_pad;
+    int kb = (int)(r % kblocks);
+    int tap = (int)(r / kblocks);
+    int sc = kb * KC + kc;
+    float v = 0.f;
+    if (sc < src_c && t < dst_c) {
+      int64_t wi;
+      switch (kind) {
+        case B200SEG_W_CONV_FPROP:   wi = ((int64_t)t * cin + sc) * taps + tap; break;
+        case B200SEG_W_CONV_DGRAD:   wi = ((int64_t)sc * cin + t) * taps + tap; break;
+        case B200SEG_W_CONVTR_FPROP: wi = ((int64_t)sc * cout + t) * taps + tap; break;
+        default:                     wi = ((int64_t)t * cout + sc) * taps + tap; break;
+      }
+      v = w[wi];
+    }
+    out[idx] = __float2bfloat16_rn(v);
+  }
+}
+
+int tc_pack_weights_batched(const b200seg_pack_entry* table_dev, int n_entries, cudaStream_t st) {
+  dim3 grid(64, (unsigned)n_entries);
+  pack_weights_batched_kernel<<<grid, 256, 0, st>>>(table_dev);
+  B200SEG_CHECK_LAUNCH("pack_weights_batched");
+  return B200SEG_OK;
+}
+
 int tc_pack_weight(const b200seg_conv_desc* d, int kind, const float* w, void* out, void* gen, cudaStream_t st) {
   bool src_is_cin = (kind == B200SEG_W_CONV_FPROP || kind == B200SEG_W_CONVTR_FPROP);
   int src_c = src_is_cin ? d->cin : d->cout, dst_c = src_is_cin ? d->cout : d->cin;

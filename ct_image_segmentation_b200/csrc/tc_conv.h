@@ -25,6 +25,7 @@ int tc_slide_wgrad_run(const b200seg_conv_desc* d, const void* x, const void* dy
 size_t tc_packed_weight_bytes(const b200seg_conv_desc* d);
 // packs the tcgen05 layout into `out` and (if gen != NULL) the generic bf16 layout into `gen`, one launch
 int tc_pack_weight(const b200seg_conv_desc* d, int kind, const float* w, void* out, void* gen, cudaStream_t st);
+int tc_pack_weights_batched(const b200seg_pack_entry* table_dev, int n_entries, cudaStream_t st);
 size_t tc_wgrad_extra_workspace(const b200seg_conv_desc* d);
 // weight gradient on tcgen05: x / dy in the layer's own terms, gw in PyTorch layout, G32 = fp32 scratch
 bool tc_wgrad_supported(const b200seg_conv_desc* d, bool transposed_layer, const void* x, const void* dy);

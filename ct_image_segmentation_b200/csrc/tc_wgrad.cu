@@ -194,21 +194,33 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
   if (warp == 1) tmem_dealloc_dyn(tmem_acc, 512);
 }
 
-// gw[b][a][tap] = sum_split G[split][tap][a][b] for the real channels (fixed order: deterministic)
-__global__ void tc_wgrad_unpack_kernel(const float* __restrict__ G, float* __restrict__ gw, int taps, int a_c,
-                                       int b_c, int a_pad, int b_pad, int splits) {
-  int64_t total = (int64_t)taps * a_c * b_c;
-  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  int b = (int)(idx % b_c);
-  int64_t r = idx / b_c;
-  int a = (int)(r % a_c);
-  int tap = (int)(r / a_c);
+// gw[b][a][tap] = sum_split G[split][tap][a][b] for the real channels.  One block per (tap, a) row:
+// threads = (split lane, b); coalesced reads along b, fixed summation order (deterministic).
+__global__ void __launch_bounds__(256)
+tc_wgrad_unpack_kernel(const float* __restrict__ G, float* __restrict__ gw, int taps, int a_c, int b_c, int a_pad,
+                       int b_pad, int splits) {
+  __shared__ float red[256];
+  const int tap = blockIdx.x / a_c, a = blockIdx.x % a_c;
+  int bw = 16;
+  while (bw < b_c && bw < 256) bw <<= 1;  // threads along b (power of two)
+  const int sy_n = 256 / bw;              // split lanes
+  const int bx = threadIdx.x % bw, sy = threadIdx.x / bw;
   const int64_t g_elems = (int64_t)taps * a_pad * b_pad;
-  const float* gp = G + ((int64_t)tap * a_pad + a) * b_pad + b;
-  float s = 0.f;
-  for (int i = 0; i < splits; ++i) s += gp[(int64_t)i * g_elems];
-  gw[((int64_t)b * a_c + a) * taps + tap] = s;
+  const float* row = G + ((int64_t)tap * a_pad + a) * b_pad;
+  for (int b0 = 0; b0 < b_c; b0 += bw) {
+    const int b = b0 + bx;
+    float s = 0.f;
+    if (b < b_c)
+      for (int i = sy; i < splits; i += sy_n) s += row[(int64_t)i * g_elems + b];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = sy_n / 2; o >= 1; o >>= 1) {
+      if (sy < o) red[threadIdx.x] += red[threadIdx.x + o * bw];
+      __syncthreads();
+    }
+    if (sy == 0 && b < b_c) gw[((int64_t)b * a_c + a) * taps + tap] = red[bx];
+    __syncthreads();
+  }
 }
 
 namespace {
@@ -403,8 +415,9 @@ int tc_wgrad_run(const b200seg_conv_desc* d, bool transposed_layer, const void* 
   B200SEG_CHECK_LAUNCH("tc_wgrad");
   count_tc_launch();
   const int64_t total = (int64_t)taps * g.a_c * g.b_c;
-  tc_wgrad_unpack_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(G32, gw, taps, g.a_c, g.b_c, a_pad, b_pad,
-                                                                       (int)splits);
+  (void)total;
+  tc_wgrad_unpack_kernel<<<(unsigned)(taps * g.a_c), 256, 0, st>>>(G32, gw, taps, g.a_c, g.b_c, a_pad, b_pad,
+                                                                   (int)splits);
   B200SEG_CHECK_LAUNCH("tc_wgrad_unpack");
   return B200SEG_OK;
 }

@@ -132,6 +132,25 @@ def pack_weight(geom: ConvGeom, kind: int, w: torch.Tensor, dtype: torch.dtype) 
     return out
 
 
+def packed_weight_layout(geom: ConvGeom, kind: int, dtype: torch.dtype):
+    """(bytes of the packed buffer, byte offset of the tcgen05 layout inside it)."""
+    lib = _lib.load()
+    d = geom.desc(1, (1, 1, 1), (1, 1, 1), geom.cin, geom.cout, 0, dtype)
+    return lib.b200seg_packed_weight_bytes(C.byref(d), kind), lib.b200seg_packed_weight_tc_offset(C.byref(d), kind)
+
+
+def make_pack_table(entries, device) -> torch.Tensor:
+    """Device-resident array of b200seg_pack_entry for pack_weights_batched."""
+    arr = (_lib.PackEntry * len(entries))(*[_lib.PackEntry(*e) for e in entries])
+    host = torch.frombuffer(bytearray(bytes(arr)), dtype=torch.uint8)
+    return host.to(device)
+
+
+def pack_weights_batched(table: torch.Tensor, n: int) -> None:
+    lib = _lib.load()
+    _lib.check(lib.b200seg_pack_weights_batched(table.data_ptr(), n, _stream()), "b200seg_pack_weights_batched")
+
+
 _PADDED = set()  # (storage pointer, C) of live zero-padded buffers handed out by alloc_activation
 
 

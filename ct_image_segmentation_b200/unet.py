@@ -203,8 +203,12 @@ class UNet(nn.Module):
         """Forget the packed weights so that the next forward re-packs every layer (needed right
         before CUDA-graph capture: the pack kernels must be recorded into the graph)."""
         self._packed.clear()
+        if getattr(self, "_batched", None) is not None:
+            self._batched["state"] = None
 
     def _pack(self, param: torch.Tensor, geom: ConvGeom, kind: int) -> torch.Tensor:
+        if self.compute_dtype == torch.bfloat16:
+            return self._batched["bufs"][(id(param), kind)]  # refreshed by _repack_all()
         key = (id(param), kind, self.compute_dtype)
         hit = self._packed.get(key)
         ver = (param._version, param.data_ptr())
@@ -212,6 +216,42 @@ class UNet(nn.Module):
             hit = (ver, ops.pack_weight(geom, kind, param, self.compute_dtype))
             self._packed[key] = hit
         return hit[1]
+
+    def _conv_params(self):
+        """(conv module, geometry) of every convolution in the tree."""
+        out = []
+        for m in self.modules():
+            if isinstance(m, Convolution):
+                out.append((m.conv, m.geom))
+            elif isinstance(m, ResidualUnit) and m.res_geom is not None:
+                out.append((m.residual, m.res_geom))
+        return out
+
+    def _repack_all(self) -> None:
+        """bf16 mode: repack EVERY weight (fprop + dgrad layouts) with one kernel launch whenever a
+        parameter changed (optimiser step) -- the launch is recorded into the CUDA graph."""
+        convs = self._conv_params()
+        state = tuple((c.weight._version, c.weight.data_ptr()) for c, _ in convs)
+        b = getattr(self, "_batched", None)
+        if b is not None and b["ptrs"] == tuple(s[1] for s in state):
+            if b["state"] == state:
+                return
+        else:  # (re)build the persistent buffers and the device table
+            bufs, entries = {}, []
+            for conv, g in convs:
+                for kind in ((_lib.W_CONVTR_FPROP, _lib.W_CONVTR_DGRAD) if g.transposed
+                             else (_lib.W_CONV_FPROP, _lib.W_CONV_DGRAD)):
+                    nbytes, tc_off = ops.packed_weight_layout(g, kind, self.compute_dtype)
+                    buf = torch.empty(nbytes, dtype=torch.uint8, device=conv.weight.device)
+                    bufs[(id(conv.weight), kind)] = buf
+                    k = g.kernel
+                    entries.append((conv.weight.data_ptr(), buf.data_ptr(), tc_off,
+                                    k ** self.dimensions, g.cin, g.cout, kind))
+            b = {"bufs": bufs, "table": ops.make_pack_table(entries, convs[0][0].weight.device),
+                 "n": len(entries), "ptrs": tuple(s[1] for s in state)}
+            self._batched = b
+        ops.pack_weights_batched(b["table"], b["n"])
+        b["state"] = state
 
     def _w_fprop(self, conv: nn.Module, geom: ConvGeom):
         kind = _lib.W_CONVTR_FPROP if geom.transposed else _lib.W_CONV_FPROP
@@ -226,6 +266,8 @@ class UNet(nn.Module):
         return ops.alloc_activation(like.shape[0], tuple(spatial), c, self.compute_dtype, like.device)
 
     def _run_forward(self, x_cl: torch.Tensor, saved: Dict, keep_all: bool = False) -> torch.Tensor:
+        if self.compute_dtype == torch.bfloat16 and x_cl.is_cuda:
+            self._repack_all()
         return self._fwd_level(self.model, x_cl, saved, None, keep_all)
 
     def _fwd_level(self, lvl: _Level, x, saved, dst, keep):

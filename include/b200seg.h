@@ -119,6 +119,20 @@ size_t b200seg_packed_weight_bytes(const b200seg_conv_desc* d, int kind);
 int b200seg_pack_weight(const b200seg_conv_desc* d, int kind, const float* w_torch,
                         void* w_packed, void* stream);
 
+/* All bf16 weights of a network in ONE launch.  `table` is an array of n_entries b200seg_pack_entry
+ * in DEVICE memory (built once; parameter and packed-buffer addresses are stable across steps):
+ * entry i repacks fp32 parameter `w` into `packed` exactly as b200seg_pack_weight(kind) would
+ * (packed must hold b200seg_packed_weight_bytes; tc_offset = offset of the tcgen05 layout in it,
+ * as returned by b200seg_packed_weight_tc_offset). */
+typedef struct b200seg_pack_entry {
+  uint64_t w;          /* const float*  (device) */
+  uint64_t packed;     /* void*         (device) */
+  uint64_t tc_offset;  /* bytes */
+  int32_t taps, cin, cout, kind;
+} b200seg_pack_entry;
+size_t b200seg_packed_weight_tc_offset(const b200seg_conv_desc* d, int kind);
+int b200seg_pack_weights_batched(const b200seg_pack_entry* table, int32_t n_entries, void* stream);
+
 /* ---- convolutions ---------------------------------------------------------
  * Replace torch.nn.Conv{2,3}d / ConvTranspose{2,3}d forward + autograd as called
  * by monai.networks.nets.UNet, which the reference instantiates at
