@@ -53,11 +53,16 @@ class GraphedTrainStep:
             self._capture(warmup)
 
     def _fwd_bwd(self):
+        from . import ops
+        ops.begin_step()
         loss = self.loss_fn(self.net(self.static_images), self.static_labels.unsqueeze(1))
         loss.backward()
         return loss
 
     def _capture(self, warmup: int):
+        from . import ops
+        # zero-padded 10-class buffers: allocated (and zeroed) once during warm-up, reused by the graph
+        ops.enable_persistent_padded_buffers(True)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm-up off the default stream, as graph capture requires

@@ -154,12 +154,39 @@ def pack_weights_batched(table: torch.Tensor, n: int) -> None:
 _PADDED = set()  # (storage pointer, C) of live zero-padded buffers handed out by alloc_activation
 
 
+# Persistent pool of zero-padded buffers (CUDA-graph mode): every kernel keeps the channel padding
+# zero, so a buffer zeroed ONCE can be handed out again every step instead of being memset
+# (134 MB per 10-class tensor at 128^3 x 2).  Only valid when a step's activations are dead before
+# the next step starts -- GraphedTrainStep switches it on; eager use keeps fresh torch.zeros.
+_PAD_POOL = None   # None = off; else {"seq": int, "bufs": {(key, seq): tensor}}
+
+
+def enable_persistent_padded_buffers(on: bool) -> None:
+    global _PAD_POOL
+    _PAD_POOL = {"seq": 0, "bufs": {}} if on else None
+
+
+def begin_step() -> None:
+    """Start of a forward+backward pass: the k-th padded allocation of a step reuses the k-th buffer."""
+    if _PAD_POOL is not None:
+        _PAD_POOL["seq"] = 0
+
+
 def alloc_activation(n: int, spatial, c: int, dtype: torch.dtype, device) -> torch.Tensor:
     """(N, *spatial, C) activation buffer.  For bf16 and C not a multiple of 16 (the 10-class
     layers) the buffer is zero-padded to the next multiple of 16 channels and marked, so the
     tcgen05 kernels can take it (B200SEG_CONV_PADDED_CHANNELS)."""
     if dtype == torch.bfloat16 and c % 16 != 0 and c >= 8:
         cp = (c + 15) // 16 * 16
+        if _PAD_POOL is not None:
+            key = ((n, *spatial, cp), str(device), _PAD_POOL["seq"])
+            _PAD_POOL["seq"] += 1
+            full = _PAD_POOL["bufs"].get(key)
+            if full is None:
+                full = torch.zeros((n, *spatial, cp), dtype=dtype, device=device)
+                _PAD_POOL["bufs"][key] = full
+                _PADDED.add((full.untyped_storage().data_ptr(), c))
+            return full[..., :c]
         full = torch.zeros((n, *spatial, cp), dtype=dtype, device=device)
         key = (full.untyped_storage().data_ptr(), c)
         _PADDED.add(key)
