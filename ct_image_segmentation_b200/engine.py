@@ -40,6 +40,7 @@ class GraphedTrainStep:
         self.loss: Optional[torch.Tensor] = None
         self.use_graph = use_graph
         self.launches_per_step = self.tc_launches_per_step = None
+        self._pad_pool = {}
         # host inputs: double-buffered staging filled on a copy stream, so the H2D transfer of step
         # k+1 overlaps the compute of step k (the static inputs are live for the whole step: the
         # first-layer wgrad reads them at the very end of the backward)
@@ -54,15 +55,18 @@ class GraphedTrainStep:
 
     def _fwd_bwd(self):
         from . import ops
-        ops.begin_step()
+        if self.use_graph:
+            # zero-padded 10-class buffers are allocated (and zeroed) once and reused by every replay:
+            # a replayed step's activations are dead before the next replay starts
+            with ops.padded_buffer_pool(self._pad_pool):
+                loss = self.loss_fn(self.net(self.static_images), self.static_labels.unsqueeze(1))
+                loss.backward()
+            return loss
         loss = self.loss_fn(self.net(self.static_images), self.static_labels.unsqueeze(1))
         loss.backward()
         return loss
 
     def _capture(self, warmup: int):
-        from . import ops
-        # zero-padded 10-class buffers: allocated (and zeroed) once during warm-up, reused by the graph
-        ops.enable_persistent_padded_buffers(True)
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm-up off the default stream, as graph capture requires

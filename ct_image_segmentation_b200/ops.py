@@ -161,15 +161,25 @@ _PADDED = set()  # (storage pointer, C) of live zero-padded buffers handed out b
 _PAD_POOL = None   # None = off; else {"seq": int, "bufs": {(key, seq): tensor}}
 
 
-def enable_persistent_padded_buffers(on: bool) -> None:
-    global _PAD_POOL
-    _PAD_POOL = {"seq": 0, "bufs": {}} if on else None
+class padded_buffer_pool:
+    """Context manager: inside it, the k-th padded allocation reuses the k-th buffer of ``pool``
+    (a dict owned by the caller, e.g. one per GraphedTrainStep)."""
 
+    def __init__(self, pool: dict):
+        self.pool = pool
 
-def begin_step() -> None:
-    """Start of a forward+backward pass: the k-th padded allocation of a step reuses the k-th buffer."""
-    if _PAD_POOL is not None:
-        _PAD_POOL["seq"] = 0
+    def __enter__(self):
+        global _PAD_POOL
+        self.prev = _PAD_POOL
+        self.pool["seq"] = 0
+        self.pool.setdefault("bufs", {})
+        _PAD_POOL = self.pool
+        return self
+
+    def __exit__(self, *exc):
+        global _PAD_POOL
+        _PAD_POOL = self.prev
+        return False
 
 
 def alloc_activation(n: int, spatial, c: int, dtype: torch.dtype, device) -> torch.Tensor:
