@@ -124,10 +124,10 @@ extern "C" int b200seg_pack_weights_batched(const b200seg_pack_entry* table, int
 
 // tcgen05 dispatch: sliding-window kernel where it applies, else the streaming kernel
 static int tc_dispatch(const b200seg_conv_desc* d, int op, const void* src, const void* w_packed,
-                       const float* bias, const void* residual, void* dst, void* stream) {
+                       const float* bias, const void* residual, void* dst, void* stream, float* stats = nullptr) {
   if (!(d->flags & B200SEG_CONV_NO_SLIDE) && tc_slide_conv_supported(d, op))
-    return tc_slide_conv_run(d, op, src, tc_weights(d, w_packed), bias, residual, dst, as_stream(stream));
-  return tc_conv_run(d, op, src, tc_weights(d, w_packed), bias, residual, dst, as_stream(stream));
+    return tc_slide_conv_run(d, op, src, tc_weights(d, w_packed), bias, residual, dst, stats, as_stream(stream));
+  return tc_conv_run(d, op, src, tc_weights(d, w_packed), bias, residual, dst, stats, as_stream(stream));
 }
 
 // ---- conv ---------------------------------------------------------------------------------------
@@ -146,6 +146,47 @@ int b200seg_conv_fprop(const b200seg_conv_desc* d, const void* x, const void* w_
   g.src_ld = d->x_ld; g.dst_ld = d->y_ld; g.res_ld = d->r_ld;
   g.transposed = 0;
   return launch_gather(g, d->dtype, x, w_packed, bias, residual, y, as_stream(stream));
+}
+
+// fprop + per-(n, channel) sum / sum of squares of y for the InstanceNorm that follows.  Returns
+// B200SEG_STATS_NOT_FUSED (1) when the convolution ran on a kernel without the fused statistics.
+static int fprop_stats_common(const b200seg_conv_desc* d, bool transposed_layer, const void* x, const void* w_packed,
+                              const float* bias, void* y, float* sums, void* stream) {
+  int op = transposed_layer ? TC_CONVTR_FPROP : TC_CONV_FPROP;
+  if (sums && tc_conv_supported(d, op, x, y, nullptr)) {
+    cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)d->n * d->cout * 2 * sizeof(float), as_stream(stream));
+    if (e != cudaSuccess) {
+      set_error("conv_fprop_stats: memset failed: %s", cudaGetErrorString(e));
+      return B200SEG_ERR_CUDA;
+    }
+    return tc_dispatch(d, op, x, w_packed, bias, nullptr, y, stream, sums);
+  }
+  int rc = transposed_layer ? b200seg_convtr_fprop(d, x, w_packed, bias, nullptr, y, stream)
+                            : b200seg_conv_fprop(d, x, w_packed, bias, nullptr, y, stream);
+  return rc ? rc : B200SEG_STATS_NOT_FUSED;
+}
+
+int b200seg_conv_fprop_stats(const b200seg_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                             void* y, float* sums, void* stream) {
+  int rc = check_conv_desc(d, false);
+  if (rc) return rc;
+  B200SEG_CHECK_ARG(x && w_packed && y, "conv_fprop_stats: NULL pointer");
+  return fprop_stats_common(d, false, x, w_packed, bias, y, sums, stream);
+}
+
+int b200seg_convtr_fprop_stats(const b200seg_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                               void* y, float* sums, void* stream) {
+  int rc = check_conv_desc(d, true);
+  if (rc) return rc;
+  B200SEG_CHECK_ARG(x && w_packed && y, "convtr_fprop_stats: NULL pointer");
+  return fprop_stats_common(d, true, x, w_packed, bias, y, sums, stream);
+}
+
+int b200seg_instnorm_stats_from_sums(const b200seg_norm_desc* d, const float* sums, float* mean, float* rstd,
+                                     void* stream) {
+  B200SEG_CHECK_ARG(d && sums && mean && rstd && d->n > 0 && d->c > 0 && d->spatial > 0,
+                    "instnorm_stats_from_sums: bad argument");
+  return launch_instnorm_stats_from_sums(*d, sums, mean, rstd, as_stream(stream));
 }
 
 int b200seg_conv_dgrad(const b200seg_conv_desc* d, const void* dy, const void* w_packed,

@@ -414,6 +414,36 @@ int launch_instnorm_prelu_bwd(const b200seg_norm_desc& d, const void* x, const f
   return B200SEG_OK;
 }
 
+// mean / rstd from per-(n, c) sum and sum of squares accumulated by a convolution epilogue
+// mean / rstd are written with `c_out` (>= c) entries per sample: entries >= c describe zero
+// padding channels (mean 0, rstd 1/sqrt(eps)), as the statistics kernel would produce for them
+__global__ void instnorm_stats_from_sums_kernel(const float* __restrict__ sums, int n, int c, int c_out,
+                                                int64_t spatial, float eps, float* __restrict__ mean,
+                                                float* __restrict__ rstd) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * c_out) return;
+  const int nn = i / c_out, ch = i % c_out;
+  double m = 0.0, var = 0.0;
+  if (ch < c) {
+    const float* sp = sums + ((int64_t)nn * c + ch) * 2;
+    m = (double)sp[0] / (double)spatial;
+    var = (double)sp[1] / (double)spatial - m * m;
+    if (var < 0.0) var = 0.0;
+  }
+  mean[i] = (float)m;
+  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+int launch_instnorm_stats_from_sums(const b200seg_norm_desc& d, const float* sums, float* mean, float* rstd,
+                                    cudaStream_t st) {
+  const int c_out = d.x_ld > d.c ? d.x_ld : d.c;  // x_ld: entries per sample in mean / rstd
+  const int total = d.n * c_out;
+  instnorm_stats_from_sums_kernel<<<(total + 127) / 128, 128, 0, st>>>(sums, d.n, d.c, c_out, d.spatial, d.eps,
+                                                                       mean, rstd);
+  B200SEG_CHECK_LAUNCH("instnorm_stats_from_sums");
+  return B200SEG_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // column sums (bias gradient):  out[c] = sum_v x[v*ld + c]   -- the statistics kernel with the
 // batch folded into the voxel axis; per-block partials, fixed-order finalisation in double

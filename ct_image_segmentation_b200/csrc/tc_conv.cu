@@ -51,6 +51,7 @@ struct alignas(64) TcConvParams {
   const float* bias;
   const bf16* res;
   bf16* dst;
+  float* stats;  // optional [n][cout][2]: += sum, sum of squares of the outputs (for InstanceNorm)
 };
 
 template <int BN, int KC>
@@ -206,6 +207,19 @@ tc_conv_kernel(const __grid_constant__ TcConvParams p) {
         }
         op[0] = o0;
         op[1] = o1;
+      }
+      if (p.stats) {  // warp-uniform: per-channel sum / sum of squares over the tile's valid rows
+        const int c0 = n0 + ch * 16;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float x = valid ? __uint_as_float(v[i]) : 0.f;
+          if (valid && p.bias && c0 + i < p.cout) x += p.bias[c0 + i];
+          const float a = warp_sum(x), b = warp_sum(x * x);
+          if (lane == 0 && c0 + i < p.cout) {
+            atomicAdd(p.stats + ((int64_t)n * p.cout + c0 + i) * 2, a);
+            atomicAdd(p.stats + ((int64_t)n * p.cout + c0 + i) * 2 + 1, b);
+          }
+        }
       }
     }
   }
@@ -478,7 +492,7 @@ bool tc_conv_supported(const b200seg_conv_desc* d, int op, const void* src, cons
 }
 
 int tc_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,
-                const void* residual, void* dst, cudaStream_t st) {
+                const void* residual, void* dst, float* stats, cudaStream_t st) {
   TcGeom g;
   tc_geom(d, op, g);
   TcConvParams p;
@@ -490,7 +504,7 @@ int tc_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void*
   p.cout = g.dst_c; p.cout_pad = dst_pad;
   p.dst_ld = g.dst_ld; p.res_ld = d->r_ld;
   p.accumulate = (d->flags & B200SEG_CONV_ACCUMULATE) ? 1 : 0;
-  p.bias = bias; p.res = (const bf16*)residual; p.dst = (bf16*)dst;
+  p.bias = bias; p.res = (const bf16*)residual; p.dst = (bf16*)dst; p.stats = stats;
   p.dD = g.dD; p.dH = g.dH; p.dW = g.dW;
   const int sdim[3] = {g.sD, g.sH, g.sW}, ddim[3] = {g.dD, g.dH, g.dW};
 

@@ -40,6 +40,7 @@ struct alignas(64) TcSlideConvParams {
   const float* bias;
   const bf16* res;
   bf16* dst;
+  float* stats;  // optional [n][cout][2]: += sum, sum of squares of the outputs (for InstanceNorm)
 };
 
 template <int BN, int KC>
@@ -158,6 +159,9 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
     const int row = q * 32 + lane;
     const int oh = h0 + row / TWV, ow = w0 + row % TWV;
     const bool valid = oh < p.H && ow < p.W;
+    float ssum[BN], ssq[BN];  // per-thread partial statistics over this CTA's slabs (same sample n)
+#pragma unroll
+    for (int c = 0; c < BN; ++c) ssum[c] = ssq[c] = 0.f;
     for (int j = 0; j < nd; ++j) {
       const int buf = j & 1;
       tc::mbar_wait(&acc_full[buf], ((uint32_t)j >> 1) & 1u);
@@ -203,6 +207,13 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
               f[8 + 2 * i] += b.x; f[8 + 2 * i + 1] += b.y;
             }
           }
+          if (p.stats) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              ssum[ch * 16 + i] += f[i];
+              ssq[ch * 16 + i] = fmaf(f[i], f[i], ssq[ch * 16 + i]);
+            }
+          }
           uint4 o0, o1;
           __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
           __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
@@ -218,6 +229,17 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+    }
+    if (p.stats) {
+      // one warp-level tree per channel, then one red.global.add per (warp, channel, moment)
+#pragma unroll
+      for (int c = 0; c < BN; ++c) {
+        const float a = warp_sum(ssum[c]), b = warp_sum(ssq[c]);
+        if (lane == 0 && c < p.cout) {
+          atomicAdd(p.stats + ((int64_t)n * p.cout + c) * 2, a);
+          atomicAdd(p.stats + ((int64_t)n * p.cout + c) * 2 + 1, b);
+        }
+      }
     }
   }
   tc::tc_fence_before();
@@ -272,7 +294,7 @@ bool tc_slide_conv_supported(const b200seg_conv_desc* d, int op) {
 }
 
 int tc_slide_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,
-                      const void* residual, void* dst, cudaStream_t st) {
+                      const void* residual, void* dst, float* stats, cudaStream_t st) {
   SlideGeom g;
   slide_geom(d, op, g);
   TcSlideConvParams p;
@@ -291,7 +313,7 @@ int tc_slide_conv_run(const b200seg_conv_desc* d, int op, const void* src, const
   p.cout = g.dst_c; p.dst_ld = g.dst_ld; p.res_ld = d->r_ld;
   p.accumulate = (d->flags & B200SEG_CONV_ACCUMULATE) ? 1 : 0;
   p.flip = (op == TC_CONV_DGRAD) ? 1 : 0;
-  p.bias = bias; p.res = (const bf16*)residual; p.dst = (bf16*)dst;
+  p.bias = bias; p.res = (const bf16*)residual; p.dst = (bf16*)dst; p.stats = stats;
   {
     uint64_t dims[5] = {(uint64_t)KC, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.D, (uint64_t)g.n};
     uint64_t strides[4] = {(uint64_t)g.src_ld * 2, (uint64_t)g.W * g.src_ld * 2, (uint64_t)g.H * g.W * g.src_ld * 2,

@@ -270,6 +270,36 @@ def conv_fprop(geom, x, wp, bias, y, residual=None, flags=0):
     return _conv_call(geom, x, wp, bias, residual, y, False, flags)
 
 
+def conv_fprop_stats(geom: ConvGeom, x, wp, bias, y, eps: float = 1e-5, flags=0):
+    """y = conv(x) + bias, and (mean, rstd) of y per (n, channel) for the InstanceNorm that follows,
+    accumulated in the convolution's epilogue.  Falls back to a separate statistics pass when the
+    layer runs on a kernel without the fusion."""
+    lib = _lib.load()
+    n, sd_, sh_, sw_, sc, s_ld = cl_info(x)
+    n2, dd_, dh_, dw_, dc, d_ld = cl_info(y)
+    if n != n2 or x.dtype != y.dtype or (sc, dc) != (geom.cin, geom.cout):
+        raise ValueError("conv_fprop_stats: shape/dtype mismatch")
+    if geom.out_spatial(sd_, sh_, sw_) != (dd_, dh_, dw_):
+        raise ValueError("conv_fprop_stats: spatial extents inconsistent with the geometry")
+    if _pad_safe(x) and _pad_safe(y):
+        flags |= _lib.CONV_PADDED_CHANNELS
+    d = geom.desc(n, (sd_, sh_, sw_), (dd_, dh_, dw_), s_ld, d_ld, 0, x.dtype, flags)
+    sums = torch.empty(n * dc * 2, dtype=torch.float32, device=x.device)
+    name = "b200seg_convtr_fprop_stats" if geom.transposed else "b200seg_conv_fprop_stats"
+    rc = getattr(lib, name)(C.byref(d), x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(), sums.data_ptr(),
+                            _stream())
+    if rc == 1:  # B200SEG_STATS_NOT_FUSED
+        return instnorm_stats(y, eps)
+    _lib.check(rc, name)
+    c_out = (dc + 15) // 16 * 16 if _expand_pad(y) is not None else dc
+    mean = torch.empty(n * c_out, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(n * c_out, dtype=torch.float32, device=x.device)
+    nd = NormDesc(n, dc, dd_ * dh_ * dw_, c_out, 0, 0, dtype_code(x.dtype), eps)
+    _lib.check(lib.b200seg_instnorm_stats_from_sums(C.byref(nd), sums.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                                    _stream()), "b200seg_instnorm_stats_from_sums")
+    return mean, rstd
+
+
 def conv_dgrad(geom, dy, wp, dx, residual=None, accumulate=False, flags=0):
     """dx = conv^T(dy) [+ residual] [+ dx]."""
     if accumulate:

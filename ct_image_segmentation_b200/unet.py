@@ -308,8 +308,8 @@ class UNet(nn.Module):
             saved[m] = {"x": x, "c": None, "out": y if (keep and residual is None) else None}
             return y
         c = self._new(x, sp, g.cout)
-        ops.conv_fprop(g, x, wp, bias, c)
-        mean, rstd = ops.instnorm_stats(c, m.norm.eps)
+        # InstanceNorm statistics come out of the convolution's epilogue where the kernel supports it
+        mean, rstd = ops.conv_fprop_stats(g, x, wp, bias, c, m.norm.eps)
         a = dst if dst is not None else self._new(x, sp, g.cout)
         ops.instnorm_prelu_fwd(c, mean, rstd, m.act.weight.detach(), a, residual, m.norm.eps)
         saved[m] = {"x": x, "c": c, "mean": mean, "rstd": rstd,

@@ -59,6 +59,11 @@ def conv_fprop(geom, x, wp, bias, y, residual=None, flags=0):
     return y
 
 
+def conv_fprop_stats(geom, x, wp, bias, y, eps=1e-5, flags=0):
+    conv_fprop(geom, x, wp, bias, y)
+    return instnorm_stats(y, eps)
+
+
 def conv_dgrad(geom, dy, wp, dx, residual=None, accumulate=False, flags=0):
     xin = torch.zeros(_nc(dx, geom.dims).shape, dtype=torch.float32, requires_grad=True)
     out = _conv(geom, xin, wp)
