@@ -56,9 +56,10 @@ SIGNATURES = {
     "b200seg_packed_weight_tc_offset": (C.c_size_t, [_CD, C.c_int]),
     "b200seg_pack_weights_batched": (C.c_int, [_P, C.c_int32, _P]),
     "b200seg_conv_fprop": (C.c_int, [_CD, _P, _P, _P, _P, _P, _P]),
-    "b200seg_conv_fprop_stats": (C.c_int, [_CD, _P, _P, _P, _P, _P, _P]),
-    "b200seg_convtr_fprop_stats": (C.c_int, [_CD, _P, _P, _P, _P, _P, _P]),
-    "b200seg_instnorm_stats_from_sums": (C.c_int, [_ND, _P, _P, _P, _P]),
+    "b200seg_conv_fprop_stats_workspace_bytes": (C.c_size_t, [_CD]),
+    "b200seg_convtr_fprop_stats_workspace_bytes": (C.c_size_t, [_CD]),
+    "b200seg_conv_fprop_stats": (C.c_int, [_CD, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_float, _P, C.c_size_t, _P]),
+    "b200seg_convtr_fprop_stats": (C.c_int, [_CD, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_float, _P, C.c_size_t, _P]),
     "b200seg_conv_dgrad": (C.c_int, [_CD, _P, _P, _P, _P, _P]),
     "b200seg_conv_wgrad_workspace_bytes": (C.c_size_t, [_CD]),
     "b200seg_conv_wgrad": (C.c_int, [_CD, _P, _P, _P, _P, _P, C.c_size_t, _P]),

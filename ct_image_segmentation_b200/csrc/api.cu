@@ -148,45 +148,67 @@ int b200seg_conv_fprop(const b200seg_conv_desc* d, const void* x, const void* w_
   return launch_gather(g, d->dtype, x, w_packed, bias, residual, y, as_stream(stream));
 }
 
-// fprop + per-(n, channel) sum / sum of squares of y for the InstanceNorm that follows.  Returns
-// B200SEG_STATS_NOT_FUSED (1) when the convolution ran on a kernel without the fused statistics.
+// fprop fused with the statistics of the InstanceNorm that follows: the conv epilogue writes per-CTA
+// partial sums into the workspace, a small kernel turns them into mean / rstd.  Returns
+// B200SEG_STATS_NOT_FUSED (1) when the convolution ran on a kernel without the fusion.
+static void stats_layout(const b200seg_conv_desc* d, int op, int* ncls, int64_t* tiles) {
+  if (!(d->flags & B200SEG_CONV_NO_SLIDE) && tc_slide_conv_supported(d, op)) {
+    *ncls = 1;
+    *tiles = tc_slide_conv_grid(d, op) / d->n;
+  } else {
+    tc_conv_grid(d, op, ncls, tiles);
+  }
+}
+
+static size_t fprop_stats_ws(const b200seg_conv_desc* d, bool transposed_layer) {
+  int ncls;
+  int64_t tiles;
+  stats_layout(d, transposed_layer ? TC_CONVTR_FPROP : TC_CONV_FPROP, &ncls, &tiles);
+  return (size_t)ncls * d->n * tiles * d->cout * 2 * sizeof(float) + 256;
+}
+
 static int fprop_stats_common(const b200seg_conv_desc* d, bool transposed_layer, const void* x, const void* w_packed,
-                              const float* bias, void* y, float* sums, void* stream) {
+                              const float* bias, void* y, float* mean, float* rstd, int stat_ld, float eps,
+                              void* ws, size_t ws_bytes, void* stream) {
   int op = transposed_layer ? TC_CONVTR_FPROP : TC_CONV_FPROP;
-  if (sums && tc_conv_supported(d, op, x, y, nullptr)) {
-    cudaError_t e = cudaMemsetAsync(sums, 0, (size_t)d->n * d->cout * 2 * sizeof(float), as_stream(stream));
-    if (e != cudaSuccess) {
-      set_error("conv_fprop_stats: memset failed: %s", cudaGetErrorString(e));
-      return B200SEG_ERR_CUDA;
+  if (mean && rstd && ws && tc_conv_supported(d, op, x, y, nullptr)) {
+    if (ws_bytes < fprop_stats_ws(d, transposed_layer)) {
+      set_error("conv_fprop_stats: workspace %zu < required %zu", ws_bytes, fprop_stats_ws(d, transposed_layer));
+      return B200SEG_ERR_WORKSPACE;
     }
-    return tc_dispatch(d, op, x, w_packed, bias, nullptr, y, stream, sums);
+    int rc = tc_dispatch(d, op, x, w_packed, bias, nullptr, y, stream, (float*)ws);
+    if (rc) return rc;
+    int ncls;
+    int64_t tiles;
+    stats_layout(d, op, &ncls, &tiles);
+    const int64_t spatial = (int64_t)d->out_d * d->out_h * d->out_w;
+    return launch_instnorm_stats_from_partials((const float*)ws, d->n, d->cout, stat_ld > d->cout ? stat_ld : d->cout,
+                                               ncls, tiles, spatial, eps, mean, rstd, as_stream(stream));
   }
   int rc = transposed_layer ? b200seg_convtr_fprop(d, x, w_packed, bias, nullptr, y, stream)
                             : b200seg_conv_fprop(d, x, w_packed, bias, nullptr, y, stream);
   return rc ? rc : B200SEG_STATS_NOT_FUSED;
 }
 
+size_t b200seg_conv_fprop_stats_workspace_bytes(const b200seg_conv_desc* d) { return d ? fprop_stats_ws(d, false) : 0; }
+size_t b200seg_convtr_fprop_stats_workspace_bytes(const b200seg_conv_desc* d) { return d ? fprop_stats_ws(d, true) : 0; }
+
 int b200seg_conv_fprop_stats(const b200seg_conv_desc* d, const void* x, const void* w_packed, const float* bias,
-                             void* y, float* sums, void* stream) {
+                             void* y, float* mean, float* rstd, int32_t stat_ld, float eps, void* workspace,
+                             size_t workspace_bytes, void* stream) {
   int rc = check_conv_desc(d, false);
   if (rc) return rc;
   B200SEG_CHECK_ARG(x && w_packed && y, "conv_fprop_stats: NULL pointer");
-  return fprop_stats_common(d, false, x, w_packed, bias, y, sums, stream);
+  return fprop_stats_common(d, false, x, w_packed, bias, y, mean, rstd, stat_ld, eps, workspace, workspace_bytes, stream);
 }
 
 int b200seg_convtr_fprop_stats(const b200seg_conv_desc* d, const void* x, const void* w_packed, const float* bias,
-                               void* y, float* sums, void* stream) {
+                               void* y, float* mean, float* rstd, int32_t stat_ld, float eps, void* workspace,
+                               size_t workspace_bytes, void* stream) {
   int rc = check_conv_desc(d, true);
   if (rc) return rc;
   B200SEG_CHECK_ARG(x && w_packed && y, "convtr_fprop_stats: NULL pointer");
-  return fprop_stats_common(d, true, x, w_packed, bias, y, sums, stream);
-}
-
-int b200seg_instnorm_stats_from_sums(const b200seg_norm_desc* d, const float* sums, float* mean, float* rstd,
-                                     void* stream) {
-  B200SEG_CHECK_ARG(d && sums && mean && rstd && d->n > 0 && d->c > 0 && d->spatial > 0,
-                    "instnorm_stats_from_sums: bad argument");
-  return launch_instnorm_stats_from_sums(*d, sums, mean, rstd, as_stream(stream));
+  return fprop_stats_common(d, true, x, w_packed, bias, y, mean, rstd, stat_ld, eps, workspace, workspace_bytes, stream);
 }
 
 int b200seg_conv_dgrad(const b200seg_conv_desc* d, const void* dy, const void* w_packed,

@@ -61,8 +61,8 @@ int norm_blocks(const b200seg_norm_desc& d);
 size_t norm_workspace_bytes(const b200seg_norm_desc& d);
 int launch_instnorm_stats(const b200seg_norm_desc& d, const void* x, float* mean, float* rstd,
                           void* ws, cudaStream_t st);
-int launch_instnorm_stats_from_sums(const b200seg_norm_desc& d, const float* sums, float* mean, float* rstd,
-                                    cudaStream_t st);
+int launch_instnorm_stats_from_partials(const float* partial, int n, int c, int c_out, int ncls, int64_t tiles,
+                                        int64_t spatial, float eps, float* mean, float* rstd, cudaStream_t st);
 int launch_instnorm_prelu_fwd(const b200seg_norm_desc& d, const void* x, const float* mean,
                               const float* rstd, const float* alpha, const void* res, void* y,
                               cudaStream_t st);

@@ -415,32 +415,43 @@ int launch_instnorm_prelu_bwd(const b200seg_norm_desc& d, const void* x, const f
 }
 
 // mean / rstd from per-(n, c) sum and sum of squares accumulated by a convolution epilogue
+// mean / rstd from the per-CTA partial sums a convolution epilogue produced.  partial index of
+// (class o, sample n, tile t) = (o * N + n) * T + t;  one warp per (n, channel), fixed order, double.
 // mean / rstd are written with `c_out` (>= c) entries per sample: entries >= c describe zero
-// padding channels (mean 0, rstd 1/sqrt(eps)), as the statistics kernel would produce for them
-__global__ void instnorm_stats_from_sums_kernel(const float* __restrict__ sums, int n, int c, int c_out,
-                                                int64_t spatial, float eps, float* __restrict__ mean,
-                                                float* __restrict__ rstd) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n * c_out) return;
-  const int nn = i / c_out, ch = i % c_out;
-  double m = 0.0, var = 0.0;
+// padding channels (mean 0, rstd 1/sqrt(eps)), as the statistics kernel would produce for them.
+__global__ void instnorm_stats_from_partials_kernel(const float* __restrict__ partial, int n, int c, int c_out,
+                                                    int ncls, int64_t tiles, int64_t spatial, float eps,
+                                                    float* __restrict__ mean, float* __restrict__ rstd) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) / 32, lane = threadIdx.x % 32;
+  if (warp >= n * c_out) return;
+  const int nn = warp / c_out, ch = warp % c_out;
+  double s1 = 0.0, s2 = 0.0;
   if (ch < c) {
-    const float* sp = sums + ((int64_t)nn * c + ch) * 2;
-    m = (double)sp[0] / (double)spatial;
-    var = (double)sp[1] / (double)spatial - m * m;
-    if (var < 0.0) var = 0.0;
+    for (int o = 0; o < ncls; ++o) {
+      const float* base = partial + (((int64_t)o * n + nn) * tiles) * c * 2;
+      for (int64_t t = lane; t < tiles; t += 32) {
+        s1 += (double)base[(t * c + ch) * 2];
+        s2 += (double)base[(t * c + ch) * 2 + 1];
+      }
+    }
   }
-  mean[i] = (float)m;
-  rstd[i] = (float)(1.0 / sqrt(var + (double)eps));
+  s1 = warp_sum_d(s1);
+  s2 = warp_sum_d(s2);
+  if (lane == 0) {
+    double m = s1 / (double)spatial;
+    double var = s2 / (double)spatial - m * m;
+    if (var < 0.0) var = 0.0;
+    mean[warp] = (float)m;
+    rstd[warp] = (float)(1.0 / sqrt(var + (double)eps));
+  }
 }
 
-int launch_instnorm_stats_from_sums(const b200seg_norm_desc& d, const float* sums, float* mean, float* rstd,
-                                    cudaStream_t st) {
-  const int c_out = d.x_ld > d.c ? d.x_ld : d.c;  // x_ld: entries per sample in mean / rstd
-  const int total = d.n * c_out;
-  instnorm_stats_from_sums_kernel<<<(total + 127) / 128, 128, 0, st>>>(sums, d.n, d.c, c_out, d.spatial, d.eps,
-                                                                       mean, rstd);
-  B200SEG_CHECK_LAUNCH("instnorm_stats_from_sums");
+int launch_instnorm_stats_from_partials(const float* partial, int n, int c, int c_out, int ncls, int64_t tiles,
+                                        int64_t spatial, float eps, float* mean, float* rstd, cudaStream_t st) {
+  const int total = n * c_out;
+  instnorm_stats_from_partials_kernel<<<(total * 32 + 255) / 256, 256, 0, st>>>(partial, n, c, c_out, ncls, tiles,
+                                                                                spatial, eps, mean, rstd);
+  B200SEG_CHECK_LAUNCH("instnorm_stats_from_partials");
   return B200SEG_OK;
 }
 

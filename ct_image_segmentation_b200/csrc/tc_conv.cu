@@ -51,7 +51,7 @@ struct alignas(64) TcConvParams {
   const float* bias;
   const bf16* res;
   bf16* dst;
-  float* stats;  // optional [n][cout][2]: += sum, sum of squares of the outputs (for InstanceNorm)
+  float* stats;  // optional [blockIdx.x][cout][2]: per-CTA sum / sum of squares of its outputs (InstanceNorm)
 };
 
 template <int BN, int KC>
@@ -209,15 +209,16 @@ tc_conv_kernel(const __grid_constant__ TcConvParams p) {
         op[1] = o1;
       }
       if (p.stats) {  // warp-uniform: per-channel sum / sum of squares over the tile's valid rows
+        float* sred = reinterpret_cast<float*>(tmem_slot + 4);  // [4 warps][BN][2]
         const int c0 = n0 + ch * 16;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           float x = valid ? __uint_as_float(v[i]) : 0.f;
           if (valid && p.bias && c0 + i < p.cout) x += p.bias[c0 + i];
           const float a = warp_sum(x), b = warp_sum(x * x);
-          if (lane == 0 && c0 + i < p.cout) {
-            atomicAdd(p.stats + ((int64_t)n * p.cout + c0 + i) * 2, a);
-            atomicAdd(p.stats + ((int64_t)n * p.cout + c0 + i) * 2 + 1, b);
+          if (lane == 0) {
+            sred[(q * BN + ch * 16 + i) * 2] = a;
+            sred[(q * BN + ch * 16 + i) * 2 + 1] = b;
           }
         }
       }
@@ -225,6 +226,16 @@ tc_conv_kernel(const __grid_constant__ TcConvParams p) {
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (p.stats) {
+    const float* sred = reinterpret_cast<const float*>(tmem_slot + 4);
+    for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) {
+      const int c = i >> 1, m = i & 1;
+      if (n0 + c < p.cout)
+        p.stats[((int64_t)blockIdx.x * p.cout + n0 + c) * 2 + m] =
+            sred[(0 * BN + c) * 2 + m] + sred[(1 * BN + c) * 2 + m] + sred[(2 * BN + c) * 2 + m] +
+            sred[(3 * BN + c) * 2 + m];
+    }
+  }
   if (warp == 1) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_acc);
 }
 
@@ -334,7 +345,7 @@ int bn_for(int dst_pad) { return dst_pad % 128 == 0 ? 128 : (dst_pad % 64 == 0 ?
 template <int BN, int KC>
 int launch_cfg(const TcConvParams& p, dim3 grid, cudaStream_t st) {
   using Cfg = TcCfg<BN, KC>;
-  size_t smem = 1024 + (size_t)p.stages * Cfg::STAGE_BYTES + (2 * p.stages + 1) * 8 + 16;
+  size_t smem = 1024 + (size_t)p.stages * Cfg::STAGE_BYTES + (2 * p.stages + 1) * 8 + 32 + 4 * BN * 2 * 4;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(tc_conv_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -489,6 +500,29 @@ bool tc_conv_supported(const b200seg_conv_desc* d, int op, const void* src, cons
       if (g.s[i] == 2 && ((i == 0 ? g.dD : (i == 1 ? g.dH : g.dW)) % 2)) return false;
   }
   return encode_fn() != nullptr;
+}
+
+// blockIdx.x = (class * n + sample) * tiles + tile: the layout of the per-CTA statistic partials
+void tc_conv_grid(const b200seg_conv_desc* d, int op, int* ncls_out, int64_t* tiles_out) {
+  TcGeom g;
+  tc_geom(d, op, g);
+  const int ddim[3] = {g.dD, g.dH, g.dW};
+  int ncls = 1, cdim[3];
+  for (int i = 0; i < 3; ++i) {
+    bool split = g.transposed && g.s[i] == 2;
+    if (split) ncls *= 2;
+    cdim[i] = ddim[i] / (split ? 2 : 1);
+  }
+  int64_t best = -1, tiles = 0;
+  for (int td = 1; td <= 128; td *= 2)
+    for (int th = 1; td * th <= 128; th *= 2) {
+      int tw = 128 / (td * th);
+      int64_t vol = (int64_t)((cdim[0] + td - 1) / td) * ((cdim[1] + th - 1) / th) * ((cdim[2] + tw - 1) / tw);
+      int64_t score = vol * 1024 - (tw > 16 ? 16 : tw) * 8 - (th > 16 ? 16 : th);
+      if (best < 0 || score < best) { best = score; tiles = vol; }
+    }
+  *ncls_out = ncls;
+  *tiles_out = tiles;
 }
 
 int tc_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,

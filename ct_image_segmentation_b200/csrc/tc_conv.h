@@ -12,7 +12,10 @@ enum TcConvOp { TC_CONV_FPROP = 0, TC_CONV_DGRAD = 1, TC_CONVTR_FPROP = 2, TC_CO
 // true when the tcgen05 kernel takes this layer/op (bf16, channel counts multiple of 16 or
 // zero-padded to it, 16-byte aligned pointers, ...)
 bool tc_conv_supported(const b200seg_conv_desc* d, int op, const void* src, const void* dst, const void* res);
-// stats (optional, fprop without residual only): [n][cout][2] fp32, += sum and sum of squares of the outputs
+// stats (optional, fprop without residual only): [blockIdx.x][cout][2] fp32 per-CTA sum / sum of squares;
+// blockIdx.x = (class * n + sample) * tiles + tile (tc_conv_grid) or sample-major (tc_slide_conv_grid)
+void tc_conv_grid(const b200seg_conv_desc* d, int op, int* ncls_out, int64_t* tiles_out);
+int64_t tc_slide_conv_grid(const b200seg_conv_desc* d, int op);
 int tc_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,
                 const void* residual, void* dst, float* stats, cudaStream_t st);
 // sliding-window variant for small-channel, high-resolution 3x3x3 stride-1 layers (tc_slide.cu)

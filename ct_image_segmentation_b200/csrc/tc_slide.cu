@@ -40,7 +40,7 @@ struct alignas(64) TcSlideConvParams {
   const float* bias;
   const bf16* res;
   bf16* dst;
-  float* stats;  // optional [n][cout][2]: += sum, sum of squares of the outputs (for InstanceNorm)
+  float* stats;  // optional [CTA][cout][2]: per-CTA sum / sum of squares of its outputs (InstanceNorm)
 };
 
 template <int BN, int KC>
@@ -231,19 +231,28 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
       if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
     }
     if (p.stats) {
-      // one warp-level tree per channel, then one red.global.add per (warp, channel, moment)
+      // warp tree per channel -> shared memory; the CTA's partial is written after the final barrier
+      float* sred = reinterpret_cast<float*>(tmem_slot + 4);  // [4 warps][BN][2], after the barriers
 #pragma unroll
       for (int c = 0; c < BN; ++c) {
         const float a = warp_sum(ssum[c]), b = warp_sum(ssq[c]);
-        if (lane == 0 && c < p.cout) {
-          atomicAdd(p.stats + ((int64_t)n * p.cout + c) * 2, a);
-          atomicAdd(p.stats + ((int64_t)n * p.cout + c) * 2 + 1, b);
+        if (lane == 0) {
+          sred[(q * BN + c) * 2] = a;
+          sred[(q * BN + c) * 2 + 1] = b;
         }
       }
     }
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (p.stats && threadIdx.x < 2 * BN) {
+    const float* sred = reinterpret_cast<const float*>(tmem_slot + 4);
+    const int c = threadIdx.x >> 1, m = threadIdx.x & 1;
+    if (c < p.cout)
+      p.stats[((int64_t)blockIdx.x * p.cout + c) * 2 + m] =
+          sred[(0 * BN + c) * 2 + m] + sred[(1 * BN + c) * 2 + m] + sred[(2 * BN + c) * 2 + m] +
+          sred[(3 * BN + c) * 2 + m];
+  }
   if (warp == 1) tc::tmem_dealloc<TMEM_COLS>(tmem_acc);
 }
 
@@ -268,7 +277,7 @@ int launch_slide(const TcSlideConvParams& p, unsigned grid, cudaStream_t st) {
   constexpr int PITCH = KC * 2;
   constexpr int SLAB = 3 * (TH + 2) * TWV * PITCH;
   constexpr int WB = (27 * BN * PITCH + 1023) / 1024 * 1024;
-  const size_t smem = 1024 + WB + RING * SLAB + 8 * PITCH * 8 + 16 * 8 + 64;
+  const size_t smem = 1024 + WB + RING * SLAB + 8 * PITCH * 8 + 16 * 8 + 64 + 4 * BN * 2 * 4;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(tc_slide_conv_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
@@ -291,6 +300,20 @@ bool tc_slide_conv_supported(const b200seg_conv_desc* d, int op) {
   if ((sp != 16 && sp != 32) || (dp != 16 && dp != 32)) return false;
   if (g.D < 8 || (int64_t)g.H * g.W < 512) return false;
   return true;
+}
+
+// number of CTAs (= per-CTA statistic partials); CTAs of one sample are contiguous
+int64_t tc_slide_conv_grid(const b200seg_conv_desc* d, int op) {
+  SlideGeom g;
+  slide_geom(d, op, g);
+  const int tilesH = (g.H + TH - 1) / TH, tilesW = (g.W + TWV - 1) / TWV;
+  const int64_t cols = (int64_t)g.n * tilesH * tilesW;
+  int nseg = (int)((148 * 4 + cols - 1) / cols);
+  if (nseg < 1) nseg = 1;
+  int dseg = (g.D + nseg - 1) / nseg;
+  if (dseg < 8) dseg = 8;
+  if (dseg > g.D) dseg = g.D;
+  return cols * ((g.D + dseg - 1) / dseg);
 }
 
 int tc_slide_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,

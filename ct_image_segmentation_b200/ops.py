@@ -284,19 +284,16 @@ def conv_fprop_stats(geom: ConvGeom, x, wp, bias, y, eps: float = 1e-5, flags=0)
     if _pad_safe(x) and _pad_safe(y):
         flags |= _lib.CONV_PADDED_CHANNELS
     d = geom.desc(n, (sd_, sh_, sw_), (dd_, dh_, dw_), s_ld, d_ld, 0, x.dtype, flags)
-    sums = torch.empty(n * dc * 2, dtype=torch.float32, device=x.device)
-    name = "b200seg_convtr_fprop_stats" if geom.transposed else "b200seg_conv_fprop_stats"
-    rc = getattr(lib, name)(C.byref(d), x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(), sums.data_ptr(),
-                            _stream())
-    if rc == 1:  # B200SEG_STATS_NOT_FUSED
-        return instnorm_stats(y, eps)
-    _lib.check(rc, name)
     c_out = (dc + 15) // 16 * 16 if _expand_pad(y) is not None else dc
     mean = torch.empty(n * c_out, dtype=torch.float32, device=x.device)
     rstd = torch.empty(n * c_out, dtype=torch.float32, device=x.device)
-    nd = NormDesc(n, dc, dd_ * dh_ * dw_, c_out, 0, 0, dtype_code(x.dtype), eps)
-    _lib.check(lib.b200seg_instnorm_stats_from_sums(C.byref(nd), sums.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
-                                                    _stream()), "b200seg_instnorm_stats_from_sums")
+    name = "b200seg_convtr_fprop_stats" if geom.transposed else "b200seg_conv_fprop_stats"
+    ws = workspace(getattr(lib, name + "_workspace_bytes")(C.byref(d)), x.device)
+    rc = getattr(lib, name)(C.byref(d), x.data_ptr(), wp.data_ptr(), _ptr(bias), y.data_ptr(), mean.data_ptr(),
+                            rstd.data_ptr(), c_out, eps, ws.data_ptr(), ws.numel(), _stream())
+    if rc == 1:  # B200SEG_STATS_NOT_FUSED
+        return instnorm_stats(y, eps)
+    _lib.check(rc, name)
     return mean, rstd
 
 

@@ -151,19 +151,21 @@ size_t b200seg_conv_wgrad_workspace_bytes(const b200seg_conv_desc* d);
 int b200seg_conv_wgrad(const b200seg_conv_desc* d, const void* x, const void* dy, float* gw,
                        float* gbias, void* workspace, size_t workspace_bytes, void* stream);
 
-/* fprop fused with the statistics pass of the InstanceNorm that follows (no residual):
- * sums[n][cout][2] (fp32, overwritten) = { sum_v y, sum_v y^2 } accumulated in the conv epilogue from the
- * fp32 accumulators.  Returns B200SEG_OK when the statistics were produced, B200SEG_STATS_NOT_FUSED (1) when
- * the convolution ran on a kernel without the fusion (y is valid, call b200seg_instnorm_stats instead).
- * b200seg_instnorm_stats_from_sums turns the sums into mean / rstd (desc: n, c, spatial, eps; x_ld = number
- * of mean / rstd entries per sample, >= c: the extra entries describe zero padding channels). */
+/* fprop fused with the statistics pass of the InstanceNorm that follows (no residual): the conv
+ * epilogue emits per-CTA partial sums of y and y^2 (from the fp32 accumulators) into the workspace
+ * and a small kernel reduces them (fixed order, double) to mean[n*stat_ld], rstd[n*stat_ld]
+ * (stat_ld >= cout entries per sample; entries >= cout describe zero padding channels).
+ * Returns B200SEG_OK when the statistics were produced, B200SEG_STATS_NOT_FUSED (1) when the
+ * convolution ran on a kernel without the fusion (y is valid; call b200seg_instnorm_stats). */
 #define B200SEG_STATS_NOT_FUSED 1
+size_t b200seg_conv_fprop_stats_workspace_bytes(const b200seg_conv_desc* d);
+size_t b200seg_convtr_fprop_stats_workspace_bytes(const b200seg_conv_desc* d);
 int b200seg_conv_fprop_stats(const b200seg_conv_desc* d, const void* x, const void* w_packed, const float* bias,
-                             void* y, float* sums, void* stream);
+                             void* y, float* mean, float* rstd, int32_t stat_ld, float eps, void* workspace,
+                             size_t workspace_bytes, void* stream);
 int b200seg_convtr_fprop_stats(const b200seg_conv_desc* d, const void* x, const void* w_packed, const float* bias,
-                               void* y, float* sums, void* stream);
-int b200seg_instnorm_stats_from_sums(const b200seg_norm_desc* d, const float* sums, float* mean, float* rstd,
-                                     void* stream);
+                               void* y, float* mean, float* rstd, int32_t stat_ld, float eps, void* workspace,
+                               size_t workspace_bytes, void* stream);
 
 int b200seg_convtr_fprop(const b200seg_conv_desc* d, const void* x, const void* w_packed,
                          const float* bias, const void* residual, void* y, void* stream);
