@@ -171,7 +171,13 @@ static int fprop_stats_common(const b200seg_conv_desc* d, bool transposed_layer,
                               const float* bias, void* y, float* mean, float* rstd, int stat_ld, float eps,
                               void* ws, size_t ws_bytes, void* stream) {
   int op = transposed_layer ? TC_CONVTR_FPROP : TC_CONV_FPROP;
-  if (mean && rstd && ws && tc_conv_supported(d, op, x, y, nullptr)) {
+  // Only the sliding-window kernel fuses the statistics: it accumulates them in registers across
+  // the slabs of a column and emits one partial per CTA (a few hundred per sample).  In the
+  // streaming kernel (one tile per CTA, up to 32 k CTAs) the per-tile warp reductions and the
+  // reduction over tens of thousands of partials cost more than the separate statistics pass
+  // (measured: ConvTranspose 32->10 fprop 258 -> 440 us).
+  if (mean && rstd && ws && tc_conv_supported(d, op, x, y, nullptr) &&
+      !(d->flags & B200SEG_CONV_NO_SLIDE) && tc_slide_conv_supported(d, op)) {
     if (ws_bytes < fprop_stats_ws(d, transposed_layer)) {
       set_error("conv_fprop_stats: workspace %zu < required %zu", ws_bytes, fprop_stats_ws(d, transposed_layer));
       return B200SEG_ERR_WORKSPACE;
