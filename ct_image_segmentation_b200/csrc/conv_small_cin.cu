@@ -171,6 +171,109 @@ conv_small_cin_wgrad_kernel(SmallCinParams p, const T* __restrict__ x, const T* 
   }
 }
 
+// Register-tiled variant for J = taps*cin <= 32 and cout in {16, 32, 64}: a chunk of 128 voxels is
+// staged in shared memory (X[j][voxel] gathered, DY[voxel][co]); a "team" of cout threads owns the
+// whole (j, co) output as 8 x 4 register tiles and walks its share of the chunk's voxels (8 scalar
+// + one 128-bit shared load per 32 FMA); the 256/cout teams of a block are summed in a fixed order.
+template <typename T, int CO>
+__global__ void __launch_bounds__(256)
+conv_small_cin_wgrad_tile_kernel(SmallCinParams p, const T* __restrict__ x, const T* __restrict__ dy,
+                                 float* __restrict__ partial, int64_t vox_per_block, int dy_vec) {
+  constexpr int VC = 128, XP = VC + 1, JP = 32;
+  constexpr int NTEAMS = 256 / CO, CQ = CO / 4;
+  extern __shared__ float sm[];
+  float* Xs = sm;                                        // [JP][XP]
+  float* Ds = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(sm + JP * XP) + 15) & ~uintptr_t(15));  // [VC][CO]
+  int4* vbase = reinterpret_cast<int4*>(Ds + VC * CO);   // [VC]: n (< 0: no voxel), id0, ih0, iw0
+  const int J = p.kd * p.kh * p.kw * p.cin;
+  const int rows = p.kd * p.kh, kwc = p.kw * p.cin;
+  const int t = threadIdx.x;
+  const int team = t / CO, jq = (t % CO) / CQ, cq = t % CQ;
+  for (int i = t; i < JP * XP; i += 256) Xs[i] = 0.f;    // rows >= J stay zero
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[i][c] = 0.f;
+  const int64_t v_begin = (int64_t)blockIdx.x * vox_per_block;
+  const int64_t v_end = min(v_begin + vox_per_block, p.nvox);
+  for (int64_t v0 = v_begin; v0 < v_end; v0 += VC) {
+    __syncthreads();
+    if (t < VC) {
+      const int64_t v = v0 + t;
+      int4 e = make_int4(-1, 0, 0, 0);
+      if (v < v_end) {
+        int64_t r = v;
+        const int ow = (int)(r % p.oW); r /= p.oW;
+        const int oh = (int)(r % p.oH); r /= p.oH;
+        const int od = (int)(r % p.oD); r /= p.oD;
+        e = make_int4((int)r, od * p.sd - p.pd, oh * p.sh - p.ph, ow * p.sw - p.pw);
+      }
+      vbase[t] = e;
+    }
+    __syncthreads();
+    for (int i = t; i < VC * rows; i += 256) {
+      const int lv = i % VC, row = i / VC;   // consecutive threads -> consecutive voxels
+      const int kd = row / p.kh, kh = row - kd * p.kh;
+      const int4 e = vbase[lv];
+      const int id = e.y + kd, ih = e.z + kh;
+      const bool ok = e.x >= 0 && id >= 0 && id < p.iD && ih >= 0 && ih < p.iH;
+      const T* xr = x + ((((int64_t)e.x * p.iD + id) * p.iH + ih) * p.iW) * (int64_t)p.x_ld;
+      float* xs = Xs + (row * kwc) * XP + lv;
+      for (int kw = 0; kw < p.kw; ++kw) {
+        const int iw = e.w + kw;
+        const bool okw = ok && iw >= 0 && iw < p.iW;
+        for (int ci = 0; ci < p.cin; ++ci)
+          xs[(kw * p.cin + ci) * XP] = okw ? to_f<T>(xr[(int64_t)iw * p.x_ld + ci]) : 0.f;
+      }
+    }
+    for (int i = t; i < VC * CQ; i += 256) {
+      const int lv = i / CQ, c4 = i % CQ;
+      const int64_t v = v0 + lv;
+      float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (v < v_end) {
+        const T* dp = dy + v * (int64_t)p.y_ld + 4 * c4;
+        if (dy_vec) {
+          Vec<T, 4> dv;
+          dv.load(dp);
+          o = make_float4(dv.v[0], dv.v[1], dv.v[2], dv.v[3]);
+        } else {
+          o = make_float4(to_f<T>(dp[0]), to_f<T>(dp[1]), to_f<T>(dp[2]), to_f<T>(dp[3]));
+        }
+      }
+      reinterpret_cast<float4*>(Ds)[i] = o;
+    }
+    __syncthreads();
+    const float* xt = Xs + (8 * jq) * XP;
+#pragma unroll 2
+    for (int lv = team; lv < VC; lv += NTEAMS) {
+      const float4 dv = reinterpret_cast<const float4*>(Ds)[lv * CQ + cq];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float xv = xt[i * XP + lv];
+        acc[i][0] = fmaf(xv, dv.x, acc[i][0]);
+        acc[i][1] = fmaf(xv, dv.y, acc[i][1]);
+        acc[i][2] = fmaf(xv, dv.z, acc[i][2]);
+        acc[i][3] = fmaf(xv, dv.w, acc[i][3]);
+      }
+    }
+  }
+  __syncthreads();
+  float* red = sm;  // [NTEAMS][JP*CO]
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) red[team * (JP * CO) + (8 * jq + i) * CO + 4 * cq + c] = acc[i][c];
+  __syncthreads();
+  float* out = partial + (int64_t)blockIdx.x * (J * CO);
+  for (int o = t; o < J * CO; o += 256) {
+    float s_ = 0.f;
+#pragma unroll
+    for (int k = 0; k < NTEAMS; ++k) s_ += red[k * (JP * CO) + o];
+    out[o] = s_;
+  }
+}
+
 // gw[co][ci][tap] = sum_blk partial[blk][tap*cin+ci][co]; one warp per output, fixed order
 __global__ void conv_small_cin_wgrad_final_kernel(const float* __restrict__ partial, int nblk, int taps,
                                                   int cin, int cout, float* __restrict__ gw) {
@@ -242,6 +345,40 @@ int launch_small_cin_wgrad(const b200seg_conv_desc* d, const void* x, const void
   int64_t per = cdiv64(cdiv64(p.nvox, nb), 64) * 64;
   size_t smem = (size_t)(65 * J + 64 * d->cout) * sizeof(float) + (size_t)(64 * 4 + J * 4) * sizeof(int);
   const int nout_ = J * d->cout;
+  if (J <= 32 && (d->cout == 16 || d->cout == 32 || d->cout == 64)) {
+    const size_t esz = d->dtype == B200SEG_BF16 ? 2 : 4;
+    const int dy_vec = (d->y_ld % 4 == 0) && ((uintptr_t)dy % (4 * esz) == 0);
+    const int64_t per128 = cdiv64(cdiv64(p.nvox, nb), 128) * 128;
+    // staging: X[32][129] + DY[128][cout] + voxel table; reused for the cross-team reduction [256/cout][32*cout]
+    size_t stage = (size_t)(32 * 129 + 4 + 128 * d->cout) * sizeof(float) + 128 * sizeof(int4);
+    size_t redb = (size_t)256 * 32 * sizeof(float);
+    size_t smem_t = stage > redb ? stage : redb;
+#define SMALL_CIN_WGRAD_TILE(TT, CC)                                                                                \
+  do {                                                                                                              \
+    static bool attr_set = false;                                                                                   \
+    if (!attr_set) {                                                                                                \
+      cudaFuncSetAttribute(conv_small_cin_wgrad_tile_kernel<TT, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize,   \
+                           64 * 1024);                                                                              \
+      attr_set = true;                                                                                              \
+    }                                                                                                               \
+    conv_small_cin_wgrad_tile_kernel<TT, CC><<<nb, 256, smem_t, st>>>(p, (const TT*)x, (const TT*)dy, partial,      \
+                                                                      per128, dy_vec);                              \
+  } while (0)
+    if (d->dtype == B200SEG_BF16) {
+      if (d->cout == 16) SMALL_CIN_WGRAD_TILE(__nv_bfloat16, 16);
+      else if (d->cout == 32) SMALL_CIN_WGRAD_TILE(__nv_bfloat16, 32);
+      else SMALL_CIN_WGRAD_TILE(__nv_bfloat16, 64);
+    } else {
+      if (d->cout == 16) SMALL_CIN_WGRAD_TILE(float, 16);
+      else if (d->cout == 32) SMALL_CIN_WGRAD_TILE(float, 32);
+      else SMALL_CIN_WGRAD_TILE(float, 64);
+    }
+#undef SMALL_CIN_WGRAD_TILE
+    B200SEG_CHECK_LAUNCH("conv_small_cin_wgrad_tile");
+    conv_small_cin_wgrad_final_kernel<<<(nout_ * 32 + 255) / 256, 256, 0, st>>>(partial, nb, taps, d->cin, d->cout, gw);
+    B200SEG_CHECK_LAUNCH("conv_small_cin_wgrad_final");
+    return B200SEG_OK;
+  }
 #define SMALL_CIN_WGRAD(TT, RR) \
   conv_small_cin_wgrad_kernel<TT, RR><<<nb, 256, smem, st>>>(p, (const TT*)x, (const TT*)dy, partial, per)
   if (d->dtype == B200SEG_BF16) {

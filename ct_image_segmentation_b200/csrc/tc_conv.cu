@@ -415,58 +415,76 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, bf16* __restr
   out[idx] = __float2bfloat16_rn(v);
 }
 
-// ---- all layers in one launch: table of b200seg_pack_entry in device memory, blockIdx.y = entry ----
-__global__ void pack_weights_batched_kernel(const b200seg_pack_entry* __restrict__ table) {
-  const b200seg_pack_entry e = table[blockIdx.y];
-  const int taps = e.taps, cin = e.cin, cout = e.cout, kind = e.kind;
-  const bool src_is_cin = (kind == B200SEG_W_CONV_FPROP || kind == B200SEG_W_CONVTR_FPROP);
-  const int src_c = src_is_cin ? cin : cout, dst_c = src_is_cin ? cout : cin;
-  const int src_pad = (src_c + 15) / 16 * 16, dst_pad = (dst_c + 15) / 16 * 16;
-  const int KC = src_pad % 64 == 0 ? 64 : (src_pad % 32 == 0 ? 32 : 16);
-  const int kblocks = src_pad / KC;
-  const int64_t total = (int64_t)taps * src_pad * dst_pad, gen_total = (int64_t)taps * src_c * dst_c;
-  const float* w = reinterpret_cast<const float*>(e.w);
-  bf16* gen = reinterpret_cast<bf16*>(e.packed);
-  bf16* out = reinterpret_cast<bf16*>(e.packed + e.tc_offset);
-  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-       idx += (int64_t)gridDim.x * blockDim.x) {
-    if (idx < gen_total) {
-      int t = (int)(idx % dst_c);
-      int64_t r = idx / dst_c;
-      int sc = (int)(r % src_c), tap = (int)(r / src_c);
-      int64_t wi;
-      switch (kind) {
-        case B200SEG_W_CONV_FPROP:   wi = ((int64_t)t * cin + sc) * taps + tap; break;
-        case B200SEG_W_CONV_DGRAD:   wi = ((int64_t)sc * cin + t) * taps + tap; break;
-        case B200SEG_W_CONVTR_FPROP: wi = ((int64_t)sc * cout + t) * taps + tap; break;
-        default:                     wi = ((int64_t)t * cout + sc) * taps + tap; break;
+// ---- all layers in one launch: table of b200seg_pack_entry in device memory.  The entries differ in
+// size by four orders of magnitude (432 ... 1.8 M elements): the work is cut into chunks of
+// PACK_CHUNK packed elements, numbered across the entries, and dealt round-robin to the blocks.
+constexpr int PACK_CHUNK = 2048;  // = 256 threads x 8 consecutive elements
+__device__ __forceinline__ int pack_src_index(int kind, int t, int sc, int tap, int taps, int cin, int cout) {
+  switch (kind) {
+    case B200SEG_W_CONV_FPROP:   return (t * cin + sc) * taps + tap;
+    case B200SEG_W_CONV_DGRAD:   return (sc * cin + t) * taps + tap;
+    case B200SEG_W_CONVTR_FPROP: return (sc * cout + t) * taps + tap;
+    default:                     return (t * cout + sc) * taps + tap;
+  }
+}
+__global__ void __launch_bounds__(256)
+pack_weights_batched_kernel(const b200seg_pack_entry* __restrict__ table, int n_entries) {
+  int64_t chunk_base = 0;
+  for (int ei = 0; ei < n_entries; ++ei) {
+    const b200seg_pack_entry e = table[ei];
+    const int taps = e.taps, cin = e.cin, cout = e.cout, kind = e.kind;
+    const bool src_is_cin = (kind == B200SEG_W_CONV_FPROP || kind == B200SEG_W_CONVTR_FPROP);
+    const int src_c = src_is_cin ? cin : cout, dst_c = src_is_cin ? cout : cin;
+    const int src_pad = (src_c + 15) / 16 * 16, dst_pad = (dst_c + 15) / 16 * 16;
+    const int KC = src_pad % 64 == 0 ? 64 : (src_pad % 32 == 0 ? 32 : 16);
+    const int kblocks = src_pad / KC;
+    const int total = taps * src_pad * dst_pad, gen_total = taps * src_c * dst_c;  // < 2^31 (checked on the host side by size)
+    const int nchunks = (total + PACK_CHUNK - 1) / PACK_CHUNK;
+    const float* w = reinterpret_cast<const float*>(e.w);
+    bf16* gen = reinterpret_cast<bf16*>(e.packed);
+    bf16* out = reinterpret_cast<bf16*>(e.packed + e.tc_offset);
+    // first chunk of this entry that falls to this block
+    int c = (int)(((int64_t)blockIdx.x - chunk_base % gridDim.x + gridDim.x) % gridDim.x);
+    for (; c < nchunks; c += gridDim.x) {
+      const int idx0 = c * PACK_CHUNK + threadIdx.x * 8;  // 8 consecutive elements per thread: one division set
+      if (idx0 < total) {  // total is a multiple of 256: the 8 elements are all inside
+        // tcgen05 layout: idx = ((tap * kblocks + kb) * dst_pad + t) * KC + kc ; KC is a multiple of 8
+        const int kc0 = idx0 % KC;
+        int r = idx0 / KC;
+        const int t = r % dst_pad; r /= dst_pad;
+        const int kb = r % kblocks, tap = r / kblocks;
+        uint4 pk;
+        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float v[2];
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int sc = kb * KC + kc0 + 2 * i + jj;
+            v[jj] = (sc < src_c && t < dst_c) ? w[pack_src_index(kind, t, sc, tap, taps, cin, cout)] : 0.f;
+          }
+          h[i] = __floats2bfloat162_rn(v[0], v[1]);
+        }
+        *reinterpret_cast<uint4*>(out + idx0) = pk;
       }
-      gen[idx] = __float2bfloat16_rn(w[wi]);
-    }
-    int kc = (int)(idx % KC);
-    int64_t r = idx / KC;
-    int t = (int)(r % dst_pad); r /= dst_pad;
-    int kb = (int)(r % kblocks);
-    int tap = (int)(r / kblocks);
-    int sc = kb * KC + kc;
-    float v = 0.f;
-    if (sc < src_c && t < dst_c) {
-      int64_t wi;
-      switch (kind) {
-        case B200SEG_W_CONV_FPROP:   wi = ((int64_t)t * cin + sc) * taps + tap; break;
-        case B200SEG_W_CONV_DGRAD:   wi = ((int64_t)sc * cin + t) * taps + tap; break;
-        case B200SEG_W_CONVTR_FPROP: wi = ((int64_t)sc * cout + t) * taps + tap; break;
-        default:                     wi = ((int64_t)t * cout + sc) * taps + tap; break;
+      if (idx0 < gen_total) {
+        // generic layout: idx = (tap * src_c + sc) * dst_c + t
+        int t = idx0 % dst_c;
+        int r = idx0 / dst_c;
+        int sc = r % src_c, tap = r / src_c;
+        const int lim = min(8, gen_total - idx0);
+        for (int i = 0; i < lim; ++i) {
+          gen[idx0 + i] = __float2bfloat16_rn(w[pack_src_index(kind, t, sc, tap, taps, cin, cout)]);
+          if (++t == dst_c) { t = 0; if (++sc == src_c) { sc = 0; ++tap; } }
+        }
       }
-      v = w[wi];
     }
-    out[idx] = __float2bfloat16_rn(v);
+    chunk_base += nchunks;
   }
 }
 
 int tc_pack_weights_batched(const b200seg_pack_entry* table_dev, int n_entries, cudaStream_t st) {
-  dim3 grid(64, (unsigned)n_entries);
-  pack_weights_batched_kernel<<<grid, 256, 0, st>>>(table_dev);
+  pack_weights_batched_kernel<<<148 * 8, 256, 0, st>>>(table_dev, n_entries);
   B200SEG_CHECK_LAUNCH("pack_weights_batched");
   return B200SEG_OK;
 }

@@ -70,6 +70,11 @@ GEOMS = [
     (2, 3, 8, 3, 2, False, (20, 24)),
     (2, 16, 8, 3, 2, True, (10, 12)),
     (2, 8, 8, 3, 1, False, (9, 16)),
+    # first-layer shapes of the three configurations (register-tiled small-Cin wgrad, ragged chunks)
+    (3, 1, 16, 3, 2, False, (18, 20, 22)),
+    (3, 1, 32, 3, 2, False, (10, 12, 14)),
+    (2, 1, 64, 3, 2, False, (30, 36)),
+    (2, 3, 16, 3, 1, False, (17, 19)),
 ]
 
 
@@ -125,6 +130,35 @@ def test_conv_fprop_dgrad_wgrad(dims, cin, cout, k, s, tr, sp, dtype):
     assert e < tol, f"wgrad rel err {e}"
     e = rel(gb, dy.sum(dim=[0] + list(range(2, 2 + dims))))
     assert e < tol, f"bias grad rel err {e}"
+
+
+def test_pack_weights_batched_matches_single():
+    """One-launch repack of many layers == per-layer b200seg_pack_weight, byte for byte."""
+    torch.manual_seed(3)
+    dtype = torch.bfloat16
+    layers = [(ConvGeom(3, 1, 16, 3, 2, False), _lib.W_CONV_FPROP), (ConvGeom(3, 16, 16, 3, 1, False), _lib.W_CONV_DGRAD),
+              (ConvGeom(3, 32, 10, 3, 2, True), _lib.W_CONVTR_FPROP), (ConvGeom(3, 32, 10, 3, 2, True), _lib.W_CONVTR_DGRAD),
+              (ConvGeom(3, 128, 256, 3, 1, False), _lib.W_CONV_FPROP), (ConvGeom(3, 128, 256, 1, 1, False), _lib.W_CONV_DGRAD),
+              (ConvGeom(2, 64, 128, 3, 2, False), _lib.W_CONV_FPROP), (ConvGeom(3, 384, 64, 3, 2, True), _lib.W_CONVTR_FPROP)]
+    ws, bufs, entries, singles = [], [], [], []
+    for g, kind in layers:
+        ks = (g.kernel,) * g.dims
+        w = torch.randn((g.cin, g.cout, *ks) if g.transposed else (g.cout, g.cin, *ks), device=DEV)
+        nbytes, tc_off = ops.packed_weight_layout(g, kind, dtype)
+        buf = torch.full((nbytes,), 0x5A, dtype=torch.uint8, device=DEV)
+        ws.append(w); bufs.append(buf)
+        entries.append((w.data_ptr(), buf.data_ptr(), tc_off, g.kernel ** g.dims, g.cin, g.cout, kind))
+        singles.append(ops.pack_weight(g, kind, w, dtype))
+    table = ops.make_pack_table(entries, torch.device(DEV))
+    ops.pack_weights_batched(table, len(entries))
+    torch.cuda.synchronize()
+    for (g, kind), buf, single in zip(layers, bufs, singles):
+        sb = single if single.dtype == torch.uint8 else single.view(torch.uint8)
+        nb, tc_off = ops.packed_weight_layout(g, kind, dtype)
+        taps = g.kernel ** g.dims
+        gen_bytes = taps * g.cin * g.cout * 2
+        assert torch.equal(buf[:gen_bytes], sb.reshape(-1)[:gen_bytes]), f"generic layout differs for {g}"
+        assert torch.equal(buf[tc_off:], sb.reshape(-1)[tc_off:nb]), f"tcgen05 layout differs for {g}"
 
 
 TC_GEOMS = [
