@@ -50,6 +50,7 @@ SIGNATURES = {
     "b200seg_last_error": (C.c_char_p, []),
     "b200seg_launch_count": (C.c_longlong, []),
     "b200seg_tc_launch_count": (C.c_longlong, []),
+    "b200seg_last_launch": (C.c_char_p, []),
     "b200seg_check_device": (C.c_int, [C.c_int]),
     "b200seg_packed_weight_bytes": (C.c_size_t, [_CD, C.c_int]),
     "b200seg_pack_weight": (C.c_int, [_CD, C.c_int, _P, _P, _P]),

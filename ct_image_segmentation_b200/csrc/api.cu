@@ -14,7 +14,9 @@ static thread_local char g_err[512] = "";
 static std::atomic<long long> g_launches{0};
 
 static std::atomic<long long> g_tc_launches{0};
+static std::atomic<const char*> g_last_launch{""};
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void note_launch(const char* what) { g_last_launch.store(what, std::memory_order_relaxed); }
 void count_tc_launch() { g_tc_launches.fetch_add(1, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
@@ -71,6 +73,7 @@ int b200seg_version(void) { return B200SEG_VERSION; }
 const char* b200seg_last_error(void) { return g_err; }
 long long b200seg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 long long b200seg_tc_launch_count(void) { return g_tc_launches.load(std::memory_order_relaxed); }
+const char* b200seg_last_launch(void) { return g_last_launch.load(std::memory_order_relaxed); }
 
 int b200seg_check_device(int device) {
   cudaDeviceProp prop;
@@ -127,6 +130,8 @@ static int tc_dispatch(const b200seg_conv_desc* d, int op, const void* src, cons
                        const float* bias, const void* residual, void* dst, void* stream, float* stats = nullptr) {
   if (!(d->flags & B200SEG_CONV_NO_SLIDE) && tc_slide_conv_supported(d, op))
     return tc_slide_conv_run(d, op, src, tc_weights(d, w_packed), bias, residual, dst, stats, as_stream(stream));
+  if (tc_convtr_slide_supported(d, op, residual))
+    return tc_convtr_slide_run(d, op, src, tc_weights(d, w_packed), bias, dst, stats, as_stream(stream));
   return tc_conv_run(d, op, src, tc_weights(d, w_packed), bias, residual, dst, stats, as_stream(stream));
 }
 
@@ -155,6 +160,9 @@ static void stats_layout(const b200seg_conv_desc* d, int op, int* ncls, int64_t*
   if (!(d->flags & B200SEG_CONV_NO_SLIDE) && tc_slide_conv_supported(d, op)) {
     *ncls = 1;
     *tiles = tc_slide_conv_grid(d, op) / d->n;
+  } else if (tc_convtr_slide_supported(d, op, nullptr)) {
+    *ncls = 1;
+    *tiles = tc_convtr_slide_grid(d, op) / d->n;
   } else {
     tc_conv_grid(d, op, ncls, tiles);
   }
@@ -177,7 +185,8 @@ static int fprop_stats_common(const b200seg_conv_desc* d, bool transposed_layer,
   // reduction over tens of thousands of partials cost more than the separate statistics pass
   // (measured: ConvTranspose 32->10 fprop 258 -> 440 us).
   if (mean && rstd && ws && tc_conv_supported(d, op, x, y, nullptr) &&
-      !(d->flags & B200SEG_CONV_NO_SLIDE) && tc_slide_conv_supported(d, op)) {
+      ((!(d->flags & B200SEG_CONV_NO_SLIDE) && tc_slide_conv_supported(d, op)) ||
+       tc_convtr_slide_supported(d, op, nullptr))) {
     if (ws_bytes < fprop_stats_ws(d, transposed_layer)) {
       set_error("conv_fprop_stats: workspace %zu < required %zu", ws_bytes, fprop_stats_ws(d, transposed_layer));
       return B200SEG_ERR_WORKSPACE;
@@ -299,6 +308,8 @@ static int wgrad_common(const b200seg_conv_desc* d, bool transposed_layer, const
     float* g32 = (float*)((char*)ws + wgrad_main_bytes(d, w) + wgrad_colsum_bytes(d));
     if (tc_slide_wgrad_supported(d, transposed_layer))
       rc = tc_slide_wgrad_run(d, x, dy, gw, g32, as_stream(stream));
+    else if (transposed_layer && tc_convtr_wgrad_supported(d))
+      rc = tc_convtr_wgrad_run(d, x, dy, gw, g32, as_stream(stream));
     else
       rc = tc_wgrad_run(d, transposed_layer, x, dy, gw, g32, as_stream(stream));
   } else if (!transposed_layer && small_cin_supported(d)) {

@@ -11,6 +11,7 @@ namespace b200seg {
 
 void set_error(const char* fmt, ...);
 void count_launch();
+void note_launch(const char* what);
 void count_tc_launch();
 
 #define B200SEG_CHECK_ARG(cond, ...)      \
@@ -25,6 +26,7 @@ void count_tc_launch();
   do {                                                                           \
     cudaError_t e__ = cudaGetLastError();                                        \
     b200seg::count_launch();                                                     \
+    b200seg::note_launch(what);                                                  \
     if (e__ != cudaSuccess) {                                                    \
       b200seg::set_error("%s: CUDA error: %s", what, cudaGetErrorString(e__));   \
       return B200SEG_ERR_CUDA;                                                   \

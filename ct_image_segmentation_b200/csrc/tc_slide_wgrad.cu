@@ -195,6 +195,16 @@ __global__ void tc_slide_wgrad_unpack_kernel(const float* __restrict__ G, float*
   if (lane == 0) gw[((int64_t)b * a_c + a) * taps + tap] = s;
 }
 
+// host launcher shared with the ConvTranspose sliding wgrad (tc_convtr.cu)
+int tc_slide_wgrad_unpack(const float* G, float* gw, int taps, int a_c, int b_c, int a_pad, int b_pad, int nparts,
+                          cudaStream_t st) {
+  const int64_t total = (int64_t)taps * a_c * b_c;
+  tc_slide_wgrad_unpack_kernel<<<(unsigned)cdiv64(total * 32, 256), 256, 0, st>>>(G, gw, taps, a_c, b_c, a_pad, b_pad,
+                                                                                 nparts);
+  B200SEG_CHECK_LAUNCH("tc_slide_wgrad_unpack");
+  return B200SEG_OK;
+}
+
 namespace {
 template <int CA, int CB>
 int launch_slide_wgrad(const TcSlideWgradParams& p, unsigned grid, cudaStream_t st) {

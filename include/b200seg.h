@@ -108,6 +108,9 @@ const char* b200seg_last_error(void);
 long long b200seg_launch_count(void);
 /* ... of which tcgen05 (tensor-core) kernels */
 long long b200seg_tc_launch_count(void);
+/* Name of the kernel family of the most recent launch made through this library (diagnostics and
+ * tests: proves which implementation a layer was dispatched to).  Static storage, never NULL. */
+const char* b200seg_last_launch(void);
 /* 0 if `device` is an sm_100 part this library can run on */
 int b200seg_check_device(int device);
 

@@ -253,6 +253,79 @@ def test_tcgen05_conv_vs_torch_and_generic(dims, cin, cout, k, s, tr, n, sp):
     assert rel(gb, dy.sum(dim=[0] + list(range(2, 2 + dims)))) < 1e-2
 
 
+CONVTR_SLIDE = [
+    # cin, cout, n, input spatial -- ConvTranspose k3 s2 layers the sliding-window kernels take
+    (32, 10, 1, (8, 24, 40)),     # top layer: 10 classes padded to 16, ragged h tile
+    (64, 16, 2, (9, 32, 16)),     # odd depth, d segments
+    (32, 16, 1, (5, 16, 36)),     # ragged w tile
+]
+
+
+@pytest.mark.parametrize("cin,cout,n,sp", CONVTR_SLIDE)
+def test_convtr_sliding_kernels(cin, cout, n, sp):
+    """Sliding-window ConvTranspose kernels (fprop with fused InstanceNorm statistics, dgrad, wgrad)
+    against torch fp32 on the same bf16-rounded inputs (1e-2) and against the streaming kernels."""
+    lib = _lib.load()
+    dtype = torch.bfloat16
+    torch.manual_seed(777)
+    g = ConvGeom(3, cin, cout, 3, 2, True)
+    w = q(torch.randn(cin, cout, 3, 3, 3) * (2.0 / (cin * 27)) ** 0.5, dtype).requires_grad_(True)
+    b = torch.randn(cout)
+    x = q(torch.randn(n, cin, *sp), dtype).requires_grad_(True)
+    y_ref = ref_conv(g, x, w, b)
+    dy = q(torch.randn_like(y_ref), dtype)
+    y_ref.backward(dy)
+
+    def dev(t_nc):
+        out = ops.alloc_activation(t_nc.shape[0], tuple(t_nc.shape[2:]), t_nc.shape[1], dtype, DEV)
+        out.copy_(t_nc.permute(0, 2, 3, 4, 1))
+        return out
+
+    wdev = w.detach().to(DEV)
+    x_cl, dy_cl = dev(x.detach()), dev(dy)
+    wp = ops.pack_weight(g, _lib.W_CONVTR_FPROP, wdev, dtype)
+    y_cl = ops.alloc_like(dy_cl)
+    t0 = lib.b200seg_tc_launch_count()
+    ops.conv_fprop(g, x_cl, wp, b.to(DEV), y_cl)
+    assert lib.b200seg_tc_launch_count() == t0 + 1
+    assert lib.b200seg_last_launch() == b"tc_convtr_fprop"
+    e = rel(nc_cpu(y_cl, 3), y_ref.detach())
+    assert e < 1e-2, f"convtr fprop rel err {e}"
+    y_str = ops.alloc_like(dy_cl)
+    ops.conv_fprop(g, x_cl, wp, b.to(DEV), y_str, flags=_lib.CONV_NO_SLIDE)
+    assert rel(y_cl, y_str) < 2e-3, "sliding vs streaming fprop"
+    if cout % 16:
+        full = y_cl.as_strided(y_cl.shape[:-1] + ((cout + 15) // 16 * 16,), y_cl.stride())
+        assert float(full[..., cout:].abs().max()) == 0.0
+    # fused statistics
+    y2 = ops.alloc_like(dy_cl)
+    mean, rstd = ops.conv_fprop_stats(g, x_cl, wp, b.to(DEV), y2)
+    assert torch.equal(y2, y_cl)
+    yd = y_ref.detach().double()
+    m_ref = yd.mean(dim=(2, 3, 4))
+    r_ref = 1.0 / torch.sqrt(yd.var(dim=(2, 3, 4), unbiased=False) + 1e-5)
+    cs = mean.numel() // n
+    assert rel(mean.view(n, cs)[:, :cout], m_ref) < 2e-3 and rel(rstd.view(n, cs)[:, :cout], r_ref) < 2e-3
+    # dgrad
+    wp_d = ops.pack_weight(g, _lib.W_CONVTR_DGRAD, wdev, dtype)
+    dx_cl = ops.alloc_like(x_cl)
+    ops.conv_dgrad(g, dy_cl, wp_d, dx_cl)
+    assert lib.b200seg_last_launch() == b"tc_convtr_dgrad"
+    e = rel(nc_cpu(dx_cl, 3), x.grad)
+    assert e < 1e-2, f"convtr dgrad rel err {e}"
+    dx_str = ops.alloc_like(x_cl)
+    ops.conv_dgrad(g, dy_cl, wp_d, dx_str, flags=_lib.CONV_NO_SLIDE)
+    assert rel(dx_cl, dx_str) < 2e-3, "sliding vs streaming dgrad"
+    # wgrad
+    gw, gb = ops.conv_wgrad(g, x_cl, dy_cl, want_bias=False)
+    if cin == 32:
+        assert lib.b200seg_last_launch() == b"tc_slide_wgrad_unpack"
+    e = rel(gw, w.grad)
+    assert e < 1e-2, f"convtr wgrad rel err {e}"
+    gw2, _ = ops.conv_wgrad(g, x_cl, dy_cl, flags=_lib.CONV_NO_SLIDE)
+    assert rel(gw, gw2) < 1e-4, "sliding vs streaming wgrad"
+
+
 NORM_CASES = [(2, 16, (6, 8, 10)), (1, 10, (8, 8, 12)), (2, 64, (4, 4, 4)), (3, 32, (1, 12, 20)),
               (1, 256, (2, 3, 4)), (2, 7, (3, 5, 7))]
 
