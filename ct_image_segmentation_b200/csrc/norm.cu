@@ -35,9 +35,9 @@ int pick_vec(const b200seg_norm_desc& d, std::initializer_list<const void*> ptrs
 }  // namespace
 
 int norm_blocks(const b200seg_norm_desc& d) {
-  // >= 8192 elements per block (256 threads x 16 B x a few iterations): deep layers with few voxels
+  // >= 16384 elements per block (256 threads x 16 B x a few iterations): deep layers with few voxels
   // but many channels still spread over tens of blocks instead of looping in one
-  int64_t nb = cdiv64(d.spatial * (int64_t)d.c, 8192);
+  int64_t nb = cdiv64(d.spatial * (int64_t)d.c, 16384);
   int64_t cap = 1184 / (d.n > 0 ? d.n : 1);
   if (cap < 1) cap = 1;
   if (nb > cap) nb = cap;

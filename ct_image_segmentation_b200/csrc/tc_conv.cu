@@ -418,15 +418,11 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, bf16* __restr
 // ---- all layers in one launch: table of b200seg_pack_entry in device memory.  The entries differ in
 // size by four orders of magnitude (432 ... 1.8 M elements): the work is cut into chunks of
 // PACK_CHUNK packed elements, numbered across the entries, and dealt round-robin to the blocks.
-constexpr int PACK_CHUNK = 2048;  // = 256 threads x 8 consecutive elements
-__device__ __forceinline__ int pack_src_index(int kind, int t, int sc, int tap, int taps, int cin, int cout) {
-  switch (kind) {
-    case B200SEG_W_CONV_FPROP:   return (t * cin + sc) * taps + tap;
-    case B200SEG_W_CONV_DGRAD:   return (sc * cin + t) * taps + tap;
-    case B200SEG_W_CONVTR_FPROP: return (sc * cout + t) * taps + tap;
-    default:                     return (t * cout + sc) * taps + tap;
-  }
-}
+// A work item is one (dst, src) channel pair: its `taps` source values are contiguous in the PyTorch
+// parameter (read once, sector-efficient through L1), its packed values are `taps` strided 2-byte
+// stores that neighbouring lanes complete to full sectors (tcgen05 layout: lanes along the source
+// channel; generic layout: lanes along the destination channel).  Chunks of PACK_CHUNK items.
+constexpr int PACK_CHUNK = 256;
 __global__ void __launch_bounds__(256)
 pack_weights_batched_kernel(const b200seg_pack_entry* __restrict__ table, int n_entries) {
   int64_t chunk_base = 0;
@@ -438,44 +434,35 @@ pack_weights_batched_kernel(const b200seg_pack_entry* __restrict__ table, int n_
     const int src_pad = (src_c + 15) / 16 * 16, dst_pad = (dst_c + 15) / 16 * 16;
     const int KC = src_pad % 64 == 0 ? 64 : (src_pad % 32 == 0 ? 32 : 16);
     const int kblocks = src_pad / KC;
-    const int total = taps * src_pad * dst_pad, gen_total = taps * src_c * dst_c;  // < 2^31 (checked on the host side by size)
-    const int nchunks = (total + PACK_CHUNK - 1) / PACK_CHUNK;
+    const int items_tc = src_pad * dst_pad, items_gen = src_c * dst_c;
+    const int chunks_tc = items_tc / PACK_CHUNK, chunks_gen = (items_gen + PACK_CHUNK - 1) / PACK_CHUNK;
+    const int nchunks = chunks_tc + chunks_gen;
     const float* w = reinterpret_cast<const float*>(e.w);
     bf16* gen = reinterpret_cast<bf16*>(e.packed);
     bf16* out = reinterpret_cast<bf16*>(e.packed + e.tc_offset);
-    // first chunk of this entry that falls to this block
+    // PyTorch layouts: Conv (cout, cin, taps), ConvTranspose (cin, cout, taps)
+    const bool conv_layer = (kind == B200SEG_W_CONV_FPROP || kind == B200SEG_W_CONV_DGRAD);
     int c = (int)(((int64_t)blockIdx.x - chunk_base % gridDim.x + gridDim.x) % gridDim.x);
     for (; c < nchunks; c += gridDim.x) {
-      const int idx0 = c * PACK_CHUNK + threadIdx.x * 8;  // 8 consecutive elements per thread: one division set
-      if (idx0 < total) {  // total is a multiple of 256: the 8 elements are all inside
-        // tcgen05 layout: idx = ((tap * kblocks + kb) * dst_pad + t) * KC + kc ; KC is a multiple of 8
-        const int kc0 = idx0 % KC;
-        int r = idx0 / KC;
-        const int t = r % dst_pad; r /= dst_pad;
-        const int kb = r % kblocks, tap = r / kblocks;
-        uint4 pk;
-        __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&pk);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          float v[2];
-#pragma unroll
-          for (int jj = 0; jj < 2; ++jj) {
-            const int sc = kb * KC + kc0 + 2 * i + jj;
-            v[jj] = (sc < src_c && t < dst_c) ? w[pack_src_index(kind, t, sc, tap, taps, cin, cout)] : 0.f;
-          }
-          h[i] = __floats2bfloat162_rn(v[0], v[1]);
-        }
-        *reinterpret_cast<uint4*>(out + idx0) = pk;
-      }
-      if (idx0 < gen_total) {
-        // generic layout: idx = (tap * src_c + sc) * dst_c + t
-        int t = idx0 % dst_c;
-        int r = idx0 / dst_c;
-        int sc = r % src_c, tap = r / src_c;
-        const int lim = min(8, gen_total - idx0);
-        for (int i = 0; i < lim; ++i) {
-          gen[idx0 + i] = __float2bfloat16_rn(w[pack_src_index(kind, t, sc, tap, taps, cin, cout)]);
-          if (++t == dst_c) { t = 0; if (++sc == src_c) { sc = 0; ++tap; } }
+      if (c < chunks_tc) {
+        const int item = c * PACK_CHUNK + threadIdx.x;  // = t * src_pad + sc
+        const int t = item / src_pad, sc = item - t * src_pad;
+        const int kb = sc / KC, kc = sc - kb * KC;
+        const bool live = sc < src_c && t < dst_c;
+        const int co = src_is_cin ? t : sc, ci = src_is_cin ? sc : t;
+        const float* wp = w + (conv_layer ? (int64_t)co * cin + ci : (int64_t)ci * cout + co) * taps;
+        bf16* op = out + ((int64_t)kb * dst_pad + t) * KC + kc;
+        const int64_t tap_stride = (int64_t)kblocks * dst_pad * KC;
+        for (int tap = 0; tap < taps; ++tap) op[tap * tap_stride] = __float2bfloat16_rn(live ? wp[tap] : 0.f);
+      } else {
+        const int item = (c - chunks_tc) * PACK_CHUNK + threadIdx.x;  // = sc * dst_c + t
+        if (item < items_gen) {
+          const int sc = item / dst_c, t = item - sc * dst_c;
+          const int co = src_is_cin ? t : sc, ci = src_is_cin ? sc : t;
+          const float* wp = w + (conv_layer ? (int64_t)co * cin + ci : (int64_t)ci * cout + co) * taps;
+          bf16* op = gen + item;
+          const int64_t tap_stride = (int64_t)items_gen;
+          for (int tap = 0; tap < taps; ++tap) op[tap * tap_stride] = __float2bfloat16_rn(wp[tap]);
         }
       }
     }

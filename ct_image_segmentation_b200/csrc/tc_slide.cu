@@ -7,9 +7,13 @@
 // shared-memory ring (box rows of exactly 8 voxels = one swizzle atom, so a shift by whole lines
 // (kh) or whole slabs (kd) is an atom-aligned descriptor offset and the w shift (kw) selects the
 // copy).  Each source voxel is therefore read 3 x 18/16 = 3.4 times from L2 instead of 27 times.
-//   conv (fprop / dgrad): per output slab 27 x (KC/16) tcgen05.mma of M=128 (16 lines x 8 voxels),
-//     N=Cout, K=16 against the 27 weight tiles resident in shared memory; two TMEM accumulator
-//     buffers so the epilogue of slab d overlaps the MMAs of slab d+1.
+//   conv (fprop / dgrad): the MMAs are organised per SOURCE slab and folded along N over the three
+//     output slabs (kd taps) the slab contributes to: 9 x (KC/16) tcgen05.mma of M=128 (16 lines x 8
+//     voxels), N = 3*Cout, K=16 per source slab instead of 27 of N = Cout per output slab -- these
+//     small-N MMAs are bound by the shared-memory read of the 4 KB A tile, which the fold cuts 3x.
+//     Output slab j lives in TMEM chunk j mod 8 (a ring of accumulators: the three live chunks are
+//     adjacent columns except at the wrap, where the MMA is split); a chunk is complete after source
+//     slab j+2 and is drained by the epilogue warps while later slabs accumulate.
 //   wgrad: see tc_slide_wgrad_kernel below.
 #include <string.h>
 
@@ -51,16 +55,17 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
   constexpr int SLAB_BYTES = 3 * COPY_BYTES;
   constexpr int WT_BYTES = BN * PITCH;                   // one weight tile (tap)
   constexpr int W_BYTES = (27 * WT_BYTES + 1023) / 1024 * 1024;
-  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  constexpr int ACCR = 8;                                // TMEM accumulator ring (output slabs)
+  constexpr uint32_t TMEM_COLS = ACCR * BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* wsm = smem;
   uint8_t* ring = smem + W_BYTES;
   uint64_t* full = reinterpret_cast<uint64_t*>(ring + RING * SLAB_BYTES);
   uint64_t* empty = full + RING;
-  uint64_t* acc_full = empty + RING;   // [2]
-  uint64_t* acc_empty = acc_full + 2;  // [2]
-  uint64_t* wbar = acc_empty + 2;
+  uint64_t* acc_full = empty + RING;      // [ACCR]
+  uint64_t* acc_empty = acc_full + ACCR;  // [ACCR]
+  uint64_t* wbar = acc_empty + ACCR;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -78,7 +83,7 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
       tc::mbar_init(&full[i], 1);
       tc::mbar_init(&empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < ACCR; ++i) {
       tc::mbar_init(&acc_full[i], 1);
       tc::mbar_init(&acc_empty[i], 4);
     }
@@ -95,8 +100,16 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
 
   if (warp == 0) {
     if (lane == 0) {
+      // weights: for every in-plane source shift (ih, iw) the three kd tiles in the order of the
+      // output slabs s-2, s-1, s a source slab s feeds: slot (ih*3+iw)*3 + i holds source-shift id = 2-i.
+      // Tile of source shift (id, ih, iw): tap (id, ih, iw) for fprop, the mirrored tap for dgrad.
       tc::mbar_expect_tx(wbar, 27 * WT_BYTES);
-      for (int t = 0; t < 27; ++t) tc::tma_load_2d(wsm + t * WT_BYTES, &p.tmB, wbar, 0, t * BN);
+      for (int hw = 0; hw < 9; ++hw)
+        for (int i = 0; i < 3; ++i) {
+          const int id = 2 - i, ih = hw / 3, iw = hw % 3;
+          const int tap = p.flip ? ((2 - id) * 3 + (2 - ih)) * 3 + (2 - iw) : (id * 3 + ih) * 3 + iw;
+          tc::tma_load_2d(wsm + (hw * 3 + i) * WT_BYTES, &p.tmB, wbar, 0, tap * BN);
+        }
       uint32_t ph = 0;
       for (int s = 0; s < nd + 2; ++s) {
         const int slot = s % RING;
@@ -112,46 +125,63 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN, false, false);
       constexpr uint64_t layout = tc::layout_for_row_bytes(PITCH);
       const uint32_t w_addr = tc::smem_u32(wsm), r_addr = tc::smem_u32(ring);
-      // descriptor template: only the 14-bit start-address field varies (keeps the issue loop short;
-      // one thread feeds the tensor pipe, every instruction on its path counts)
       const uint64_t tmpl = tc::make_smem_desc(0, 16, 8 * PITCH, layout);
       const uint64_t w_desc = tmpl + (w_addr >> 4);
       tc::mbar_wait(wbar, 0);
-      int waited = 0;
-      for (int j = 0; j < nd; ++j) {
-        const int buf = j & 1;
-        tc::mbar_wait(&acc_empty[buf], (((uint32_t)j >> 1) & 1u) ^ 1u);
-        while (waited <= j + 2) {
-          tc::mbar_wait(&full[waited % RING], ((uint32_t)(waited / RING)) & 1u);
-          ++waited;
-        }
+      for (int s = 0; s < nd + 2; ++s) {
+        // source slab s (absolute d = d_begin - 1 + s) feeds output slabs s-2, s-1, s (clipped to [0, nd))
+        const int lo = max(s - 2, 0), hi = min(s, nd - 1);
+        const bool fresh = s < nd;  // output slab s receives its first contribution: overwrite
+        if (fresh) tc::mbar_wait(&acc_empty[s % ACCR], (((uint32_t)(s / ACCR)) & 1u) ^ 1u);
+        tc::mbar_wait(&full[s % RING], ((uint32_t)(s / RING)) & 1u);
         tc::tc_fence_after();
-        uint32_t first = 1;
-#pragma unroll 1
-        for (int id = 0; id < 3; ++id) {
-          const uint64_t slab = tmpl + ((r_addr + ((j + id) % RING) * SLAB_BYTES) >> 4);
-          const uint64_t wd = w_desc + (((p.flip ? (2 - id) : id) * 9 * WT_BYTES) >> 4);
-#pragma unroll
-          for (int ih = 0; ih < 3; ++ih)
-#pragma unroll
-            for (int iw = 0; iw < 3; ++iw) {
-              // weight tile (id, ih, iw) for fprop, the mirrored tap for dgrad (constant offsets)
-              const uint64_t a = slab + ((iw * COPY_BYTES + ih * (TWV * PITCH)) >> 4);
-              const uint64_t bf = wd + (((ih * 3 + iw) * WT_BYTES) >> 4);
-              const uint64_t bb = wd + ((((2 - ih) * 3 + (2 - iw)) * WT_BYTES) >> 4);
-              const uint64_t b = p.flip ? bb : bf;
-#pragma unroll
-              for (int k = 0; k < KC / 16; ++k) {
-                tc::umma_bf16(tmem_acc + buf * BN, a + 2 * k, b + 2 * k, idesc, first ? 0u : 1u);
-                first = 0;
-              }
-            }
+        // segments (TMEM column, first weight tile of the group, #output slabs): the accumulating range,
+        // split at the wrap of the accumulator ring; for the very first MMA the fresh chunk is separate
+        int seg_col[3], seg_row[3], seg_n[3], nseg_rest = 0;
+        {
+          int j = lo;
+          while (j <= hi) {
+            const int c = j % ACCR;
+            const int len = min(hi - j + 1, ACCR - c);
+            seg_col[nseg_rest] = c * BN; seg_row[nseg_rest] = j - (s - 2); seg_n[nseg_rest] = len;
+            ++nseg_rest;
+            j += len;
+          }
         }
-        tc::umma_commit(&acc_full[buf]);
-        tc::umma_commit(&empty[j % RING]);
+        const uint64_t slab = tmpl + ((r_addr + (s % RING) * SLAB_BYTES) >> 4);
+        bool first = true;
+#pragma unroll 1
+        for (int ih = 0; ih < 3; ++ih)
+#pragma unroll 1
+          for (int iw = 0; iw < 3; ++iw) {
+            const uint64_t a = slab + ((iw * COPY_BYTES + ih * (TWV * PITCH)) >> 4);
+            const uint64_t bg = w_desc + (((ih * 3 + iw) * 3 * WT_BYTES) >> 4);
+#pragma unroll
+            for (int k = 0; k < KC / 16; ++k) {
+              if (first && fresh) {
+                // accumulating part [lo, s-1] (if any), then the fresh chunk of output slab s
+                int j = lo;
+                while (j <= s - 1) {
+                  const int c = j % ACCR;
+                  const int len = min(s - j, ACCR - c);
+                  tc::umma_bf16(tmem_acc + c * BN, a + 2 * k, bg + (((j - (s - 2)) * WT_BYTES) >> 4) + 2 * k,
+                                tc::make_idesc_bf16(128, len * BN, false, false), 1u);
+                  j += len;
+                }
+                tc::umma_bf16(tmem_acc + (s % ACCR) * BN, a + 2 * k, bg + ((2 * WT_BYTES) >> 4) + 2 * k,
+                              tc::make_idesc_bf16(128, BN, false, false), 0u);
+              } else {
+                for (int g = 0; g < nseg_rest; ++g)
+                  tc::umma_bf16(tmem_acc + seg_col[g], a + 2 * k, bg + ((seg_row[g] * WT_BYTES) >> 4) + 2 * k,
+                                tc::make_idesc_bf16(128, seg_n[g] * BN, false, false), 1u);
+              }
+              first = false;
+            }
+          }
+        tc::umma_commit(&empty[s % RING]);
+        if (s >= 2) tc::umma_commit(&acc_full[(s - 2) % ACCR]);
       }
     }
   } else {
@@ -163,8 +193,8 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
 #pragma unroll
     for (int c = 0; c < BN; ++c) ssum[c] = ssq[c] = 0.f;
     for (int j = 0; j < nd; ++j) {
-      const int buf = j & 1;
-      tc::mbar_wait(&acc_full[buf], ((uint32_t)j >> 1) & 1u);
+      const int buf = j % ACCR;
+      tc::mbar_wait(&acc_full[buf], ((uint32_t)(j / ACCR)) & 1u);
       tc::tc_fence_after();
       const int od = d_begin + j;
       const int64_t lin = (((int64_t)n * p.D + od) * p.H + oh) * p.W + ow;

@@ -182,6 +182,7 @@ TC_GEOMS = [
     (3, 10, 10, 3, 1, False, 1, (20, 32, 40)),
     (3, 16, 32, 3, 1, False, 1, (9, 48, 16)),
     (3, 32, 16, 3, 1, False, 1, (16, 24, 32)),
+    (3, 16, 16, 3, 1, False, 2, (40, 128, 128)),   # long sweeps: the TMEM accumulator ring wraps
 ]
 
 
