@@ -67,6 +67,23 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// ---- cp.async (LDGSTS) producer path --------------------------------------------------------------
+// 16-byte global -> shared copy; src_bytes = 0 zero-fills (out-of-bounds halo), L1-allocating (.ca)
+__device__ __forceinline__ void cp_async_16(uint32_t smem_dst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(smem_dst), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one (pre-counted) arrival when all prior cp.async of this thread have landed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// byte offset inside a tile -> offset in the 32 / 64 / 128-byte swizzled layout TMA and UMMA use
+// (Swizzle<B,4,3>: address bits [4, 4+B) ^= bits [7, 7+B)); the tile base is aligned to the repeat
+template <int ROW_BYTES>
+__device__ __forceinline__ uint32_t swizzle_offset(uint32_t off) {
+  constexpr uint32_t mask = ROW_BYTES == 128 ? 0x70u : (ROW_BYTES == 64 ? 0x30u : 0x10u);
+  return off ^ ((off >> 3) & mask);
+}
+
 // ---- TMEM / tcgen05 ------------------------------------------------------------------------------
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {  // one full warp

@@ -137,48 +137,36 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
         if (fresh) tc::mbar_wait(&acc_empty[s % ACCR], (((uint32_t)(s / ACCR)) & 1u) ^ 1u);
         tc::mbar_wait(&full[s % RING], ((uint32_t)(s / RING)) & 1u);
         tc::tc_fence_after();
-        // segments (TMEM column, first weight tile of the group, #output slabs): the accumulating range,
-        // split at the wrap of the accumulator ring; for the very first MMA the fresh chunk is separate
-        int seg_col[3], seg_row[3], seg_n[3], nseg_rest = 0;
-        {
-          int j = lo;
-          while (j <= hi) {
-            const int c = j % ACCR;
-            const int len = min(hi - j + 1, ACCR - c);
-            seg_col[nseg_rest] = c * BN; seg_row[nseg_rest] = j - (s - 2); seg_n[nseg_rest] = len;
-            ++nseg_rest;
-            j += len;
-          }
-        }
+        // The accumulating range [lo, hi] is one MMA (adjacent TMEM chunks) or two where the
+        // accumulator ring wraps.  Everything below is registers + constants: one thread feeds the
+        // tensor pipe, every instruction on its path counts.
+        const int c_lo = lo % ACCR;
+        const int len0 = min(hi - lo + 1, ACCR - c_lo), len1 = hi - lo + 1 - len0;
+        const uint32_t d0 = tmem_acc + c_lo * BN, d1 = tmem_acc;  // a wrapped part starts at chunk 0
+        const uint32_t i0 = tc::make_idesc_bf16(128, len0 * BN, false, false);
+        const uint32_t i1 = tc::make_idesc_bf16(128, (len1 > 0 ? len1 : 1) * BN, false, false);
+        const uint64_t b0 = w_desc + (((lo - (s - 2)) * WT_BYTES) >> 4);
+        const uint64_t b1 = b0 + ((len0 * WT_BYTES) >> 4);
         const uint64_t slab = tmpl + ((r_addr + (s % RING) * SLAB_BYTES) >> 4);
-        bool first = true;
-#pragma unroll 1
-        for (int ih = 0; ih < 3; ++ih)
-#pragma unroll 1
-          for (int iw = 0; iw < 3; ++iw) {
-            const uint64_t a = slab + ((iw * COPY_BYTES + ih * (TWV * PITCH)) >> 4);
-            const uint64_t bg = w_desc + (((ih * 3 + iw) * 3 * WT_BYTES) >> 4);
+        if (fresh) {
+          // first MMA of the slab: output slab s is overwritten (its own instruction), the older ones accumulate
+          constexpr uint32_t idesc1 = tc::make_idesc_bf16(128, BN, false, false);
+          for (int j = lo; j < s; ++j)
+            tc::umma_bf16(tmem_acc + (j % ACCR) * BN, slab, w_desc + (((j - (s - 2)) * WT_BYTES) >> 4), idesc1, 1u);
+          tc::umma_bf16(tmem_acc + (s % ACCR) * BN, slab, w_desc + ((2 * WT_BYTES) >> 4), idesc1, 0u);
+        } else {
+          tc::umma_bf16(d0, slab, b0, i0, 1u);
+          if (len1 > 0) tc::umma_bf16(d1, slab, b1, i1, 1u);
+        }
 #pragma unroll
-            for (int k = 0; k < KC / 16; ++k) {
-              if (first && fresh) {
-                // accumulating part [lo, s-1] (if any), then the fresh chunk of output slab s
-                int j = lo;
-                while (j <= s - 1) {
-                  const int c = j % ACCR;
-                  const int len = min(s - j, ACCR - c);
-                  tc::umma_bf16(tmem_acc + c * BN, a + 2 * k, bg + (((j - (s - 2)) * WT_BYTES) >> 4) + 2 * k,
-                                tc::make_idesc_bf16(128, len * BN, false, false), 1u);
-                  j += len;
-                }
-                tc::umma_bf16(tmem_acc + (s % ACCR) * BN, a + 2 * k, bg + ((2 * WT_BYTES) >> 4) + 2 * k,
-                              tc::make_idesc_bf16(128, BN, false, false), 0u);
-              } else {
-                for (int g = 0; g < nseg_rest; ++g)
-                  tc::umma_bf16(tmem_acc + seg_col[g], a + 2 * k, bg + ((seg_row[g] * WT_BYTES) >> 4) + 2 * k,
-                                tc::make_idesc_bf16(128, seg_n[g] * BN, false, false), 1u);
-              }
-              first = false;
-            }
+        for (int hw = 0; hw < 9; ++hw)
+#pragma unroll
+          for (int k = 0; k < KC / 16; ++k) {
+            if (hw == 0 && k == 0) continue;
+            const uint64_t a = slab + (((hw % 3) * COPY_BYTES + (hw / 3) * (TWV * PITCH)) >> 4) + 2 * k;
+            const uint64_t bo = ((hw * 3 * WT_BYTES) >> 4) + 2 * k;
+            tc::umma_bf16(d0, a, b0 + bo, i0, 1u);
+            if (len1 > 0) tc::umma_bf16(d1, a, b1 + bo, i1, 1u);
           }
         tc::umma_commit(&empty[s % RING]);
         if (s >= 2) tc::umma_commit(&acc_full[(s - 2) % ACCR]);
@@ -190,8 +178,12 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
     const int oh = h0 + row / TWV, ow = w0 + row % TWV;
     const bool valid = oh < p.H && ow < p.W;
     float ssum[BN], ssq[BN];  // per-thread partial statistics over this CTA's slabs (same sample n)
+    float bias[BN];           // hoisted: the epilogue runs once per slab
 #pragma unroll
-    for (int c = 0; c < BN; ++c) ssum[c] = ssq[c] = 0.f;
+    for (int c = 0; c < BN; ++c) {
+      ssum[c] = ssq[c] = 0.f;
+      bias[c] = (p.bias && c < p.cout) ? p.bias[c] : 0.f;
+    }
     for (int j = 0; j < nd; ++j) {
       const int buf = j % ACCR;
       tc::mbar_wait(&acc_full[buf], ((uint32_t)(j / ACCR)) & 1u);
@@ -208,11 +200,8 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
           float f[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-          if (p.bias) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i)
-              if (c0 + i < p.cout) f[i] += p.bias[c0 + i];
-          }
+          for (int i = 0; i < 16; ++i) f[i] += bias[ch * 16 + i];
           if (p.res) {
             const uint4* rp = reinterpret_cast<const uint4*>(p.res + lin * p.res_ld + c0);
             uint4 r0 = rp[0], r1 = rp[1];
