@@ -55,6 +55,7 @@ SIGNATURES = {
     "b200seg_packed_weight_bytes": (C.c_size_t, [_CD, C.c_int]),
     "b200seg_pack_weight": (C.c_int, [_CD, C.c_int, _P, _P, _P]),
     "b200seg_packed_weight_tc_offset": (C.c_size_t, [_CD, C.c_int]),
+    "b200seg_dice_loss_epilogue": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P, _P, _P, _P]),
     "b200seg_pack_weights_batched": (C.c_int, [_P, C.c_int32, _P]),
     "b200seg_conv_fprop": (C.c_int, [_CD, _P, _P, _P, _P, _P, _P]),
     "b200seg_conv_fprop_stats_workspace_bytes": (C.c_size_t, [_CD]),

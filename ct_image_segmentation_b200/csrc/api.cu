@@ -184,9 +184,19 @@ static int fprop_stats_common(const b200seg_conv_desc* d, bool transposed_layer,
   // streaming kernel (one tile per CTA, up to 32 k CTAs) the per-tile warp reductions and the
   // reduction over tens of thousands of partials cost more than the separate statistics pass
   // (measured: ConvTranspose 32->10 fprop 258 -> 440 us).
-  if (mean && rstd && ws && tc_conv_supported(d, op, x, y, nullptr) &&
-      ((!(d->flags & B200SEG_CONV_NO_SLIDE) && tc_slide_conv_supported(d, op)) ||
-       tc_convtr_slide_supported(d, op, nullptr))) {
+  // The streaming kernel (one tile per CTA) fuses them only while the partials stay few (deep layers).
+  bool fuse = false;
+  if (mean && rstd && ws && tc_conv_supported(d, op, x, y, nullptr)) {
+    fuse = (!(d->flags & B200SEG_CONV_NO_SLIDE) && tc_slide_conv_supported(d, op)) ||
+           tc_convtr_slide_supported(d, op, nullptr);
+    if (!fuse) {
+      int ncls;
+      int64_t tiles;
+      tc_conv_grid(d, op, &ncls, &tiles);
+      fuse = (int64_t)ncls * d->n * tiles <= 512;
+    }
+  }
+  if (fuse) {
     if (ws_bytes < fprop_stats_ws(d, transposed_layer)) {
       set_error("conv_fprop_stats: workspace %zu < required %zu", ws_bytes, fprop_stats_ws(d, transposed_layer));
       return B200SEG_ERR_WORKSPACE;
@@ -459,6 +469,15 @@ int b200seg_softmax_dice_bwd(const b200seg_dice_desc* d, const void* logits, con
   if (rc) return rc;
   B200SEG_CHECK_ARG(logits && labels && gI && gP && dlogits, "softmax_dice_bwd: NULL pointer");
   return launch_softmax_dice_bwd(*d, logits, labels, gI, gP, dlogits, as_stream(stream));
+}
+
+int b200seg_dice_loss_epilogue(const float* sums, int32_t n, int32_t c, int32_t include_background, float smooth,
+                               int32_t mean, float* loss, float* gI, float* gP, void* stream) {
+  B200SEG_CHECK_ARG(sums && loss && gI && gP && n > 0 && c > 0, "dice_loss_epilogue: bad argument");
+  const int c0 = include_background ? 0 : 1;
+  B200SEG_CHECK_ARG(c > c0, "dice_loss_epilogue: no foreground class");
+  const float inv_count = mean ? 1.f / (float)(n * (c - c0)) : 1.f;
+  return launch_dice_loss_epilogue(sums, n, c, c0, smooth, inv_count, loss, gI, gP, as_stream(stream));
 }
 
 int b200seg_argmax_dice_counts(const b200seg_dice_desc* d, const void* logits, const void* target,

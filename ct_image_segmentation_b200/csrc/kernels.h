@@ -76,6 +76,8 @@ int launch_softmax_dice_fwd(const b200seg_dice_desc& d, const void* logits, cons
                             float* sums, void* ws, cudaStream_t st);
 int launch_softmax_dice_bwd(const b200seg_dice_desc& d, const void* logits, const void* labels,
                             const float* gI, const float* gP, void* dlogits, cudaStream_t st);
+int launch_dice_loss_epilogue(const float* sums, int n, int c, int c0, float smooth, float inv_count, float* loss,
+                              float* gI, float* gP, cudaStream_t st);
 int launch_argmax_dice_counts(const b200seg_dice_desc& d, const void* logits, const void* target,
                               uint8_t* pred_out, int64_t* counts, cudaStream_t st);
 int launch_label_dice_counts(int n, int64_t spatial, int c, const uint8_t* pred, const void* target,

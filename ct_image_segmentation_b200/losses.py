@@ -51,6 +51,23 @@ class _SoftmaxDiceSums(torch.autograd.Function):
         return ops.softmax_dice_bwd(logits_cl, labels, g[..., 0], g[..., 2]), None
 
 
+class _FusedDiceLoss(torch.autograd.Function):
+    """mean / sum softmax-Dice loss as three launches forward (sums, their reduction, the (B, C)
+    epilogue with the gradient coefficients) and one backward kernel (+ a scalar scale)."""
+
+    @staticmethod
+    def forward(ctx, logits_cl, labels, include_background, smooth, mean):
+        sums = ops.softmax_dice_sums(logits_cl, labels)
+        loss, g_i, g_p = ops.dice_loss_epilogue(sums, include_background, smooth, mean)
+        ctx.save_for_backward(logits_cl, labels, g_i, g_p)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        logits_cl, labels, g_i, g_p = ctx.saved_tensors
+        return ops.softmax_dice_bwd(logits_cl, labels, g_i * g, g_p * g), None, None, None, None
+
+
 def softmax_dice_sums(input: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     """(B, C, 3) = [I, G, P] with autograd through the fused kernels."""
     cl = _as_cl(input)
@@ -80,6 +97,10 @@ class DiceLoss(nn.Module):
     def forward(self, input: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
         if target.shape[1] != 1:
             raise AssertionError("labels must have a singleton channel dim (to_onehot_y=True)")
+        if self.reduction in ("mean", "sum"):
+            cl = _as_cl(input)
+            return _FusedDiceLoss.apply(cl, target[:, 0], self.include_background, self.smooth,
+                                        self.reduction == "mean")
         sums = softmax_dice_sums(input, target)
         if not self.include_background:
             sums = sums[:, 1:]

@@ -459,6 +459,19 @@ def softmax_dice_sums(logits, labels) -> torch.Tensor:
     return sums
 
 
+def dice_loss_epilogue(sums: torch.Tensor, include_background: bool, smooth: float, mean: bool):
+    """(loss scalar, gI (N, C), gP (N, C)) from the (N, C, 3) Dice sums -- one launch."""
+    lib = _lib.load()
+    n, c, _ = sums.shape
+    loss = torch.empty((), dtype=torch.float32, device=sums.device)
+    g_i = torch.empty(n, c, dtype=torch.float32, device=sums.device)
+    g_p = torch.empty(n, c, dtype=torch.float32, device=sums.device)
+    _lib.check(lib.b200seg_dice_loss_epilogue(sums.data_ptr(), n, c, int(include_background), float(smooth),
+                                              int(mean), loss.data_ptr(), g_i.data_ptr(), g_p.data_ptr(), _stream()),
+               "b200seg_dice_loss_epilogue")
+    return loss, g_i, g_p
+
+
 def softmax_dice_bwd(logits, labels, g_i, g_p, dlogits=None) -> torch.Tensor:
     lib = _lib.load()
     n, d, h, w, c, ld = cl_info(logits)

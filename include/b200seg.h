@@ -217,6 +217,15 @@ int b200seg_softmax_dice_fwd(const b200seg_dice_desc* d, const void* logits, con
 int b200seg_softmax_dice_bwd(const b200seg_dice_desc* d, const void* logits, const void* labels,
                              const float* gI, const float* gP, void* dlogits, void* stream);
 
+/* Dice loss value and gradient coefficients from the (n, c, 3) sums of b200seg_softmax_dice_fwd, in one
+ * launch: the arithmetic of monai.losses.DiceLoss.forward after the spatial sums
+ * (capstone/models/losses.py:80-85 configures it; formula in SURVEY.md A.6):
+ *   f = 1 - (2 I + smooth) / (G + P + smooth); loss = mean (mean != 0) or sum of f over (n, foreground c);
+ *   gI = d loss / d I, gP = d loss / d P (n*c floats each, zero for an excluded background) -- the
+ *   inputs of b200seg_softmax_dice_bwd. */
+int b200seg_dice_loss_epilogue(const float* sums, int32_t n, int32_t c, int32_t include_background,
+                               float smooth, int32_t mean, float* loss, float* gI, float* gP, void* stream);
+
 /* ---- label maps and the Dice metric -------------------------------------------
  * argmax:  pred[v] = argmax_c softmax(logits)[c], first maximum wins
  *          (capstone/training/utils.py:19-20 `_squash_predictions`).

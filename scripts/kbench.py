@@ -66,6 +66,7 @@ def conv_case(name, cin, cout, k, s, tr, n, sp_in, x_wide=None, stats=False):
 CASES = {
     "head": lambda: conv_case("head", 10, 10, 3, 1, False, 2, (128, 128, 128)),
     "headL2": lambda: conv_case("headL2", 10, 10, 3, 1, False, 2, (32, 128, 128)),
+    "col": lambda: conv_case("col", 27, 16, 1, 1, False, 2, (64, 64, 64), stats=True),
     "l0": lambda: conv_case("l0", 16, 16, 3, 1, False, 2, (64, 64, 64), stats=True),
     "l1": lambda: conv_case("l1", 32, 32, 3, 1, False, 2, (32, 32, 32), stats=True),
     "convtr": lambda: conv_case("convtr", 32, 10, 3, 2, True, 2, (64, 64, 64), stats=True),
