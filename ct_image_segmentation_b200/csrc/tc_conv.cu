@@ -357,10 +357,14 @@ int launch_cfg(const TcConvParams& p, dim3 grid, cudaStream_t st) {
   return B200SEG_OK;
 }
 
+// ring depth: ~72 KB per CTA when the grid fills the machine several times over (2-3 CTAs per SM
+// share the shared memory); the whole SM when there is at most one CTA per SM (deep layers: 8..64
+// CTAs, each streaming megabytes -- bytes in flight per CTA are what bounds them)
 template <int BN, int KC>
-int stages_for() {
+int stages_for(int64_t ctas) {
   using Cfg = TcCfg<BN, KC>;
-  int s = (72 * 1024) / Cfg::STAGE_BYTES;
+  const int budget = ctas <= 148 ? 200 * 1024 : 72 * 1024;
+  int s = budget / Cfg::STAGE_BYTES;
   if (s > 8) s = 8;
   if (s < 3) s = 3;
   return s;
@@ -641,7 +645,7 @@ int tc_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void*
 
 #define TC_CASE(bn, kc)                                   \
   if (BN == bn && KC == kc) {                             \
-    p.stages = stages_for<bn, kc>();                      \
+    p.stages = stages_for<bn, kc>(gx * (dst_pad / BN));    \
     return launch_cfg<bn, kc>(p, grid, st);               \
   }
   TC_CASE(16, 16) TC_CASE(16, 32) TC_CASE(16, 64)

@@ -11,6 +11,7 @@
 // TMEM columns accumulate concurrently ("pass"); voxel tiles are split across CTAs (split-K) and
 // the fp32 partial sums are combined with red.global.add.f32 into a zeroed workspace, which a
 // small kernel then transposes into the PyTorch parameter layout.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -332,6 +333,17 @@ int tc_wgrad_run(const b200seg_conv_desc* d, bool transposed_layer, const void* 
   p.nslots = ns;
   const int mtiles_total = (ns + p.spm - 1) / p.spm;
   p.mt_per_pass = mtiles_total < gcap ? mtiles_total : gcap;
+  // Voxels per stage (a 4-deep ring in ~190 KB) shrink with the number of M tiles staged together;
+  // 16-voxel stages are a string of 2 KB TMA boxes and one K step per MMA tile.  Prefer fewer M tiles
+  // per pass (more passes = more CTAs, T is re-read from L2) until a stage holds >= 64 voxels.
+  auto kv_for = [&](int mt) {
+    const int pv = p.nb * CB * 2 + mt * p.spm * CA * 2;
+    int k = 128;
+    while (k > 16 && (size_t)k * pv * 4 > 190 * 1024) k /= 2;
+    return k;
+  };
+  static const int kv_target = getenv("B200SEG_WGRAD_KV") ? atoi(getenv("B200SEG_WGRAD_KV")) : 64;
+  while (p.mt_per_pass > 1 && kv_for(p.mt_per_pass) < kv_target) p.mt_per_pass = (p.mt_per_pass + 1) / 2;
   const int passes = (mtiles_total + p.mt_per_pass - 1) / p.mt_per_pass;
 
   // ---- voxels per stage and ring depth (shared memory budget ~ 190 KB)

@@ -12,17 +12,28 @@ DT = torch.bfloat16
 lib = _lib.load()
 
 
-def timeit(fn, reps=20, warm=3):
-    for _ in range(warm):
-        fn()
+def timeit(fn, reps=10, warm=3):
+    """us per call, replayed from a CUDA graph (no host launch overhead in the number)."""
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(warm):
+            fn()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(reps):
+            fn()
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(reps):
-        fn()
+    for _ in range(3):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / reps * 1e3
+    return e0.elapsed_time(e1) / (3 * reps) * 1e3
 
 
 def conv_case(name, cin, cout, k, s, tr, n, sp_in, x_wide=None, stats=False):
@@ -59,6 +70,9 @@ def conv_case(name, cin, cout, k, s, tr, n, sp_in, x_wide=None, stats=False):
     vox_in = n * sp_in[0] * sp_in[1] * sp_in[2]
     vox_out = n * sp_out[0] * sp_out[1] * sp_out[2]
     mb = (vox_in * max(cin, 8) + vox_out * ((cout + 15) // 16 * 16)) * 2 / 1e6
+    if os.environ.get("KB_COMPACT"):
+        print(f"{name}: " + " ".join(f"{a}={t:.1f}" for a, t, _ in out), end=" | ", flush=True)
+        return
     print(f"{name:10s} {cin:3d}->{cout:3d} k{k} s{s} {'T' if tr else ' '} in {sp_in}: " +
           "  ".join(f"{a} {t:7.1f} us [{kn}]" for a, t, kn in out) + f"   (x+y = {mb:.0f} MB)")
 
