@@ -318,8 +318,8 @@ static int wgrad_common(const b200seg_conv_desc* d, bool transposed_layer, const
     float* g32 = (float*)((char*)ws + wgrad_main_bytes(d, w) + wgrad_colsum_bytes(d));
     if (tc_slide_wgrad_supported(d, transposed_layer))
       rc = tc_slide_wgrad_run(d, x, dy, gw, g32, as_stream(stream));
-    else if (transposed_layer && tc_convtr_wgrad_supported(d))
-      rc = tc_convtr_wgrad_run(d, x, dy, gw, g32, as_stream(stream));
+    else if (tc_convtr_wgrad_supported(d, transposed_layer))
+      rc = tc_convtr_wgrad_run(d, transposed_layer, x, dy, gw, g32, as_stream(stream));
     else
       rc = tc_wgrad_run(d, transposed_layer, x, dy, gw, g32, as_stream(stream));
   } else if (!transposed_layer && small_cin_supported(d)) {

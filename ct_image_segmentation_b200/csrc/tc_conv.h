@@ -22,15 +22,15 @@ int tc_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void*
 bool tc_slide_conv_supported(const b200seg_conv_desc* d, int op);
 int tc_slide_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,
                       const void* residual, void* dst, float* stats, cudaStream_t st);
-// sliding-window ConvTranspose (k3 s2) kernels for the high-resolution decoder layers (tc_convtr.cu)
+// sliding-window kernels for the high-resolution stride-2 layers, ConvTranspose and Conv (tc_convtr.cu)
 bool tc_convtr_slide_supported(const b200seg_conv_desc* d, int op, const void* residual);
 int64_t tc_convtr_slide_grid(const b200seg_conv_desc* d, int op);
 int tc_convtr_slide_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,
                         void* dst, float* stats, cudaStream_t st);
-bool tc_convtr_wgrad_supported(const b200seg_conv_desc* d);
-size_t tc_convtr_wgrad_workspace(const b200seg_conv_desc* d);
-int tc_convtr_wgrad_run(const b200seg_conv_desc* d, const void* x, const void* dy, float* gw, float* G32,
-                        cudaStream_t st);
+bool tc_convtr_wgrad_supported(const b200seg_conv_desc* d, bool transposed_layer);
+size_t tc_convtr_wgrad_workspace(const b200seg_conv_desc* d, bool transposed_layer);
+int tc_convtr_wgrad_run(const b200seg_conv_desc* d, bool transposed_layer, const void* x, const void* dy, float* gw,
+                        float* G32, cudaStream_t st);
 bool tc_slide_wgrad_supported(const b200seg_conv_desc* d, bool transposed_layer);
 size_t tc_slide_wgrad_workspace(const b200seg_conv_desc* d);
 int tc_slide_wgrad_run(const b200seg_conv_desc* d, const void* x, const void* dy, float* gw, float* G32,

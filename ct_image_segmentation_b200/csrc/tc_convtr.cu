@@ -52,6 +52,7 @@ struct alignas(64) TcConvTrFpropParams {
   int n, D, H, W;  // input extent
   int tilesH, tilesW, dseg, nseg;
   int cout, dst_ld;
+  int accumulate;  // dst += result (gradient fan-in of a strided conv's dgrad)
   const float* bias;
   bf16* dst;
   float* stats;  // optional [CTA][cout][2]
@@ -203,6 +204,18 @@ tc_convtr_fprop_kernel(const __grid_constant__ TcConvTrFpropParams p) {
             float f[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(pw ? v1[i] : v0[i]) + bias[i];
+            uint4* o4 = reinterpret_cast<uint4*>(op + (int64_t)pw * p.dst_ld);
+            if (p.accumulate) {
+              const uint4 r0 = o4[0], r1 = o4[1];
+              const __nv_bfloat162* g0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
+              const __nv_bfloat162* g1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 a = __bfloat1622float2(g0[i]), b = __bfloat1622float2(g1[i]);
+                f[2 * i] += a.x; f[2 * i + 1] += a.y;
+                f[8 + 2 * i] += b.x; f[8 + 2 * i + 1] += b.y;
+              }
+            }
             if (p.stats) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
@@ -218,7 +231,6 @@ tc_convtr_fprop_kernel(const __grid_constant__ TcConvTrFpropParams p) {
               q0[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
               q1[i] = __floats2bfloat162_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
             }
-            uint4* o4 = reinterpret_cast<uint4*>(op + (int64_t)pw * p.dst_ld);
             o4[0] = o0;
             o4[1] = o1;
           }
@@ -294,7 +306,10 @@ struct alignas(64) TcConvTrDgradParams {
   int n, D, H, W;      // input (dx) extent
   int tilesH, tilesW, dseg, nseg;
   int dst_ld;
+  int cout;            // real destination channels (bias / statistics)
+  const float* bias;   // optional (strided-conv fprop)
   bf16* dst;
+  float* stats;        // optional [CTA][cout][2]
 };
 
 // dx[j, ci] = sum_taps dy[2j - 1 + k, co] * W[ci, co, k]:  M = 128 input voxels, K = 16 (co), N = CI
@@ -399,6 +414,12 @@ tc_convtr_dgrad_kernel(const __grid_constant__ TcConvTrDgradParams p) {
     const int row = q * 32 + lane;
     const int ih = h0 + row / TWV, iw = w0 + row % TWV;
     const bool valid = ih < p.H && iw < p.W;
+    float bias[CI], ssum[CI], ssq[CI];
+#pragma unroll
+    for (int c = 0; c < CI; ++c) {
+      bias[c] = (p.bias && c < p.cout) ? p.bias[c] : 0.f;
+      ssum[c] = ssq[c] = 0.f;
+    }
     for (int j = 0; j < nd; ++j) {
       const int buf = j & 1;
       tc::mbar_wait(&acc_full[buf], ((uint32_t)j >> 1) & 1u);
@@ -410,13 +431,23 @@ tc_convtr_dgrad_kernel(const __grid_constant__ TcConvTrDgradParams p) {
         tc::tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + buf * CI + ch * 16, v);
         tc::tmem_ld_wait();
         if (valid) {
+          float f[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]) + bias[ch * 16 + i];
+          if (p.stats) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              ssum[ch * 16 + i] += f[i];
+              ssq[ch * 16 + i] = fmaf(f[i], f[i], ssq[ch * 16 + i]);
+            }
+          }
           uint4 o0, o1;
           __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
           __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            q0[i] = __floats2bfloat162_rn(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-            q1[i] = __floats2bfloat162_rn(__uint_as_float(v[8 + 2 * i]), __uint_as_float(v[8 + 2 * i + 1]));
+            q0[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+            q1[i] = __floats2bfloat162_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
           }
           uint4* op = reinterpret_cast<uint4*>(p.dst + lin * p.dst_ld + ch * 16);
           op[0] = o0;
@@ -427,9 +458,28 @@ tc_convtr_dgrad_kernel(const __grid_constant__ TcConvTrDgradParams p) {
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
     }
+    if (p.stats) {
+      float* sred = reinterpret_cast<float*>(tmem_slot + 4);  // [4 warps][CI][2]
+#pragma unroll
+      for (int c = 0; c < CI; ++c) {
+        const float a = warp_sum(ssum[c]), b = warp_sum(ssq[c]);
+        if (lane == 0) {
+          sred[(q * CI + c) * 2] = a;
+          sred[(q * CI + c) * 2 + 1] = b;
+        }
+      }
+    }
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (p.stats && threadIdx.x < 2 * CI) {
+    const float* sred = reinterpret_cast<const float*>(tmem_slot + 4);
+    const int c = threadIdx.x >> 1, m = threadIdx.x & 1;
+    if (c < p.cout)
+      p.stats[((int64_t)blockIdx.x * p.cout + c) * 2 + m] =
+          sred[(0 * CI + c) * 2 + m] + sred[(1 * CI + c) * 2 + m] + sred[(2 * CI + c) * 2 + m] +
+          sred[(3 * CI + c) * 2 + m];
+  }
   if (warp == 1) tc::tmem_dealloc<TMEM_COLS>(tmem_acc);
 }
 
@@ -580,31 +630,86 @@ int tc_slide_wgrad_unpack(const float* G, float* gw, int taps, int a_c, int b_c,
                           cudaStream_t st);
 
 // ------------------------------------------------------------------------------------------------
+// host side.  The three kernels are written in terms of a LOW-resolution tensor (32 / 64 channels)
+// and a HIGH-resolution tensor (2x in every dimension, <= 16 channels, padded rows) related by
+// hi = 2 * lo - 1 + tap.  Both stride-2 layer types of the network map onto them:
+//   ConvTranspose k3 s2 (lo = x, hi = y):  fprop = lo->hi (F),  dgrad = hi->lo (D),  wgrad = W
+//   Conv          k3 s2 (hi = x, lo = y):  fprop = hi->lo (D),  dgrad = lo->hi (F),  wgrad = W
+// with the weight tiles of the layer's own packed layout (tap index identical in all six cases).
 namespace {
 
-// column / d-segment decomposition: as many CTAs as fit in ONE wave (`per_sm` resident CTAs per SM)
-void convtr_grid(const b200seg_conv_desc* d, int per_sm, int& tilesH, int& tilesW, int& dseg, int& nseg, int64_t& grid) {
-  tilesH = (d->in_h + TH - 1) / TH;
-  tilesW = (d->in_w + TWV - 1) / TWV;
-  const int64_t cols = (int64_t)d->n * tilesH * tilesW;
-  int ns = (int)((148 * per_sm) / cols);
-  if (ns < 1) ns = 1;
-  dseg = (d->in_d + ns - 1) / ns;
-  if (dseg < 4) dseg = 4;
-  if (dseg > d->in_d) dseg = d->in_d;
-  nseg = (d->in_d + dseg - 1) / dseg;
-  grid = cols * nseg;
-}
+struct HiLo {
+  int n, D, H, W;      // low-resolution extent
+  int lo_c, hi_c;      // channels (hi_c <= 16)
+  int lo_ld, hi_ld;
+  bool transposed_layer;
+};
 
-bool convtr_shape_ok(const b200seg_conv_desc* d) {
+bool hilo(const b200seg_conv_desc* d, bool transposed_layer, HiLo& g) {
   if (d->kd != 3 || d->kh != 3 || d->kw != 3 || d->sd != 2 || d->sh != 2 || d->sw != 2) return false;
-  if (d->out_d != 2 * d->in_d || d->out_h != 2 * d->in_h || d->out_w != 2 * d->in_w) return false;
-  if (d->in_d < 4 || (int64_t)d->in_h * d->in_w < 512) return false;
+  g.transposed_layer = transposed_layer;
+  g.n = d->n;
+  if (transposed_layer) {
+    if (d->out_d != 2 * d->in_d || d->out_h != 2 * d->in_h || d->out_w != 2 * d->in_w) return false;
+    g.D = d->in_d; g.H = d->in_h; g.W = d->in_w;
+    g.lo_c = d->cin; g.hi_c = d->cout; g.lo_ld = d->x_ld; g.hi_ld = d->y_ld;
+  } else {
+    if (d->in_d != 2 * d->out_d || d->in_h != 2 * d->out_h || d->in_w != 2 * d->out_w) return false;
+    g.D = d->out_d; g.H = d->out_h; g.W = d->out_w;
+    g.lo_c = d->cout; g.hi_c = d->cin; g.lo_ld = d->y_ld; g.hi_ld = d->x_ld;
+  }
+  if (g.D < 4 || (int64_t)g.H * g.W < 512) return false;
+  if ((g.lo_c != 32 && g.lo_c != 64) || round16(g.hi_c) != 16 || g.hi_c < 8) return false;
   return true;
 }
 
+// column / d-segment decomposition: as many CTAs as fit in ONE wave (`per_sm` resident CTAs per SM)
+void hilo_grid(const HiLo& g, int per_sm, int& tilesH, int& tilesW, int& dseg, int& nseg, int64_t& grid) {
+  tilesH = (g.H + TH - 1) / TH;
+  tilesW = (g.W + TWV - 1) / TWV;
+  const int64_t cols = (int64_t)g.n * tilesH * tilesW;
+  int ns = (int)((148 * per_sm) / cols);
+  if (ns < 1) ns = 1;
+  dseg = (g.D + ns - 1) / ns;
+  if (dseg < 4) dseg = 4;
+  if (dseg > g.D) dseg = g.D;
+  nseg = (g.D + dseg - 1) / dseg;
+  grid = cols * nseg;
+}
+
+enum { KERNEL_F = 0, KERNEL_D = 1 };
+// which kernel an op of a layer runs on (-1: none)
+int kernel_of(bool transposed_layer, int op) {
+  if (transposed_layer) return op == TC_CONVTR_FPROP ? KERNEL_F : (op == TC_CONVTR_DGRAD ? KERNEL_D : -1);
+  return op == TC_CONV_FPROP ? KERNEL_D : (op == TC_CONV_DGRAD ? KERNEL_F : -1);
+}
+
+// the 8 parity-class tensor maps of the high-resolution tensor (16 padded channels), boxes of 16 / 17 lines
+int make_hi_maps(CUtensorMap* maps, const HiLo& g, const void* hi) {
+  const int oD = 2 * g.D, oH = 2 * g.H, oW = 2 * g.W, ld = g.hi_ld;
+  for (int m = 0; m < 8; ++m) {
+    const int pd = (m >> 2) & 1, ph = (m >> 1) & 1, pw = m & 1;
+    const bf16* base = (const bf16*)hi + (((int64_t)pd * oH + ph) * oW + pw) * ld;
+    uint64_t dims[5] = {16, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.D, (uint64_t)g.n};
+    uint64_t strides[4] = {(uint64_t)ld * 2 * 2, (uint64_t)oW * ld * 2 * 2, (uint64_t)oH * oW * ld * 2 * 2,
+                           (uint64_t)oD * oH * oW * ld * 2};
+    uint32_t box[5] = {16, (uint32_t)TWV, (uint32_t)(ph ? TH + 1 : TH), 1, 1};
+    int rc = tc_make_map(&maps[m], base, 5, dims, strides, box, 32);
+    if (rc) return rc;
+  }
+  return B200SEG_OK;
+}
+
+int make_lo_map(CUtensorMap* map, const HiLo& g, const void* lo, int lines) {
+  uint64_t dims[5] = {(uint64_t)g.lo_c, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.D, (uint64_t)g.n};
+  uint64_t strides[4] = {(uint64_t)g.lo_ld * 2, (uint64_t)g.W * g.lo_ld * 2, (uint64_t)g.H * g.W * g.lo_ld * 2,
+                         (uint64_t)g.D * g.H * g.W * g.lo_ld * 2};
+  uint32_t box[5] = {(uint32_t)g.lo_c, (uint32_t)TWV, (uint32_t)lines, 1, 1};
+  return tc_make_map(map, lo, 5, dims, strides, box, g.lo_c * 2);
+}
+
 template <int KC>
-int launch_convtr_fprop(const TcConvTrFpropParams& p, unsigned grid, cudaStream_t st) {
+int launch_f(const TcConvTrFpropParams& p, unsigned grid, cudaStream_t st) {
   constexpr int RING = KC == 32 ? 4 : 3;
   constexpr int SLAB = 2 * (TH + 1) * TWV * KC * 2;
   constexpr int WB = (27 * 16 * KC * 2 + 1023) / 1024 * 1024;
@@ -620,56 +725,10 @@ int launch_convtr_fprop(const TcConvTrFpropParams& p, unsigned grid, cudaStream_
   return B200SEG_OK;
 }
 
-}  // namespace
-
-// ConvTranspose fprop layers the sliding kernel takes (on top of tc_conv_supported): 3-D k3 s2,
-// Cin in {32, 64} (exact), Cout <= 16 (padded rows), no residual / accumulate.
-bool tc_convtr_slide_supported(const b200seg_conv_desc* d, int op, const void* residual) {
-  if (d->flags & B200SEG_CONV_NO_SLIDE) return false;
-  if (!convtr_shape_ok(d)) return false;
-  if (op == TC_CONVTR_FPROP) {
-    if (residual || (d->flags & B200SEG_CONV_ACCUMULATE)) return false;
-    if ((d->cin != 32 && d->cin != 64) || round16(d->cout) != 16) return false;
-    return true;
-  }
-  if (op == TC_CONVTR_DGRAD) {
-    if (residual || (d->flags & B200SEG_CONV_ACCUMULATE)) return false;
-    if ((d->cin != 32 && d->cin != 64) || round16(d->cout) != 16) return false;
-    return true;
-  }
-  return false;
-}
-
-int64_t tc_convtr_slide_grid(const b200seg_conv_desc* d, int op) {
-  (void)op;
-  int th, tw, dseg, nseg;
-  int64_t grid;
-  convtr_grid(d, d->cin == 32 ? 2 : 1, th, tw, dseg, nseg, grid);
-  return grid;
-}
-
-namespace {
-
-// the 8 parity-class tensor maps of dy (2x resolution, 16 padded channels), boxes of 16 / 17 lines
-int make_dy_maps(CUtensorMap* maps, const b200seg_conv_desc* d, const void* dy) {
-  const int oD = d->out_d, oH = d->out_h, oW = d->out_w, ld = d->y_ld;
-  for (int m = 0; m < 8; ++m) {
-    const int pd = (m >> 2) & 1, ph = (m >> 1) & 1, pw = m & 1;
-    const bf16* base = (const bf16*)dy + (((int64_t)pd * oH + ph) * oW + pw) * ld;
-    uint64_t dims[5] = {16, (uint64_t)d->in_w, (uint64_t)d->in_h, (uint64_t)d->in_d, (uint64_t)d->n};
-    uint64_t strides[4] = {(uint64_t)ld * 2 * 2, (uint64_t)oW * ld * 2 * 2, (uint64_t)oH * oW * ld * 2 * 2,
-                           (uint64_t)oD * oH * oW * ld * 2};
-    uint32_t box[5] = {16, (uint32_t)TWV, (uint32_t)(ph ? TH + 1 : TH), 1, 1};
-    int rc = tc_make_map(&maps[m], base, 5, dims, strides, box, 32);
-    if (rc) return rc;
-  }
-  return B200SEG_OK;
-}
-
 template <int CI>
-int launch_convtr_dgrad(const TcConvTrDgradParams& p, unsigned grid, cudaStream_t st) {
+int launch_d(const TcConvTrDgradParams& p, unsigned grid, cudaStream_t st) {
   constexpr int WB = (27 * CI * DY_PITCH + 1023) / 1024 * 1024;
-  const size_t smem = 1024 + WB + 3 * DY_UNIT + 16 * 8 + 64;
+  const size_t smem = 1024 + WB + 3 * DY_UNIT + 16 * 8 + 64 + 4 * CI * 2 * 4;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(tc_convtr_dgrad_kernel<CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
@@ -681,62 +740,122 @@ int launch_convtr_dgrad(const TcConvTrDgradParams& p, unsigned grid, cudaStream_
   return B200SEG_OK;
 }
 
-int convtr_dgrad_run(const b200seg_conv_desc* d, const void* dy, const void* w_tc, void* dx, cudaStream_t st) {
-  TcConvTrDgradParams p;
+// lo -> hi
+int run_f(const HiLo& g, const void* lo, const void* w_tc, const float* bias, void* hi, float* stats, int accumulate,
+          cudaStream_t st) {
+  TcConvTrFpropParams p;
   memset(&p, 0, sizeof(p));
-  p.n = d->n; p.D = d->in_d; p.H = d->in_h; p.W = d->in_w;
+  p.n = g.n; p.D = g.D; p.H = g.H; p.W = g.W;
   int64_t grid;
-  convtr_grid(d, 1, p.tilesH, p.tilesW, p.dseg, p.nseg, grid);
-  p.dst_ld = d->x_ld; p.dst = (bf16*)dx;
-  int rc = make_dy_maps(p.tmA, d, dy);
+  hilo_grid(g, g.lo_c == 32 ? 2 : 1, p.tilesH, p.tilesW, p.dseg, p.nseg, grid);
+  p.cout = g.hi_c; p.dst_ld = g.hi_ld; p.accumulate = accumulate;
+  p.bias = bias; p.dst = (bf16*)hi; p.stats = stats;
+  int rc = make_lo_map(&p.tmA, g, lo, TH + 1);
   if (rc) return rc;
   {
-    uint64_t dims[2] = {16, (uint64_t)27 * d->cin};
+    uint64_t dims[2] = {(uint64_t)g.lo_c, (uint64_t)27 * 16};
+    uint64_t strides[1] = {(uint64_t)g.lo_c * 2};
+    uint32_t box[2] = {(uint32_t)g.lo_c, 16};
+    rc = tc_make_map(&p.tmB, w_tc, 2, dims, strides, box, g.lo_c * 2);
+    if (rc) return rc;
+  }
+  if (grid > 0x7fffffffLL) { set_error("tc_convtr_slide: grid too large"); return B200SEG_ERR_ARG; }
+  if (g.lo_c == 32) return launch_f<32>(p, (unsigned)grid, st);
+  return launch_f<64>(p, (unsigned)grid, st);
+}
+
+// hi -> lo
+int run_d(const HiLo& g, const void* hi, const void* w_tc, const float* bias, void* lo, float* stats, cudaStream_t st) {
+  TcConvTrDgradParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = g.n; p.D = g.D; p.H = g.H; p.W = g.W;
+  int64_t grid;
+  hilo_grid(g, 1, p.tilesH, p.tilesW, p.dseg, p.nseg, grid);
+  p.dst_ld = g.lo_ld; p.dst = (bf16*)lo; p.cout = g.lo_c; p.bias = bias; p.stats = stats;
+  int rc = make_hi_maps(p.tmA, g, hi);
+  if (rc) return rc;
+  {
+    uint64_t dims[2] = {16, (uint64_t)27 * g.lo_c};
     uint64_t strides[1] = {32};
-    uint32_t box[2] = {16, (uint32_t)d->cin};
+    uint32_t box[2] = {16, (uint32_t)g.lo_c};
     rc = tc_make_map(&p.tmB, w_tc, 2, dims, strides, box, 32);
     if (rc) return rc;
   }
   if (grid > 0x7fffffffLL) { set_error("tc_convtr_dgrad: grid too large"); return B200SEG_ERR_ARG; }
-  if (d->cin == 32) return launch_convtr_dgrad<32>(p, (unsigned)grid, st);
-  return launch_convtr_dgrad<64>(p, (unsigned)grid, st);
+  if (g.lo_c == 32) return launch_d<32>(p, (unsigned)grid, st);
+  return launch_d<64>(p, (unsigned)grid, st);
 }
 
 }  // namespace
 
-// ConvTranspose wgrad layers the sliding kernel takes: Cin = 32 (9 accumulators x 32 columns), Cout <= 16
-bool tc_convtr_wgrad_supported(const b200seg_conv_desc* d) {
+// Stride-2 layers the sliding kernels take (on top of tc_conv_supported): 3-D k3 s2 with exact 2x
+// extents, low-resolution side 32 / 64 channels, high-resolution side <= 16 channels (padded rows).
+// No fused residual; in-place accumulation only for the lo->hi kernel (strided-conv dgrad fan-in).
+bool tc_convtr_slide_supported(const b200seg_conv_desc* d, int op, const void* residual) {
   if (d->flags & B200SEG_CONV_NO_SLIDE) return false;
-  if (!convtr_shape_ok(d)) return false;
-  return d->cin == 32 && round16(d->cout) == 16;
+  const bool transposed_layer = (op == TC_CONVTR_FPROP || op == TC_CONVTR_DGRAD);
+  HiLo g;
+  if (!hilo(d, transposed_layer, g)) return false;
+  const int k = kernel_of(transposed_layer, op);
+  if (k < 0 || residual) return false;
+  if ((d->flags & B200SEG_CONV_ACCUMULATE) && k != KERNEL_F) return false;
+  return true;
 }
 
-size_t tc_convtr_wgrad_workspace(const b200seg_conv_desc* d) {
+// number of CTAs (= per-CTA statistic partials, fprop only); CTAs of one sample are contiguous
+int64_t tc_convtr_slide_grid(const b200seg_conv_desc* d, int op) {
+  const bool transposed_layer = (op == TC_CONVTR_FPROP || op == TC_CONVTR_DGRAD);
+  HiLo g;
+  hilo(d, transposed_layer, g);
   int th, tw, dseg, nseg;
   int64_t grid;
-  convtr_grid(d, 1, th, tw, dseg, nseg, grid);
-  return (size_t)grid * 27 * 16 * d->cin * sizeof(float);
+  hilo_grid(g, (kernel_of(transposed_layer, op) == KERNEL_F && g.lo_c == 32) ? 2 : 1, th, tw, dseg, nseg, grid);
+  return grid;
 }
 
-int tc_convtr_wgrad_run(const b200seg_conv_desc* d, const void* x, const void* dy, float* gw, float* G32,
-                        cudaStream_t st) {
+int tc_convtr_slide_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,
+                        void* dst, float* stats, cudaStream_t st) {
+  const bool transposed_layer = (op == TC_CONVTR_FPROP || op == TC_CONVTR_DGRAD);
+  HiLo g;
+  if (!hilo(d, transposed_layer, g)) { set_error("tc_convtr_slide: unsupported layer"); return B200SEG_ERR_UNSUPPORTED; }
+  if (kernel_of(transposed_layer, op) == KERNEL_F)
+    return run_f(g, src, w_tc, bias, dst, stats, (d->flags & B200SEG_CONV_ACCUMULATE) ? 1 : 0, st);
+  return run_d(g, src, w_tc, bias, dst, stats, st);
+}
+
+// wgrad of the same layers: low-resolution side exactly 32 channels (9 accumulators x 32 TMEM columns)
+bool tc_convtr_wgrad_supported(const b200seg_conv_desc* d, bool transposed_layer) {
+  if (d->flags & B200SEG_CONV_NO_SLIDE) return false;
+  HiLo g;
+  return hilo(d, transposed_layer, g) && g.lo_c == 32;
+}
+
+size_t tc_convtr_wgrad_workspace(const b200seg_conv_desc* d, bool transposed_layer) {
+  HiLo g;
+  if (!hilo(d, transposed_layer, g)) return 0;
+  int th, tw, dseg, nseg;
+  int64_t grid;
+  hilo_grid(g, 1, th, tw, dseg, nseg, grid);
+  return (size_t)grid * 27 * 16 * g.lo_c * sizeof(float);
+}
+
+int tc_convtr_wgrad_run(const b200seg_conv_desc* d, bool transposed_layer, const void* x, const void* dy, float* gw,
+                        float* G32, cudaStream_t st) {
+  HiLo g;
+  if (!hilo(d, transposed_layer, g)) { set_error("tc_convtr_wgrad: unsupported layer"); return B200SEG_ERR_UNSUPPORTED; }
+  const void* hi = transposed_layer ? dy : x;
+  const void* lo = transposed_layer ? x : dy;
   TcConvTrWgradParams p;
   memset(&p, 0, sizeof(p));
   constexpr int CI = 32;
-  p.n = d->n; p.D = d->in_d; p.H = d->in_h; p.W = d->in_w;
+  p.n = g.n; p.D = g.D; p.H = g.H; p.W = g.W;
   int64_t grid;
-  convtr_grid(d, 1, p.tilesH, p.tilesW, p.dseg, p.nseg, grid);
+  hilo_grid(g, 1, p.tilesH, p.tilesW, p.dseg, p.nseg, grid);
   p.out = G32;
-  int rc = make_dy_maps(p.tmA, d, dy);
+  int rc = make_hi_maps(p.tmA, g, hi);
   if (rc) return rc;
-  {
-    uint64_t dims[5] = {(uint64_t)CI, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.D, (uint64_t)p.n};
-    uint64_t strides[4] = {(uint64_t)d->x_ld * 2, (uint64_t)p.W * d->x_ld * 2, (uint64_t)p.H * p.W * d->x_ld * 2,
-                           (uint64_t)p.D * p.H * p.W * d->x_ld * 2};
-    uint32_t box[5] = {(uint32_t)CI, (uint32_t)TWV, (uint32_t)TH, 1, 1};
-    rc = tc_make_map(&p.tmX, x, 5, dims, strides, box, CI * 2);
-    if (rc) return rc;
-  }
+  rc = make_lo_map(&p.tmX, g, lo, TH);
+  if (rc) return rc;
   const size_t smem = 1024 + 3 * DY_UNIT + 3 * (TH * TWV * CI * 2) + 16 * 8 + 64;
   static bool attr_set = false;
   if (!attr_set) {
@@ -746,38 +865,9 @@ int tc_convtr_wgrad_run(const b200seg_conv_desc* d, const void* x, const void* d
   tc_convtr_wgrad_kernel<CI><<<(unsigned)grid, 192, smem, st>>>(p);
   B200SEG_CHECK_LAUNCH("tc_convtr_wgrad");
   count_tc_launch();
-  return tc_slide_wgrad_unpack(G32, gw, 27, d->cout, d->cin, 16, CI, (int)grid, st);
-}
-
-int tc_convtr_slide_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,
-                        void* dst, float* stats, cudaStream_t st) {
-  if (op == TC_CONVTR_DGRAD) return convtr_dgrad_run(d, src, w_tc, dst, st);
-  TcConvTrFpropParams p;
-  memset(&p, 0, sizeof(p));
-  const int KC = d->cin;
-  p.n = d->n; p.D = d->in_d; p.H = d->in_h; p.W = d->in_w;
-  int64_t grid;
-  convtr_grid(d, KC == 32 ? 2 : 1, p.tilesH, p.tilesW, p.dseg, p.nseg, grid);
-  p.cout = d->cout; p.dst_ld = d->y_ld;
-  p.bias = bias; p.dst = (bf16*)dst; p.stats = stats;
-  {
-    uint64_t dims[5] = {(uint64_t)KC, (uint64_t)p.W, (uint64_t)p.H, (uint64_t)p.D, (uint64_t)p.n};
-    uint64_t strides[4] = {(uint64_t)d->x_ld * 2, (uint64_t)p.W * d->x_ld * 2, (uint64_t)p.H * p.W * d->x_ld * 2,
-                           (uint64_t)p.D * p.H * p.W * d->x_ld * 2};
-    uint32_t box[5] = {(uint32_t)KC, (uint32_t)TWV, (uint32_t)(TH + 1), 1, 1};
-    int rc = tc_make_map(&p.tmA, src, 5, dims, strides, box, KC * 2);
-    if (rc) return rc;
-  }
-  {
-    uint64_t dims[2] = {(uint64_t)KC, (uint64_t)27 * 16};
-    uint64_t strides[1] = {(uint64_t)KC * 2};
-    uint32_t box[2] = {(uint32_t)KC, 16};
-    int rc = tc_make_map(&p.tmB, w_tc, 2, dims, strides, box, KC * 2);
-    if (rc) return rc;
-  }
-  if (grid > 0x7fffffffLL) { set_error("tc_convtr_slide: grid too large"); return B200SEG_ERR_ARG; }
-  if (KC == 32) return launch_convtr_fprop<32>(p, (unsigned)grid, st);
-  return launch_convtr_fprop<64>(p, (unsigned)grid, st);
+  // G[cta][tap][hi channel][lo channel]; both PyTorch layouts are [lo channel][hi channel][tap]:
+  // ConvTranspose (cin = lo, cout = hi, taps), Conv (cout = lo, cin = hi, taps)
+  return tc_slide_wgrad_unpack(G32, gw, 27, g.hi_c, g.lo_c, 16, CI, (int)grid, st);
 }
 
 }  // namespace b200seg

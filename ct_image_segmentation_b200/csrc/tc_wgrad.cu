@@ -268,7 +268,9 @@ size_t tc_wgrad_extra_workspace(const b200seg_conv_desc* d) {
   const size_t g = (size_t)d->kd * d->kh * d->kw * round16(d->cin) * round16(d->cout);
   size_t streaming = (g + (4u << 20)) * sizeof(float);
   size_t sliding = tc_slide_wgrad_supported(d, false) ? tc_slide_wgrad_workspace(d) : 0;
-  if (tc_convtr_wgrad_supported(d) && tc_convtr_wgrad_workspace(d) > sliding) sliding = tc_convtr_wgrad_workspace(d);
+  for (int tl = 0; tl < 2; ++tl)
+    if (tc_convtr_wgrad_supported(d, tl != 0) && tc_convtr_wgrad_workspace(d, tl != 0) > sliding)
+      sliding = tc_convtr_wgrad_workspace(d, tl != 0);
   return align_up(streaming > sliding ? streaming : sliding, 256);
 }
 

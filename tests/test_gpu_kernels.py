@@ -327,6 +327,74 @@ def test_convtr_sliding_kernels(cin, cout, n, sp):
     assert rel(gw, gw2) < 1e-4, "sliding vs streaming wgrad"
 
 
+CONV_S2_SLIDE = [
+    # cin, cout, n, input spatial -- Conv k3 s2 layers the same hi/lo sliding kernels take
+    (16, 32, 1, (16, 48, 64)),
+    (16, 32, 2, (10, 64, 48)),
+    (10, 32, 1, (8, 64, 32)),     # padded hi side
+]
+
+
+@pytest.mark.parametrize("cin,cout,n,sp", CONV_S2_SLIDE)
+def test_conv_stride2_sliding_kernels(cin, cout, n, sp):
+    """Stride-2 Conv on the hi/lo sliding kernels: fprop (+ fused statistics) = hi->lo, dgrad (plain and
+    accumulating into a channel slice of a wider buffer) = lo->hi, wgrad; vs torch fp32 and streaming."""
+    lib = _lib.load()
+    dtype = torch.bfloat16
+    torch.manual_seed(778)
+    g = ConvGeom(3, cin, cout, 3, 2, False)
+    w = q(torch.randn(cout, cin, 3, 3, 3) * (2.0 / (cin * 27)) ** 0.5, dtype).requires_grad_(True)
+    b = torch.randn(cout)
+    x = q(torch.randn(n, cin, *sp), dtype).requires_grad_(True)
+    y_ref = ref_conv(g, x, w, b)
+    dy = q(torch.randn_like(y_ref), dtype)
+    y_ref.backward(dy)
+
+    def dev(t_nc):
+        out = ops.alloc_activation(t_nc.shape[0], tuple(t_nc.shape[2:]), t_nc.shape[1], dtype, DEV)
+        out.copy_(t_nc.permute(0, 2, 3, 4, 1))
+        return out
+
+    wdev = w.detach().to(DEV)
+    x_cl, dy_cl = dev(x.detach()), dev(dy)
+    wp = ops.pack_weight(g, _lib.W_CONV_FPROP, wdev, dtype)
+    y_cl = ops.alloc_like(dy_cl)
+    ops.conv_fprop(g, x_cl, wp, b.to(DEV), y_cl)
+    assert lib.b200seg_last_launch() == b"tc_convtr_dgrad"
+    e = rel(nc_cpu(y_cl, 3), y_ref.detach())
+    assert e < 1e-2, f"conv s2 fprop rel err {e}"
+    y2 = ops.alloc_like(dy_cl)
+    mean, rstd = ops.conv_fprop_stats(g, x_cl, wp, b.to(DEV), y2)
+    assert torch.equal(y2, y_cl)
+    yd = y_ref.detach().double()
+    m_ref = yd.mean(dim=(2, 3, 4))
+    r_ref = 1.0 / torch.sqrt(yd.var(dim=(2, 3, 4), unbiased=False) + 1e-5)
+    assert rel(mean.view(n, -1)[:, :cout], m_ref) < 2e-3 and rel(rstd.view(n, -1)[:, :cout], r_ref) < 2e-3
+    # dgrad, plain
+    wp_d = ops.pack_weight(g, _lib.W_CONV_DGRAD, wdev, dtype)
+    dx_cl = ops.alloc_like(x_cl)
+    ops.conv_dgrad(g, dy_cl, wp_d, dx_cl)
+    assert lib.b200seg_last_launch() == b"tc_convtr_fprop"
+    e = rel(nc_cpu(dx_cl, 3), x.grad)
+    assert e < 1e-2, f"conv s2 dgrad rel err {e}"
+    if cin % 16 == 0:
+        # accumulate into the first channels of a wider buffer (the skip half of a gradient concat buffer)
+        base = q(torch.randn(n, 2 * cin, *sp), dtype)
+        wide = dev(base)
+        ops.conv_dgrad(g, dy_cl, wp_d, wide[..., :cin], accumulate=True)
+        assert lib.b200seg_last_launch() == b"tc_convtr_fprop"
+        got = nc_cpu(wide, 3)
+        assert rel(got[:, :cin], x.grad + base[:, :cin]) < 2e-2
+        assert torch.equal(got[:, cin:], base[:, cin:])
+    # wgrad
+    gw, _ = ops.conv_wgrad(g, x_cl, dy_cl, want_bias=False)
+    assert lib.b200seg_last_launch() == b"tc_slide_wgrad_unpack"
+    e = rel(gw, w.grad)
+    assert e < 1e-2, f"conv s2 wgrad rel err {e}"
+    gw2, _ = ops.conv_wgrad(g, x_cl, dy_cl, flags=_lib.CONV_NO_SLIDE)
+    assert rel(gw, gw2) < 1e-4, "sliding vs streaming wgrad"
+
+
 NORM_CASES = [(2, 16, (6, 8, 10)), (1, 10, (8, 8, 12)), (2, 64, (4, 4, 4)), (3, 32, (1, 12, 20)),
               (1, 256, (2, 3, 4)), (2, 7, (3, 5, 7))]
 
