@@ -15,6 +15,7 @@ F32, BF16 = 0, 1
 LABEL_U8, LABEL_I64 = 0, 1
 W_CONV_FPROP, W_CONV_DGRAD, W_CONVTR_FPROP, W_CONVTR_DGRAD = 0, 1, 2, 3
 CONV_ACCUMULATE, CONV_FORCE_GENERIC, CONV_PADDED_CHANNELS, CONV_NO_SLIDE = 1, 2, 4, 8
+PACK_TC_ONLY = 0x100
 
 
 class ConvDesc(C.Structure):
@@ -56,6 +57,7 @@ SIGNATURES = {
     "b200seg_pack_weight": (C.c_int, [_CD, C.c_int, _P, _P, _P]),
     "b200seg_packed_weight_tc_offset": (C.c_size_t, [_CD, C.c_int]),
     "b200seg_dice_loss_epilogue": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P, _P, _P, _P]),
+    "b200seg_im2col": (C.c_int, [_P, _P, _P, C.c_int32, _P]),
     "b200seg_pack_weights_batched": (C.c_int, [_P, C.c_int32, _P]),
     "b200seg_conv_fprop": (C.c_int, [_CD, _P, _P, _P, _P, _P, _P]),
     "b200seg_conv_fprop_stats_workspace_bytes": (C.c_size_t, [_CD]),

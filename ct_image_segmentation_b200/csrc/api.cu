@@ -252,6 +252,18 @@ int b200seg_conv_dgrad(const b200seg_conv_desc* d, const void* dy, const void* w
   return launch_gather(g, d->dtype, dy, w_packed, nullptr, residual, dx, as_stream(stream));
 }
 
+int b200seg_im2col(const b200seg_conv_desc* d, const void* x, void* col, int32_t col_ld, void* stream) {
+  int rc = check_conv_desc(d, false);
+  if (rc) return rc;
+  B200SEG_CHECK_ARG(x && col, "im2col: NULL pointer");
+  const int J = d->kd * d->kh * d->kw * d->cin;
+  const int ve = d->dtype == B200SEG_BF16 ? 8 : 4;
+  B200SEG_CHECK_ARG(d->cin <= 4 && J <= 32, "im2col: only small-Cin layers (taps*cin <= 32), got %d", J);
+  B200SEG_CHECK_ARG(col_ld >= J && col_ld % ve == 0 && ((uintptr_t)col % 16) == 0,
+                    "im2col: col_ld must cover taps*cin and keep 16-byte rows");
+  return launch_im2col(d, x, col, col_ld, as_stream(stream));
+}
+
 static void conv_wgrad_params(const b200seg_conv_desc* d, WgradParams& w) {
   w.n = d->n;
   w.sD = d->in_d; w.sH = d->in_h; w.sW = d->in_w;

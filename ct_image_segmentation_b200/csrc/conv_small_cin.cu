@@ -290,6 +290,51 @@ __global__ void conv_small_cin_wgrad_final_kernel(const float* __restrict__ part
   }
 }
 
+// im2col of a small-Cin layer: col[v][ci*taps + tap] = x[in(v, tap)][ci] (zero outside the volume) for
+// every OUTPUT voxel v.  J = taps*cin <= 32 values per voxel, written as 16-byte vectors; channels
+// [J, col_ld) are the buffer's zero padding and are rewritten as zeros.  With the PyTorch weight
+// (cout, cin, taps) read as a (cout, J) matrix the layer becomes a 1x1x1 convolution with J input
+// channels on `col`: fprop and wgrad then run on the tcgen05 kernels, and the two first-layer convs of
+// a residual unit (same input, same geometry) share one im2col.
+template <typename T>
+__global__ void __launch_bounds__(128)
+im2col_small_cin_kernel(SmallCinParams p, const T* __restrict__ x, T* __restrict__ col, int col_ld) {
+  extern __shared__ int4 jtab[];  // (kd - pd, kh - ph, kw - pw, ci) of column j
+  const int taps = p.kd * p.kh * p.kw;
+  const int J = taps * p.cin;
+  for (int j = threadIdx.x; j < J; j += blockDim.x) {
+    const int ci = j / taps, tap = j % taps;
+    jtab[j] = make_int4(tap / (p.kw * p.kh) - p.pd, (tap / p.kw) % p.kh - p.ph, tap % p.kw - p.pw, ci);
+  }
+  __syncthreads();
+  const int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= p.nvox) return;
+  int64_t r = v;
+  const int ow = (int)(r % p.oW); r /= p.oW;
+  const int oh = (int)(r % p.oH); r /= p.oH;
+  const int od = (int)(r % p.oD); r /= p.oD;
+  const int id0 = od * p.sd, ih0 = oh * p.sh, iw0 = ow * p.sw;
+  const T* xn = x + r * (int64_t)p.iD * p.iH * p.iW * p.x_ld;
+  T* out = col + v * (int64_t)col_ld;
+  constexpr int VE = 16 / sizeof(T);  // elements per 16-byte store
+  for (int j0 = 0; j0 < col_ld; j0 += VE) {
+    Vec<T, VE> o;
+#pragma unroll
+    for (int i = 0; i < VE; ++i) {
+      const int j = j0 + i;
+      float val = 0.f;
+      if (j < J) {
+        const int4 e = jtab[j];
+        const int id = id0 + e.x, ih = ih0 + e.y, iw = iw0 + e.z;
+        if (id >= 0 && id < p.iD && ih >= 0 && ih < p.iH && iw >= 0 && iw < p.iW)
+          val = to_f<T>(xn[(((int64_t)id * p.iH + ih) * p.iW + iw) * p.x_ld + e.w]);
+      }
+      o.v[i] = val;
+    }
+    o.store(out + j0);
+  }
+}
+
 namespace {
 void fill(SmallCinParams& p, const b200seg_conv_desc* d) {
   p.n = d->n; p.cin = d->cin; p.cout = d->cout;
@@ -395,6 +440,20 @@ int launch_small_cin_wgrad(const b200seg_conv_desc* d, const void* x, const void
   const int nout = J * d->cout;
   conv_small_cin_wgrad_final_kernel<<<(nout * 32 + 255) / 256, 256, 0, st>>>(partial, nb, taps, d->cin, d->cout, gw);
   B200SEG_CHECK_LAUNCH("conv_small_cin_wgrad_final");
+  return B200SEG_OK;
+}
+
+int launch_im2col(const b200seg_conv_desc* d, const void* x, void* col, int col_ld, cudaStream_t st) {
+  SmallCinParams p;
+  fill(p, d);
+  const int J = d->kd * d->kh * d->kw * d->cin;
+  const unsigned grid = (unsigned)cdiv64(p.nvox, 128);
+  const size_t smem = (size_t)J * sizeof(int4);
+  if (d->dtype == B200SEG_BF16)
+    im2col_small_cin_kernel<__nv_bfloat16><<<grid, 128, smem, st>>>(p, (const __nv_bfloat16*)x, (__nv_bfloat16*)col, col_ld);
+  else
+    im2col_small_cin_kernel<float><<<grid, 128, smem, st>>>(p, (const float*)x, (float*)col, col_ld);
+  B200SEG_CHECK_LAUNCH("im2col_small_cin");
   return B200SEG_OK;
 }
 

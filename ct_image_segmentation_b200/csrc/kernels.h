@@ -53,6 +53,7 @@ bool small_cin_supported(const b200seg_conv_desc* d);
 size_t small_cin_wgrad_workspace(const b200seg_conv_desc* d);
 int launch_small_cin_fprop(const b200seg_conv_desc* d, const void* x, const void* w, const float* bias,
                            const void* res, void* y, cudaStream_t st);
+int launch_im2col(const b200seg_conv_desc* d, const void* x, void* col, int col_ld, cudaStream_t st);
 int launch_small_cin_wgrad(const b200seg_conv_desc* d, const void* x, const void* dy, float* gw, float* partial,
                            cudaStream_t st);
 

@@ -432,13 +432,14 @@ pack_weights_batched_kernel(const b200seg_pack_entry* __restrict__ table, int n_
   int64_t chunk_base = 0;
   for (int ei = 0; ei < n_entries; ++ei) {
     const b200seg_pack_entry e = table[ei];
-    const int taps = e.taps, cin = e.cin, cout = e.cout, kind = e.kind;
+    const int taps = e.taps, cin = e.cin, cout = e.cout, kind = e.kind & 0xff;
     const bool src_is_cin = (kind == B200SEG_W_CONV_FPROP || kind == B200SEG_W_CONVTR_FPROP);
     const int src_c = src_is_cin ? cin : cout, dst_c = src_is_cin ? cout : cin;
     const int src_pad = (src_c + 15) / 16 * 16, dst_pad = (dst_c + 15) / 16 * 16;
     const int KC = src_pad % 64 == 0 ? 64 : (src_pad % 32 == 0 ? 32 : 16);
     const int kblocks = src_pad / KC;
-    const int items_tc = src_pad * dst_pad, items_gen = src_c * dst_c;
+    const int items_tc = src_pad * dst_pad;
+    const int items_gen = (e.kind & B200SEG_PACK_TC_ONLY) ? 0 : src_c * dst_c;
     const int chunks_tc = items_tc / PACK_CHUNK, chunks_gen = (items_gen + PACK_CHUNK - 1) / PACK_CHUNK;
     const int nchunks = chunks_tc + chunks_gen;
     const float* w = reinterpret_cast<const float*>(e.w);

@@ -297,6 +297,29 @@ def conv_fprop_stats(geom: ConvGeom, x, wp, bias, y, eps: float = 1e-5, flags=0)
     return mean, rstd
 
 
+def col_geom(geom: ConvGeom) -> Optional[ConvGeom]:
+    """The 1x1x1 geometry a small-Cin conv layer becomes on its im2col buffer (None: not applicable)."""
+    j = geom.cin * geom.kernel ** geom.dims
+    if geom.transposed or geom.cin > 4 or geom.kernel == 1 or not (8 <= j <= 32):
+        return None
+    return ConvGeom(geom.dims, j, geom.cout, 1, 1, False)
+
+
+def im2col(geom: ConvGeom, x: torch.Tensor) -> torch.Tensor:
+    """(N, *out_spatial, taps*cin) zero-padded channels-last im2col buffer of a small-Cin layer."""
+    lib = _lib.load()
+    n, d, h, w, c, x_ld = cl_info(x)
+    if c != geom.cin:
+        raise ValueError("im2col: channel mismatch")
+    out_sp = geom.out_spatial(d, h, w)
+    j = geom.cin * geom.kernel ** geom.dims
+    col = alloc_activation(n, out_sp, j, x.dtype, x.device)
+    col_ld = cl_info(col)[5]
+    desc = geom.desc(n, (d, h, w), out_sp, x_ld, geom.cout, 0, x.dtype)
+    _lib.check(lib.b200seg_im2col(C.byref(desc), x.data_ptr(), col.data_ptr(), col_ld, _stream()), "b200seg_im2col")
+    return col
+
+
 def conv_dgrad(geom, dy, wp, dx, residual=None, accumulate=False, flags=0):
     """dx = conv^T(dy) [+ residual] [+ dx]."""
     if accumulate:

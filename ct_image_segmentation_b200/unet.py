@@ -206,9 +206,9 @@ class UNet(nn.Module):
         if getattr(self, "_batched", None) is not None:
             self._batched["state"] = None
 
-    def _pack(self, param: torch.Tensor, geom: ConvGeom, kind: int) -> torch.Tensor:
+    def _pack(self, param: torch.Tensor, geom: ConvGeom, kind: int, col: bool = False) -> torch.Tensor:
         if self.compute_dtype == torch.bfloat16:
-            return self._batched["bufs"][(id(param), kind)]  # refreshed by _repack_all()
+            return self._batched["bufs"][(id(param), kind, col)]  # refreshed by _repack_all()
         key = (id(param), kind, self.compute_dtype)
         hit = self._packed.get(key)
         ver = (param._version, param.data_ptr())
@@ -243,10 +243,23 @@ class UNet(nn.Module):
                              else (_lib.W_CONV_FPROP, _lib.W_CONV_DGRAD)):
                     nbytes, tc_off = ops.packed_weight_layout(g, kind, self.compute_dtype)
                     buf = torch.empty(nbytes, dtype=torch.uint8, device=conv.weight.device)
-                    bufs[(id(conv.weight), kind)] = buf
+                    bufs[(id(conv.weight), kind, False)] = buf
                     k = g.kernel
+                    # stride-1 layers with 16-aligned channel counts never leave the tcgen05 kernels in
+                    # bf16 mode: their generic (CUDA-core) layout is not packed
+                    tc_only = (g.stride == 1 and g.cin % 16 == 0 and g.cout % 16 == 0)
                     entries.append((conv.weight.data_ptr(), buf.data_ptr(), tc_off,
-                                    k ** self.dimensions, g.cin, g.cout, kind))
+                                    k ** self.dimensions, g.cin, g.cout,
+                                    kind | (_lib.PACK_TC_ONLY if tc_only else 0)))
+                g1 = ops.col_geom(g)
+                if g1 is not None:
+                    # small-Cin layer run as a 1x1x1 conv on its im2col buffer: the PyTorch weight
+                    # (cout, cin, taps) is the (cout, cin*taps) matrix of that conv as it stands
+                    nbytes, tc_off = ops.packed_weight_layout(g1, _lib.W_CONV_FPROP, self.compute_dtype)
+                    buf = torch.empty(nbytes, dtype=torch.uint8, device=conv.weight.device)
+                    bufs[(id(conv.weight), _lib.W_CONV_FPROP, True)] = buf
+                    entries.append((conv.weight.data_ptr(), buf.data_ptr(), tc_off, 1, g1.cin, g1.cout,
+                                    _lib.W_CONV_FPROP))
             b = {"bufs": bufs, "table": ops.make_pack_table(entries, convs[0][0].weight.device),
                  "n": len(entries), "ptrs": tuple(s[1] for s in state)}
             self._batched = b
@@ -265,10 +278,31 @@ class UNet(nn.Module):
     def _new(self, like: torch.Tensor, spatial, c: int) -> torch.Tensor:
         return ops.alloc_activation(like.shape[0], tuple(spatial), c, self.compute_dtype, like.device)
 
-    def _run_forward(self, x_cl: torch.Tensor, saved: Dict, keep_all: bool = False) -> torch.Tensor:
+    def _run_forward(self, x_cl: torch.Tensor, saved: Dict, keep_all: bool = False,
+                     use_cols: bool = True) -> torch.Tensor:
         if self.compute_dtype == torch.bfloat16 and x_cl.is_cuda:
             self._repack_all()
-        return self._fwd_level(self.model, x_cl, saved, None, keep_all)
+        # small-Cin first layers as im2col + 1x1x1 tcgen05 convs (bf16; no input gradient possible there)
+        self._cols = {} if (use_cols and self.compute_dtype == torch.bfloat16) else None
+        try:
+            return self._fwd_level(self.model, x_cl, saved, None, keep_all)
+        finally:
+            self._cols = None
+
+    def _col_input(self, g: ConvGeom, x: torch.Tensor):
+        """(1x1x1 geometry, im2col buffer) for a small-Cin layer in col mode, else (None, None).  Layers
+        with the same input and geometry (unit0 conv and residual conv of a ResidualUnit) share it."""
+        if getattr(self, "_cols", None) is None:
+            return None, None
+        g1 = ops.col_geom(g)
+        if g1 is None:
+            return None, None
+        key = (x.data_ptr(), tuple(x.shape), g.kernel, g.stride)
+        col = self._cols.get(key)
+        if col is None:
+            col = ops.im2col(g, x)
+            self._cols[key] = col
+        return g1, col
 
     def _fwd_level(self, lvl: _Level, x, saved, dst, keep):
         down, skip, up = lvl[0], lvl[1], lvl[2]
@@ -299,13 +333,18 @@ class UNet(nn.Module):
     def _fwd_convolution(self, m: Convolution, x, saved, dst, residual, keep):
         g = m.geom
         sp = g.out_spatial(*x.shape[1:4])
-        wp = self._w_fprop(m.conv, g)
+        g1, col = self._col_input(g, x)
+        if g1 is not None:
+            g, x = g1, col
+            wp = self._pack(m.conv.weight, g1, _lib.W_CONV_FPROP, col=True)
+        else:
+            wp = self._w_fprop(m.conv, g)
         bias = m.conv.bias.detach()
         if m.conv_only:
             y = dst if dst is not None else self._new(x, sp, g.cout)
             ops.conv_fprop(g, x, wp, bias, y, residual)
             # with a fused residual the module's own output is never materialised: no tap
-            saved[m] = {"x": x, "c": None, "out": y if (keep and residual is None) else None}
+            saved[m] = {"x": x, "c": None, "out": y if (keep and residual is None) else None, "col_geom": g1}
             return y
         c = self._new(x, sp, g.cout)
         # InstanceNorm statistics come out of the convolution's epilogue where the kernel supports it
@@ -313,7 +352,7 @@ class UNet(nn.Module):
         a = dst if dst is not None else self._new(x, sp, g.cout)
         ops.instnorm_prelu_fwd(c, mean, rstd, m.act.weight.detach(), a, residual, m.norm.eps)
         saved[m] = {"x": x, "c": c, "mean": mean, "rstd": rstd,
-                    "out": a if (keep and residual is None) else None}
+                    "out": a if (keep and residual is None) else None, "col_geom": g1}
         return a
 
     def _fwd_resunit(self, ru: ResidualUnit, x, saved, dst, keep):
@@ -321,14 +360,20 @@ class UNet(nn.Module):
         if ru.res_geom is not None:
             rg = ru.res_geom
             r = self._new(x, rg.out_spatial(*x.shape[1:4]), rg.cout)
-            ops.conv_fprop(rg, x, self._w_fprop(ru.residual, rg), ru.residual.bias.detach(), r)
+            rg1, rcol = self._col_input(rg, x)
+            if rg1 is not None:
+                ops.conv_fprop(rg1, rcol, self._pack(ru.residual.weight, rg1, _lib.W_CONV_FPROP, col=True),
+                               ru.residual.bias.detach(), r)
+            else:
+                ops.conv_fprop(rg, x, self._w_fprop(ru.residual, rg), ru.residual.bias.detach(), r)
         else:
             r = x
+            rg1 = rcol = None
         h = x
         for i, u in enumerate(units):
             last = i == len(units) - 1
             h = self._fwd_convolution(u, h, saved, dst if last else None, r if last else None, keep)
-        saved[ru] = {"x": x}
+        saved[ru] = {"x": x, "col_geom": rg1, "col": rcol}
         return h
 
     # ---- backward plan -------------------------------------------------------------------------
@@ -378,7 +423,13 @@ class UNet(nn.Module):
         # A bias in front of an affine-less InstanceNorm is cancelled by the mean subtraction: its
         # gradient is identically zero (sum_v g_c = 0 analytically; the reference holds rounding noise
         # there).  Only live biases (conv-only head) get a column sum.
-        gw, gb = ops.conv_wgrad(g, x, g_c, want_bias=m.conv_only)
+        if s.get("col_geom") is not None:  # x is the im2col buffer; gw comes out as the (cout, cin*taps) matrix
+            if need_gx:
+                raise RuntimeError("input gradient requested through an im2col first layer")
+            gw, gb = ops.conv_wgrad(s["col_geom"], x, g_c, want_bias=m.conv_only)
+            gw = gw.view(m.conv.weight.shape)
+        else:
+            gw, gb = ops.conv_wgrad(g, x, g_c, want_bias=m.conv_only)
         grads[m.conv.weight] = gw
         grads[m.conv.bias] = gb if gb is not None else torch.zeros_like(m.conv.bias)
         if not need_gx:
@@ -389,7 +440,8 @@ class UNet(nn.Module):
 
     def _bwd_resunit(self, ru: ResidualUnit, g_out, saved, grads, need_gx, gx_dst, gx_accum):
         units = list(ru.conv.children())
-        x = saved.pop(ru)["x"]
+        sru = saved.pop(ru)
+        x = sru["x"]
         g = g_out
         for i in range(len(units) - 1, 0, -1):
             g = self._bwd_convolution(units[i], g, saved, grads, True, None, False, None)
@@ -398,7 +450,11 @@ class UNet(nn.Module):
             return self._bwd_convolution(units[0], g, saved, grads, need_gx, gx_dst, gx_accum, g_out)
         gx = self._bwd_convolution(units[0], g, saved, grads, need_gx, gx_dst, gx_accum, None)
         rg = ru.res_geom
-        gw, gb = ops.conv_wgrad(rg, x, g_out)
+        if sru.get("col_geom") is not None:
+            gw, gb = ops.conv_wgrad(sru["col_geom"], sru["col"], g_out)
+            gw = gw.view(ru.residual.weight.shape)
+        else:
+            gw, gb = ops.conv_wgrad(rg, x, g_out)
         grads[ru.residual.weight], grads[ru.residual.bias] = gw, gb
         if need_gx:
             ops.conv_dgrad(rg, g_out, self._w_dgrad(ru.residual, rg), gx, accumulate=True)
@@ -412,7 +468,7 @@ class _UNetFunction(torch.autograd.Function):
     def forward(ctx, net: UNet, x: torch.Tensor, *params):
         x_cl = ops.to_channels_last(x.detach(), net.compute_dtype)
         saved: Dict = {}
-        out = net._run_forward(x_cl, saved)
+        out = net._run_forward(x_cl, saved, use_cols=not ctx.needs_input_grad[1])
         need = any(ctx.needs_input_grad[1:])
         ctx.net = net
         ctx.saved = saved if need else None

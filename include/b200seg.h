@@ -127,6 +127,7 @@ int b200seg_pack_weight(const b200seg_conv_desc* d, int kind, const float* w_tor
  * entry i repacks fp32 parameter `w` into `packed` exactly as b200seg_pack_weight(kind) would
  * (packed must hold b200seg_packed_weight_bytes; tc_offset = offset of the tcgen05 layout in it,
  * as returned by b200seg_packed_weight_tc_offset). */
+#define B200SEG_PACK_TC_ONLY 0x100 /* OR-ed into `kind`: skip the generic layout (layer always runs on tcgen05) */
 typedef struct b200seg_pack_entry {
   uint64_t w;          /* const float*  (device) */
   uint64_t packed;     /* void*         (device) */
@@ -153,6 +154,14 @@ int b200seg_conv_dgrad(const b200seg_conv_desc* d, const void* dy, const void* w
 size_t b200seg_conv_wgrad_workspace_bytes(const b200seg_conv_desc* d);
 int b200seg_conv_wgrad(const b200seg_conv_desc* d, const void* x, const void* dy, float* gw,
                        float* gbias, void* workspace, size_t workspace_bytes, void* stream);
+
+/* im2col of a small-Cin conv layer (taps*cin <= 32, the network's first convolutions, Cin = 1 or 3):
+ * col[n, o, ci*taps + tap] = x[n, o*stride - pad + tap, ci] for every output voxel o, zero outside the
+ * volume; `col` is (N, out_d, out_h, out_w, col_ld) channels-last with col_ld >= taps*cin (the rest is
+ * written as zero padding).  With the PyTorch weight (cout, cin, k..) read as a (cout, cin*taps) matrix
+ * the layer is a 1x1x1 convolution on `col`, which b200seg_conv_fprop / _wgrad run on the tcgen05
+ * kernels (replaces the F.conv3d call of the first monai Convolution, capstone/volumetric/base_trainer.py:65-78). */
+int b200seg_im2col(const b200seg_conv_desc* d, const void* x, void* col, int32_t col_ld, void* stream);
 
 /* fprop fused with the statistics pass of the InstanceNorm that follows (no residual): the conv
  * epilogue emits per-CTA partial sums of y and y^2 (from the fp32 accumulators) into the workspace

@@ -395,6 +395,47 @@ def test_conv_stride2_sliding_kernels(cin, cout, n, sp):
     assert rel(gw, gw2) < 1e-4, "sliding vs streaming wgrad"
 
 
+@pytest.mark.parametrize("dims,cin,cout,s,n,sp", [(3, 1, 16, 2, 2, (16, 20, 24)), (3, 1, 32, 2, 1, (8, 16, 16)),
+                                                  (2, 1, 64, 2, 2, (32, 40)), (2, 3, 16, 1, 1, (17, 19))])
+def test_first_layer_im2col(dims, cin, cout, s, n, sp):
+    """Small-Cin layer as im2col + 1x1x1 tcgen05 conv: im2col bit-exact against F.unfold-style
+    gathering, fprop / wgrad within 1e-2 of torch fp32 on the same bf16-rounded inputs."""
+    dtype = torch.bfloat16
+    torch.manual_seed(91)
+    g = ConvGeom(dims, cin, cout, 3, s, False)
+    g1 = ops.col_geom(g)
+    assert g1 is not None and g1.cin == cin * 3 ** dims
+    w = q(torch.randn(cout, cin, *(3,) * dims) * 0.2, dtype).requires_grad_(True)
+    b = torch.randn(cout)
+    x = q(torch.randn(n, cin, *sp), dtype)
+    y_ref = ref_conv(g, x, w, b)
+    dy = q(torch.randn_like(y_ref), dtype)
+    y_ref.backward(dy)
+    x_cl = cl_dev(x, dtype)
+    col = ops.im2col(g, x_cl)
+    # reference im2col: column ci*taps + tap of output voxel o = x[o*s - 1 + tap, ci]
+    xp = F.pad(x, (1, 1) * dims)
+    cols = []
+    for ci in range(cin):
+        for tap in range(3 ** dims):
+            k = [(tap // 3 ** (dims - 1 - i)) % 3 for i in range(dims)]
+            sl = [slice(None), ci] + [slice(k[i], k[i] + s * (y_ref.shape[2 + i] - 1) + 1, s) for i in range(dims)]
+            cols.append(xp[tuple(sl)])
+    col_ref = torch.stack(cols, dim=1)
+    assert torch.equal(nc_cpu(col, dims), col_ref), "im2col differs"
+    full = col.as_strided(col.shape[:-1] + ((g1.cin + 15) // 16 * 16,), col.stride())
+    assert float(full[..., g1.cin:].abs().max()) == 0.0
+    wdev = w.detach().to(DEV).reshape(cout, g1.cin, *(1,) * dims)
+    y_cl = ops.alloc_activation(n, col.shape[1:4], cout, dtype, DEV)
+    ops.conv_fprop(g1, col, ops.pack_weight(g1, _lib.W_CONV_FPROP, wdev, dtype), b.to(DEV), y_cl)
+    assert rel(nc_cpu(y_cl, dims), y_ref.detach()) < 1e-2
+    dy_cl = ops.alloc_like(y_cl)
+    dy_cl.copy_((dy.unsqueeze(2) if dims == 2 else dy).permute(0, 2, 3, 4, 1))
+    gw, gb = ops.conv_wgrad(g1, col, dy_cl)
+    assert rel(gw.view(w.shape), w.grad) < 1e-2
+    assert rel(gb, dy.sum(dim=[0] + list(range(2, 2 + dims)))) < 1e-2
+
+
 NORM_CASES = [(2, 16, (6, 8, 10)), (1, 10, (8, 8, 12)), (2, 64, (4, 4, 4)), (3, 32, (1, 12, 20)),
               (1, 256, (2, 3, 4)), (2, 7, (3, 5, 7))]
 

@@ -155,7 +155,9 @@ def test_unet_layerwise_backward(dims, inc, ch, st, res, shape, dtype):
     x = torch.randn(*shape)
     lab = sparse_labels(shape[0], shape[2:])
     saved = {}
-    out = net._run_forward(ops.to_channels_last(x.to(DEV), dtype), saved)
+    # use_cols=False: the taps must hold every layer's real input (the im2col first-layer path is
+    # covered by test_first_layer_im2col and by the whole-network tests)
+    out = net._run_forward(ops.to_channels_last(x.to(DEV), dtype), saved, use_cols=False)
     lg = ops.from_channels_last(out, dims).detach().requires_grad_(True)
     loss = B.DiceLoss(include_background=False, to_onehot_y=True, softmax=True)(lg, lab.to(DEV).unsqueeze(1))
     loss.backward()
