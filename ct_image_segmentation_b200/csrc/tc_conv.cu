@@ -126,7 +126,7 @@ tc_conv_kernel(const __grid_constant__ TcConvParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // warp-uniform issue loop, one elected lane issues (see umma_bf16_warp)
       constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN, false, false);
       constexpr uint64_t layout = tc::layout_for_row_bytes(Cfg::ROW_BYTES);
       int st = 0;
@@ -140,12 +140,12 @@ tc_conv_kernel(const __grid_constant__ TcConvParams p) {
         for (int k = 0; k < KC / 16; ++k) {
           const uint64_t ad = tc::make_smem_desc(a_addr + k * 32, 16, 8 * Cfg::ROW_BYTES, layout);
           const uint64_t bd = tc::make_smem_desc(b_addr + k * 32, 16, 8 * Cfg::ROW_BYTES, layout);
-          tc::umma_bf16(tmem_acc, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          tc::umma_bf16_warp(tmem_acc, ad, bd, idesc, (it > 0 || k > 0) ? 1u : 0u);
         }
-        tc::umma_commit(&empty[st]);
+        tc::umma_commit_warp(&empty[st]);
         if (++st == stages) { st = 0; ph ^= 1u; }
       }
-      tc::umma_commit(acc_full);
+      tc::umma_commit_warp(acc_full);
     }
   } else {
     // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32)

@@ -134,7 +134,7 @@ tc_convtr_fprop_kernel(const __grid_constant__ TcConvTrFpropParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // warp-uniform issue loop, one elected lane issues
       constexpr uint64_t layout = tc::layout_for_row_bytes(PITCH);
       const uint32_t w_addr = tc::smem_u32(wsm), r_addr = tc::smem_u32(ring);
       const uint64_t tmpl = tc::make_smem_desc(0, 16, 8 * PITCH, layout);
@@ -164,11 +164,11 @@ tc_convtr_fprop_kernel(const __grid_constant__ TcConvTrFpropParams p) {
             const uint64_t a = (ru.sd ? slab1 : slab0) + ((ru.sw * COPY_BYTES + ru.sh * LINE) >> 4) + 2 * k;
             const uint64_t b = w_desc + ((ru.slot0 * WT_BYTES) >> 4) + 2 * k;
             const uint32_t idesc = ru.ncls == 8 ? idesc8 : (ru.ncls == 4 ? idesc4 : (ru.ncls == 2 ? idesc2 : idesc1));
-            tc::umma_bf16(acc + ru.cls0 * BN, a, b, idesc, (r == 0 && k == 0) ? 0u : 1u);
+            tc::umma_bf16_warp(acc + ru.cls0 * BN, a, b, idesc, (r == 0 && k == 0) ? 0u : 1u);
           }
         }
-        tc::umma_commit(&acc_full[buf]);
-        tc::umma_commit(&empty[j % RING]);
+        tc::umma_commit_warp(&acc_full[buf]);
+        tc::umma_commit_warp(&empty[j % RING]);
       }
     }
   } else {
@@ -376,7 +376,7 @@ tc_convtr_dgrad_kernel(const __grid_constant__ TcConvTrDgradParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // warp-uniform issue loop, one elected lane issues
       constexpr uint32_t idesc = tc::make_idesc_bf16(128, CI, false, false);
       const uint32_t w_addr = tc::smem_u32(wsm), r_addr = tc::smem_u32(ring);
       const uint64_t tmpl = tc::make_smem_desc(0, 16, 8 * DY_PITCH, tc::LAYOUT_SW32);
@@ -401,12 +401,12 @@ tc_convtr_dgrad_kernel(const __grid_constant__ TcConvTrDgradParams p) {
 #pragma unroll
             for (int kw = 0; kw < 3; ++kw) {
               const int tap = (kd * 3 + kh) * 3 + kw;
-              tc::umma_bf16(tmem_acc + buf * CI, part + (dy_tap_offset(kh, kw) >> 4), w_desc + ((tap * WT_BYTES) >> 4),
+              tc::umma_bf16_warp(tmem_acc + buf * CI, part + (dy_tap_offset(kh, kw) >> 4), w_desc + ((tap * WT_BYTES) >> 4),
                             idesc, tap ? 1u : 0u);
             }
         }
-        tc::umma_commit(&acc_full[buf]);
-        tc::umma_commit(&empty[j % RING]);
+        tc::umma_commit_warp(&acc_full[buf]);
+        tc::umma_commit_warp(&empty[j % RING]);
       }
     }
   } else {
@@ -558,7 +558,7 @@ tc_convtr_wgrad_kernel(const __grid_constant__ TcConvTrWgradParams p) {
       }
     }
   }
-  if (warp >= 1 && warp <= 3 && lane == 0) {
+  if (warp >= 1 && warp <= 3) {  // warp-uniform issue loop, one elected lane issues
     constexpr uint32_t idesc = tc::make_idesc_bf16(64, CI, true, true);
     constexpr uint64_t layB = tc::layout_for_row_bytes(PX);
     const int kd = warp - 1;
@@ -585,13 +585,13 @@ tc_convtr_wgrad_kernel(const __grid_constant__ TcConvTrWgradParams p) {
         const uint32_t acc = tmem_acc + (kd * 3 + kh) * CI;
 #pragma unroll
         for (int t = 0; t < TH / 2; ++t)
-          tc::umma_bf16(acc, a0 + (((2 * t) * DY_LINE) >> 4), xb + (((2 * t) * (TWV * PX)) >> 4), idesc,
+          tc::umma_bf16_warp(acc, a0 + (((2 * t) * DY_LINE) >> 4), xb + (((2 * t) * (TWV * PX)) >> 4), idesc,
                         (j > 0 || t > 0) ? 1u : 0u);
       }
-      tc::umma_commit(&empty[j % RING]);
-      tc::umma_commit(&emptyX[j % XR]);
+      tc::umma_commit_warp(&empty[j % RING]);
+      tc::umma_commit_warp(&emptyX[j % XR]);
     }
-    tc::umma_commit(acc_full);
+    tc::umma_commit_warp(acc_full);
   }
   if (warp >= 2) {
     const int q = warp & 3;  // TMEM quarter = slot = w copy: kw = 1, 0, 2

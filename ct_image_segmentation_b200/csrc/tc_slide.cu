@@ -124,7 +124,7 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {  // the whole warp runs the (warp-uniform) issue loop; one elected lane issues each MMA / commit
       constexpr uint64_t layout = tc::layout_for_row_bytes(PITCH);
       const uint32_t w_addr = tc::smem_u32(wsm), r_addr = tc::smem_u32(ring);
       const uint64_t tmpl = tc::make_smem_desc(0, 16, 8 * PITCH, layout);
@@ -151,12 +151,14 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
         if (fresh) {
           // first MMA of the slab: output slab s is overwritten (its own instruction), the older ones accumulate
           constexpr uint32_t idesc1 = tc::make_idesc_bf16(128, BN, false, false);
-          for (int j = lo; j < s; ++j)
-            tc::umma_bf16(tmem_acc + (j % ACCR) * BN, slab, w_desc + (((j - (s - 2)) * WT_BYTES) >> 4), idesc1, 1u);
-          tc::umma_bf16(tmem_acc + (s % ACCR) * BN, slab, w_desc + ((2 * WT_BYTES) >> 4), idesc1, 0u);
+          const int na = s - lo;                       // older output slabs: 0, 1 or 2
+          const int la0 = min(na, ACCR - c_lo), la1 = na - la0;
+          if (la0 > 0) tc::umma_bf16_warp(d0, slab, b0, tc::make_idesc_bf16(128, la0 * BN, false, false), 1u);
+          if (la1 > 0) tc::umma_bf16_warp(d1, slab, b0 + ((la0 * WT_BYTES) >> 4), idesc1, 1u);
+          tc::umma_bf16_warp(tmem_acc + (s % ACCR) * BN, slab, w_desc + ((2 * WT_BYTES) >> 4), idesc1, 0u);
         } else {
-          tc::umma_bf16(d0, slab, b0, i0, 1u);
-          if (len1 > 0) tc::umma_bf16(d1, slab, b1, i1, 1u);
+          tc::umma_bf16_warp(d0, slab, b0, i0, 1u);
+          if (len1 > 0) tc::umma_bf16_warp(d1, slab, b1, i1, 1u);
         }
 #pragma unroll
         for (int hw = 0; hw < 9; ++hw)
@@ -165,11 +167,11 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
             if (hw == 0 && k == 0) continue;
             const uint64_t a = slab + (((hw % 3) * COPY_BYTES + (hw / 3) * (TWV * PITCH)) >> 4) + 2 * k;
             const uint64_t bo = ((hw * 3 * WT_BYTES) >> 4) + 2 * k;
-            tc::umma_bf16(d0, a, b0 + bo, i0, 1u);
-            if (len1 > 0) tc::umma_bf16(d1, a, b1 + bo, i1, 1u);
+            tc::umma_bf16_warp(d0, a, b0 + bo, i0, 1u);
+            if (len1 > 0) tc::umma_bf16_warp(d1, a, b1 + bo, i1, 1u);
           }
-        tc::umma_commit(&empty[s % RING]);
-        if (s >= 2) tc::umma_commit(&acc_full[(s - 2) % ACCR]);
+        tc::umma_commit_warp(&empty[s % RING]);
+        if (s >= 2) tc::umma_commit_warp(&acc_full[(s - 2) % ACCR]);
       }
     }
   } else {

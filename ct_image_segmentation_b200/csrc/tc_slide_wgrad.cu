@@ -109,7 +109,7 @@ tc_slide_wgrad_kernel(const __grid_constant__ TcSlideWgradParams p) {
   // ---- MMA issue: warps 1, 2, 3 each own one kd (three accumulators); a single thread can only
   // issue ~1 MMA per 50-100 cycles (descriptor arithmetic + issue), which starves the tensor pipe
   // when every MMA is this small, so the 72 MMAs per slab are spread over three issuing threads.
-  if (warp >= 1 && warp <= 3 && lane == 0) {
+  if (warp >= 1 && warp <= 3) {  // warp-uniform issue loop, one elected lane issues
     constexpr uint32_t idesc = tc::make_idesc_bf16(MM, CB, true, true);
     constexpr uint64_t layA = tc::layout_for_row_bytes(PA), layB = tc::layout_for_row_bytes(PB);
     const int id = warp - 1;
@@ -133,14 +133,14 @@ tc_slide_wgrad_kernel(const __grid_constant__ TcSlideWgradParams p) {
 #pragma unroll
         for (int t = 0; t < TH / 2; ++t) {
           // K step t = output lines 2t, 2t+1; slot i of A starts at S line 2t + i
-          tc::umma_bf16(acc, sa + ((iw * COPY_BYTES + (2 * t) * (TWV * PA)) >> 4),
+          tc::umma_bf16_warp(acc, sa + ((iw * COPY_BYTES + (2 * t) * (TWV * PA)) >> 4),
                         tb + (((2 * t) * (TWV * PB)) >> 4), idesc, (j > 0 || t > 0) ? 1u : 0u);
         }
       }
-      tc::umma_commit(&emptyS[j % RING]);
-      tc::umma_commit(&emptyT[j % RT]);
+      tc::umma_commit_warp(&emptyS[j % RING]);
+      tc::umma_commit_warp(&emptyT[j % RT]);
     }
-    tc::umma_commit(acc_full);
+    tc::umma_commit_warp(acc_full);
   }
   if (warp >= 2) {
     const int q = warp & 3;

@@ -134,7 +134,7 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
         }
       }
     }
-    if (warp >= 1 && warp <= nissue && lane == 0) {
+    if (warp >= 1 && warp <= nissue) {  // warp-uniform issue loop, one elected lane issues
       const uint32_t idesc = tc::make_idesc_bf16(128, p.N, true, true);
       const uint64_t layA = tc::layout_for_row_bytes(pitchA), layB = tc::layout_for_row_bytes(pitchB);
       const uint64_t a_tmpl = tc::make_smem_desc(0, tileA, 8 * pitchA, layA);
@@ -152,12 +152,12 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
           const uint64_t ad0 = a_tmpl + ((b_addr + p.nb * tileB + mt * p.spm * tileA) >> 4);
           const uint32_t acc = tmem_acc + mt * p.N;
           for (int j = 0; j < ksteps; ++j)
-            tc::umma_bf16(acc, ad0 + j * a_kstep, bd0 + j * b_kstep, idesc, (it > 0 || j > 0) ? 1u : 0u);
+            tc::umma_bf16_warp(acc, ad0 + j * a_kstep, bd0 + j * b_kstep, idesc, (it > 0 || j > 0) ? 1u : 0u);
         }
-        tc::umma_commit(&empty[st]);
+        tc::umma_commit_warp(&empty[st]);
         if (++st == stages) { st = 0; ph ^= 1u; }
       }
-      tc::umma_commit(acc_full);
+      tc::umma_commit_warp(acc_full);
     }
     if (warp >= 2) {
       const int q = warp & 3;

@@ -7,15 +7,15 @@
 #include "../../ct_image_segmentation_b200/csrc/tc_common.cuh"
 using namespace b200seg;
 
-template <int M, int N, int ROWB, int DISTINCT_A, int NACC>
+template <int M, int N, int ROWB, int DISTINCT_A, int NACC, int NA = 4, int ASTR = 0, int NB = 1>
 __global__ void __launch_bounds__(128) k(long long* out, int iters) {
   extern __shared__ uint8_t raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t bar;
   __shared__ uint32_t slot;
-  for (int i = threadIdx.x; i < (4 * M * ROWB + 256 * ROWB) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+  for (int i = threadIdx.x; i < (NA * M * ROWB + NB * N * ROWB) / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
   if (threadIdx.x == 0) { tc::mbar_init(&bar, 1); tc::fence_barrier_init(); }
-  if (threadIdx.x < 32) tc::tmem_alloc<256>(&slot);
+  if (threadIdx.x < 32) tc::tmem_alloc<128>(&slot);
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(128) k(long long* out, int iters) {
   if (threadIdx.x == 0) {
     const uint32_t idesc = tc::make_idesc_bf16(M, N, false, false);
     const uint64_t lay = tc::layout_for_row_bytes(ROWB);
-    const uint32_t a_addr = tc::smem_u32(smem), b_addr = a_addr + 4 * M * ROWB;
+    const uint32_t a_addr = tc::smem_u32(smem), b_addr = a_addr + NA * M * ROWB;
     const uint64_t ad = tc::make_smem_desc(a_addr, 16, 8 * ROWB, lay);
     const uint64_t bd = tc::make_smem_desc(b_addr, 16, 8 * ROWB, lay);
     // warm
@@ -33,8 +33,9 @@ __global__ void __launch_bounds__(128) k(long long* out, int iters) {
     long long t0 = clock64();
     for (int i = 0; i < iters; ++i) {
       // DISTINCT_A: walk over 4 different A tiles (as the conv kernels do), else the same tile
-      const uint64_t a = DISTINCT_A ? ad + (uint64_t)((i & 3) * (M * ROWB / 16)) : ad;
-      tc::umma_bf16(acc + (NACC > 1 ? (i % NACC) * N : 0), a, bd, idesc, 1u);
+      const uint64_t a = DISTINCT_A ? ad + (uint64_t)((i % NA) * ((ASTR ? ASTR : M * ROWB) / 16)) : ad;
+      const uint64_t b = bd + (uint64_t)((i % NB) * (N * ROWB / 16));
+      tc::umma_bf16(acc + (NACC > 1 ? (i % NACC) * N : 0), a, b, idesc, 1u);
     }
     tc::umma_commit(&bar);
     tc::mbar_wait(&bar, 1);
@@ -43,39 +44,29 @@ __global__ void __launch_bounds__(128) k(long long* out, int iters) {
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (threadIdx.x < 32) tc::tmem_dealloc<256>(acc);
+  if (threadIdx.x < 32) tc::tmem_dealloc<128>(acc);
 }
 
-template <int M, int N, int ROWB, int DA, int NACC = 1>
+template <int M, int N, int ROWB, int DA, int NACC = 1, int NA = 4, int ASTR = 0, int NB = 1>
 void run(long long* d, int grid) {
-  const int iters = 2000;
-  const int smem = 4 * M * ROWB + 256 * ROWB + 2048;
-  cudaFuncSetAttribute(k<M, N, ROWB, DA, NACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  k<M, N, ROWB, DA, NACC><<<grid, 128, smem>>>(d, iters);
+  const int iters = 1998;
+  const int smem = NA * M * ROWB + NB * N * ROWB + 2048;
+  cudaFuncSetAttribute(k<M, N, ROWB, DA, NACC, NA, ASTR, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  k<M, N, ROWB, DA, NACC, NA, ASTR, NB><<<grid, 128, smem>>>(d, iters);
   cudaError_t e = cudaDeviceSynchronize();
   long long h = 0;
   cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost);
-  printf("M=%3d N=%3d rowbytes=%3d distinctA=%d nacc=%d ctas/SM=%d : %.1f cycles/MMA  (%s)\n", M, N, ROWB, DA, NACC, grid / 148,
+  printf("M=%3d N=%3d rowbytes=%3d nA=%d aStride=%d nB=%d nacc=%d ctas/SM=%d : %.1f cycles/MMA  (%s)\n", M, N, ROWB, DA ? NA : 1, ASTR ? ASTR : M * ROWB, NB, NACC, grid / 148,
          (double)h / iters, cudaGetErrorString(e));
 }
 
 int main() {
   long long* d;
   cudaMalloc(&d, 8);
-  for (int g : {148, 296, 444}) {
-    run<128, 16, 32, 1>(d, g);
-    run<128, 48, 32, 1>(d, g);
-    run<128, 64, 32, 1>(d, g);
-    run<128, 128, 32, 1>(d, g);
-    run<128, 16, 32, 1, 4>(d, g);
-    run<128, 48, 32, 1, 4>(d, g);
-    run<128, 64, 32, 1, 4>(d, g);
-    run<64, 32, 32, 1, 4>(d, g);
+  for (int g : {148, 296, 444, 592}) {
+    run<128, 48, 32, 1, 1, 4, 0, 1>(d, g);
+    run<128, 16, 32, 1, 1, 4, 0, 1>(d, g);
+    run<128, 96, 32, 1, 1, 4, 0, 1>(d, g);
   }
-  run<128, 16, 128, 1>(d, 148);
-  run<128, 64, 128, 1>(d, 148);
-  run<128, 128, 128, 1>(d, 148);
-  run<128, 256, 128, 1>(d, 148);
-  run<128, 64, 128, 1, 4>(d, 148);
   return 0;
 }
