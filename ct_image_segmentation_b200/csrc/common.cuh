@@ -105,6 +105,31 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
+// Sum 16 per-lane values over the 32 lanes of a warp with 16 shuffles (recursive halving: at every
+// step a lane keeps half of its values and receives the partner's partial sums for them) instead of
+// 16 x 5.  On return EVERY lane holds the complete sum of channel (lane >> 1) & 15.
+__device__ __forceinline__ float warp_sum16(const float (&v)[16], int lane) {
+  float a8[8], a4[4], a2[2];
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float keep = b4 ? v[8 + i] : v[i], give = b4 ? v[i] : v[8 + i];
+    a8[i] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float keep = b3 ? a8[4 + i] : a8[i], give = b3 ? a8[i] : a8[4 + i];
+    a4[i] = keep + __shfl_xor_sync(0xffffffffu, give, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float keep = b2 ? a4[2 + i] : a4[i], give = b2 ? a4[i] : a4[2 + i];
+    a2[i] = keep + __shfl_xor_sync(0xffffffffu, give, 4);
+  }
+  const float keep = b1 ? a2[1] : a2[0], give = b1 ? a2[0] : a2[1];
+  const float a1 = keep + __shfl_xor_sync(0xffffffffu, give, 2);
+  return a1 + __shfl_xor_sync(0xffffffffu, a1, 1);
+}
 __device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -211,15 +211,20 @@ tc_conv_kernel(const __grid_constant__ TcConvParams p) {
       if (p.stats) {  // warp-uniform: per-channel sum / sum of squares over the tile's valid rows
         float* sred = reinterpret_cast<float*>(tmem_slot + 4);  // [4 warps][BN][2]
         const int c0 = n0 + ch * 16;
+        float x[16], x2[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float x = valid ? __uint_as_float(v[i]) : 0.f;
-          if (valid && p.bias && c0 + i < p.cout) x += p.bias[c0 + i];
-          const float a = warp_sum(x), b = warp_sum(x * x);
-          if (lane == 0) {
-            sred[(q * BN + ch * 16 + i) * 2] = a;
-            sred[(q * BN + ch * 16 + i) * 2 + 1] = b;
-          }
+          x[i] = valid ? __uint_as_float(v[i]) : 0.f;
+          if (valid && p.bias && c0 + i < p.cout) x[i] += p.bias[c0 + i];
+          x2[i] = x[i] * x[i];
+        }
+        // 32 shuffles per 16-channel chunk (recursive halving), not 160: with a handful of CTAs on the
+        // deep layers this epilogue was as long as the whole main loop
+        const float a = warp_sum16(x, lane), b = warp_sum16(x2, lane);
+        if ((lane & 1) == 0) {
+          const int c = (lane >> 1) & 15;
+          sred[(q * BN + ch * 16 + c) * 2] = a;
+          sred[(q * BN + ch * 16 + c) * 2 + 1] = b;
         }
       }
     }
