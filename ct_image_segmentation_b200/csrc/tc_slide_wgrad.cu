@@ -3,11 +3,15 @@
 //
 // Same column sweep and 3-copy source-slab ring as tc_slide.cu (each S voxel is read 3.4x from L2
 // instead of 27x); T is loaded once per slab.  Voxels are the K dimension, so both operands are
-// MN-major exactly as TMA delivers them.  One tcgen05.mma covers a (kd, kw) pair: its 128 M rows
-// are 128/CA "slots" = consecutive LINE offsets into the S copy (leading-dimension byte offset =
-// one line = one swizzle atom); the first three slots are the taps kh = 0, 1, 2, the other rows are
-// never read back.  The 9 (kd, kw) accumulators x N columns stay in TMEM for the whole sweep and are
-// added to the fp32 result with red.global.add.f32 at the end.
+// MN-major exactly as TMA delivers them.  The M rows of a tcgen05.mma are "slots" = consecutive LINE
+// offsets into an S copy (leading-dimension byte offset = one line = one swizzle atom): the first
+// three slots are the taps kh = 0, 1, 2, the other rows are never read back.  Its N columns are
+// folded over kd: an S slab s pairs with the T slabs s-2, s-1, s (taps kd = 2, 1, 0), which lie in
+// adjacent slots of the T ring (N-chunk stride = one T slab; split in two where the ring wraps), so
+// one instruction of N = 3*CB replaces three of N = CB -- these small MMAs are bound by the
+// shared-memory read of their A tile.  Three accumulators (one per kw, one issuing warp each) of
+// 3*CB columns stay in TMEM for the whole sweep (zeroed with tcgen05.st, every MMA accumulates);
+// per-CTA partial tiles are summed by the unpack kernel.
 #include <string.h>
 
 #include "common.cuh"
@@ -24,7 +28,7 @@ int tc_make_map(CUtensorMap* out, const void* base, int rank, const uint64_t* di
 namespace {
 constexpr int TH = 16;
 constexpr int TWV = 8;
-constexpr int RT = 3;
+constexpr int RT = 6;
 inline int round16(int c) { return (c + 15) / 16 * 16; }
 }  // namespace
 
@@ -40,7 +44,7 @@ struct alignas(64) TcSlideWgradParams {
 template <int CA, int CB>
 __global__ void __launch_bounds__(192)
 tc_slide_wgrad_kernel(const __grid_constant__ TcSlideWgradParams p) {
-  constexpr int RING = 6;  // source slabs in flight: deep enough to hide the TMA latency
+  constexpr int RING = 5;  // source slabs in flight: deep enough to hide the TMA latency
   constexpr int PA = CA * 2, PB = CB * 2;
   constexpr int COPY_BYTES = (TH + 2) * TWV * PA;
   constexpr int SLAB_BYTES = 3 * COPY_BYTES;
@@ -86,6 +90,17 @@ tc_slide_wgrad_kernel(const __grid_constant__ TcSlideWgradParams p) {
   tc::tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
 
+  // ---- accumulators start at zero: every MMA accumulates (the N-folded instructions touch several
+  // kd chunks whose first contributions come at different slabs)
+  if (warp >= 2) {
+    const uint32_t lane_base = tmem_acc + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < 9 * CB; c += 16) tc::tmem_st16_zero(lane_base + c);
+    tc::tmem_st_wait();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
   if (warp == 0) {
     if (lane == 0) {
       for (int s = 0; s < nd + 2; ++s) {
@@ -97,8 +112,8 @@ tc_slide_wgrad_kernel(const __grid_constant__ TcSlideWgradParams p) {
 #pragma unroll
         for (int kw = 0; kw < 3; ++kw)
           tc::tma_load_5d(dst + kw * COPY_BYTES, &p.tmS, &fullS[slot], 0, w0 + kw - 1, h0 - 1, ds, n);
-        if (s >= 2) {
-          const int j = s - 2, ts = j % RT;
+        if (s < nd) {  // T slab j = s is first needed together with S slab s (tap kd = 0)
+          const int j = s, ts = j % RT;
           tc::mbar_wait(&emptyT[ts], (((uint32_t)(j / RT)) & 1u) ^ 1u);
           tc::mbar_expect_tx(&fullT[ts], TSLAB_BYTES);
           tc::tma_load_5d(tring + ts * TSLAB_BYTES, &p.tmT, &fullT[ts], 0, w0, h0, d_begin + j, n);
@@ -106,39 +121,45 @@ tc_slide_wgrad_kernel(const __grid_constant__ TcSlideWgradParams p) {
       }
     }
   }
-  // ---- MMA issue: warps 1, 2, 3 each own one kd (three accumulators); a single thread can only
-  // issue ~1 MMA per 50-100 cycles (descriptor arithmetic + issue), which starves the tensor pipe
-  // when every MMA is this small, so the 72 MMAs per slab are spread over three issuing threads.
-  if (warp >= 1 && warp <= 3) {  // warp-uniform issue loop, one elected lane issues
-    constexpr uint32_t idesc = tc::make_idesc_bf16(MM, CB, true, true);
+  // ---- MMA issue: warps 1, 2, 3 each own one kw (one accumulator of 3*CB columns); warp-uniform loop,
+  // one elected lane issues
+  if (warp >= 1 && warp <= 3) {
     constexpr uint64_t layA = tc::layout_for_row_bytes(PA), layB = tc::layout_for_row_bytes(PB);
-    const int id = warp - 1;
+    const int iw = warp - 1;
     const uint32_t r_addr = tc::smem_u32(ring), t_addr = tc::smem_u32(tring);
-    // descriptor templates: only the 14-bit start-address field changes below
-    const uint64_t a_tmpl = tc::make_smem_desc(0, TWV * PA, TWV * PA, layA);
-    const uint64_t b_tmpl = tc::make_smem_desc(0, 16, TWV * PB, layB);
-    int waited = 0;
-    for (int j = 0; j < nd; ++j) {
-      while (waited <= j + 2) {
-        tc::mbar_wait(&fullS[waited % RING], ((uint32_t)(waited / RING)) & 1u);
-        ++waited;
+    const uint64_t a_tmpl = tc::make_smem_desc(0, TWV * PA, TWV * PA, layA);    // slots one line apart
+    const uint64_t b_tmpl = tc::make_smem_desc(0, TSLAB_BYTES, TWV * PB, layB); // N chunks one T slab apart
+    const uint32_t acc = tmem_acc + iw * 3 * CB;
+    int waitedT = 0;
+    for (int s = 0; s < nd + 2; ++s) {
+      tc::mbar_wait(&fullS[s % RING], ((uint32_t)(s / RING)) & 1u);
+      const int t_last = min(s, nd - 1);
+      while (waitedT <= t_last) {
+        tc::mbar_wait(&fullT[waitedT % RT], ((uint32_t)(waitedT / RT)) & 1u);
+        ++waitedT;
       }
-      tc::mbar_wait(&fullT[j % RT], ((uint32_t)(j / RT)) & 1u);
       tc::tc_fence_after();
-      const uint64_t tb = b_tmpl + ((t_addr + (j % RT) * TSLAB_BYTES) >> 4);
-      const uint64_t sa = a_tmpl + ((r_addr + ((j + id) % RING) * SLAB_BYTES) >> 4);
+      // chunk i of the accumulator <-> T slab j = s - 2 + i <-> tap kd = 2 - i; valid chunks are contiguous
+      const int i_lo = max(0, 2 - s), i_hi = min(2, nd + 1 - s);
+      const int cnt = i_hi - i_lo + 1;
+      const int slot_lo = (s - 2 + i_lo) % RT;
+      const int len0 = min(cnt, RT - slot_lo), len1 = cnt - len0;
+      const uint32_t i0 = tc::make_idesc_bf16(MM, len0 * CB, true, true);
+      const uint32_t i1 = tc::make_idesc_bf16(MM, (len1 > 0 ? len1 : 1) * CB, true, true);
+      const uint32_t d0 = acc + i_lo * CB, d1 = d0 + len0 * CB;
+      const uint64_t sa = a_tmpl + ((r_addr + (s % RING) * SLAB_BYTES + iw * COPY_BYTES) >> 4);
+      const uint64_t tb0 = b_tmpl + ((t_addr + slot_lo * TSLAB_BYTES) >> 4);
+      const uint64_t tb1 = b_tmpl + (t_addr >> 4);  // a wrapped part starts at ring slot 0
 #pragma unroll
-      for (int iw = 0; iw < 3; ++iw) {
-        const uint32_t acc = tmem_acc + (id * 3 + iw) * CB;
-#pragma unroll
-        for (int t = 0; t < TH / 2; ++t) {
-          // K step t = output lines 2t, 2t+1; slot i of A starts at S line 2t + i
-          tc::umma_bf16_warp(acc, sa + ((iw * COPY_BYTES + (2 * t) * (TWV * PA)) >> 4),
-                        tb + (((2 * t) * (TWV * PB)) >> 4), idesc, (j > 0 || t > 0) ? 1u : 0u);
-        }
+      for (int t = 0; t < TH / 2; ++t) {
+        // K step t = output lines 2t, 2t+1; slot i of A starts at S line 2t + i
+        const uint64_t a = sa + (((2 * t) * (TWV * PA)) >> 4);
+        const uint32_t bo = ((2 * t) * (TWV * PB)) >> 4;
+        tc::umma_bf16_warp(d0, a, tb0 + bo, i0, 1u);
+        if (len1 > 0) tc::umma_bf16_warp(d1, a, tb1 + bo, i1, 1u);
       }
-      tc::umma_commit_warp(&emptyS[j % RING]);
-      tc::umma_commit_warp(&emptyT[j % RT]);
+      tc::umma_commit_warp(&emptyS[s % RING]);
+      if (s >= 2) tc::umma_commit_warp(&emptyT[(s - 2) % RT]);
     }
     tc::umma_commit_warp(acc_full);
   }
@@ -152,7 +173,7 @@ tc_slide_wgrad_kernel(const __grid_constant__ TcSlideWgradParams p) {
     tc::tc_fence_after();
     if (MM == 64 ? (q < 3) : (q * 32 < 3 * CA)) {  // warp-uniform: only rows that are taps
       for (int acc = 0; acc < 9; ++acc) {
-        const int id = acc / 3, iw = acc % 3;
+        const int iw = acc / 3, id = 2 - acc % 3;  // column chunk (iw, i) holds tap kd = 2 - i
         const int tap = (id * 3 + (valid ? ih : 0)) * 3 + iw;
         float* orow = p.out + (int64_t)blockIdx.x * 27 * p.a_pad * p.b_pad + ((int64_t)tap * p.a_pad + a) * p.b_pad;
 #pragma unroll
@@ -208,7 +229,7 @@ int tc_slide_wgrad_unpack(const float* G, float* gw, int taps, int a_c, int b_c,
 namespace {
 template <int CA, int CB>
 int launch_slide_wgrad(const TcSlideWgradParams& p, unsigned grid, cudaStream_t st) {
-  constexpr int RING = 6;
+  constexpr int RING = 5;
   constexpr int SLAB = 3 * (TH + 2) * TWV * CA * 2;
   constexpr int TSLAB = TH * TWV * CB * 2;
   const size_t smem = 1024 + RING * SLAB + RT * TSLAB + 40 * 8 + 64;
