@@ -98,6 +98,18 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
   tc::tc_fence_after();
   const uint32_t tmem_acc = *tmem_slot;
 
+  // accumulator chunks start (and are handed back by the epilogue) zeroed: every MMA accumulates, so a
+  // source slab is ONE N-folded instruction per tap even for the output slab it touches first
+  if (warp >= 2) {
+    const uint32_t lane_base = tmem_acc + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < ACCR * BN; c += 16) tc::tmem_st16_zero(lane_base + c);
+    tc::tmem_st_wait();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+
   if (warp == 0) {
     if (lane == 0) {
       // weights: for every in-plane source shift (ih, iw) the three kd tiles in the order of the
@@ -148,18 +160,8 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
         const uint64_t b0 = w_desc + (((lo - (s - 2)) * WT_BYTES) >> 4);
         const uint64_t b1 = b0 + ((len0 * WT_BYTES) >> 4);
         const uint64_t slab = tmpl + ((r_addr + (s % RING) * SLAB_BYTES) >> 4);
-        if (fresh) {
-          // first MMA of the slab: output slab s is overwritten (its own instruction), the older ones accumulate
-          constexpr uint32_t idesc1 = tc::make_idesc_bf16(128, BN, false, false);
-          const int na = s - lo;                       // older output slabs: 0, 1 or 2
-          const int la0 = min(na, ACCR - c_lo), la1 = na - la0;
-          if (la0 > 0) tc::umma_bf16_warp(d0, slab, b0, tc::make_idesc_bf16(128, la0 * BN, false, false), 1u);
-          if (la1 > 0) tc::umma_bf16_warp(d1, slab, b0 + ((la0 * WT_BYTES) >> 4), idesc1, 1u);
-          tc::umma_bf16_warp(tmem_acc + (s % ACCR) * BN, slab, w_desc + ((2 * WT_BYTES) >> 4), idesc1, 0u);
-        } else {
-          tc::umma_bf16_warp(d0, slab, b0, i0, 1u);
-          if (len1 > 0) tc::umma_bf16_warp(d1, slab, b1, i1, 1u);
-        }
+        tc::umma_bf16_warp(d0, slab, b0, i0, 1u);
+        if (len1 > 0) tc::umma_bf16_warp(d1, slab, b1, i1, 1u);
 #pragma unroll
         for (int hw = 0; hw < 9; ++hw)
 #pragma unroll
@@ -247,6 +249,10 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
           op[1] = o1;
         }
       }
+      // hand the chunk back zeroed
+#pragma unroll
+      for (int ch = 0; ch < BN / 16; ++ch) tc::tmem_st16_zero(tmem_acc + ((uint32_t)(q * 32) << 16) + buf * BN + ch * 16);
+      tc::tmem_st_wait();
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
