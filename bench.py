@@ -272,9 +272,10 @@ def roofline_probe(args, dev, dtype, pk):
     """Dominant layer timed alone with CUDA events on the launching stream: the head convolution
     10->10 (3x3x3, stride 1) at full resolution -- 29 % of the network's conv FLOPs (SURVEY.md F11 /
     Appendix B), run by the sliding-window tcgen05 kernel `tc_slide_conv_kernel<16,16>` (fprop here;
-    its dgrad is the same kernel with flipped taps).  AI = 135 FLOP/B < ridge (211), so the layer is
-    judged against HBM; the binding unit in practice is the tensor pipe's shared-memory operand fetch
-    (N = 16 MMAs), see profiles/r1_ncu_full_head_conv_slide.csv."""
+    its dgrad is the same kernel with mirrored taps; together the largest kernel share of the step).
+    AI = 135 FLOP/B < ridge (211), so the layer is judged against HBM; the measured binding unit is the
+    tensor core's shared-memory operand fetch (N-folded MMAs of N = 48, K = 16), see DESIGN.md section 3
+    and profiles/r1_ncu_full_head_conv_slide_nfold.csv."""
     from ct_image_segmentation_b200 import _lib, ops
     g = ops.ConvGeom(3, 10, 10, 3, 1, False)
     n, p = args.batch, args.patch
@@ -309,17 +310,20 @@ def roofline_probe(args, dev, dtype, pk):
             "bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
             "frac": ach_gbs / pk["hbm_gbs"],
             # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of this
-            # kernel at batch 2 x 128^3 (profiles/r1_ncu_full_head_conv_slide.csv)
-            "traffic": 236.6e6 if (n, p, esz) == (2, 128, 2) else None,
+            # kernel at batch 2 x 128^3 (profiles/r1_ncu_full_head_conv_slide_nfold.csv: 139.9 + 95.6 MB)
+            "traffic": 235.5e6 if (n, p, esz) == (2, 128, 2) else None,
             "ms": ms, "achieved_tflops": ach_tf, "tensor_frac": ach_tf / pk["bf16_tflops"],
-            "tc_pipe_active_pct_ncu": 78.0, "peak_source": pk["src"],
-            "note": "HBM is the bound by arithmetic intensity; the measured binding unit is the tensor pipe's "
-                    "shared-memory operand fetch (sm__pipe_tc_cycles_active 78 %): with N = 16 every MMA re-reads "
-                    "a 4 KB activation tile for 32 k MAC",
+            "tc_pipe_active_pct_ncu": 70.0, "peak_source": pk["src"],
+            "note": "HBM is the bound by arithmetic intensity (168 MB algorithmic: 16-channel padded rows in + "
+                    "out; 236 MB measured DRAM traffic incl. the halo re-reads that miss L2); the measured binding "
+                    "unit is the tensor core's shared-memory operand fetch: an MMA of M=128, K=16 costs "
+                    "(4 KB + N*32 B)/128 B per clock whatever N <= 128 is, so the kernel folds the three kd taps "
+                    "along N (9 MMAs of N=48 per slab instead of 27 of N=16); with the loads switched off it "
+                    "still takes ~100 us (scripts/ubench/mma_rate.cu, DESIGN.md section 3)",
             "algorithmic_bytes": bytes_alg, "algorithmic_flops": flops,
-            "step_share_ncu": "this kernel: 6 launches = 9 % of the step (largest single kernel after the "
-                              "16-launch streaming wgrad family, 13 %); all convolution kernels together 57 % "
-                              "(profiles/r1_step_launch_summary.txt)"}
+            "step_share_ncu": "this kernel: 6 launches = 10 % of the step's kernel time, the largest single kernel "
+                              "(profiles/r1_step_launch_summary.txt); InstanceNorm/PReLU passes together 24 % at "
+                              "4.3-6 TB/s"}
 
 
 def main():
