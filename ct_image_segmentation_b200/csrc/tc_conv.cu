@@ -463,6 +463,7 @@ pack_weights_batched_kernel(const b200seg_pack_entry* __restrict__ table, int n_
         const float* wp = w + (conv_layer ? (int64_t)co * cin + ci : (int64_t)ci * cout + co) * taps;
         bf16* op = out + ((int64_t)kb * dst_pad + t) * KC + kc;
         const int64_t tap_stride = (int64_t)kblocks * dst_pad * KC;
+#pragma unroll 9
         for (int tap = 0; tap < taps; ++tap) op[tap * tap_stride] = __float2bfloat16_rn(live ? wp[tap] : 0.f);
       } else {
         const int item = (c - chunks_tc) * PACK_CHUNK + threadIdx.x;  // = sc * dst_c + t
@@ -472,6 +473,7 @@ pack_weights_batched_kernel(const b200seg_pack_entry* __restrict__ table, int n_
           const float* wp = w + (conv_layer ? (int64_t)co * cin + ci : (int64_t)ci * cout + co) * taps;
           bf16* op = gen + item;
           const int64_t tap_stride = (int64_t)items_gen;
+#pragma unroll 9
           for (int tap = 0; tap < taps; ++tap) op[tap * tap_stride] = __float2bfloat16_rn(wp[tap]);
         }
       }

@@ -197,33 +197,15 @@ tc_slide_wgrad_kernel(const __grid_constant__ TcSlideWgradParams p) {
   if (warp == 1) tc::tmem_dealloc<TMEM_COLS>(tmem_acc);
 }
 
-// gw[b][a][tap] = sum_cta G[cta][tap][a][b]: one warp per output element, fixed order (deterministic)
-__global__ void tc_slide_wgrad_unpack_kernel(const float* __restrict__ G, float* __restrict__ gw, int taps, int a_c,
-                                             int b_c, int a_pad, int b_pad, int nparts) {
-  int64_t total = (int64_t)taps * a_c * b_c;
-  int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) / 32;
-  const int lane = threadIdx.x % 32;
-  if (idx >= total) return;
-  int b = (int)(idx % b_c);
-  int64_t r = idx / b_c;
-  int a = (int)(r % a_c);
-  int tap = (int)(r / a_c);
-  const int64_t g_elems = (int64_t)taps * a_pad * b_pad;
-  const float* gp = G + ((int64_t)tap * a_pad + a) * b_pad + b;
-  float s = 0.f;
-  for (int i = lane; i < nparts; i += 32) s += gp[(int64_t)i * g_elems];
-  s = warp_sum(s);
-  if (lane == 0) gw[((int64_t)b * a_c + a) * taps + tap] = s;
-}
+// gw[b][a][tap] = sum_cta G[cta][tap][a][b]: the block-per-row unpack of tc_wgrad.cu (coalesced along b,
+// partial tiles dealt over split lanes, fixed summation order)
+int tc_wgrad_unpack(const float* G, float* gw, int taps, int a_c, int b_c, int a_pad, int b_pad, int parts,
+                    const char* what, cudaStream_t st);
 
-// host launcher shared with the ConvTranspose sliding wgrad (tc_convtr.cu)
+// host launcher shared with the hi/lo sliding wgrad (tc_convtr.cu)
 int tc_slide_wgrad_unpack(const float* G, float* gw, int taps, int a_c, int b_c, int a_pad, int b_pad, int nparts,
                           cudaStream_t st) {
-  const int64_t total = (int64_t)taps * a_c * b_c;
-  tc_slide_wgrad_unpack_kernel<<<(unsigned)cdiv64(total * 32, 256), 256, 0, st>>>(G, gw, taps, a_c, b_c, a_pad, b_pad,
-                                                                                 nparts);
-  B200SEG_CHECK_LAUNCH("tc_slide_wgrad_unpack");
-  return B200SEG_OK;
+  return tc_wgrad_unpack(G, gw, taps, a_c, b_c, a_pad, b_pad, nparts, "tc_slide_wgrad_unpack", st);
 }
 
 namespace {
@@ -251,7 +233,9 @@ void slide_wgrad_grid(const b200seg_conv_desc* d, int& tilesH, int& tilesW, int&
   tilesH = (d->in_h + TH - 1) / TH;
   tilesW = (d->in_w + TWV - 1) / TWV;
   const int64_t cols = (int64_t)d->n * tilesH * tilesW;
-  int ns = (int)((148 * 3 + cols - 1) / cols);
+  // one wave: 2 resident CTAs per SM for 16/16 channels (TMEM 256 columns, ~95 KB), else 1
+  const int per_sm = (round16(d->cin) == 16 && round16(d->cout) == 16) ? 2 : 1;
+  int ns = (int)((148 * per_sm) / cols);
   if (ns < 1) ns = 1;
   dseg = (d->in_d + ns - 1) / ns;
   if (dseg < 8) dseg = 8;
@@ -311,11 +295,7 @@ int tc_slide_wgrad_run(const b200seg_conv_desc* d, const void* x, const void* dy
   else if (CA == 32 && CB == 16) rc = launch_slide_wgrad<32, 16>(p, (unsigned)grid, st);
   else rc = launch_slide_wgrad<32, 32>(p, (unsigned)grid, st);
   if (rc) return rc;
-  const int64_t total = (int64_t)27 * d->cin * d->cout;
-  tc_slide_wgrad_unpack_kernel<<<(unsigned)cdiv64(total * 32, 256), 256, 0, st>>>(G32, gw, 27, d->cin, d->cout, CA, CB,
-                                                                                 (int)grid);
-  B200SEG_CHECK_LAUNCH("tc_slide_wgrad_unpack");
-  return B200SEG_OK;
+  return tc_slide_wgrad_unpack(G32, gw, 27, d->cin, d->cout, CA, CB, (int)grid, st);
 }
 
 }  // namespace b200seg

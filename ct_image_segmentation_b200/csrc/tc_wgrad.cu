@@ -224,6 +224,14 @@ tc_wgrad_unpack_kernel(const float* __restrict__ G, float* __restrict__ gw, int 
   }
 }
 
+// gw (PyTorch layout) = sum over `parts` partial tiles G[part][tap][a_pad][b_pad]; shared by the sliding kernels
+int tc_wgrad_unpack(const float* G, float* gw, int taps, int a_c, int b_c, int a_pad, int b_pad, int parts,
+                    const char* what, cudaStream_t st) {
+  tc_wgrad_unpack_kernel<<<(unsigned)(taps * a_c), 256, 0, st>>>(G, gw, taps, a_c, b_c, a_pad, b_pad, parts);
+  B200SEG_CHECK_LAUNCH(what);
+  return B200SEG_OK;
+}
+
 namespace {
 
 inline int round16(int c) { return (c + 15) / 16 * 16; }
@@ -431,10 +439,7 @@ int tc_wgrad_run(const b200seg_conv_desc* d, bool transposed_layer, const void* 
   count_tc_launch();
   const int64_t total = (int64_t)taps * g.a_c * g.b_c;
   (void)total;
-  tc_wgrad_unpack_kernel<<<(unsigned)(taps * g.a_c), 256, 0, st>>>(G32, gw, taps, g.a_c, g.b_c, a_pad, b_pad,
-                                                                   (int)splits);
-  B200SEG_CHECK_LAUNCH("tc_wgrad_unpack");
-  return B200SEG_OK;
+  return tc_wgrad_unpack(G32, gw, taps, g.a_c, g.b_c, a_pad, b_pad, (int)splits, "tc_wgrad_unpack", st);
 }
 
 }  // namespace b200seg
