@@ -14,6 +14,7 @@
 // Stride-2 gathers never touch inserted zeros or skipped taps: forward gathers read one of 8
 // parity-subsampled tensor maps (doubled strides), transposed gathers are decomposed into 8
 // destination parity classes with 1..8 contributing taps each.
+#include <stdlib.h>
 #include <mutex>
 #include <unordered_map>
 #include <vector>
@@ -549,7 +550,8 @@ int tc_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void*
   TcConvParams p;
   memset(&p, 0, sizeof(p));
   const int src_pad = round16(g.src_c), dst_pad = round16(g.dst_c);
-  const int KC = kc_for(src_pad), BN = bn_for(dst_pad);
+  const int KC = kc_for(src_pad);
+  int BN = bn_for(dst_pad);
   p.kblocks = src_pad / KC;
   p.n = g.n;
   p.cout = g.dst_c; p.cout_pad = dst_pad;
@@ -619,6 +621,14 @@ int tc_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void*
       }
   }
   p.tilesD = (cdim[0] + p.tD - 1) / p.tD; p.tilesH = (cdim[1] + p.tH - 1) / p.tH; p.tilesW = (cdim[2] + p.tW - 1) / p.tW;
+
+  // ---- deep layers have only a handful of 128-voxel tiles: narrower N tiles spread them over more SMs
+  // (each CTA streams its A tiles from L2 at ~64 B/clk whatever BN is; B shrinks with BN)
+  {
+    static const int min_ctas = getenv("B200SEG_CONV_MIN_CTAS") ? atoi(getenv("B200SEG_CONV_MIN_CTAS")) : 128;
+    const int64_t mtiles = (int64_t)ncls[0] * ncls[1] * ncls[2] * g.n * p.tilesD * p.tilesH * p.tilesW;
+    while (BN > 32 && mtiles * (dst_pad / BN) < min_ctas) BN /= 2;
+  }
 
   // ---- tensor maps
   const int row_bytes = KC * 2;
