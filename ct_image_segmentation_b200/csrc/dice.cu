@@ -28,8 +28,10 @@ __device__ __forceinline__ int load_label(const void* labels, int64_t idx) {
 // softmax of one voxel: p[0..C) (entries >= C are 0).  Plain expf / division in fp32, i.e. the
 // arithmetic `torch.softmax` performs (max-subtracted exponentials over their sum).
 // vec16: the voxel row is 16 bf16 (32 B, 16-byte aligned): two 128-bit loads instead of C scalar ones
-template <typename T, int CMAX>
+// CE > 0: the class count is the compile-time constant CE (C is ignored): all loops run over exactly CE classes
+template <typename T, int CMAX, int CE = 0>
 __device__ __forceinline__ void voxel_softmax(const T* z, int C, float (&p)[CMAX], bool vec16 = false) {
+  if constexpr (CE > 0) C = CE;
   float mx = -INFINITY;
   if constexpr (sizeof(T) == 2 && CMAX == 16) {
     if (vec16) {
@@ -92,11 +94,13 @@ size_t dice_workspace_bytes(const b200seg_dice_desc& d) {
 }
 
 // partial[n][blk][c][3] = { I, G, P }
-template <typename T, int CMAX, int LT>
+template <typename T, int CMAX, int LT, int CE = 0>
 __global__ void __launch_bounds__(kDiceThreads)
 softmax_dice_fwd_kernel(const T* __restrict__ logits, const void* __restrict__ labels,
                         int64_t spatial, int C, int ld, int64_t vox_per_block,
                         float* __restrict__ partial, bool vec16) {
+  if constexpr (CE > 0) C = CE;
+  constexpr int CL = CE > 0 ? CE : CMAX;  // classes that exist at compile time
   __shared__ float red[kDiceThreads / 32][CMAX * 3];
   const int n = blockIdx.y;
   const int64_t v_begin = (int64_t)blockIdx.x * vox_per_block;
@@ -107,10 +111,10 @@ softmax_dice_fwd_kernel(const T* __restrict__ logits, const void* __restrict__ l
   for (int64_t v = v_begin + threadIdx.x; v < v_end; v += kDiceThreads) {
     int64_t vox = (int64_t)n * spatial + v;
     float p[CMAX];
-    voxel_softmax<T, CMAX>(logits + vox * ld, C, p, vec16);
+    voxel_softmax<T, CMAX, CE>(logits + vox * ld, C, p, vec16);
     int lab = load_label<LT>(labels, vox);
 #pragma unroll
-    for (int c = 0; c < CMAX; ++c) {
+    for (int c = 0; c < CL; ++c) {
       bool hit = (lab == c);
       aI[c] += hit ? p[c] : 0.f;
       aG[c] += hit ? 1.f : 0.f;
@@ -119,7 +123,7 @@ softmax_dice_fwd_kernel(const T* __restrict__ logits, const void* __restrict__ l
   }
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 #pragma unroll
-  for (int c = 0; c < CMAX; ++c) {
+  for (int c = 0; c < CL; ++c) {
     float i_ = warp_sum(aI[c]), g_ = warp_sum(aG[c]), p_ = warp_sum(aP[c]);
     if (lane == 0) {
       red[warp][c * 3 + 0] = i_;
@@ -147,11 +151,13 @@ __global__ void dice_sums_final_kernel(const float* __restrict__ partial, int nb
   if (lane == 0) sums[warp] = (float)s;
 }
 
-template <typename T, int CMAX, int LT>
+template <typename T, int CMAX, int LT, int CE = 0>
 __global__ void __launch_bounds__(kDiceThreads)
 softmax_dice_bwd_kernel(const T* __restrict__ logits, const void* __restrict__ labels,
                         const float* __restrict__ gI, const float* __restrict__ gP,
                         T* __restrict__ dlogits, int64_t spatial, int C, int ld, bool vec16) {
+  if constexpr (CE > 0) C = CE;
+  constexpr int CL = CE > 0 ? CE : CMAX;
   const int n = blockIdx.y;
   float cI[CMAX], cP[CMAX];
 #pragma unroll
@@ -163,14 +169,18 @@ softmax_dice_bwd_kernel(const T* __restrict__ logits, const void* __restrict__ l
        v += (int64_t)gridDim.x * kDiceThreads) {
     int64_t vox = (int64_t)n * spatial + v;
     float p[CMAX];
-    voxel_softmax<T, CMAX>(logits + vox * ld, C, p, vec16);
+    voxel_softmax<T, CMAX, CE>(logits + vox * ld, C, p, vec16);
     int lab = load_label<LT>(labels, vox);
     float g[CMAX];
     float dot = 0.f;
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
-      g[c] = (lab == c ? cI[c] : 0.f) + cP[c];
-      dot = fmaf(g[c], p[c], dot);
+      if (c < CL) {
+        g[c] = (lab == c ? cI[c] : 0.f) + cP[c];
+        dot = fmaf(g[c], p[c], dot);
+      } else {
+        g[c] = 0.f;
+      }
     }
     T* o = dlogits + vox * ld;
     bool done = false;
@@ -486,12 +496,27 @@ int launch_crop_window_norm(int dtype, const int16_t* hu, const uint8_t* lab, co
     else                          { using T = float;         constexpr int CM = 32; constexpr int LT = B200SEG_LABEL_I64; __VA_ARGS__; } \
   } while (0)
 
+// the reference's 10 classes (9 structures + background) as a compile-time constant: the padded
+// 16-wide loops shrink to exactly 10 (these kernels are instruction-bound, not memory-bound)
+#define DISPATCH_DICE10(d, ...)                                                            \
+  do {                                                                                     \
+    const bool bf = (d).dtype == B200SEG_BF16, u8 = (d).label_dtype == B200SEG_LABEL_U8;   \
+    if (bf && u8)      { using T = __nv_bfloat16; constexpr int LT = B200SEG_LABEL_U8;  __VA_ARGS__; } \
+    else if (bf)       { using T = __nv_bfloat16; constexpr int LT = B200SEG_LABEL_I64; __VA_ARGS__; } \
+    else if (u8)       { using T = float;         constexpr int LT = B200SEG_LABEL_U8;  __VA_ARGS__; } \
+    else               { using T = float;         constexpr int LT = B200SEG_LABEL_I64; __VA_ARGS__; } \
+  } while (0)
+
 int launch_softmax_dice_fwd(const b200seg_dice_desc& d, const void* logits, const void* labels,
                             float* sums, void* ws, cudaStream_t st) {
   int nb = dice_blocks(d.spatial, d.n);
   int64_t per = cdiv64(d.spatial, nb);
   dim3 grid(nb, d.n);
   float* partial = (float*)ws;
+  if (d.c == 10) {
+    DISPATCH_DICE10(d, (softmax_dice_fwd_kernel<T, 16, LT, 10><<<grid, kDiceThreads, 0, st>>>(
+                           (const T*)logits, labels, d.spatial, d.c, d.ld, per, partial, vec16_ok(d, logits, nullptr))));
+  } else
   DISPATCH_DICE(d, (softmax_dice_fwd_kernel<T, CM, LT><<<grid, kDiceThreads, 0, st>>>(
                        (const T*)logits, labels, d.spatial, d.c, d.ld, per, partial, vec16_ok(d, logits, nullptr))));
   B200SEG_CHECK_LAUNCH("softmax_dice_fwd");
@@ -508,6 +533,11 @@ int launch_softmax_dice_bwd(const b200seg_dice_desc& d, const void* logits, cons
   if (cap < 1) cap = 1;
   if (nb > cap) nb = cap;
   dim3 grid((unsigned)nb, d.n);
+  if (d.c == 10) {
+    DISPATCH_DICE10(d, (softmax_dice_bwd_kernel<T, 16, LT, 10><<<grid, kDiceThreads, 0, st>>>(
+                           (const T*)logits, labels, gI, gP, (T*)dlogits, d.spatial, d.c, d.ld,
+                           vec16_ok(d, logits, dlogits))));
+  } else
   DISPATCH_DICE(d, (softmax_dice_bwd_kernel<T, CM, LT><<<grid, kDiceThreads, 0, st>>>(
                        (const T*)logits, labels, gI, gP, (T*)dlogits, d.spatial, d.c, d.ld,
                        vec16_ok(d, logits, dlogits))));
