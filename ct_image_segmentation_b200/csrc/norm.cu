@@ -301,6 +301,83 @@ instnorm_prelu_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ d
   }
 }
 
+// Small-instance backward in ONE launch (deep layers: <= 4096 voxels per sample, tensors of a MB that
+// live in L2): a CTA owns V channels of one sample for ALL voxels, so the three spatial sums never
+// leave the block -- pass 1 accumulates them, a shared-memory tree makes them block-wide, pass 2
+// re-reads x / dy (L2 hits) and writes dx.  Replaces partial + final + apply (three launches of
+// ~5-10 us each at these sizes).  sums[nc][3] is still written for the dalpha reduction.
+template <typename T, int V>
+__global__ void __launch_bounds__(512)
+instnorm_prelu_bwd_small_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean,
+                                const float* __restrict__ rstd, const float* __restrict__ alpha, T* __restrict__ dx,
+                                int64_t spatial, int c, int x_ld, int dy_ld, int dx_ld, float* __restrict__ sums) {
+  __shared__ float red[16][3 * V];
+  __shared__ float tot[3 * V];
+  const int t = threadIdx.x, n = blockIdx.y, c0 = blockIdx.x * V;
+  float m[V], r[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    m[i] = mean[n * c + c0 + i];
+    r[i] = rstd[n * c + c0 + i];
+  }
+  const float a = alpha[0];
+  const int64_t vox0 = (int64_t)n * spatial;
+  float acc[3][V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[0][i] = acc[1][i] = acc[2][i] = 0.f;
+  for (int64_t v = t; v < spatial; v += 512) {
+    Vec<T, V> xv, gv;
+    xv.load(x + (vox0 + v) * x_ld + c0);
+    gv.load(dy + (vox0 + v) * dy_ld + c0);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float h = (xv.v[i] - m[i]) * r[i];
+      const bool pos = h > 0.f;
+      const float g = pos ? gv.v[i] : a * gv.v[i];
+      acc[0][i] += g;
+      acc[1][i] = fmaf(g, h, acc[1][i]);
+      acc[2][i] += pos ? 0.f : gv.v[i] * h;
+    }
+  }
+  const int warp = t >> 5, lane = t & 31;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float w = warp_sum(acc[k][i]);
+      if (lane == 0) red[warp][k * V + i] = w;
+    }
+  __syncthreads();
+  if (t < 3 * V) {
+    float s_ = 0.f;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) s_ += red[w][t];  // fixed order
+    const int k = t / V, i = t % V;
+    const float o = k < 2 ? s_ / (float)spatial : s_;
+    tot[t] = o;
+    sums[(n * c + c0 + i) * 3 + k] = o;
+  }
+  __syncthreads();
+  float s1[V], s2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    s1[i] = tot[i];
+    s2[i] = tot[V + i];
+  }
+  for (int64_t v = t; v < spatial; v += 512) {
+    Vec<T, V> xv, gv, ov;
+    xv.load(x + (vox0 + v) * x_ld + c0);
+    gv.load(dy + (vox0 + v) * dy_ld + c0);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float h = (xv.v[i] - m[i]) * r[i];
+      const float g = h > 0.f ? gv.v[i] : a * gv.v[i];
+      ov.v[i] = r[i] * (g - s1[i] - h * s2[i]);
+    }
+    ov.store(dx + (vox0 + v) * dx_ld + c0);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 namespace {
 
@@ -394,6 +471,17 @@ int launch_instnorm_prelu_bwd(const b200seg_norm_desc& d, const void* x, const f
   if (rc) return rc;
   float* partial = (float*)ws;
   float* sums = partial + (size_t)d.n * g.nblk * d.c * 3;
+  if (d.spatial <= 4096 && V >= 4) {  // deep layers: one launch, sums stay in the block
+    dim3 gs(d.c / V, d.n);
+    DISPATCH_TV(d.dtype, V,
+                (instnorm_prelu_bwd_small_kernel<T, VV><<<gs, 512, 0, st>>>(
+                    (const T*)x, (const T*)dy, mean, rstd, alpha, (T*)dx, d.spatial, d.c, d.x_ld, d.y_ld,
+                    d.r_ld, sums)));
+    B200SEG_CHECK_LAUNCH("instnorm_prelu_bwd_small");
+    dalpha_final_kernel<<<1, 256, 0, st>>>(sums, d.n * d.c, dalpha);
+    B200SEG_CHECK_LAUNCH("dalpha_final");
+    return B200SEG_OK;
+  }
   int64_t per = cdiv64(d.spatial, g.nblk);
   dim3 grid(g.nblk, d.n);
   size_t smem = 256 * 3 * V * sizeof(float);
