@@ -7,15 +7,15 @@ Drop-in surface (reference ``capstone/models/__init__.py:1-3``)::
 The CUDA library (``lib/libb200seg.so``) is loaded lazily on first use; there is no CPU or
 PyTorch fallback for the hot path.
 """
-from .losses import (DiceLoss, DiceLossWrapper, GeneralizedDiceLoss, MultipleLossWrapper,
-                     MultipleLossWrapper3D, N_CLASSES, STRUCTURES, apply_missing_mask)
+from .losses import (CrossEntropyLoss, DiceLoss, DiceLossWrapper, FocalLoss, GeneralizedDiceLoss,
+                     MultipleLossWrapper, MultipleLossWrapper3D, N_CLASSES, STRUCTURES, apply_missing_mask)
 from .metrics import (DiceMetricWrapper, DiceMetricWrapper3D, dice_from_counts, squash_masks,
                       squash_predictions)
 from .unet import UNet
 from .engine import GraphedTrainStep
 
 __all__ = [
-    "UNet", "GraphedTrainStep", "DiceLoss", "GeneralizedDiceLoss", "DiceLossWrapper", "MultipleLossWrapper",
+    "UNet", "GraphedTrainStep", "DiceLoss", "GeneralizedDiceLoss", "FocalLoss", "CrossEntropyLoss", "DiceLossWrapper", "MultipleLossWrapper",
     "MultipleLossWrapper3D", "DiceMetricWrapper", "DiceMetricWrapper3D", "apply_missing_mask",
     "squash_masks", "squash_predictions", "dice_from_counts", "STRUCTURES", "N_CLASSES",
 ]

@@ -1,2 +1,3 @@
-from ...losses import (LOSSES, BaseLossWrapper, DiceLossWrapper, GeneralizedDiceLossWrapper,  # noqa: F401
-                       MultipleLossWrapper, apply_missing_mask)
+from ...losses import (LOSSES, WEIGHT, BaseLossWrapper, CrossEntropyWrapper, DiceLossWrapper,  # noqa: F401
+                       FocalLossWrapper, GeneralizedDiceLossWrapper, MultipleLossWrapper,
+                       WeightedCrossEntropyWrapper, apply_missing_mask)

@@ -1,1 +1,2 @@
-from ...losses import DiceLossWrapper3D, GeneralizedDiceLossWrapper3D, MultipleLossWrapper3D  # noqa: F401
+from ...losses import (WEIGHT, CrossEntropyWrapper3D, DiceLossWrapper3D, FocalLossWrapper3D,  # noqa: F401
+                       GeneralizedDiceLossWrapper3D, MultipleLossWrapper3D, WeightedCrossEntropyWrapper3D)

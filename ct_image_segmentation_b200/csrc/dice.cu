@@ -30,7 +30,8 @@ __device__ __forceinline__ int load_label(const void* labels, int64_t idx) {
 // vec16: the voxel row is 16 bf16 (32 B, 16-byte aligned): two 128-bit loads instead of C scalar ones
 // CE > 0: the class count is the compile-time constant CE (C is ignored): all loops run over exactly CE classes
 template <typename T, int CMAX, int CE = 0>
-__device__ __forceinline__ void voxel_softmax(const T* z, int C, float (&p)[CMAX], bool vec16 = false) {
+__device__ __forceinline__ void voxel_softmax(const T* z, int C, float (&p)[CMAX], bool vec16 = false,
+                                              float* mx_out = nullptr, float* logs_out = nullptr) {
   if constexpr (CE > 0) C = CE;
   float mx = -INFINITY;
   if constexpr (sizeof(T) == 2 && CMAX == 16) {
@@ -69,6 +70,7 @@ __device__ __forceinline__ void voxel_softmax(const T* z, int C, float (&p)[CMAX
     const float inv = __frcp_rn(s);
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) p[c] *= inv;
+    if (mx_out) { *mx_out = mx; *logs_out = __logf(s); }
   } else {
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) {
@@ -77,6 +79,7 @@ __device__ __forceinline__ void voxel_softmax(const T* z, int C, float (&p)[CMAX
     }
 #pragma unroll
     for (int c = 0; c < CMAX; ++c) p[c] = p[c] / s;
+    if (mx_out) { *mx_out = mx; *logs_out = logf(s); }
   }
 }
 
@@ -206,6 +209,147 @@ softmax_dice_bwd_kernel(const T* __restrict__ logits, const void* __restrict__ l
 #pragma unroll
       for (int c = 0; c < CMAX; ++c)
         if (c < C) o[c] = from_f<T>(p[c] * (g[c] - dot));
+    }
+  }
+}
+
+// ---- all voxel-wise losses of the reference through ONE softmax pass --------------------------------
+// sums5[n][c][5] = { I, G, P, F, N } per sample and class over the voxels of class c:
+//   I = sum p_c t_c, G = sum t_c, P = sum p_c                          (Dice / GeneralizedDice)
+//   F = sum t_c (1 - p_c)^gamma (-log p_c)                              (monai FocalLoss, one-hot target)
+//   N = sum t_c (-log p_c)                                              (F.cross_entropy, plain or class-weighted)
+// log p = (z - max) - log sum exp, as log_softmax computes it.
+template <typename T, int CMAX, int LT, int CE = 0>
+__global__ void __launch_bounds__(kDiceThreads)
+softmax_loss_fwd_kernel(const T* __restrict__ logits, const void* __restrict__ labels, int64_t spatial, int C,
+                        int ld, int64_t vox_per_block, float gamma, float* __restrict__ partial, bool vec16) {
+  if constexpr (CE > 0) C = CE;
+  constexpr int CL = CE > 0 ? CE : CMAX;
+  __shared__ float red[kDiceThreads / 32][CMAX * 5];
+  const int n = blockIdx.y;
+  const int64_t v_begin = (int64_t)blockIdx.x * vox_per_block;
+  const int64_t v_end = min(v_begin + vox_per_block, spatial);
+  float aI[CMAX], aG[CMAX], aP[CMAX], aF[CMAX], aN[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) aI[c] = aG[c] = aP[c] = aF[c] = aN[c] = 0.f;
+  for (int64_t v = v_begin + threadIdx.x; v < v_end; v += kDiceThreads) {
+    const int64_t vox = (int64_t)n * spatial + v;
+    float p[CMAX], mx, ls;
+    const T* zrow = logits + vox * ld;
+    voxel_softmax<T, CMAX, CE>(zrow, C, p, vec16, &mx, &ls);
+    const int lab = load_label<LT>(labels, vox);
+    const bool in = lab >= 0 && lab < C;
+    const float nll = in ? ls - (to_f<T>(zrow[in ? lab : 0]) - mx) : 0.f;
+    const float om = 1.f - __expf(-nll);
+    const float fw = gamma == 2.f ? om * om : __powf(fmaxf(om, 0.f), gamma);
+#pragma unroll
+    for (int c = 0; c < CL; ++c) {
+      const bool hit = (lab == c);
+      aI[c] += hit ? p[c] : 0.f;
+      aG[c] += hit ? 1.f : 0.f;
+      aP[c] += p[c];
+      aF[c] += hit ? fw * nll : 0.f;
+      aN[c] += hit ? nll : 0.f;
+    }
+  }
+  const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
+#pragma unroll
+  for (int c = 0; c < CL; ++c) {
+    const float i_ = warp_sum(aI[c]), g_ = warp_sum(aG[c]), p_ = warp_sum(aP[c]), f_ = warp_sum(aF[c]),
+                n_ = warp_sum(aN[c]);
+    if (lane == 0) {
+      red[warp][c * 5 + 0] = i_;
+      red[warp][c * 5 + 1] = g_;
+      red[warp][c * 5 + 2] = p_;
+      red[warp][c * 5 + 3] = f_;
+      red[warp][c * 5 + 4] = n_;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < C * 5) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kDiceThreads / 32; ++w) s += red[w][threadIdx.x];
+    partial[((int64_t)n * gridDim.x + blockIdx.x) * C * 5 + threadIdx.x] = s;
+  }
+}
+
+// dlogits for d(loss)/d(sums5) = (gI, -, gP, gF, gN) per (n, c):
+//   dz_j = p_j (g_j - sum_k g_k p_k) + (delta_{lab,j} - p_j) * A,   g_c = gI_c t_c + gP_c,
+//   A = gF_lab * u f'(u) - gN_lab,  u = p_lab,  u f'(u) = -gamma (1-u)^(gamma-1) u nll - (1-u)^gamma
+template <typename T, int CMAX, int LT, int CE = 0>
+__global__ void __launch_bounds__(kDiceThreads)
+softmax_loss_bwd_kernel(const T* __restrict__ logits, const void* __restrict__ labels, const float* __restrict__ gI,
+                        const float* __restrict__ gP, const float* __restrict__ gF, const float* __restrict__ gN,
+                        T* __restrict__ dlogits, int64_t spatial, int C, int ld, float gamma, bool vec16) {
+  if constexpr (CE > 0) C = CE;
+  constexpr int CL = CE > 0 ? CE : CMAX;
+  __shared__ float sF[CMAX], sN[CMAX];
+  const int n = blockIdx.y;
+  if (threadIdx.x < CMAX) {
+    sF[threadIdx.x] = threadIdx.x < C ? gF[n * C + threadIdx.x] : 0.f;
+    sN[threadIdx.x] = threadIdx.x < C ? gN[n * C + threadIdx.x] : 0.f;
+  }
+  float cI[CMAX], cP[CMAX];
+#pragma unroll
+  for (int c = 0; c < CMAX; ++c) {
+    cI[c] = c < C ? gI[n * C + c] : 0.f;
+    cP[c] = c < C ? gP[n * C + c] : 0.f;
+  }
+  __syncthreads();
+  for (int64_t v = (int64_t)blockIdx.x * kDiceThreads + threadIdx.x; v < spatial;
+       v += (int64_t)gridDim.x * kDiceThreads) {
+    const int64_t vox = (int64_t)n * spatial + v;
+    float p[CMAX], mx, ls;
+    const T* zrow = logits + vox * ld;
+    voxel_softmax<T, CMAX, CE>(zrow, C, p, vec16, &mx, &ls);
+    const int lab = load_label<LT>(labels, vox);
+    const bool in = lab >= 0 && lab < C;
+    const float nll = in ? ls - (to_f<T>(zrow[in ? lab : 0]) - mx) : 0.f;
+    const float u = __expf(-nll), om = 1.f - u;
+    float ufp;  // u * f'(u)
+    if (gamma == 2.f) ufp = -2.f * om * u * nll - om * om;
+    else {
+      const float omc = fmaxf(om, 0.f);
+      ufp = -gamma * __powf(omc, gamma - 1.f) * u * nll - __powf(omc, gamma);
+    }
+    const float A = in ? sF[lab] * ufp - sN[lab] : 0.f;
+    float g[CMAX];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c) {
+      if (c < CL) {
+        g[c] = (lab == c ? cI[c] : 0.f) + cP[c];
+        dot = fmaf(g[c], p[c], dot);
+      } else {
+        g[c] = 0.f;
+      }
+    }
+    T* o = dlogits + vox * ld;
+    float dz[CMAX];
+#pragma unroll
+    for (int c = 0; c < CMAX; ++c)
+      dz[c] = c < C ? p[c] * (g[c] - dot) + ((lab == c ? 1.f : 0.f) - p[c]) * A : 0.f;
+    bool done = false;
+    if constexpr (sizeof(T) == 2 && CMAX == 16) {
+      if (vec16) {
+        uint4 o0, o1;
+        __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+        __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          q0[i] = __floats2bfloat162_rn(dz[2 * i], dz[2 * i + 1]);
+          q1[i] = __floats2bfloat162_rn(dz[8 + 2 * i], dz[8 + 2 * i + 1]);
+        }
+        reinterpret_cast<uint4*>(o)[0] = o0;
+        reinterpret_cast<uint4*>(o)[1] = o1;
+        done = true;
+      }
+    }
+    if (!done) {
+#pragma unroll
+      for (int c = 0; c < CMAX; ++c)
+        if (c < C) o[c] = from_f<T>(dz[c]);
     }
   }
 }
@@ -542,6 +686,55 @@ int launch_softmax_dice_bwd(const b200seg_dice_desc& d, const void* logits, cons
                        (const T*)logits, labels, gI, gP, (T*)dlogits, d.spatial, d.c, d.ld,
                        vec16_ok(d, logits, dlogits))));
   B200SEG_CHECK_LAUNCH("softmax_dice_bwd");
+  return B200SEG_OK;
+}
+
+size_t loss_workspace_bytes(const b200seg_dice_desc& d) {
+  return (size_t)d.n * dice_blocks(d.spatial, d.n) * d.c * 5 * sizeof(float) + 256;
+}
+
+int launch_softmax_loss_fwd(const b200seg_dice_desc& d, const void* logits, const void* labels, float gamma,
+                            float* sums5, void* ws, cudaStream_t st) {
+  int nb = dice_blocks(d.spatial, d.n);
+  int64_t per = cdiv64(d.spatial, nb);
+  dim3 grid(nb, d.n);
+  float* partial = (float*)ws;
+  if (d.c > 16) { set_error("softmax_loss: at most 16 classes, got %d", d.c); return B200SEG_ERR_UNSUPPORTED; }
+  if (d.c == 10) {
+    DISPATCH_DICE10(d, (softmax_loss_fwd_kernel<T, 16, LT, 10><<<grid, kDiceThreads, 0, st>>>(
+                           (const T*)logits, labels, d.spatial, d.c, d.ld, per, gamma, partial,
+                           vec16_ok(d, logits, nullptr))));
+  } else {
+    DISPATCH_DICE10(d, (softmax_loss_fwd_kernel<T, 16, LT, 0><<<grid, kDiceThreads, 0, st>>>(
+                           (const T*)logits, labels, d.spatial, d.c, d.ld, per, gamma, partial,
+                           vec16_ok(d, logits, nullptr))));
+  }
+  B200SEG_CHECK_LAUNCH("softmax_loss_fwd");
+  int total = d.n * d.c * 5;
+  dice_sums_final_kernel<<<(total * 32 + 255) / 256, 256, 0, st>>>(partial, nb, d.c * 5, total, sums5);
+  B200SEG_CHECK_LAUNCH("dice_sums_final");
+  return B200SEG_OK;
+}
+
+int launch_softmax_loss_bwd(const b200seg_dice_desc& d, const void* logits, const void* labels, float gamma,
+                            const float* gI, const float* gP, const float* gF, const float* gN, void* dlogits,
+                            cudaStream_t st) {
+  int64_t nb = cdiv64(d.spatial, kDiceThreads * 2);
+  int64_t cap = 4736 / (d.n > 0 ? d.n : 1);
+  if (cap < 1) cap = 1;
+  if (nb > cap) nb = cap;
+  dim3 grid((unsigned)nb, d.n);
+  if (d.c > 16) { set_error("softmax_loss: at most 16 classes, got %d", d.c); return B200SEG_ERR_UNSUPPORTED; }
+  if (d.c == 10) {
+    DISPATCH_DICE10(d, (softmax_loss_bwd_kernel<T, 16, LT, 10><<<grid, kDiceThreads, 0, st>>>(
+                           (const T*)logits, labels, gI, gP, gF, gN, (T*)dlogits, d.spatial, d.c, d.ld, gamma,
+                           vec16_ok(d, logits, dlogits))));
+  } else {
+    DISPATCH_DICE10(d, (softmax_loss_bwd_kernel<T, 16, LT, 0><<<grid, kDiceThreads, 0, st>>>(
+                           (const T*)logits, labels, gI, gP, gF, gN, (T*)dlogits, d.spatial, d.c, d.ld, gamma,
+                           vec16_ok(d, logits, dlogits))));
+  }
+  B200SEG_CHECK_LAUNCH("softmax_loss_bwd");
   return B200SEG_OK;
 }
 

@@ -77,6 +77,12 @@ int launch_softmax_dice_fwd(const b200seg_dice_desc& d, const void* logits, cons
                             float* sums, void* ws, cudaStream_t st);
 int launch_softmax_dice_bwd(const b200seg_dice_desc& d, const void* logits, const void* labels,
                             const float* gI, const float* gP, void* dlogits, cudaStream_t st);
+size_t loss_workspace_bytes(const b200seg_dice_desc& d);
+int launch_softmax_loss_fwd(const b200seg_dice_desc& d, const void* logits, const void* labels, float gamma,
+                            float* sums5, void* ws, cudaStream_t st);
+int launch_softmax_loss_bwd(const b200seg_dice_desc& d, const void* logits, const void* labels, float gamma,
+                            const float* gI, const float* gP, const float* gF, const float* gN, void* dlogits,
+                            cudaStream_t st);
 int launch_dice_loss_epilogue(const float* sums, int n, int c, int c0, float smooth, float inv_count, float* loss,
                               float* gI, float* gP, cudaStream_t st);
 int launch_argmax_dice_counts(const b200seg_dice_desc& d, const void* logits, const void* target,

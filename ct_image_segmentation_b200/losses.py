@@ -68,6 +68,36 @@ class _FusedDiceLoss(torch.autograd.Function):
         return ops.softmax_dice_bwd(logits_cl, labels, g_i * g, g_p * g), None, None, None, None
 
 
+class _SoftmaxLossSums(torch.autograd.Function):
+    """(B, C, 5) = [I, G, P, F, N] of ``b200seg_softmax_loss_fwd`` with autograd through the fused backward."""
+
+    @staticmethod
+    def forward(ctx, logits_cl, labels, gamma):
+        ctx.save_for_backward(logits_cl, labels)
+        ctx.gamma = gamma
+        return ops.softmax_loss_sums(logits_cl, labels, gamma)
+
+    @staticmethod
+    def backward(ctx, g):
+        logits_cl, labels = ctx.saved_tensors
+        return ops.softmax_loss_bwd(logits_cl, labels, ctx.gamma, g[..., 0], g[..., 2], g[..., 3], g[..., 4]), None, None
+
+
+def softmax_loss_sums(input: torch.Tensor, target: torch.Tensor, gamma: float = 2.0) -> torch.Tensor:
+    """One softmax pass for every voxel-wise loss of the reference: (B, C, 5) = [I, G, P, F, N]."""
+    cl = _as_cl(input)
+    if target.dim() == cl.dim() and target.shape[1] == 1:
+        target = target[:, 0]
+    return _SoftmaxLossSums.apply(cl, target, float(gamma))
+
+
+def _n_voxels(input: torch.Tensor) -> int:
+    n = 1
+    for e in input.shape[2:]:
+        n *= int(e)
+    return n
+
+
 def softmax_dice_sums(input: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
     """(B, C, 3) = [I, G, P] with autograd through the fused kernels."""
     cl = _as_cl(input)
@@ -94,14 +124,15 @@ class DiceLoss(nn.Module):
         self.reduction = reduction
         self.smooth = float(smooth)
 
-    def forward(self, input: torch.Tensor, target: torch.Tensor) -> torch.Tensor:
+    def forward(self, input: torch.Tensor, target: torch.Tensor, sums=None) -> torch.Tensor:
         if target.shape[1] != 1:
             raise AssertionError("labels must have a singleton channel dim (to_onehot_y=True)")
-        if self.reduction in ("mean", "sum"):
+        if sums is None and self.reduction in ("mean", "sum"):
             cl = _as_cl(input)
             return _FusedDiceLoss.apply(cl, target[:, 0], self.include_background, self.smooth,
                                         self.reduction == "mean")
-        sums = softmax_dice_sums(input, target)
+        if sums is None:
+            sums = softmax_dice_sums(input, target)
         if not self.include_background:
             sums = sums[:, 1:]
         inter, ground, pred = sums[..., 0], sums[..., 1], sums[..., 2]
@@ -125,8 +156,9 @@ class GeneralizedDiceLoss(nn.Module):
         self.include_background, self.w_type, self.reduction = include_background, str(w_type), reduction
         self.smooth_nr, self.smooth_dr = float(smooth_nr), float(smooth_dr)
 
-    def forward(self, input, target):
-        sums = softmax_dice_sums(input, target)
+    def forward(self, input, target, sums=None):
+        if sums is None:
+            sums = softmax_dice_sums(input, target)
         if not self.include_background:
             sums = sums[:, 1:]
         inter, ground, pred = sums[..., 0], sums[..., 1], sums[..., 2]
@@ -146,6 +178,52 @@ class GeneralizedDiceLoss(nn.Module):
         if self.reduction == "sum":
             return f.sum()
         return f
+
+
+class FocalLoss(nn.Module):
+    """``monai.losses.FocalLoss(gamma=2.0, reduction)`` on a one-hot target, as the reference builds it
+    (``capstone/models/losses.py:105-124``): per (sample, class) the mean over voxels of
+    ``-(1 - p)^gamma * t * log p`` -> (B, C); ``mean`` / ``sum`` reduce that matrix.  ``target`` is the
+    label map (B, 1, *S) the one-hot is made from."""
+
+    def __init__(self, gamma: float = 2.0, reduction: str = "mean"):
+        super().__init__()
+        self.gamma, self.reduction = float(gamma), reduction
+
+    def forward(self, input, target, sums=None):
+        if sums is None:
+            sums = softmax_loss_sums(input, target, self.gamma)
+        f = sums[..., 3] / float(_n_voxels(input))
+        if self.reduction == "mean":
+            return f.mean()
+        if self.reduction == "sum":
+            return f.sum()
+        return f
+
+
+class CrossEntropyLoss(nn.Module):
+    """``F.cross_entropy(input, target[, weight])`` (mean reduction) as the reference's
+    ``CrossEntropyWrapper`` / ``WeightedCrossEntropyWrapper`` call it (``capstone/models/losses.py:45-68``)."""
+
+    def __init__(self, weight=None):
+        super().__init__()
+        self.register_buffer("weight", None if weight is None else torch.as_tensor(weight, dtype=torch.float32))
+
+    def forward(self, input, target, sums=None):
+        if sums is None:
+            sums = softmax_loss_sums(input, target)
+        nll, cnt = sums[..., 4], sums[..., 1]
+        if self.weight is None:
+            return nll.sum() / cnt.sum()
+        w = self.weight.to(nll.device)
+        return (nll * w).sum() / (cnt * w).sum()
+
+
+WEIGHT = {  # inverse pixel frequency, reference capstone/models/losses.py:10-21
+    "Background": 1e-10, "BrainStem": 0.007, "Chiasm": 0.3296, "Mandible": 0.0046, "OpticNerve_L": 0.2619,
+    "OpticNerve_R": 0.3035, "Parotid_L": 0.0068, "Parotid_R": 0.0065, "Submandibular_L": 0.0374,
+    "Submandibular_R": 0.0426,
+}
 
 
 # ---- reference wrapper API ------------------------------------------------------------------
@@ -174,10 +252,38 @@ class GeneralizedDiceLossWrapper(BaseLossWrapper):
                                            reduction=reduction)
 
 
+class FocalLossWrapper(BaseLossWrapper):
+    def __init__(self, reduction="mean"):
+        super().__init__()
+        self.reduction = reduction
+        self.loss_fx = FocalLoss(reduction=reduction)
+
+
+class CrossEntropyWrapper(nn.Module):
+    """Takes (and ignores) the ``reduction`` keyword like the reference (``**kwargs``): always the mean."""
+
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.loss_fx = CrossEntropyLoss()
+
+    def forward(self, input, target):
+        return self.loss_fx(input, target)
+
+
+class WeightedCrossEntropyWrapper(CrossEntropyWrapper):
+    def __init__(self, **kwargs):
+        super().__init__()
+        self.loss_fx = CrossEntropyLoss(weight=list(WEIGHT.values()))
+
+
 DiceLossWrapper3D = DiceLossWrapper
 GeneralizedDiceLossWrapper3D = GeneralizedDiceLossWrapper
+FocalLossWrapper3D = FocalLossWrapper
+CrossEntropyWrapper3D = CrossEntropyWrapper
+WeightedCrossEntropyWrapper3D = WeightedCrossEntropyWrapper
 
-LOSSES = {"Dice": DiceLossWrapper, "GeneralizedDice": GeneralizedDiceLossWrapper}
+LOSSES = {"CrossEntropy": CrossEntropyWrapper, "WeightedCrossEntropy": WeightedCrossEntropyWrapper,
+          "Focal": FocalLossWrapper, "Dice": DiceLossWrapper, "GeneralizedDice": GeneralizedDiceLossWrapper}
 
 
 def apply_missing_mask(name, loss, mask_indicator):
@@ -212,9 +318,19 @@ class MultipleLossWrapper(nn.Module):
         values = {}
         if mask_indicator is not None:
             mask_indicator = mask_indicator.float()
+        # Focal / CrossEntropy present: ONE softmax pass feeds every requested loss (the reference runs a
+        # softmax / log_softmax per loss); Dice alone keeps its 3-sum kernel and one-launch epilogue
+        shared = None
+        if any(n in ("Focal", "CrossEntropy", "WeightedCrossEntropy") for n in self.losses):
+            shared = softmax_loss_sums(input, target.unsqueeze(1))
         for name, fx in self.losses.items():
-            loss = fx(input, target)
-            if self.exclude_missing:
+            if shared is None:
+                loss = fx(input, target)
+            elif name in ("CrossEntropy", "WeightedCrossEntropy"):
+                loss = fx.loss_fx(input, target, sums=shared)
+            else:
+                loss = fx.loss_fx(input, target.unsqueeze(1), sums=shared)
+            if self.exclude_missing and name not in ("CrossEntropy", "WeightedCrossEntropy"):
                 loss = apply_missing_mask(name, loss, mask_indicator)
             values[name] = loss
         return values

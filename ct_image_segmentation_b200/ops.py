@@ -482,6 +482,38 @@ def softmax_dice_sums(logits, labels) -> torch.Tensor:
     return sums
 
 
+def softmax_loss_sums(logits, labels, gamma: float = 2.0) -> torch.Tensor:
+    """(N, C, 5) fp32: I, G, P (Dice), F = sum t (1-p)^gamma (-log p) (Focal), N = sum t (-log p) (CE)."""
+    lib = _lib.load()
+    n, d, h, w, c, ld = cl_info(logits)
+    labels, code = _labels(labels, n, d * h * w)
+    desc = _dice_desc(logits, code)
+    sums = torch.empty(n, c, 5, dtype=torch.float32, device=logits.device)
+    ws = workspace(lib.b200seg_softmax_loss_workspace_bytes(C.byref(desc)), logits.device)
+    _lib.check(lib.b200seg_softmax_loss_fwd(C.byref(desc), logits.data_ptr(), labels.data_ptr(), float(gamma),
+                                            sums.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+               "b200seg_softmax_loss_fwd")
+    return sums
+
+
+def softmax_loss_bwd(logits, labels, gamma, g_i, g_p, g_f, g_n) -> torch.Tensor:
+    lib = _lib.load()
+    n, d, h, w, c, ld = cl_info(logits)
+    labels, code = _labels(labels, n, d * h * w)
+    if ld > c:  # keep the (zero) channel padding of the logits buffer
+        dlogits = alloc_activation(n, (d, h, w), c, logits.dtype, logits.device)
+        if cl_info(dlogits)[5] != ld:
+            dlogits = torch.zeros((n, d, h, w, ld), dtype=logits.dtype, device=logits.device)[..., :c]
+    else:
+        dlogits = torch.empty(logits.shape, dtype=logits.dtype, device=logits.device)
+    gs = [g.contiguous().float() for g in (g_i, g_p, g_f, g_n)]
+    desc = _dice_desc(logits, code)
+    _lib.check(lib.b200seg_softmax_loss_bwd(C.byref(desc), logits.data_ptr(), labels.data_ptr(), float(gamma),
+                                            gs[0].data_ptr(), gs[1].data_ptr(), gs[2].data_ptr(), gs[3].data_ptr(),
+                                            dlogits.data_ptr(), _stream()), "b200seg_softmax_loss_bwd")
+    return dlogits
+
+
 def dice_loss_epilogue(sums: torch.Tensor, include_background: bool, smooth: float, mean: bool):
     """(loss scalar, gI (N, C), gP (N, C)) from the (N, C, 3) Dice sums -- one launch."""
     lib = _lib.load()

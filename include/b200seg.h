@@ -226,6 +226,20 @@ int b200seg_softmax_dice_fwd(const b200seg_dice_desc* d, const void* logits, con
 int b200seg_softmax_dice_bwd(const b200seg_dice_desc* d, const void* logits, const void* labels,
                              const float* gI, const float* gP, void* dlogits, void* stream);
 
+/* Every voxel-wise loss the reference offers through ONE softmax pass (capstone/models/losses.py:45-124,
+ * LOSSES table :160-167; 3-D twins capstone/volumetric/losses.py:37-126): sums5[n][c][5] = {I, G, P, F, N},
+ *   I = sum p t, G = sum t, P = sum p             -> monai DiceLoss / in-tree GeneralizedDiceLoss
+ *   F = sum t (1 - p)^gamma (-log p)              -> monai FocalLoss(gamma) on the one-hot target (AsDiscrete)
+ *   N = sum t (-log p)                            -> F.cross_entropy, plain or with the class WEIGHT table
+ * with p = softmax(logits), t = one_hot(labels), log p as log_softmax computes it.  bwd: dlogits from
+ * d loss / d{I, P, F, N} per (n, c) (n*c floats each).  At most 16 classes. */
+size_t b200seg_softmax_loss_workspace_bytes(const b200seg_dice_desc* d);
+int b200seg_softmax_loss_fwd(const b200seg_dice_desc* d, const void* logits, const void* labels, float gamma,
+                             float* sums5, void* workspace, size_t workspace_bytes, void* stream);
+int b200seg_softmax_loss_bwd(const b200seg_dice_desc* d, const void* logits, const void* labels, float gamma,
+                             const float* gI, const float* gP, const float* gF, const float* gN, void* dlogits,
+                             void* stream);
+
 /* Dice loss value and gradient coefficients from the (n, c, 3) sums of b200seg_softmax_dice_fwd, in one
  * launch: the arithmetic of monai.losses.DiceLoss.forward after the spatial sums
  * (capstone/models/losses.py:80-85 configures it; formula in SURVEY.md A.6):

@@ -468,6 +468,61 @@ def test_instnorm_prelu(n, c, sp, dtype):
     assert abs(dalpha.item() - alpha.grad.item()) < (1e-4 if dtype == torch.float32 else 1e-2) * max(1.0, abs(alpha.grad.item()))
 
 
+# ---- Focal / CrossEntropy through the shared softmax pass ----------------------------------------
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("c,sp", [(10, (6, 10, 12)), (4, (1, 9, 11)), (10, (16, 32, 32))])
+def test_focal_and_cross_entropy_vs_oracle(c, sp, dtype):
+    """Focal (monai 0.3, one-hot target), CrossEntropy and class-weighted CrossEntropy values and logit
+    gradients from ONE fused softmax pass, against the oracle / torch on the same rounded logits."""
+    torch.manual_seed(5)
+    n = 2
+    z = q(torch.randn(n, c, *sp) * 2.0, dtype).requires_grad_(True)
+    lab = torch.randint(0, c, (n, *sp))
+    lab[0, 0, 0, :3] = 0
+    onehot = O.one_hot(lab.unsqueeze(1), c)
+    w = torch.rand(c) + 0.05
+    tol = 1e-4 if dtype == torch.float32 else 2e-3
+    zd = cl_dev(z.detach(), dtype)                      # channels-last device logits
+    zin = zd.permute(0, 4, 1, 2, 3).requires_grad_(True)
+    cases = {
+        "focal_mean": (lambda: O.FocalLoss(reduction="mean")(z, onehot),
+                       lambda x: losses.FocalLoss(reduction="mean")(x, lab.to(DEV).unsqueeze(1))),
+        "focal_none": (lambda: O.FocalLoss(reduction="none")(z, onehot).square().sum(),
+                       lambda x: losses.FocalLoss(reduction="none")(x, lab.to(DEV).unsqueeze(1)).square().sum()),
+        "ce": (lambda: F.cross_entropy(z, lab), lambda x: losses.CrossEntropyLoss()(x, lab.to(DEV))),
+        "wce": (lambda: F.cross_entropy(z, lab, weight=w),
+                lambda x: losses.CrossEntropyLoss(weight=w)(x, lab.to(DEV))),
+    }
+    for name, (ref_fn, dev_fn) in cases.items():
+        z.grad = None
+        lr = ref_fn()
+        lr.backward()
+        zin.grad = None
+        ld = dev_fn(zin)
+        ld.backward()
+        assert abs(ld.item() - lr.item()) < tol * max(1.0, abs(lr.item())), f"{name}: {ld.item()} vs {lr.item()}"
+        e = rel(zin.grad.float().cpu(), z.grad)
+        assert e < (1e-4 if dtype == torch.float32 else 1e-2), f"{name} gradient rel err {e}"
+
+
+def test_multiple_loss_wrapper_shared_pass():
+    """MultipleLossWrapper with Dice + Focal + CrossEntropy (one fused pass) == the oracle's separate losses,
+    with and without the AnatomyNet missing-annotation weighting."""
+    torch.manual_seed(11)
+    n, c, sp = 3, 10, (4, 12, 12)
+    z = torch.randn(n, c, *sp) * 1.5
+    lab = torch.randint(0, c, (n, *sp))
+    ind = torch.ones(n, c - 1)
+    ind[0, 2] = 0
+    ind[1, 5] = 0
+    for excl in (False, True):
+        names = ["CrossEntropy", "Dice", "Focal"]
+        got = losses.MultipleLossWrapper(names, exclude_missing=excl)(z.to(DEV), lab.to(DEV), ind.to(DEV))
+        ref = O.MultipleLossWrapper(names, exclude_missing=excl)(z, lab, ind)
+        for k in names:
+            assert abs(got[k].item() - ref[k].item()) < 1e-4 * max(1.0, abs(ref[k].item())), (excl, k, got[k].item(), ref[k].item())
+
+
 # ---- softmax + Dice ---------------------------------------------------------------------------
 @pytest.mark.parametrize("tag", ["dense", "sparse"])
 @pytest.mark.parametrize("label_dtype", [torch.uint8, torch.int64])
