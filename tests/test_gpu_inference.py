@@ -95,3 +95,24 @@ def test_patch_sampler_pads_outside_volume():
     v = img[0, 0].float().cpu()
     assert abs(v[-o[0], -o[1], -o[2]].item() - inside) < 2e-2
     assert abs(v[31, 31, 31].item() - outside) < 2e-2
+
+
+def test_patient_npz_to_gpu_sampler(tmp_path):
+    """Reference .npz patient file -> resident volume + fused mask squashing -> GPU patch sampler."""
+    import numpy as np
+    from ct_image_segmentation_b200 import data
+    rng = np.random.default_rng(3)
+    vol = rng.integers(-1000, 2000, size=(1, 20, 24, 28)).astype(np.int16)
+    masks = np.zeros((9, 20, 24, 28), dtype=np.uint8)
+    for c in range(9):
+        masks[c, 2 * c:2 * c + 3, 4:12, 6:16] = 1
+    np.savez(tmp_path / "p.npz", image=vol, masks=masks, mask_indicator=np.ones(9))
+    pat = data.load_patient_npz(tmp_path / "p.npz")
+    smp = pat.sampler((16, 16, 16), window="soft_tissue", dtype=torch.float32, foreground_prob=1.0)
+    img, lab = smp.sample(3)
+    assert img.shape == (3, 1, 16, 16, 16) and lab.shape == (3, 16, 16, 16) and lab.dtype == torch.uint8
+    full = torch.from_numpy(pat.labels())
+    for b, (d0, h0, w0) in enumerate(smp.last_origins.cpu().tolist()):
+        ref = full[d0:d0 + 16, h0:h0 + 16, w0:w0 + 16]
+        assert torch.equal(lab[b].cpu()[:ref.shape[0], :ref.shape[1], :ref.shape[2]], ref)
+    assert int(lab.max()) > 0
