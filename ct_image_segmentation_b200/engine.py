@@ -51,6 +51,7 @@ class GraphedTrainStep:
         self._consumed = [torch.cuda.Event() for _ in range(2)]
         self._k = 0
         if use_graph:
+            net.enable_wgrad_stream(True)  # weight gradients as a parallel branch of the captured graph
             self._capture(warmup)
 
     def _fwd_bwd(self):

@@ -382,8 +382,36 @@ class UNet(nn.Module):
         Convolution's backward (g_out, g_c, x, c, mean, rstd)."""
         grads: Dict[torch.Tensor, torch.Tensor] = {}
         self._bwd_taps = taps
+        self._wgrad_keep = []
         gx = self._bwd_level(self.model, g_out, saved, grads, need_gx, None, False)
+        side = self._wgrad_side if self.wgrad_stream else None
+        if side is not None and g_out.is_cuda:
+            torch.cuda.current_stream().wait_stream(side)  # join: weight gradients complete
+        self._wgrad_keep = []
         return grads, gx
+
+    # Weight gradients are leaves of the backward data flow (nothing in the step reads them before the
+    # optimiser), while dgrad -> InstanceNorm backward -> dgrad is a serial chain whose deep layers fill a
+    # fraction of the 148 SMs.  With ``wgrad_stream`` the wgrad launches go to a second stream (a parallel
+    # branch of the captured graph) and overlap that chain.  Operands stay referenced until the join:
+    # the caching allocator must not hand their memory to later main-stream kernels.
+    wgrad_stream = False
+    _wgrad_side = None
+
+    def enable_wgrad_stream(self, on: bool = True) -> None:
+        self.wgrad_stream = bool(on)
+        if on and self._wgrad_side is None:
+            self._wgrad_side = torch.cuda.Stream()
+
+    def _wgrad(self, geom: ConvGeom, x, g, want_bias: bool = True):
+        if not (self.wgrad_stream and x.is_cuda):
+            return ops.conv_wgrad(geom, x, g, want_bias=want_bias)
+        side = self._wgrad_side
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            gw, gb = ops.conv_wgrad(geom, x, g, want_bias=want_bias)
+        self._wgrad_keep.append((x, g, gw, gb))
+        return gw, gb
 
     def _bwd_level(self, lvl: _Level, g_out, saved, grads, need_gx, gx_dst, gx_accum):
         down, skip, up = lvl[0], lvl[1], lvl[2]
@@ -426,10 +454,10 @@ class UNet(nn.Module):
         if s.get("col_geom") is not None:  # x is the im2col buffer; gw comes out as the (cout, cin*taps) matrix
             if need_gx:
                 raise RuntimeError("input gradient requested through an im2col first layer")
-            gw, gb = ops.conv_wgrad(s["col_geom"], x, g_c, want_bias=m.conv_only)
+            gw, gb = self._wgrad(s["col_geom"], x, g_c, want_bias=m.conv_only)
             gw = gw.view(m.conv.weight.shape)
         else:
-            gw, gb = ops.conv_wgrad(g, x, g_c, want_bias=m.conv_only)
+            gw, gb = self._wgrad(g, x, g_c, want_bias=m.conv_only)
         grads[m.conv.weight] = gw
         grads[m.conv.bias] = gb if gb is not None else torch.zeros_like(m.conv.bias)
         if not need_gx:
@@ -451,10 +479,10 @@ class UNet(nn.Module):
         gx = self._bwd_convolution(units[0], g, saved, grads, need_gx, gx_dst, gx_accum, None)
         rg = ru.res_geom
         if sru.get("col_geom") is not None:
-            gw, gb = ops.conv_wgrad(sru["col_geom"], sru["col"], g_out)
+            gw, gb = self._wgrad(sru["col_geom"], sru["col"], g_out)
             gw = gw.view(ru.residual.weight.shape)
         else:
-            gw, gb = ops.conv_wgrad(rg, x, g_out)
+            gw, gb = self._wgrad(rg, x, g_out)
         grads[ru.residual.weight], grads[ru.residual.bias] = gw, gb
         if need_gx:
             ops.conv_dgrad(rg, g_out, self._w_dgrad(ru.residual, rg), gx, accumulate=True)

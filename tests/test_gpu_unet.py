@@ -301,3 +301,24 @@ def test_lightning_module_2d_step():
     loss = mod.training_step((images, masks, torch.ones(2, 9, device=DEV)), 0)
     loss.backward()
     assert torch.isfinite(loss) and all(p.grad is not None for p in mod.unet.parameters())
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_wgrad_side_stream_is_bitwise_identical(dtype):
+    """Weight gradients launched on the second stream (parallel graph branch) == single-stream backward."""
+    ref, net = make_pair(3, 1, [16, 32, 64], [2, 2], 2, dtype)
+    torch.manual_seed(3)
+    x = torch.randn(2, 1, 32, 32, 32, device=DEV)
+    lab = torch.randint(0, 10, (2, 1, 32, 32, 32), device=DEV)
+    fx = B.DiceLoss(include_background=False, to_onehot_y=True, softmax=True)
+    grads = []
+    for side in (False, True, True):
+        net.enable_wgrad_stream(side)
+        for p in net.parameters():
+            p.grad = None
+        fx(net(x), lab).backward()
+        torch.cuda.synchronize()
+        grads.append([p.grad.clone() for p in net.parameters()])
+    net.enable_wgrad_stream(False)
+    for a, b, c in zip(*grads):
+        assert torch.equal(a, b) and torch.equal(a, c)
