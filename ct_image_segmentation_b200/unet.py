@@ -15,6 +15,7 @@ concatenation in both directions).
 """
 from __future__ import annotations
 
+import contextlib
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -361,17 +362,26 @@ class UNet(nn.Module):
             rg = ru.res_geom
             r = self._new(x, rg.out_spatial(*x.shape[1:4]), rg.cout)
             rg1, rcol = self._col_input(rg, x)
-            if rg1 is not None:
-                ops.conv_fprop(rg1, rcol, self._pack(ru.residual.weight, rg1, _lib.W_CONV_FPROP, col=True),
-                               ru.residual.bias.detach(), r)
-            else:
-                ops.conv_fprop(rg, x, self._w_fprop(ru.residual, rg), ru.residual.bias.detach(), r)
+            # the residual conv is only consumed by the unit's last InstanceNorm+PReLU: with the second
+            # stream enabled it runs beside the unit0 -> unit1 chain
+            side = self._wgrad_side if (self.wgrad_stream and x.is_cuda) else None
+            if side is not None:
+                side.wait_stream(torch.cuda.current_stream())
+            with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+                if rg1 is not None:
+                    ops.conv_fprop(rg1, rcol, self._pack(ru.residual.weight, rg1, _lib.W_CONV_FPROP, col=True),
+                                   ru.residual.bias.detach(), r)
+                else:
+                    ops.conv_fprop(rg, x, self._w_fprop(ru.residual, rg), ru.residual.bias.detach(), r)
         else:
             r = x
             rg1 = rcol = None
+            side = None
         h = x
         for i, u in enumerate(units):
             last = i == len(units) - 1
+            if last and side is not None:
+                torch.cuda.current_stream().wait_stream(side)  # join before r is read
             h = self._fwd_convolution(u, h, saved, dst if last else None, r if last else None, keep)
         saved[ru] = {"x": x, "col_geom": rg1, "col": rcol}
         return h
