@@ -126,8 +126,11 @@ class GraphedTrainStep:
             for p, v in zip(self.bucket.params, self.bucket.views):
                 p.grad = v
         if dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.SUM)
-            self.bucket.flat.mul_(1.0 / dist.get_world_size())
+            if dist.get_backend() == "nccl":  # the average is taken inside the collective
+                dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.AVG)
+            else:
+                dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.SUM)
+                self.bucket.flat.mul_(1.0 / dist.get_world_size())
         if self.optimizer is not None:
             self.optimizer.step()
         return loss
