@@ -275,7 +275,7 @@ def roofline_probe(args, dev, dtype, pk):
     its dgrad is the same kernel with mirrored taps; together the largest kernel share of the step).
     AI = 135 FLOP/B < ridge (211), so the layer is judged against HBM; the measured binding unit is the
     tensor core's shared-memory operand fetch (N-folded MMAs of N = 48, K = 16), see DESIGN.md section 3
-    and profiles/r1_ncu_full_head_conv_slide_nfold.csv."""
+    and profiles/r1_ncu_full_head_final.csv."""
     from ct_image_segmentation_b200 import _lib, ops
     g = ops.ConvGeom(3, 10, 10, 3, 1, False)
     n, p = args.batch, args.patch
@@ -310,10 +310,10 @@ def roofline_probe(args, dev, dtype, pk):
             "bound": "hbm", "achieved": ach_gbs, "peak": pk["hbm_gbs"], "unit": "GB/s",
             "frac": ach_gbs / pk["hbm_gbs"],
             # dram__bytes_read.sum + dram__bytes_write.sum per launch, ncu --set full capture of this
-            # kernel at batch 2 x 128^3 (profiles/r1_ncu_full_head_conv_slide_nfold.csv: 139.9 + 95.6 MB)
-            "traffic": 235.5e6 if (n, p, esz) == (2, 128, 2) else None,
+            # kernel at batch 2 x 128^3 (profiles/r1_ncu_full_head_final.csv: 139.0 + 99.8 MB)
+            "traffic": 238.8e6 if (n, p, esz) == (2, 128, 2) else None,
             "ms": ms, "achieved_tflops": ach_tf, "tensor_frac": ach_tf / pk["bf16_tflops"],
-            "tc_pipe_active_pct_ncu": 70.0, "peak_source": pk["src"],
+            "tc_pipe_active_pct_ncu": 65.0, "peak_source": pk["src"],
             "note": "HBM is the bound by arithmetic intensity (168 MB algorithmic: 16-channel padded rows in + "
                     "out; 236 MB measured DRAM traffic incl. the halo re-reads that miss L2); the measured binding "
                     "unit is the tensor core's shared-memory operand fetch: an MMA of M=128, K=16 costs "
@@ -321,9 +321,9 @@ def roofline_probe(args, dev, dtype, pk):
                     "along N (9 MMAs of N=48 per slab instead of 27 of N=16); with the loads switched off it "
                     "still takes ~100 us (scripts/ubench/mma_rate.cu, DESIGN.md section 3)",
             "algorithmic_bytes": bytes_alg, "algorithmic_flops": flops,
-            "step_share_ncu": "this kernel: 6 launches = 10 % of the step's kernel time, the largest single kernel "
-                              "(profiles/r1_step_launch_summary.txt); InstanceNorm/PReLU passes together 24 % at "
-                              "4.3-6 TB/s"}
+            "step_share_ncu": "this kernel: 6 launches = 11 % of the step's kernel time, the largest single kernel "
+                              "(profiles/r1_step_launch_summary.txt); InstanceNorm/PReLU passes together 22 % at "
+                              "4.3-6 TB/s for the full-resolution ones"}
 
 
 def main():
