@@ -84,7 +84,11 @@ class GraphedTrainStep:
         lib = _lib.load()
         before = (lib.b200seg_launch_count(), lib.b200seg_tc_launch_count())
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # capture on a high-priority stream: the serial chain (main branch) is scheduled ahead of the
+        # weight-gradient branch, which was created at default (lower) priority
+        import os
+        cap_stream = torch.cuda.Stream(priority=-1) if os.environ.get("B200SEG_GRAPH_PRIO", "1") == "1" else None
+        with torch.cuda.graph(self.graph, stream=cap_stream):
             self.loss = self._fwd_bwd()
             grads = [p.grad for p in self.bucket.params]
             torch._foreach_copy_(self.bucket.views, grads)

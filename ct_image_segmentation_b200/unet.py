@@ -237,9 +237,14 @@ class UNet(nn.Module):
         if b is not None and b["ptrs"] == tuple(s[1] for s in state):
             if b["state"] == state:
                 return
-        else:  # (re)build the persistent buffers and the device table
-            bufs, entries = {}, []
+        else:  # (re)build the persistent buffers and the device tables
+            # two tables: the first down layer's weights (needed at once, a few KB) and everything else
+            # (95 % of the bytes; with the second stream enabled it is packed beside the first layers)
+            early_ids = {id(p) for p in self.model[0].parameters()}
+            bufs, entries, late = {}, [], []
             for conv, g in convs:
+                entries_all = entries
+                entries = entries_all if id(conv.weight) in early_ids else late
                 for kind in ((_lib.W_CONVTR_FPROP, _lib.W_CONVTR_DGRAD) if g.transposed
                              else (_lib.W_CONV_FPROP, _lib.W_CONV_DGRAD)):
                     nbytes, tc_off = ops.packed_weight_layout(g, kind, self.compute_dtype)
@@ -261,10 +266,22 @@ class UNet(nn.Module):
                     bufs[(id(conv.weight), _lib.W_CONV_FPROP, True)] = buf
                     entries.append((conv.weight.data_ptr(), buf.data_ptr(), tc_off, 1, g1.cin, g1.cout,
                                     _lib.W_CONV_FPROP))
-            b = {"bufs": bufs, "table": ops.make_pack_table(entries, convs[0][0].weight.device),
-                 "n": len(entries), "ptrs": tuple(s[1] for s in state)}
+                entries = entries_all
+            dev = convs[0][0].weight.device
+            b = {"bufs": bufs, "table": ops.make_pack_table(entries, dev), "n": len(entries),
+                 "table_late": ops.make_pack_table(late, dev) if late else None, "n_late": len(late),
+                 "ptrs": tuple(s[1] for s in state)}
             self._batched = b
         ops.pack_weights_batched(b["table"], b["n"])
+        if b["n_late"]:
+            side = self._wgrad_side if self.wgrad_stream else None
+            if side is not None:
+                side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(side):
+                    ops.pack_weights_batched(b["table_late"], b["n_late"])
+                self._pack_join = True  # joined after the first down layer (_fwd_level)
+            else:
+                ops.pack_weights_batched(b["table_late"], b["n_late"])
         b["state"] = state
 
     def _w_fprop(self, conv: nn.Module, geom: ConvGeom):
@@ -312,6 +329,9 @@ class UNet(nn.Module):
         sp = self._down_geom(down).out_spatial(*x.shape[1:4])
         cat = self._new(x, sp, c_x + c_sub)  # skip concatenation buffer: [x | sub(x)]
         xd = self._fwd_layer(down, x, saved, cat[..., :c_x], keep)
+        if getattr(self, "_pack_join", False):
+            torch.cuda.current_stream().wait_stream(self._wgrad_side)  # the other layers' weights are packed
+            self._pack_join = False
         if isinstance(sub, _Level):
             self._fwd_level(sub, xd, saved, cat[..., c_x:], keep)
         else:
