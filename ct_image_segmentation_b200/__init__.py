@@ -13,9 +13,10 @@ from .metrics import (DiceMetricWrapper, DiceMetricWrapper3D, dice_from_counts, 
                       squash_predictions)
 from .unet import UNet
 from .engine import GraphedTrainStep
+from .optim import FlatAdam
 
 __all__ = [
-    "UNet", "GraphedTrainStep", "DiceLoss", "GeneralizedDiceLoss", "FocalLoss", "CrossEntropyLoss", "DiceLossWrapper", "MultipleLossWrapper",
+    "UNet", "GraphedTrainStep", "FlatAdam", "DiceLoss", "GeneralizedDiceLoss", "FocalLoss", "CrossEntropyLoss", "DiceLossWrapper", "MultipleLossWrapper",
     "MultipleLossWrapper3D", "DiceMetricWrapper", "DiceMetricWrapper3D", "apply_missing_mask",
     "squash_masks", "squash_predictions", "dice_from_counts", "STRUCTURES", "N_CLASSES",
 ]

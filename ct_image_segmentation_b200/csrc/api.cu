@@ -448,6 +448,15 @@ int b200seg_instnorm_prelu_bwd(const b200seg_norm_desc* d, const void* x, const 
   return launch_instnorm_prelu_bwd(*d, x, mean, rstd, alpha, dy, dx, dalpha, workspace, as_stream(stream));
 }
 
+// ---- optimiser --------------------------------------------------------------------------------------
+int b200seg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                      float beta1, float beta2, float eps, int64_t step, void* stream) {
+  B200SEG_CHECK_ARG(params && grads && exp_avg && exp_avg_sq && n > 0 && step >= 1, "adam_step: bad argument");
+  B200SEG_CHECK_ARG((((uintptr_t)params | (uintptr_t)grads | (uintptr_t)exp_avg | (uintptr_t)exp_avg_sq) % 16) == 0,
+                    "adam_step: buffers must be 16-byte aligned");
+  return launch_adam_flat(params, grads, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, step, as_stream(stream));
+}
+
 // ---- softmax + Dice -------------------------------------------------------------------------------------
 static int check_dice_desc(const b200seg_dice_desc* d) {
   B200SEG_CHECK_ARG(d != nullptr, "dice desc is NULL");

@@ -71,6 +71,9 @@ int launch_instnorm_prelu_bwd(const b200seg_norm_desc& d, const void* x, const f
                               const float* rstd, const float* alpha, const void* dy, void* dx,
                               float* dalpha, void* ws, cudaStream_t st);
 
+int launch_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                     float eps, int64_t step, cudaStream_t st);
+
 // dice.cu
 size_t dice_workspace_bytes(const b200seg_dice_desc& d);
 int launch_softmax_dice_fwd(const b200seg_dice_desc& d, const void* logits, const void* labels,

@@ -589,4 +589,52 @@ int launch_colsum(int dtype, const void* x, int64_t nvox, int c, int ld, float* 
   return B200SEG_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// Adam on ONE flat fp32 parameter / gradient / moment buffer (torch.optim.Adam semantics: no weight
+// decay, no amsgrad):  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+//                      p -= (lr / (1 - b1^t)) * m / (sqrt(v) / sqrt(1 - b2^t) + eps)
+// 128-bit accesses, 7 x 4 bytes of traffic per parameter.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 int64_t n, float beta1, float beta2, float step_size, float inv_bc2_sqrt, float eps) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < n; i += stride) {
+    if (i + 4 <= n) {
+      float4 pp = *reinterpret_cast<float4*>(p + i), mm = *reinterpret_cast<float4*>(m + i),
+             vv = *reinterpret_cast<float4*>(v + i);
+      const float4 gg = *reinterpret_cast<const float4*>(g + i);
+      float* pa = &pp.x; float* ma = &mm.x; float* va = &vv.x; const float* ga = &gg.x;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        ma[k] = beta1 * ma[k] + (1.f - beta1) * ga[k];
+        va[k] = beta2 * va[k] + (1.f - beta2) * ga[k] * ga[k];
+        pa[k] -= step_size * (ma[k] / (sqrtf(va[k]) * inv_bc2_sqrt + eps));
+      }
+      *reinterpret_cast<float4*>(p + i) = pp;
+      *reinterpret_cast<float4*>(m + i) = mm;
+      *reinterpret_cast<float4*>(v + i) = vv;
+    } else {
+      for (int64_t j = i; j < n; ++j) {
+        const float gj = g[j];
+        m[j] = beta1 * m[j] + (1.f - beta1) * gj;
+        v[j] = beta2 * v[j] + (1.f - beta2) * gj * gj;
+        p[j] -= step_size * (m[j] / (sqrtf(v[j]) * inv_bc2_sqrt + eps));
+      }
+    }
+  }
+}
+
+int launch_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                     float eps, int64_t step, cudaStream_t st) {
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  const float step_size = (float)((double)lr / bc1), inv_bc2_sqrt = (float)(1.0 / sqrt(bc2));
+  int64_t nb = cdiv64(n, 256 * 4 * 4);
+  if (nb > 148 * 16) nb = 148 * 16;
+  if (nb < 1) nb = 1;
+  adam_flat_kernel<<<(unsigned)nb, 256, 0, st>>>(p, g, m, v, n, beta1, beta2, step_size, inv_bc2_sqrt, eps);
+  B200SEG_CHECK_LAUNCH("adam_flat");
+  return B200SEG_OK;
+}
+
 }  // namespace b200seg

@@ -36,6 +36,8 @@ class GraphedTrainStep:
         self.static_images.copy_(images)
         self.static_labels.copy_(labels)
         self.bucket = GradientBucket(net.parameters())
+        if hasattr(optimizer, "bind_grad_buffer"):  # FlatAdam reads the all-reduced bucket directly
+            optimizer.bind_grad_buffer(self.bucket.flat, self.bucket.params)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.loss: Optional[torch.Tensor] = None
         self.use_graph = use_graph

@@ -226,6 +226,12 @@ int b200seg_softmax_dice_fwd(const b200seg_dice_desc* d, const void* logits, con
 int b200seg_softmax_dice_bwd(const b200seg_dice_desc* d, const void* logits, const void* labels,
                              const float* gI, const float* gP, void* dlogits, void* stream);
 
+/* torch.optim.Adam step (the reference's configure_optimizers, capstone/volumetric/base_trainer.py:178-182:
+ * Adam(lr), default betas / eps, no weight decay, no amsgrad) on ONE flat fp32 parameter buffer whose
+ * gradient is the flat all-reduce bucket; `step` is the 1-based update count (bias correction). */
+int b200seg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                      float beta1, float beta2, float eps, int64_t step, void* stream);
+
 /* Every voxel-wise loss the reference offers through ONE softmax pass (capstone/models/losses.py:45-124,
  * LOSSES table :160-167; 3-D twins capstone/volumetric/losses.py:37-126): sums5[n][c][5] = {I, G, P, F, N},
  *   I = sum p t, G = sum t, P = sum p             -> monai DiceLoss / in-tree GeneralizedDiceLoss

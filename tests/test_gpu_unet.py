@@ -322,3 +322,22 @@ def test_wgrad_side_stream_is_bitwise_identical(dtype):
     net.enable_wgrad_stream(False)
     for a, b, c in zip(*grads):
         assert torch.equal(a, b) and torch.equal(a, c)
+
+
+def test_flat_adam_matches_torch_adam():
+    """FlatAdam (one kernel on the flat parameter / gradient buffers) == torch.optim.Adam over several steps."""
+    torch.manual_seed(0)
+    shapes = [(16, 1, 3, 3, 3), (16,), (1,), (32, 16, 3, 3, 3), (7,)]
+    pa = [torch.nn.Parameter(torch.randn(s, device=DEV)) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa = torch.optim.Adam(pa, lr=3e-3)
+    ob = B.FlatAdam(pb, lr=3e-3)
+    for step in range(6):
+        for x, y in zip(pa, pb):
+            g = torch.randn_like(x) * (10.0 ** (step - 3))
+            x.grad, y.grad = g, g.clone()
+        oa.step()
+        ob.step()
+    for x, y in zip(pa, pb):
+        assert rel(y.detach(), x.detach()) < 1e-6
+    assert all(y.data_ptr() >= ob.flat.data_ptr() for y in pb)  # parameters live in the flat buffer
