@@ -61,6 +61,8 @@ SIGNATURES = {
     "b200seg_softmax_loss_bwd": (C.c_int, [_P, _P, _P, C.c_float, _P, _P, _P, _P, _P, _P]),
     "b200seg_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, _P]),
     "b200seg_dice_loss_epilogue": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P, _P, _P, _P]),
+    "b200seg_conv_fprop_partials": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, C.c_size_t, _P, _P, _P]),
+    "b200seg_instnorm_prelu_fwd_partials": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int64, C.c_int32, _P, _P, _P, _P, _P, _P]),
     "b200seg_im2col": (C.c_int, [_P, _P, _P, C.c_int32, _P]),
     "b200seg_pack_weights_batched": (C.c_int, [_P, C.c_int32, _P]),
     "b200seg_conv_fprop": (C.c_int, [_CD, _P, _P, _P, _P, _P, _P]),

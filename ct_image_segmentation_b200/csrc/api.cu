@@ -175,9 +175,11 @@ static size_t fprop_stats_ws(const b200seg_conv_desc* d, bool transposed_layer) 
   return (size_t)ncls * d->n * tiles * d->cout * 2 * sizeof(float) + 256;
 }
 
+// deferred != NULL: leave the partials in `ws` and report their layout (ncls, tiles) instead of finalising them
+struct StatsLayout { int ncls; int64_t tiles; };
 static int fprop_stats_common(const b200seg_conv_desc* d, bool transposed_layer, const void* x, const void* w_packed,
                               const float* bias, void* y, float* mean, float* rstd, int stat_ld, float eps,
-                              void* ws, size_t ws_bytes, void* stream) {
+                              void* ws, size_t ws_bytes, void* stream, StatsLayout* deferred = nullptr) {
   int op = transposed_layer ? TC_CONVTR_FPROP : TC_CONV_FPROP;
   // Only the sliding-window kernel fuses the statistics: it accumulates them in registers across
   // the slabs of a column and emits one partial per CTA (a few hundred per sample).  In the
@@ -186,7 +188,7 @@ static int fprop_stats_common(const b200seg_conv_desc* d, bool transposed_layer,
   // (measured: ConvTranspose 32->10 fprop 258 -> 440 us).
   // The streaming kernel (one tile per CTA) fuses them only while the partials stay few (deep layers).
   bool fuse = false;
-  if (mean && rstd && ws && tc_conv_supported(d, op, x, y, nullptr)) {
+  if ((deferred || (mean && rstd)) && ws && tc_conv_supported(d, op, x, y, nullptr)) {
     fuse = (!(d->flags & B200SEG_CONV_NO_SLIDE) && tc_slide_conv_supported(d, op)) ||
            tc_convtr_slide_supported(d, op, nullptr);
     if (!fuse) {
@@ -206,6 +208,11 @@ static int fprop_stats_common(const b200seg_conv_desc* d, bool transposed_layer,
     int ncls;
     int64_t tiles;
     stats_layout(d, op, &ncls, &tiles);
+    if (deferred) {
+      deferred->ncls = ncls;
+      deferred->tiles = tiles;
+      return B200SEG_OK;
+    }
     const int64_t spatial = (int64_t)d->out_d * d->out_h * d->out_w;
     return launch_instnorm_stats_from_partials((const float*)ws, d->n, d->cout, stat_ld > d->cout ? stat_ld : d->cout,
                                                ncls, tiles, spatial, eps, mean, rstd, as_stream(stream));
@@ -234,6 +241,35 @@ int b200seg_convtr_fprop_stats(const b200seg_conv_desc* d, const void* x, const 
   if (rc) return rc;
   B200SEG_CHECK_ARG(x && w_packed && y, "convtr_fprop_stats: NULL pointer");
   return fprop_stats_common(d, true, x, w_packed, bias, y, mean, rstd, stat_ld, eps, workspace, workspace_bytes, stream);
+}
+
+static int check_norm_desc(const b200seg_norm_desc* d);
+
+int b200seg_conv_fprop_partials(const b200seg_conv_desc* d, int32_t transposed_layer, const void* x,
+                                const void* w_packed, const float* bias, void* y, float* partials,
+                                size_t partials_bytes, int32_t* ncls, int64_t* tiles, void* stream) {
+  int rc = check_conv_desc(d, transposed_layer != 0);
+  if (rc) return rc;
+  B200SEG_CHECK_ARG(x && w_packed && y && partials && ncls && tiles, "conv_fprop_partials: NULL pointer");
+  StatsLayout lay{0, 0};
+  rc = fprop_stats_common(d, transposed_layer != 0, x, w_packed, bias, y, nullptr, nullptr, 0, 0.f, partials,
+                          partials_bytes, stream, &lay);
+  *ncls = lay.ncls;
+  *tiles = lay.tiles;
+  return rc;
+}
+
+int b200seg_instnorm_prelu_fwd_partials(const b200seg_norm_desc* d, const void* x, const float* partials,
+                                        int32_t ncls, int64_t tiles, int32_t cstat, float* mean, float* rstd,
+                                        const float* alpha, const void* residual, void* y, void* stream) {
+  int rc = check_norm_desc(d);
+  if (rc) return rc;
+  B200SEG_CHECK_ARG(x && partials && mean && rstd && alpha && y, "instnorm_prelu_fwd_partials: NULL pointer");
+  B200SEG_CHECK_ARG(ncls > 0 && tiles > 0 && cstat > 0 && cstat <= d->c && d->c <= 256,
+                    "instnorm_prelu_fwd_partials: bad partial layout (ncls %d, cstat %d, c %d)", ncls, cstat, d->c);
+  B200SEG_CHECK_ARG(d->y_ld >= d->c && (!residual || d->r_ld >= d->c), "instnorm_prelu_fwd_partials: bad ld");
+  return launch_instnorm_prelu_fwd_partials(*d, x, partials, ncls, tiles, cstat, alpha, residual, y, mean, rstd,
+                                            as_stream(stream));
 }
 
 int b200seg_conv_dgrad(const b200seg_conv_desc* d, const void* dy, const void* w_packed,

@@ -67,6 +67,9 @@ int launch_instnorm_stats_from_partials(const float* partial, int n, int c, int 
 int launch_instnorm_prelu_fwd(const b200seg_norm_desc& d, const void* x, const float* mean,
                               const float* rstd, const float* alpha, const void* res, void* y,
                               cudaStream_t st);
+int launch_instnorm_prelu_fwd_partials(const b200seg_norm_desc& d, const void* x, const float* partial, int ncls,
+                                       int64_t tiles, int cstat, const float* alpha, const void* res, void* y,
+                                       float* mean, float* rstd, cudaStream_t st);
 int launch_instnorm_prelu_bwd(const b200seg_norm_desc& d, const void* x, const float* mean,
                               const float* rstd, const float* alpha, const void* dy, void* dx,
                               float* dalpha, void* ws, cudaStream_t st);

@@ -168,6 +168,91 @@ instnorm_prelu_fwd_kernel(const T* __restrict__ x, const float* __restrict__ mea
   }
 }
 
+// InstanceNorm + PReLU forward straight from the PARTIAL statistics a convolution epilogue produced
+// (row (o * N + n) * tiles + t holds cstat x {sum, sum of squares}): every block first reduces the
+// ncls * tiles rows of its sample (256 threads = (row group, entry), double, fixed order) into
+// mean / rstd in shared memory, then applies them.  Saves the separate few-microsecond finalisation
+// launch that sat on the forward chain after every convolution; block 0 of each sample also writes
+// mean / rstd out for the backward pass.  Channels >= cstat are zero padding (mean 0, rstd 1/sqrt(eps)).
+template <typename T, int V>
+__global__ void __launch_bounds__(256)
+instnorm_prelu_fwd_partials_kernel(const T* __restrict__ x, const float* __restrict__ partial, int ncls, int n_total,
+                                   int64_t tiles, int cstat, float eps, const float* __restrict__ alpha,
+                                   const T* __restrict__ res, T* __restrict__ y, int64_t spatial, int c, int x_ld,
+                                   int y_ld, int r_ld, int L, int VB, int64_t vox_per_block,
+                                   float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+  __shared__ double dsum[512];
+  __shared__ float smean[256], srstd[256];
+  const int t = threadIdx.x, n = blockIdx.y;
+  const int E = 2 * cstat;
+  const int G = E <= 256 ? 256 / E : 1;
+  const int ntile = (int)tiles;
+  for (int sl = t; sl < G * E; sl += 256) {
+    const int g = sl / E, e = sl % E;
+    double acc = 0.0;
+    for (int o = 0; o < ncls; ++o) {
+      const float* base = partial + ((int64_t)(o * n_total + n) * ntile) * E + e;
+      // row group g takes tiles g, g + G, ...: the same rows in the same order whatever the unrolling
+#pragma unroll 8
+      for (int tt = g; tt < ntile; tt += G) acc += (double)__ldg(base + (int64_t)tt * E);
+    }
+    dsum[sl] = acc;
+  }
+  __syncthreads();
+  for (int ch = t; ch < c; ch += 256) {
+    float m = 0.f, rs = rsqrtf(eps);
+    if (ch < cstat) {
+      double s1 = 0.0, s2 = 0.0;
+      for (int g = 0; g < G; ++g) {
+        s1 += dsum[g * E + 2 * ch];
+        s2 += dsum[g * E + 2 * ch + 1];
+      }
+      const double mm = s1 / (double)spatial;
+      double var = s2 / (double)spatial - mm * mm;
+      if (var < 0.0) var = 0.0;
+      m = (float)mm;
+      rs = (float)(1.0 / sqrt(var + (double)eps));
+    } else {
+      rs = (float)(1.0 / sqrt((double)eps));
+    }
+    smean[ch] = m;
+    srstd[ch] = rs;
+    if (blockIdx.x == 0) {
+      mean_out[n * c + ch] = m;
+      rstd_out[n * c + ch] = rs;
+    }
+  }
+  __syncthreads();
+  const int vi = t / L, l = t % L;
+  if (vi >= VB) return;
+  const int64_t v_begin = (int64_t)blockIdx.x * vox_per_block;
+  const int64_t v_end = min(v_begin + vox_per_block, spatial);
+  float m[V], r[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    m[i] = smean[l * V + i];
+    r[i] = srstd[l * V + i];
+  }
+  const float a = alpha[0];
+  const int64_t vox0 = (int64_t)n * spatial;
+  for (int64_t v = v_begin + vi; v < v_end; v += VB) {
+    Vec<T, V> xv, ov;
+    xv.load(x + (vox0 + v) * x_ld + l * V);
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      float h = (xv.v[i] - m[i]) * r[i];
+      ov.v[i] = h > 0.f ? h : a * h;
+    }
+    if (res) {
+      Vec<T, V> rv;
+      rv.load(res + (vox0 + v) * r_ld + l * V);
+#pragma unroll
+      for (int i = 0; i < V; ++i) ov.v[i] += rv.v[i];
+    }
+    ov.store(y + (vox0 + v) * y_ld + l * V);
+  }
+}
+
 // partial[n][blk][c][3] = { sum g~, sum g~*xhat, sum dy*xhat*[xhat<=0] },  g~ = dy * prelu'(xhat)
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
@@ -458,6 +543,23 @@ int launch_instnorm_prelu_fwd(const b200seg_norm_desc& d, const void* x, const f
                   (const T*)x, mean, rstd, alpha, (const T*)res, (T*)y, d.spatial, d.c, d.x_ld,
                   d.y_ld, d.r_ld, g.L, g.VB, per)));
   B200SEG_CHECK_LAUNCH("instnorm_prelu_fwd");
+  return B200SEG_OK;
+}
+
+int launch_instnorm_prelu_fwd_partials(const b200seg_norm_desc& d, const void* x, const float* partial, int ncls,
+                                       int64_t tiles, int cstat, const float* alpha, const void* res, void* y,
+                                       float* mean, float* rstd, cudaStream_t st) {
+  NormGeom g;
+  int V = res ? pick_vec(d, {x, y, res}, {d.x_ld, d.y_ld, d.r_ld}) : pick_vec(d, {x, y}, {d.x_ld, d.y_ld});
+  int rc = make_geom(d, V, g);
+  if (rc) return rc;
+  int64_t per = cdiv64(d.spatial, g.nblk_apply);
+  dim3 grid(g.nblk_apply, d.n);
+  DISPATCH_TV(d.dtype, V,
+              (instnorm_prelu_fwd_partials_kernel<T, VV><<<grid, 256, 0, st>>>(
+                  (const T*)x, partial, ncls, d.n, tiles, cstat, d.eps, alpha, (const T*)res, (T*)y, d.spatial, d.c,
+                  d.x_ld, d.y_ld, d.r_ld, g.L, g.VB, per, mean, rstd)));
+  B200SEG_CHECK_LAUNCH("instnorm_prelu_fwd_partials");
   return B200SEG_OK;
 }
 

@@ -320,6 +320,56 @@ def im2col(geom: ConvGeom, x: torch.Tensor) -> torch.Tensor:
     return col
 
 
+def conv_fprop_partials(geom: ConvGeom, x, wp, bias, y, flags=0):
+    """y = conv(x) + bias with the InstanceNorm statistics left as per-CTA PARTIALS for
+    ``instnorm_prelu_fwd_partials`` (which finalises them itself: one launch less on the forward chain).
+    Returns (partials, ncls, tiles, cstat), or None when the layer ran on a kernel without the fusion."""
+    lib = _lib.load()
+    n, sd_, sh_, sw_, sc, s_ld = cl_info(x)
+    n2, dd_, dh_, dw_, dc, d_ld = cl_info(y)
+    if n != n2 or x.dtype != y.dtype or (sc, dc) != (geom.cin, geom.cout):
+        raise ValueError("conv_fprop_partials: shape/dtype mismatch")
+    if geom.out_spatial(sd_, sh_, sw_) != (dd_, dh_, dw_):
+        raise ValueError("conv_fprop_partials: spatial extents inconsistent with the geometry")
+    if _pad_safe(x) and _pad_safe(y):
+        flags |= _lib.CONV_PADDED_CHANNELS
+    d = geom.desc(n, (sd_, sh_, sw_), (dd_, dh_, dw_), s_ld, d_ld, 0, x.dtype, flags)
+    name = "b200seg_convtr_fprop_stats" if geom.transposed else "b200seg_conv_fprop_stats"
+    nbytes = getattr(lib, name + "_workspace_bytes")(C.byref(d))
+    part = torch.empty((nbytes + 3) // 4, dtype=torch.float32, device=x.device)
+    ncls, tiles = C.c_int32(0), C.c_int64(0)
+    rc = lib.b200seg_conv_fprop_partials(C.byref(d), int(geom.transposed), x.data_ptr(), wp.data_ptr(), _ptr(bias),
+                                         y.data_ptr(), part.data_ptr(), part.numel() * 4, C.byref(ncls),
+                                         C.byref(tiles), _stream())
+    if rc == 1:  # B200SEG_STATS_NOT_FUSED
+        return None
+    _lib.check(rc, "b200seg_conv_fprop_partials")
+    return part, ncls.value, tiles.value, dc
+
+
+def instnorm_prelu_fwd_partials(x, handle, alpha, y, residual=None, eps: float = 1e-5):
+    """InstanceNorm + PReLU (+ residual) of the convolution output ``x`` from its partial statistics;
+    returns (mean, rstd) for the backward pass (taken over the zero-padded channel count where ``x``,
+    ``y`` and ``residual`` are all padded buffers, like ``conv_fprop_stats``)."""
+    lib = _lib.load()
+    part, ncls, tiles, cstat = handle
+    ex = _expand_all(x, y, residual)
+    if ex is not None:
+        x, y, residual = ex
+    y_ld = cl_info(y)[5]
+    r_ld = cl_info(residual)[5] if residual is not None else 0
+    if y.shape != x.shape or (residual is not None and residual.shape != x.shape):
+        raise ValueError("instnorm_prelu_fwd_partials: shape mismatch")
+    d, (n, c) = _norm_desc(x, y_ld, r_ld, eps)
+    mean = torch.empty(n * c, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(n * c, dtype=torch.float32, device=x.device)
+    _lib.check(lib.b200seg_instnorm_prelu_fwd_partials(C.byref(d), x.data_ptr(), part.data_ptr(), ncls, tiles, cstat,
+                                                       mean.data_ptr(), rstd.data_ptr(), alpha.data_ptr(),
+                                                       _ptr(residual), y.data_ptr(), _stream()),
+               "b200seg_instnorm_prelu_fwd_partials")
+    return mean, rstd
+
+
 def conv_dgrad(geom, dy, wp, dx, residual=None, accumulate=False, flags=0):
     """dx = conv^T(dy) [+ residual] [+ dx]."""
     if accumulate:

@@ -179,6 +179,20 @@ int b200seg_convtr_fprop_stats(const b200seg_conv_desc* d, const void* x, const 
                                void* y, float* mean, float* rstd, int32_t stat_ld, float eps, void* workspace,
                                size_t workspace_bytes, void* stream);
 
+/* The same fusion with the finalisation moved into the CONSUMER: conv_fprop_partials runs the convolution
+ * (transposed_layer != 0: ConvTranspose) and leaves the per-CTA partial statistics in `partials`
+ * (b200seg_conv[tr]_fprop_stats_workspace_bytes bytes), reporting their layout; returns
+ * B200SEG_STATS_NOT_FUSED (1) when the layer ran on a kernel without the fusion (y is complete, use
+ * b200seg_instnorm_stats).  instnorm_prelu_fwd_partials = InstanceNorm + PReLU (+ residual) whose blocks
+ * reduce those partials themselves (cstat = the convolution's cout; channels [cstat, d->c) are zero padding)
+ * and write mean / rstd (n * d->c floats each) for the backward pass. */
+int b200seg_conv_fprop_partials(const b200seg_conv_desc* d, int32_t transposed_layer, const void* x,
+                                const void* w_packed, const float* bias, void* y, float* partials,
+                                size_t partials_bytes, int32_t* ncls, int64_t* tiles, void* stream);
+int b200seg_instnorm_prelu_fwd_partials(const b200seg_norm_desc* d, const void* x, const float* partials,
+                                        int32_t ncls, int64_t tiles, int32_t cstat, float* mean, float* rstd,
+                                        const float* alpha, const void* residual, void* y, void* stream);
+
 int b200seg_convtr_fprop(const b200seg_conv_desc* d, const void* x, const void* w_packed,
                          const float* bias, const void* residual, void* y, void* stream);
 int b200seg_convtr_dgrad(const b200seg_conv_desc* d, const void* dy, const void* w_packed,

@@ -468,6 +468,67 @@ def test_instnorm_prelu(n, c, sp, dtype):
     assert abs(dalpha.item() - alpha.grad.item()) < (1e-4 if dtype == torch.float32 else 1e-2) * max(1.0, abs(alpha.grad.item()))
 
 
+PARTIALS_CASES = [
+    # cin, cout, stride, transposed, n, input spatial
+    (16, 16, 1, False, 2, (12, 40, 24)),    # stride-1 sliding kernel
+    (32, 32, 1, False, 1, (8, 32, 32)),
+    (32, 10, 2, True, 2, (8, 24, 40)),      # ConvTranspose lo->hi, 10 classes padded to 16
+    (16, 32, 2, False, 1, (16, 48, 64)),    # stride-2 conv hi->lo
+    (64, 64, 1, False, 2, (8, 8, 8)),       # deep layer on the streaming kernel (few partials)
+    (128, 256, 1, False, 1, (6, 6, 6)),
+]
+
+
+@pytest.mark.parametrize("with_res", [False, True])
+@pytest.mark.parametrize("cin,cout,s,tr,n,sp", PARTIALS_CASES)
+def test_conv_partials_instnorm_prelu(cin, cout, s, tr, n, sp, with_res):
+    """Convolution -> per-CTA partial statistics -> InstanceNorm+PReLU that finalises them itself,
+    against torch fp32 on the same bf16-rounded inputs (1e-2) and against the two-launch path
+    (conv_fprop_stats + instnorm_prelu_fwd): same conv output bit for bit, statistics within 1e-6."""
+    dtype = torch.bfloat16
+    torch.manual_seed(991)
+    g = ConvGeom(3, cin, cout, 3, s, tr)
+    w = q(torch.randn((cin, cout, 3, 3, 3) if tr else (cout, cin, 3, 3, 3)) * (2.0 / (cin * 27)) ** 0.5, dtype)
+    b = torch.randn(cout)
+    x = q(torch.randn(n, cin, *sp), dtype)
+    alpha = torch.tensor([0.3])
+    c_ref = ref_conv(g, x, w, b)
+    res = q(torch.randn_like(c_ref), dtype) if with_res else None
+
+    def dev(t_nc):
+        out = ops.alloc_activation(t_nc.shape[0], tuple(t_nc.shape[2:]), t_nc.shape[1], dtype, DEV)
+        out.copy_(t_nc.permute(0, 2, 3, 4, 1))
+        return out
+
+    x_cl = dev(x)
+    res_cl = dev(res) if with_res else None
+    wp = ops.pack_weight(g, _lib.W_CONVTR_FPROP if tr else _lib.W_CONV_FPROP, w.to(DEV), dtype)
+    c1 = ops.alloc_activation(n, tuple(c_ref.shape[2:]), cout, dtype, DEV)
+    handle = ops.conv_fprop_partials(g, x_cl, wp, b.to(DEV), c1)
+    assert handle is not None, "layer did not run on a kernel with fused statistics"
+    a1 = ops.alloc_like(c1)
+    mean1, rstd1 = ops.instnorm_prelu_fwd_partials(c1, handle, alpha.to(DEV), a1, res_cl)
+    c2, a2 = ops.alloc_like(c1), ops.alloc_like(c1)
+    mean2, rstd2 = ops.conv_fprop_stats(g, x_cl, wp, b.to(DEV), c2)
+    ops.instnorm_prelu_fwd(c2, mean2, rstd2, alpha.to(DEV), a2, res_cl)
+    assert torch.equal(c1, c2)
+    assert mean1.shape == mean2.shape
+    assert rel(mean1, mean2) < 1e-6 and rel(rstd1, rstd2) < 1e-6
+    assert rel(a1, a2) < 1e-3
+    # the conv output is stored in bf16; the statistics come from the fp32 accumulators
+    cd = c_ref.double()
+    m_ref = cd.mean(dim=(2, 3, 4))
+    r_ref = 1.0 / torch.sqrt(cd.var(dim=(2, 3, 4), unbiased=False) + 1e-5)
+    assert rel(mean1.view(n, -1)[:, :cout], m_ref) < 2e-3 and rel(rstd1.view(n, -1)[:, :cout], r_ref) < 2e-3
+    y_ref = F.prelu(F.instance_norm(c_ref, eps=1e-5), alpha)
+    if with_res:
+        y_ref = y_ref + res
+    assert rel(nc_cpu(a1, 3), y_ref) < 1e-2
+    if cout % 16:  # channel padding stays zero
+        full = a1.as_strided(a1.shape[:-1] + ((cout + 15) // 16 * 16,), a1.stride())
+        assert float(full[..., cout:].abs().max()) == 0.0
+
+
 # ---- Focal / CrossEntropy through the shared softmax pass ----------------------------------------
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("c,sp", [(10, (6, 10, 12)), (4, (1, 9, 11)), (10, (16, 32, 32))])
