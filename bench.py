@@ -153,7 +153,7 @@ def workload_config(args, world, note=None):
                     f"fwd+bwd+Adam (BASELINE.json configs[2])",
         "patch": args.patch, "batch_per_gpu": args.batch, "global_batch": args.batch * world,
         "parallelism": f"dp{world}", "optimizer": "Adam (FlatAdam: torch.optim.Adam semantics, one launch; inside the timed region)",
-        "execution": "eager launches" if getattr(args, "no_graph", False) else "fwd+loss+bwd replayed from one CUDA graph",
+        "execution": "eager launches" if getattr(args, "no_graph", False) else ("fwd+loss+bwd replayed from one CUDA graph" + (" incl. the NCCL gradient all-reduce (deep levels' range overlapped with the rest of the backward pass)" if world > 1 else "")),
         "l2": "per-step activations+gradients (>1 GB) exceed the 126 MB L2; no explicit flush",
     }
     if note:

@@ -10,6 +10,7 @@ replays are picked up.
 """
 from __future__ import annotations
 
+import os
 from typing import Callable, Optional
 
 import torch
@@ -20,15 +21,22 @@ from .unet import UNet
 
 
 class GraphedTrainStep:
-    """``step(images, labels) -> loss`` with forward + loss + backward replayed from a CUDA graph,
-    then (eagerly) one flat gradient all-reduce over the data-parallel group and the optimiser.
+    """``step(images, labels) -> loss`` with forward + loss + backward + the gradient all-reduce of the
+    data-parallel group replayed from a CUDA graph, then (eagerly) the optimiser.
+
+    The weight-gradient kernels write straight into the flat fp32 bucket (``UNet.bind_grad_sink``): nothing is
+    gathered after the backward pass.  With more than one rank the bucket range of the deep levels (98 % of the
+    parameters; their gradients are complete when the reverse plan returns to the two high-resolution encoder
+    levels) is all-reduced on a communication stream BESIDE the rest of the backward pass; only the two small
+    outer ranges are reduced after it.
 
     ``images`` / ``labels`` may live on the host (pinned) or on the device; they are copied into
     the graph's static input buffers.  The returned loss is a device scalar (no host sync).
     """
 
     def __init__(self, net: UNet, loss_fn: Callable, optimizer: Optional[torch.optim.Optimizer],
-                 images: torch.Tensor, labels: torch.Tensor, warmup: int = 2, use_graph: bool = True):
+                 images: torch.Tensor, labels: torch.Tensor, warmup: int = 2, use_graph: bool = True,
+                 overlap_allreduce: Optional[bool] = None):
         self.net, self.loss_fn, self.optimizer = net, loss_fn, optimizer
         dev = next(net.parameters()).device
         self.static_images = torch.empty(images.shape, dtype=images.dtype, device=dev)
@@ -38,6 +46,15 @@ class GraphedTrainStep:
         self.bucket = GradientBucket(net.parameters())
         if hasattr(optimizer, "bind_grad_buffer"):  # FlatAdam reads the all-reduced bucket directly
             optimizer.bind_grad_buffer(self.bucket.flat, self.bucket.params)
+        self._sink = dict(zip(self.bucket.params, self.bucket.views))
+        for p, v in zip(self.bucket.params, self.bucket.views):
+            p.grad = v  # the optimiser reads the (all-reduced) bucket
+        self._world = dist.get_world_size() if dist.is_initialized() else 1
+        if overlap_allreduce is None:
+            overlap_allreduce = os.environ.get("B200SEG_OVERLAP_ALLREDUCE", "1") == "1"
+        self._deep = self._deep_range(net) if (self._world > 1 and overlap_allreduce) else None
+        self._comm_stream = torch.cuda.Stream(device=dev) if self._deep is not None else None
+        self._deep_issued = False
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.loss: Optional[torch.Tensor] = None
         self.use_graph = use_graph
@@ -56,31 +73,88 @@ class GraphedTrainStep:
             net.enable_wgrad_stream(True)  # weight gradients as a parallel branch of the captured graph
             self._capture(warmup)
 
+    # ---- gradient exchange -------------------------------------------------------------------------
+    def _deep_range(self, net: UNet):
+        """(depth, lo, hi): the flat-bucket range [lo, hi) of the parameters of level ``depth`` and below,
+        all-reduced as soon as the reverse plan has issued their weight gradients.  ``parameters()`` walks
+        the module tree depth first, so a level's parameters are one contiguous range of the bucket.
+        Depth 2 leaves the two full-resolution encoder levels (a third of the backward pass) to hide the
+        exchange behind; shallower nets use depth 1."""
+        levels, m = 0, net.model
+        while isinstance(m, torch.nn.Sequential) and len(m) == 3 and hasattr(m[1], "submodule"):
+            levels, m = levels + 1, m[1].submodule
+        depth = 2 if levels >= 3 else 1
+        m = net.model
+        for _ in range(depth):
+            m = m[1].submodule
+        ids = {id(p) for p in m.parameters()}
+        idx = [i for i, p in enumerate(self.bucket.params) if id(p) in ids]
+        if not idx or idx != list(range(idx[0], idx[-1] + 1)):
+            return None
+        lo = sum(self.bucket.sizes[:idx[0]])
+        hi = lo + sum(self.bucket.sizes[idx[0]:idx[-1] + 1])
+        return depth, lo, hi
+
+    def _allreduce_mean(self, t: torch.Tensor) -> None:
+        if t.numel() == 0:
+            return
+        if dist.get_backend() == "nccl":  # the average is taken inside the collective
+            dist.all_reduce(t, op=dist.ReduceOp.AVG)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            t.mul_(1.0 / self._world)
+
+    def _on_level_done(self, depth: int) -> None:
+        """Reverse-plan hook (runs on the autograd thread, on the step's stream): level ``depth`` and below
+        have issued all their launches -> all-reduce their bucket range beside the rest of the backward."""
+        if self._deep is None or depth != self._deep[0]:
+            return
+        comm = self._comm_stream
+        comm.wait_stream(torch.cuda.current_stream())
+        if self.net.wgrad_stream and self.net._wgrad_side is not None:
+            comm.wait_stream(self.net._wgrad_side)  # the weight gradients are written on the second stream
+        with torch.cuda.stream(comm):
+            self._allreduce_mean(self.bucket.flat[self._deep[1]:self._deep[2]])
+        self._deep_issued = True
+
+    def _exchange_rest(self) -> None:
+        if self._world == 1:
+            return
+        if self._deep_issued:
+            _, lo, hi = self._deep
+            self._allreduce_mean(self.bucket.flat[:lo])
+            self._allreduce_mean(self.bucket.flat[hi:])
+            torch.cuda.current_stream().wait_stream(self._comm_stream)
+        else:
+            self._allreduce_mean(self.bucket.flat)
+
     def _fwd_bwd(self):
         from . import ops
-        if self.use_graph:
-            # zero-padded 10-class buffers are allocated (and zeroed) once and reused by every replay:
-            # a replayed step's activations are dead before the next replay starts
-            with ops.padded_buffer_pool(self._pad_pool):
+        self._deep_issued = False
+        self.net.bind_grad_sink(self._sink, self._on_level_done if self._deep is not None else None)
+        try:
+            if self.use_graph:
+                # zero-padded 10-class buffers are allocated (and zeroed) once and reused by every replay:
+                # a replayed step's activations are dead before the next replay starts
+                with ops.padded_buffer_pool(self._pad_pool):
+                    loss = self.loss_fn(self.net(self.static_images), self.static_labels.unsqueeze(1))
+                    loss.backward()
+            else:
                 loss = self.loss_fn(self.net(self.static_images), self.static_labels.unsqueeze(1))
                 loss.backward()
-            return loss
-        loss = self.loss_fn(self.net(self.static_images), self.static_labels.unsqueeze(1))
-        loss.backward()
+        finally:
+            self.net.bind_grad_sink(None)
+        self._exchange_rest()
         return loss
 
     def _capture(self, warmup: int):
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):  # warm-up off the default stream, as graph capture requires
-            for _ in range(max(1, warmup)):
-                for p in self.bucket.params:
-                    p.grad = None
+            for _ in range(max(1, warmup)):  # (also brings the NCCL communicator up before the capture)
                 self._fwd_bwd()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        for p in self.bucket.params:
-            p.grad = None
         self.net.reset_packed_cache()  # the weight-repack kernels must be part of the graph
         from . import _lib
         lib = _lib.load()
@@ -88,17 +162,12 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         # capture on a high-priority stream: the serial chain (main branch) is scheduled ahead of the
         # weight-gradient branch, which was created at default (lower) priority
-        import os
         cap_stream = torch.cuda.Stream(priority=-1) if os.environ.get("B200SEG_GRAPH_PRIO", "1") == "1" else None
         with torch.cuda.graph(self.graph, stream=cap_stream):
             self.loss = self._fwd_bwd()
-            grads = [p.grad for p in self.bucket.params]
-            torch._foreach_copy_(self.bucket.views, grads)
         # b200seg kernels recorded into the graph = launched again on every replay
         self.launches_per_step = lib.b200seg_launch_count() - before[0]
         self.tc_launches_per_step = lib.b200seg_tc_launch_count() - before[1]
-        for p, v in zip(self.bucket.params, self.bucket.views):
-            p.grad = v  # the optimiser reads the (all-reduced) bucket
 
     def __call__(self, images: Optional[torch.Tensor] = None, labels: Optional[torch.Tensor] = None):
         if images is not None and not images.is_cuda:
@@ -125,18 +194,7 @@ class GraphedTrainStep:
             self.graph.replay()
             loss = self.loss
         else:
-            for p in self.bucket.params:
-                p.grad = None
             loss = self._fwd_bwd()
-            torch._foreach_copy_(self.bucket.views, [p.grad for p in self.bucket.params])
-            for p, v in zip(self.bucket.params, self.bucket.views):
-                p.grad = v
-        if dist.is_initialized() and dist.get_world_size() > 1:
-            if dist.get_backend() == "nccl":  # the average is taken inside the collective
-                dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.AVG)
-            else:
-                dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.SUM)
-                self.bucket.flat.mul_(1.0 / dist.get_world_size())
         if self.optimizer is not None:
             self.optimizer.step()
         return loss

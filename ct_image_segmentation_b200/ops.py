@@ -8,6 +8,7 @@ Nothing here falls back to PyTorch arithmetic: a missing library or a failed lau
 from __future__ import annotations
 
 import ctypes as C
+import math
 import weakref
 from dataclasses import dataclass
 from typing import Optional, Tuple
@@ -377,8 +378,15 @@ def conv_dgrad(geom, dy, wp, dx, residual=None, accumulate=False, flags=0):
     return _conv_call(geom, dy, wp, None, residual, dx, True, flags)
 
 
-def conv_wgrad(geom: ConvGeom, x, dy, want_bias: bool = True, flags=0):
-    """(gw, gbias): fp32 gradients in PyTorch parameter layout."""
+def _grad_out(out, shape, what):
+    if out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != math.prod(shape):
+        raise ValueError(f"{what}: destination must be a contiguous fp32 tensor of {math.prod(shape)} elements")
+    return out
+
+
+def conv_wgrad(geom: ConvGeom, x, dy, want_bias: bool = True, flags=0, out_w=None, out_b=None):
+    """(gw, gbias): fp32 gradients in PyTorch parameter layout; ``out_w`` / ``out_b`` (contiguous fp32,
+    e.g. views of a flat gradient bucket) receive them in place."""
     lib = _lib.load()
     n, xd, xh, xw, xc, x_ld = cl_info(x)
     n2, yd, yh, yw, yc, y_ld = cl_info(dy)
@@ -390,8 +398,11 @@ def conv_wgrad(geom: ConvGeom, x, dy, want_bias: bool = True, flags=0):
     k = geom.kernel
     ks = (k, k) if geom.dims == 2 else (k, k, k)
     shape = (geom.cin, geom.cout, *ks) if geom.transposed else (geom.cout, geom.cin, *ks)
-    gw = torch.empty(shape, dtype=torch.float32, device=x.device)
-    gb = torch.empty(geom.cout, dtype=torch.float32, device=x.device) if want_bias else None
+    gw = torch.empty(shape, dtype=torch.float32, device=x.device) if out_w is None else _grad_out(out_w, shape, "conv wgrad")
+    gb = None
+    if want_bias:
+        gb = (torch.empty(geom.cout, dtype=torch.float32, device=x.device) if out_b is None
+              else _grad_out(out_b, (geom.cout,), "conv wgrad bias"))
     pre = "b200seg_convtr_wgrad" if geom.transposed else "b200seg_conv_wgrad"
     nbytes = getattr(lib, pre + "_workspace_bytes")(C.byref(d))
     ws = workspace(nbytes, x.device)
@@ -478,14 +489,15 @@ def instnorm_prelu_fwd(x, mean, rstd, alpha, y, residual=None, eps: float = 1e-5
     return y_out
 
 
-def instnorm_prelu_bwd(x, mean, rstd, alpha, dy, dx, eps: float = 1e-5):
-    """Writes dx; returns dalpha (1-element fp32 tensor)."""
+def instnorm_prelu_bwd(x, mean, rstd, alpha, dy, dx, eps: float = 1e-5, out_dalpha=None):
+    """Writes dx; returns dalpha (1-element fp32 tensor; ``out_dalpha`` receives it in place)."""
     lib = _lib.load()
     if dy.shape != x.shape or dx.shape != x.shape:
         raise ValueError("instnorm_prelu_bwd: shape mismatch")
     mean, rstd, x, dy, dx = _match_stats(mean, rstd, "instnorm_prelu_bwd", x, dy, dx)
     d, _ = _norm_desc(x, cl_info(dy)[5], cl_info(dx)[5], eps)
-    dalpha = torch.empty(1, dtype=torch.float32, device=x.device)
+    dalpha = (torch.empty(1, dtype=torch.float32, device=x.device) if out_dalpha is None
+              else _grad_out(out_dalpha, (1,), "instnorm_prelu_bwd dalpha"))
     nbytes = lib.b200seg_instnorm_workspace_bytes(C.byref(d))
     ws = workspace(nbytes, x.device)
     _lib.check(lib.b200seg_instnorm_prelu_bwd(C.byref(d), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),

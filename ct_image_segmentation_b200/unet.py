@@ -430,7 +430,7 @@ class UNet(nn.Module):
         grads: Dict[torch.Tensor, torch.Tensor] = {}
         self._bwd_taps = taps
         self._wgrad_keep = []
-        gx = self._bwd_level(self.model, g_out, saved, grads, need_gx, None, False)
+        gx = self._bwd_level(self.model, g_out, saved, grads, need_gx, None, False, 0)
         side = self._wgrad_side if self.wgrad_stream else None
         if side is not None and g_out.is_cuda:
             torch.cuda.current_stream().wait_stream(side)  # join: weight gradients complete
@@ -450,17 +450,34 @@ class UNet(nn.Module):
         if on and self._wgrad_side is None:
             self._wgrad_side = torch.cuda.Stream()
 
-    def _wgrad(self, geom: ConvGeom, x, g, want_bias: bool = True):
+    # Gradient sink (GraphedTrainStep): {parameter: contiguous fp32 view of a flat gradient bucket}.  With a
+    # sink the weight-gradient / bias / PReLU kernels write straight into the bucket, dead biases are left to
+    # the bucket's zeros, and the autograd node reports no parameter gradients (nothing to gather afterwards).
+    _grad_sink: Optional[Dict] = None
+    # called as hook(depth) from the reverse plan when every launch of level `depth` and below has been
+    # issued (main stream + weight-gradient stream): the point where their bucket range can be all-reduced
+    _level_done_hook = None
+
+    def bind_grad_sink(self, sink: Optional[Dict], level_done_hook=None) -> None:
+        self._grad_sink = sink
+        self._level_done_hook = level_done_hook
+
+    def _wgrad(self, geom: ConvGeom, x, g, want_bias: bool = True, weight=None, bias=None):
+        sink = self._grad_sink
+        out_w = out_b = None
+        if sink is not None:
+            out_w = sink[weight]
+            out_b = sink[bias] if want_bias else None
         if not (self.wgrad_stream and x.is_cuda):
-            return ops.conv_wgrad(geom, x, g, want_bias=want_bias)
+            return ops.conv_wgrad(geom, x, g, want_bias=want_bias, out_w=out_w, out_b=out_b)
         side = self._wgrad_side
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            gw, gb = ops.conv_wgrad(geom, x, g, want_bias=want_bias)
+            gw, gb = ops.conv_wgrad(geom, x, g, want_bias=want_bias, out_w=out_w, out_b=out_b)
         self._wgrad_keep.append((x, g, gw, gb))
         return gw, gb
 
-    def _bwd_level(self, lvl: _Level, g_out, saved, grads, need_gx, gx_dst, gx_accum):
+    def _bwd_level(self, lvl: _Level, g_out, saved, grads, need_gx, gx_dst, gx_accum, depth: int = 0):
         down, skip, up = lvl[0], lvl[1], lvl[2]
         sub = skip.submodule
         c_x = saved.pop(lvl)["c_x"]
@@ -468,9 +485,11 @@ class UNet(nn.Module):
         g_x, g_sub = g_cat[..., :c_x], g_cat[..., c_x:]
         # the sub-network's input gradient is accumulated in place into the skip half of g_cat
         if isinstance(sub, _Level):
-            self._bwd_level(sub, g_sub, saved, grads, True, g_x, True)
+            self._bwd_level(sub, g_sub, saved, grads, True, g_x, True, depth + 1)
         else:
             self._bwd_layer(sub, g_sub, saved, grads, True, g_x, True)
+        if self._level_done_hook is not None:
+            self._level_done_hook(depth + 1)
         return self._bwd_layer(down, g_x, saved, grads, need_gx, gx_dst, gx_accum)
 
     def _bwd_layer(self, layer, g_out, saved, grads, need_gx, gx_dst, gx_accum):
@@ -490,8 +509,11 @@ class UNet(nn.Module):
         else:
             c = s["c"]
             g_c = ops.alloc_like(c)
-            grads[m.act.weight] = ops.instnorm_prelu_bwd(c, s["mean"], s["rstd"], m.act.weight.detach(),
-                                                         g_out, g_c, m.norm.eps)
+            sink = self._grad_sink
+            dalpha = ops.instnorm_prelu_bwd(c, s["mean"], s["rstd"], m.act.weight.detach(), g_out, g_c, m.norm.eps,
+                                            out_dalpha=None if sink is None else sink[m.act.weight])
+            if sink is None:
+                grads[m.act.weight] = dalpha
         if getattr(self, "_bwd_taps", None) is not None:
             self._bwd_taps[m] = {"g_out": g_out, "g_c": g_c, "x": x, "c": s.get("c"),
                                  "mean": s.get("mean"), "rstd": s.get("rstd")}
@@ -501,12 +523,13 @@ class UNet(nn.Module):
         if s.get("col_geom") is not None:  # x is the im2col buffer; gw comes out as the (cout, cin*taps) matrix
             if need_gx:
                 raise RuntimeError("input gradient requested through an im2col first layer")
-            gw, gb = self._wgrad(s["col_geom"], x, g_c, want_bias=m.conv_only)
+            gw, gb = self._wgrad(s["col_geom"], x, g_c, m.conv_only, m.conv.weight, m.conv.bias)
             gw = gw.view(m.conv.weight.shape)
         else:
-            gw, gb = self._wgrad(g, x, g_c, want_bias=m.conv_only)
-        grads[m.conv.weight] = gw
-        grads[m.conv.bias] = gb if gb is not None else torch.zeros_like(m.conv.bias)
+            gw, gb = self._wgrad(g, x, g_c, m.conv_only, m.conv.weight, m.conv.bias)
+        if self._grad_sink is None:
+            grads[m.conv.weight] = gw
+            grads[m.conv.bias] = gb if gb is not None else torch.zeros_like(m.conv.bias)
         if not need_gx:
             return None
         gx = gx_dst if gx_dst is not None else ops.alloc_like(x)
@@ -526,11 +549,12 @@ class UNet(nn.Module):
         gx = self._bwd_convolution(units[0], g, saved, grads, need_gx, gx_dst, gx_accum, None)
         rg = ru.res_geom
         if sru.get("col_geom") is not None:
-            gw, gb = self._wgrad(sru["col_geom"], sru["col"], g_out)
+            gw, gb = self._wgrad(sru["col_geom"], sru["col"], g_out, True, ru.residual.weight, ru.residual.bias)
             gw = gw.view(ru.residual.weight.shape)
         else:
-            gw, gb = self._wgrad(rg, x, g_out)
-        grads[ru.residual.weight], grads[ru.residual.bias] = gw, gb
+            gw, gb = self._wgrad(rg, x, g_out, True, ru.residual.weight, ru.residual.bias)
+        if self._grad_sink is None:
+            grads[ru.residual.weight], grads[ru.residual.bias] = gw, gb
         if need_gx:
             ops.conv_dgrad(rg, g_out, self._w_dgrad(ru.residual, rg), gx, accumulate=True)
         return gx

@@ -77,7 +77,7 @@ def conv_dgrad(geom, dy, wp, dx, residual=None, accumulate=False, flags=0):
     return dx
 
 
-def conv_wgrad(geom, x, dy, want_bias=True, flags=0):
+def conv_wgrad(geom, x, dy, want_bias=True, flags=0, out_w=None, out_b=None):
     k = geom.kernel
     ks = (k, k) if geom.dims == 2 else (k, k, k)
     shape = (geom.cin, geom.cout, *ks) if geom.transposed else (geom.cout, geom.cin, *ks)
@@ -85,6 +85,12 @@ def conv_wgrad(geom, x, dy, want_bias=True, flags=0):
     out = _conv(geom, _nc(x, geom.dims).float(), w)
     (gw,) = torch.autograd.grad(out, w, _nc(dy, geom.dims).float())
     gb = dy.float().sum(dim=(0, 1, 2, 3)) if want_bias else None
+    if out_w is not None:
+        out_w.view(-1).copy_(gw.reshape(-1))
+        gw = out_w
+    if out_b is not None and gb is not None:
+        out_b.copy_(gb)
+        gb = out_b
     return gw, gb
 
 
@@ -105,7 +111,7 @@ def instnorm_prelu_fwd(x, mean, rstd, alpha, y, residual=None, eps=1e-5):
     return y
 
 
-def instnorm_prelu_bwd(x, mean, rstd, alpha, dy, dx, eps=1e-5):
+def instnorm_prelu_bwd(x, mean, rstd, alpha, dy, dx, eps=1e-5, out_dalpha=None):
     n, c = x.shape[0], x.shape[4]
     r = rstd.view(n, 1, 1, 1, c)
     h = (x.float() - mean.view(n, 1, 1, 1, c)) * r
@@ -116,4 +122,7 @@ def instnorm_prelu_bwd(x, mean, rstd, alpha, dy, dx, eps=1e-5):
     s1 = gt.mean(dim=(1, 2, 3), keepdim=True)
     s2 = (gt * h).mean(dim=(1, 2, 3), keepdim=True)
     dx.copy_(r * (gt - s1 - h * s2))
+    if out_dalpha is not None:
+        out_dalpha.copy_(dalpha)
+        return out_dalpha
     return dalpha

@@ -49,3 +49,47 @@ def test_plan_matches_autograd(monkeypatch, dims, inc, ch, st, res, shape):
             assert (grads[p] - rg).abs().max().item() <= 1e-2 * wscale + 1e-3, name
             continue
         assert (grads[p] - rg).abs().max().item() <= 5e-3 * scale + 1e-4, name
+
+
+def test_gradient_sink_and_level_hook(monkeypatch):
+    """With a gradient sink the reverse plan writes every live gradient into the bucket views (dead biases
+    stay zero, nothing is handed to autograd), and the level hook fires once per depth, deepest first, at a
+    point where the gradients of that level and everything below it are already in the bucket."""
+    from ct_image_segmentation_b200.parallel import GradientBucket
+    monkeypatch.setattr(U, "ops", _torch_ops)
+    torch.manual_seed(5)
+    dims, inc, ch, st, res, shape = CASES[0]
+    net = U.UNet(dims, inc, 10, ch, st, num_res_units=res, dtype=torch.float32)
+    x = torch.randn(*shape)
+    g = torch.randn(shape[0], 10, *shape[2:])
+
+    saved = {}
+    net._run_forward(_torch_ops.to_channels_last(x, torch.float32), saved)
+    grads, _ = net._run_backward(saved, _torch_ops.to_channels_last(g, torch.float32), False)
+
+    bucket = GradientBucket(net.parameters())
+    sink = dict(zip(bucket.params, bucket.views))
+    names = {id(p): n for n, p in net.named_parameters()}
+    fired = []
+
+    def hook(depth):
+        m = net.model
+        for _ in range(depth):
+            m = m[1].submodule
+        for p in m.parameters():  # complete at hook time
+            torch.testing.assert_close(sink[p], grads[p].view_as(p), rtol=0, atol=0, msg=names[id(p)])
+        fired.append(depth)
+
+    net.bind_grad_sink(sink, hook)
+    saved = {}
+    net._run_forward(_torch_ops.to_channels_last(x, torch.float32), saved)
+    grads2, _ = net._run_backward(saved, _torch_ops.to_channels_last(g, torch.float32), False)
+    net.bind_grad_sink(None)
+    assert fired == [4, 3, 2, 1]
+    assert not any(p in grads2 for p in net.parameters())
+    for p in net.parameters():
+        torch.testing.assert_close(sink[p], grads[p].view_as(p), rtol=0, atol=0, msg=names[id(p)])
+    # the deep range the engine all-reduces early is one contiguous slice of the bucket
+    m = net.model[1].submodule[1].submodule
+    ids = [i for i, p in enumerate(bucket.params) if any(p is q for q in m.parameters())]
+    assert ids == list(range(ids[0], ids[-1] + 1)) and len(ids) == len(list(m.parameters()))

@@ -341,3 +341,35 @@ def test_flat_adam_matches_torch_adam():
     for x, y in zip(pa, pb):
         assert rel(y.detach(), x.detach()) < 1e-6
     assert all(y.data_ptr() >= ob.flat.data_ptr() for y in pb)  # parameters live in the flat buffer
+
+
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_graphed_train_step_matches_autograd(use_graph):
+    """GraphedTrainStep (weight gradients written straight into the flat bucket, CUDA-graph replay) gives the
+    gradients and the loss of the plain autograd call, bit for bit, and keeps doing so over replays."""
+    ref, net = make_pair(3, 1, [16, 32, 64, 64], [2, 2, 2], 2, torch.bfloat16)
+    torch.manual_seed(11)
+    x = torch.randn(2, 1, 32, 32, 32, device=DEV)
+    lab = torch.randint(0, 10, (2, 32, 32, 32), device=DEV)
+    fx = B.DiceLoss(include_background=False, to_onehot_y=True, softmax=True)
+    loss0 = fx(net(x), lab.unsqueeze(1))
+    loss0.backward()
+    # drop the autograd graph: its AccumulateGrad nodes are bound to the default stream and would be reused
+    # (and synchronised with) inside the capture
+    loss0 = loss0.detach()
+    want = [p.grad.clone() for p in net.parameters()]
+    for p in net.parameters():
+        p.grad = None
+    train = B.GraphedTrainStep(net, fx, None, x, lab, use_graph=use_graph)
+    names = [n for n, _ in net.named_parameters()]
+    for _ in range(3):
+        for v, w in zip(train.bucket.views, want):
+            if w.any():
+                v.fill_(float("nan"))  # every live gradient is rewritten by the step
+        loss = train(None, None)
+        torch.cuda.synchronize()
+        assert torch.equal(loss, loss0.detach())
+        for n, p, v, w in zip(names, train.bucket.params, train.bucket.views, want):
+            assert p.grad.data_ptr() == v.data_ptr()
+            assert torch.equal(v, w), n  # dead biases: exactly zero on both sides (never written)
+    net.enable_wgrad_stream(False)
