@@ -25,10 +25,10 @@ class GraphedTrainStep:
     data-parallel group replayed from a CUDA graph, then (eagerly) the optimiser.
 
     The weight-gradient kernels write straight into the flat fp32 bucket (``UNet.bind_grad_sink``): nothing is
-    gathered after the backward pass.  With more than one rank the bucket range of the deep levels (98 % of the
-    parameters; their gradients are complete when the reverse plan returns to the two high-resolution encoder
-    levels) is all-reduced on a communication stream BESIDE the rest of the backward pass; only the two small
-    outer ranges are reduced after it.
+    gathered after the backward pass.  With more than one rank the bucket range holding everything but the two
+    outermost down layers (99 % of the parameters; complete when the reverse plan returns to the two
+    high-resolution encoder levels) is all-reduced on a communication stream BESIDE the rest of the backward
+    pass; only that small first range is reduced after it.
 
     ``images`` / ``labels`` may live on the host (pinned) or on the device; they are copied into
     the graph's static input buffers.  The returned loss is a device scalar (no host sync).
@@ -55,6 +55,10 @@ class GraphedTrainStep:
         self._deep = self._deep_range(net) if (self._world > 1 and overlap_allreduce) else None
         self._comm_stream = torch.cuda.Stream(device=dev) if self._deep is not None else None
         self._deep_issued = False
+        # graph mode: the exchange is part of the captured step (B200SEG_EXCHANGE_IN_GRAPH=0: after the replay)
+        self._exchange_in_graph = os.environ.get("B200SEG_EXCHANGE_IN_GRAPH", "1") == "1"
+        if use_graph and not self._exchange_in_graph:
+            self._deep = None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.loss: Optional[torch.Tensor] = None
         self.use_graph = use_graph
@@ -75,25 +79,28 @@ class GraphedTrainStep:
 
     # ---- gradient exchange -------------------------------------------------------------------------
     def _deep_range(self, net: UNet):
-        """(depth, lo, hi): the flat-bucket range [lo, hi) of the parameters of level ``depth`` and below,
-        all-reduced as soon as the reverse plan has issued their weight gradients.  ``parameters()`` walks
-        the module tree depth first, so a level's parameters are one contiguous range of the bucket.
-        Depth 2 leaves the two full-resolution encoder levels (a third of the backward pass) to hide the
-        exchange behind; shallower nets use depth 1."""
+        """(depth, lo, hi): the flat-bucket range [lo, hi) that is all-reduced as soon as the reverse plan
+        has issued the weight gradients of level ``depth``.  ``parameters()`` walks the module tree depth
+        first -- down layers, then the levels below, then the up layers -- and the reverse plan runs the up
+        layers first, so when level ``depth`` is done everything FROM its first parameter TO THE END of the
+        bucket is complete: one contiguous range; only the down layers above it (a few 10^4 parameters)
+        remain for after the backward pass.  Depth 2 leaves the two full-resolution encoder levels (a third of
+        the backward pass) to hide the exchange behind; shallower nets use depth 1."""
         levels, m = 0, net.model
         while isinstance(m, torch.nn.Sequential) and len(m) == 3 and hasattr(m[1], "submodule"):
             levels, m = levels + 1, m[1].submodule
-        depth = 2 if levels >= 3 else 1
-        m = net.model
-        for _ in range(depth):
-            m = m[1].submodule
-        ids = {id(p) for p in m.parameters()}
-        idx = [i for i, p in enumerate(self.bucket.params) if id(p) in ids]
-        if not idx or idx != list(range(idx[0], idx[-1] + 1)):
+        if levels < 1:
             return None
-        lo = sum(self.bucket.sizes[:idx[0]])
-        hi = lo + sum(self.bucket.sizes[idx[0]:idx[-1] + 1])
-        return depth, lo, hi
+        depth = 2 if levels >= 3 else 1
+        outer, m = [], net.model
+        for _ in range(depth):  # down layers of the levels above `depth`: the first parameters of the bucket
+            outer += list(m[0].parameters())
+            m = m[1].submodule
+        n_outer = len(outer)
+        if [id(p) for p in self.bucket.params[:n_outer]] != [id(p) for p in outer]:
+            return None  # not the depth-first order (e.g. frozen parameters): plain exchange
+        lo = sum(self.bucket.sizes[:n_outer])
+        return depth, lo, self.bucket.flat.numel()
 
     def _allreduce_mean(self, t: torch.Tensor) -> None:
         if t.numel() == 0:
@@ -121,9 +128,7 @@ class GraphedTrainStep:
         if self._world == 1:
             return
         if self._deep_issued:
-            _, lo, hi = self._deep
-            self._allreduce_mean(self.bucket.flat[:lo])
-            self._allreduce_mean(self.bucket.flat[hi:])
+            self._allreduce_mean(self.bucket.flat[:self._deep[1]])
             torch.cuda.current_stream().wait_stream(self._comm_stream)
         else:
             self._allreduce_mean(self.bucket.flat)
@@ -144,7 +149,8 @@ class GraphedTrainStep:
                 loss.backward()
         finally:
             self.net.bind_grad_sink(None)
-        self._exchange_rest()
+        if not (self.use_graph and not self._exchange_in_graph and torch.cuda.is_current_stream_capturing()):
+            self._exchange_rest()
         return loss
 
     def _capture(self, warmup: int):
@@ -159,12 +165,29 @@ class GraphedTrainStep:
         from . import _lib
         lib = _lib.load()
         before = (lib.b200seg_launch_count(), lib.b200seg_tc_launch_count())
-        self.graph = torch.cuda.CUDAGraph()
         # capture on a high-priority stream: the serial chain (main branch) is scheduled ahead of the
         # weight-gradient branch, which was created at default (lower) priority
         cap_stream = torch.cuda.Stream(priority=-1) if os.environ.get("B200SEG_GRAPH_PRIO", "1") == "1" else None
-        with torch.cuda.graph(self.graph, stream=cap_stream):
-            self.loss = self._fwd_bwd()
+        try:
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=cap_stream):
+                self.loss = self._fwd_bwd()
+        except Exception as e:  # noqa: BLE001
+            if self._world == 1 or not self._exchange_in_graph:
+                raise
+            # a communicator that cannot be captured (NCCL build / transport): keep the compute in the graph
+            # and run the gradient exchange eagerly after every replay
+            import warnings
+            warnings.warn(f"b200seg: NCCL all-reduce could not be captured into the CUDA graph ({e}); "
+                          f"the gradient exchange runs after the graph replay instead")
+            self._exchange_in_graph = False
+            self._deep = None
+            torch.cuda.synchronize()
+            self.net.reset_packed_cache()
+            before = (lib.b200seg_launch_count(), lib.b200seg_tc_launch_count())
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=cap_stream):
+                self.loss = self._fwd_bwd()
         # b200seg kernels recorded into the graph = launched again on every replay
         self.launches_per_step = lib.b200seg_launch_count() - before[0]
         self.tc_launches_per_step = lib.b200seg_tc_launch_count() - before[1]
@@ -193,6 +216,8 @@ class GraphedTrainStep:
         if self.graph is not None:
             self.graph.replay()
             loss = self.loss
+            if not self._exchange_in_graph:
+                self._exchange_rest()
         else:
             loss = self._fwd_bwd()
         if self.optimizer is not None:

@@ -73,10 +73,14 @@ def test_gradient_sink_and_level_hook(monkeypatch):
     fired = []
 
     def hook(depth):
-        m = net.model
+        # complete at hook time: everything but the down layers of the levels above `depth` -- the first
+        # parameters of the depth-first bucket -- i.e. one contiguous range up to the END of the bucket
+        outer, m = [], net.model
         for _ in range(depth):
+            outer += list(m[0].parameters())
             m = m[1].submodule
-        for p in m.parameters():  # complete at hook time
+        assert all(a is b for a, b in zip(bucket.params, outer))
+        for p in bucket.params[len(outer):]:
             torch.testing.assert_close(sink[p], grads[p].view_as(p), rtol=0, atol=0, msg=names[id(p)])
         fired.append(depth)
 
@@ -89,7 +93,3 @@ def test_gradient_sink_and_level_hook(monkeypatch):
     assert not any(p in grads2 for p in net.parameters())
     for p in net.parameters():
         torch.testing.assert_close(sink[p], grads[p].view_as(p), rtol=0, atol=0, msg=names[id(p)])
-    # the deep range the engine all-reduces early is one contiguous slice of the bucket
-    m = net.model[1].submodule[1].submodule
-    ids = [i for i, p in enumerate(bucket.params) if any(p is q for q in m.parameters())]
-    assert ids == list(range(ids[0], ids[-1] + 1)) and len(ids) == len(list(m.parameters()))
