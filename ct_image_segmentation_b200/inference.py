@@ -22,6 +22,43 @@ from . import _lib, ops
 from .parallel import shard_indices
 
 
+class GraphedPredictor:
+    """``predictor`` for :func:`sliding_window_inference`: the network's forward pass for ONE batch shape
+    (``sw_batch_size`` windows of the ROI) captured into a CUDA graph and replayed per batch -- a forward pass
+    of the 16-256 U-Net is ~85 launches of a few microseconds, host-bound when issued from Python.  Batches
+    of another shape (the last, ragged one) run eagerly.  The returned tensor is the graph's output buffer:
+    consume it (as ``sliding_window_inference`` does) before the next call."""
+
+    def __init__(self, net, example: torch.Tensor, warmup: int = 2):
+        if not example.is_cuda:
+            raise RuntimeError("b200seg inference runs on CUDA tensors only")
+        self.net = net
+        self.static_in = example.clone()
+        self._pool: dict = {}
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side), torch.no_grad():  # warm-up off the default stream, as capture requires
+            for _ in range(max(1, warmup)):
+                with ops.padded_buffer_pool(self._pool):
+                    net(self.static_in)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        if hasattr(net, "reset_packed_cache"):
+            net.reset_packed_cache()  # the weight-repack launch must be part of the graph
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph), torch.no_grad(), ops.padded_buffer_pool(self._pool):
+            self.static_out = net(self.static_in)
+
+    def __call__(self, batch: torch.Tensor) -> torch.Tensor:
+        if batch.shape != self.static_in.shape or batch.dtype != self.static_in.dtype:
+            with torch.no_grad():
+                return self.net(batch)
+        self.static_in.copy_(batch)
+        self.graph.replay()
+        return self.static_out
+
+
 def scan_starts(size: int, roi: int, overlap: float) -> List[int]:
     """Window start offsets along one axis."""
     if roi >= size:

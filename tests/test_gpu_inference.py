@@ -56,6 +56,25 @@ def test_sliding_window_sharded_equals_single():
     assert full.dtype == torch.uint8 and int(full.max()) <= 9
 
 
+def test_graphed_predictor_equals_eager():
+    """Forward pass replayed from a CUDA graph (full batches) + eager ragged last batch == eager predictor,
+    bit for bit, also after the weights changed (the repack is part of the graph)."""
+    from ct_image_segmentation_b200.inference import GraphedPredictor
+    torch.manual_seed(2)
+    net = B.UNet(3, 1, 10, [16, 32, 64], [2, 2], num_res_units=2, dtype=torch.bfloat16).to(DEV)
+    x = torch.randn(1, 1, 40, 40, 24, device=DEV)
+    roi = (16, 16, 16)
+    assert len(window_list(x.shape[2:], roi, 0.25)) % 4 != 0  # the last batch is ragged
+    pred = GraphedPredictor(net, torch.zeros(4, 1, *roi, device=DEV))
+    for _ in range(2):
+        lab_e, log_e = sliding_window_inference(x, roi, 4, net, 0.25, return_logits=True, rank=0, world=1)
+        lab_g, log_g = sliding_window_inference(x, roi, 4, pred, 0.25, return_logits=True, rank=0, world=1)
+        assert torch.equal(lab_e, lab_g) and torch.equal(log_e, log_g)
+        with torch.no_grad():
+            for p in net.parameters():
+                p.mul_(1.01)
+
+
 def test_small_volume_is_padded_to_roi():
     net = B.UNet(3, 1, 10, [8, 16, 16], [2, 2], num_res_units=1, dtype=torch.float32).to(DEV)
     x = torch.randn(1, 1, 12, 20, 16, device=DEV)
