@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libb200seg.so")
 F32, BF16 = 0, 1
 LABEL_U8, LABEL_I64 = 0, 1
 W_CONV_FPROP, W_CONV_DGRAD, W_CONVTR_FPROP, W_CONVTR_DGRAD = 0, 1, 2, 3
-CONV_ACCUMULATE, CONV_FORCE_GENERIC, CONV_PADDED_CHANNELS, CONV_NO_SLIDE = 1, 2, 4, 8
+CONV_ACCUMULATE, CONV_FORCE_GENERIC, CONV_PADDED_CHANNELS, CONV_NO_SLIDE, CONV_SPLIT_K = 1, 2, 4, 8, 16
 PACK_TC_ONLY = 0x100
 
 

@@ -53,6 +53,7 @@ struct alignas(64) TcConvParams {
   const bf16* res;
   bf16* dst;
   float* stats;  // optional [blockIdx.x][cout][2]: per-CTA sum / sum of squares of its outputs (InstanceNorm)
+  int ksplit;    // split-K kernel only: CTAs per cluster sharing one output tile (appended: offsets above unchanged)
 };
 
 template <int BN, int KC>
@@ -246,6 +247,244 @@ tc_conv_kernel(const __grid_constant__ TcConvParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Split-K variant for the deep layers (EXPERIMENTAL: opt-in with the B200SEG_CONV_SPLIT_K flag or
+// B200SEG_CONV_SPLITK=1; compiled and SASS-checked, NOT yet run on a GPU -- see DESIGN.md section 7).  The 8^3 layers have 8 output tiles x 4..8 channel tiles = 32..64 CTAs,
+// each streaming 27 taps x Cin of A and B tiles through ONE SM's L2 port (2.2 MB per CTA for 256 -> 256:
+// ~16 us at ~70 B/clk, whatever the tensor core does).  Here a thread-block cluster of `ksplit` CTAs
+// (cluster dims (1, 1, ksplit), blockIdx.z = rank) shares one output tile: every CTA runs the same
+// producer / MMA pipeline over 1/ksplit of the (tap, K-block) iterations into its own TMEM accumulator;
+// ranks > 0 then push their fp32 partial tile into rank 0's shared memory (st.shared::cluster, staged
+// column-major so that a warp writes 128 contiguous bytes), the cluster synchronises, and rank 0 adds the
+// partials in rank order (deterministic) and runs the usual epilogue (bias / residual / accumulate /
+// statistics).  Per-CTA traffic and MMA count drop by ksplit; the cost is one cluster barrier and
+// (ksplit - 1) x 128 x BN x 4 bytes over the SM-to-SM network.
+// ------------------------------------------------------------------------------------------------
+namespace tcx {
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// shared::cta address of this CTA -> shared::cluster address of the same offset in CTA `rank`
+__device__ __forceinline__ uint32_t map_to_rank(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t caddr, float v) {
+  asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(caddr), "f"(v) : "memory");
+}
+}  // namespace tcx
+
+template <int BN, int KC>
+__global__ void __launch_bounds__(192)
+tc_conv_splitk_kernel(const __grid_constant__ TcConvParams p) {
+  using Cfg = TcCfg<BN, KC>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int stages = p.stages;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + (size_t)stages * Cfg::STAGE_BYTES);
+  uint64_t* empty = full + stages;
+  uint64_t* acc_full = empty + stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
+  float* sred = reinterpret_cast<float*>(tmem_slot + 4);  // [4 warps][BN][2]
+  float* staging = sred + 4 * BN * 2;                     // [ksplit - 1][BN][128]: partial tiles of ranks 1..
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nsplit = p.ksplit;
+  const int z = (int)tcx::cluster_ctarank();  // == blockIdx.z (cluster dims (1, 1, ksplit), gridDim.z == ksplit)
+
+  int bx = blockIdx.x;
+  const int tw_i = bx % p.tilesW; bx /= p.tilesW;
+  const int th_i = bx % p.tilesH; bx /= p.tilesH;
+  const int td_i = bx % p.tilesD; bx /= p.tilesD;
+  const int n = bx % p.n;
+  const int cls = bx / p.n;
+  const int cls_w = cls % p.ncls_w, cls_h = (cls / p.ncls_w) % p.ncls_h, cls_d = cls / (p.ncls_w * p.ncls_h);
+  const int d0 = td_i * p.tD, h0 = th_i * p.tH, w0 = tw_i * p.tW;
+  const int n0 = blockIdx.y * BN;
+  const int s_begin = p.cls_begin[cls], s_end = p.cls_begin[cls + 1];
+  // this rank's share of the (step, K-block) iterations: [it0, it1)
+  const int all_iters = (s_end - s_begin) * p.kblocks;
+  const int per = (all_iters + nsplit - 1) / nsplit;
+  const int it0 = min(z * per, all_iters), it1 = min(it0 + per, all_iters);
+
+  if (warp == 0 && lane == 0) {
+    for (int i = 0; i < stages; ++i) {
+      tc::mbar_init(&full[i], 1);
+      tc::mbar_init(&empty[i], 1);
+    }
+    tc::mbar_init(acc_full, 1);
+    tc::fence_barrier_init();
+    tc::prefetch_tmap(&p.tmB);
+  }
+  if (warp == 1) tc::tmem_alloc<Cfg::TMEM_COLS>(tmem_slot);
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem_acc = *tmem_slot;
+  // every CTA of the cluster is running before anyone touches a peer's shared memory
+  tcx::cluster_arrive();
+  tcx::cluster_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int st = 0;
+      uint32_t ph = 0;
+      for (int it = it0; it < it1; ++it) {
+        const int s = s_begin + it / p.kblocks, kb = it % p.kblocks;
+        const TcStep step = p.steps[s];
+        tc::mbar_wait(&empty[st], ph ^ 1u);
+        uint8_t* a = smem + (size_t)st * Cfg::STAGE_BYTES;
+        tc::mbar_expect_tx(&full[st], Cfg::A_BYTES + Cfg::B_BYTES);
+        tc::tma_load_5d(a, &p.tmA[step.map], &full[st], kb * KC, w0 + step.dw, h0 + step.dh, d0 + step.dd, n);
+        tc::tma_load_2d(a + Cfg::A_BYTES, &p.tmB, &full[st], 0, (step.wtile * p.kblocks + kb) * p.cout_pad + n0);
+        if (++st == stages) { st = 0; ph ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN, false, false);
+    constexpr uint64_t layout = tc::layout_for_row_bytes(Cfg::ROW_BYTES);
+    int st = 0;
+    uint32_t ph = 0;
+    for (int it = it0; it < it1; ++it) {
+      tc::mbar_wait(&full[st], ph);
+      tc::tc_fence_after();
+      const uint32_t a_addr = tc::smem_u32(smem + (size_t)st * Cfg::STAGE_BYTES);
+      const uint32_t b_addr = a_addr + Cfg::A_BYTES;
+#pragma unroll
+      for (int k = 0; k < KC / 16; ++k) {
+        const uint64_t ad = tc::make_smem_desc(a_addr + k * 32, 16, 8 * Cfg::ROW_BYTES, layout);
+        const uint64_t bd = tc::make_smem_desc(b_addr + k * 32, 16, 8 * Cfg::ROW_BYTES, layout);
+        tc::umma_bf16_warp(tmem_acc, ad, bd, idesc, (it > it0 || k > 0) ? 1u : 0u);
+      }
+      tc::umma_commit_warp(&empty[st]);
+      if (++st == stages) { st = 0; ph ^= 1u; }
+    }
+    tc::umma_commit_warp(acc_full);
+  } else if (z != 0) {
+    // ---- ranks > 0: push the fp32 partial tile into rank 0's staging area, [col][row] so that the 32 lanes
+    // of a warp (32 consecutive rows) write 128 contiguous bytes per column
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t base = tcx::map_to_rank(tc::smem_u32(staging), 0) + (uint32_t)((z - 1) * BN * 128 + row) * 4u;
+    tc::mbar_wait(acc_full, 0);
+    tc::tc_fence_after();
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 16; ++ch) {
+      uint32_t v[16];
+      tc::tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + ch * 16, v);
+      tc::tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        tcx::st_cluster_f32(base + (uint32_t)((ch * 16 + i) * 128) * 4u, it1 > it0 ? __uint_as_float(v[i]) : 0.f);
+    }
+  }
+  // ---- partial tiles are in rank 0's shared memory (release / acquire at cluster scope)
+  tc::tc_fence_before();
+  tcx::cluster_arrive();
+  tcx::cluster_wait();
+
+  if (warp >= 2 && z == 0) {
+    // ---- rank 0 epilogue: own accumulator + the peers' partials (rank order), then as tc_conv_kernel
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int lw = row % p.tW, lh = (row / p.tW) % p.tH, ldp = row / (p.tW * p.tH);
+    const int jd = d0 + ldp, jh = h0 + lh, jw = w0 + lw;
+    const bool valid = jd < p.cD && jh < p.cH && jw < p.cW;
+    const int od = jd * p.os_d + cls_d, oh = jh * p.os_h + cls_h, ow = jw * p.os_w + cls_w;
+    const int64_t lin = (((int64_t)n * p.dD + od) * p.dH + oh) * p.dW + ow;
+    tc::mbar_wait(acc_full, 0);
+    tc::tc_fence_after();
+#pragma unroll 1
+    for (int ch = 0; ch < BN / 16; ++ch) {
+      uint32_t v[16];
+      tc::tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + ch * 16, v);
+      tc::tmem_ld_wait();
+      float f[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+      for (int r = 1; r < nsplit; ++r) {
+        const float* sp = staging + ((size_t)(r - 1) * BN + ch * 16) * 128 + row;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) f[i] += sp[i * 128];
+      }
+      const int c0 = n0 + ch * 16;
+      if (p.bias) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i)
+          if (c0 + i < p.cout) f[i] += p.bias[c0 + i];
+      }
+      if (p.stats) {  // statistics of conv + bias, before the residual / accumulate addends (as tc_conv_kernel)
+        float x[16], x2[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          x[i] = valid ? f[i] : 0.f;
+          x2[i] = x[i] * x[i];
+        }
+        const float a = warp_sum16(x, lane), b = warp_sum16(x2, lane);
+        if ((lane & 1) == 0) {
+          const int c = (lane >> 1) & 15;
+          sred[(q * BN + ch * 16 + c) * 2] = a;
+          sred[(q * BN + ch * 16 + c) * 2 + 1] = b;
+        }
+      }
+      if (valid) {
+        if (p.res) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.res + lin * p.res_ld + c0);
+          uint4 r0 = rp[0], r1 = rp[1];
+          const __nv_bfloat162* h0_ = reinterpret_cast<const __nv_bfloat162*>(&r0);
+          const __nv_bfloat162* h1_ = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float2 a = __bfloat1622float2(h0_[i]), b = __bfloat1622float2(h1_[i]);
+            f[2 * i] += a.x; f[2 * i + 1] += a.y;
+            f[8 + 2 * i] += b.x; f[8 + 2 * i + 1] += b.y;
+          }
+        }
+        uint4* op = reinterpret_cast<uint4*>(p.dst + lin * p.dst_ld + c0);
+        if (p.accumulate) {
+          uint4 r0 = op[0], r1 = op[1];
+          const __nv_bfloat162* h0_ = reinterpret_cast<const __nv_bfloat162*>(&r0);
+          const __nv_bfloat162* h1_ = reinterpret_cast<const __nv_bfloat162*>(&r1);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            float2 a = __bfloat1622float2(h0_[i]), b = __bfloat1622float2(h1_[i]);
+            f[2 * i] += a.x; f[2 * i + 1] += a.y;
+            f[8 + 2 * i] += b.x; f[8 + 2 * i + 1] += b.y;
+          }
+        }
+        uint4 o0, o1;
+        __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+        __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          q0[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+          q1[i] = __floats2bfloat162_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
+        }
+        op[0] = o0;
+        op[1] = o1;
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (p.stats && z == 0) {
+    for (int i = threadIdx.x; i < 2 * BN; i += blockDim.x) {
+      const int c = i >> 1, m = i & 1;
+      if (n0 + c < p.cout)
+        p.stats[((int64_t)blockIdx.x * p.cout + n0 + c) * 2 + m] =
+            sred[(0 * BN + c) * 2 + m] + sred[(1 * BN + c) * 2 + m] + sred[(2 * BN + c) * 2 + m] +
+            sred[(3 * BN + c) * 2 + m];
+    }
+  }
+  if (warp == 1) tc::tmem_dealloc<Cfg::TMEM_COLS>(tmem_acc);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 namespace {
@@ -359,6 +598,44 @@ int launch_cfg(const TcConvParams& p, dim3 grid, cudaStream_t st) {
   }
   tc_conv_kernel<BN, KC><<<grid, 192, smem, st>>>(p);
   B200SEG_CHECK_LAUNCH("tc_conv");
+  count_tc_launch();
+  return B200SEG_OK;
+}
+
+template <int BN, int KC>
+int launch_splitk(TcConvParams& p, dim3 grid, cudaStream_t st) {
+  using Cfg = TcCfg<BN, KC>;
+  const size_t fixed = 1024 + (2 * 8 + 1) * 8 + 32 + 4 * BN * 2 * 4 + (size_t)(p.ksplit - 1) * BN * 128 * 4;
+  int stages = (int)((200 * 1024 - fixed) / Cfg::STAGE_BYTES);
+  if (stages > 8) stages = 8;
+  if (stages < 2) return B200SEG_ERR_UNSUPPORTED;
+  p.stages = stages;
+  const size_t smem = 1024 + (size_t)stages * Cfg::STAGE_BYTES + (2 * stages + 1) * 8 + 32 + 4 * BN * 2 * 4 +
+                      (size_t)(p.ksplit - 1) * BN * 128 * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(tc_conv_splitk_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    attr_set = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid.x, grid.y, (unsigned)p.ksplit);
+  cfg.blockDim = dim3(192);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = (unsigned)p.ksplit;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, tc_conv_splitk_kernel<BN, KC>, p);
+  if (e != cudaSuccess) {
+    set_error("tc_conv_splitk launch failed: %s", cudaGetErrorString(e));
+    return B200SEG_ERR_CUDA;
+  }
+  B200SEG_CHECK_LAUNCH("tc_conv_splitk");
   count_tc_launch();
   return B200SEG_OK;
 }
@@ -660,6 +937,20 @@ int tc_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void*
   int64_t gx = (int64_t)ncls_total * g.n * p.tilesD * p.tilesH * p.tilesW;
   if (gx > 0x7fffffffLL) { set_error("tc_conv: grid too large"); return B200SEG_ERR_ARG; }
   dim3 grid((unsigned)gx, (unsigned)(dst_pad / BN));
+
+  // ---- EXPERIMENTAL (flag B200SEG_CONV_SPLIT_K or B200SEG_CONV_SPLITK=1): deep layers with <= 74 CTAs share an output tile between the 2 or
+  // 4 CTAs of a cluster, each taking a share of the (tap, K-block) iterations (tc_conv_splitk_kernel)
+  {
+    static const int splitk_env = getenv("B200SEG_CONV_SPLITK") ? atoi(getenv("B200SEG_CONV_SPLITK")) : 0;
+    const bool splitk = splitk_env || (d->flags & B200SEG_CONV_SPLIT_K);
+    const int64_t ctas = gx * (dst_pad / BN);
+    const int iters = (ns / (ncls_total > 0 ? ncls_total : 1)) * p.kblocks;  // smallest class has >= this / 8
+    if (splitk && ctas * 2 <= 148 && iters >= 16 && (BN == 32 || BN == 64) && KC == 64) {
+      p.ksplit = (ctas * 4 <= 148 && BN == 32) ? 4 : 2;
+      if (BN == 32) return launch_splitk<32, 64>(p, grid, st);
+      return launch_splitk<64, 64>(p, grid, st);
+    }
+  }
 
 #define TC_CASE(bn, kc)                                   \
   if (BN == bn && KC == kc) {                             \

@@ -63,7 +63,12 @@ enum b200seg_conv_flags {
    * ZERO padding in channels [C, round_up(C,16)) (so ld >= round_up(C,16)); kernels may read the
    * padding and rewrite it with zeros.  Lets the tcgen05 kernels take the 10-class layers. */
   B200SEG_CONV_PADDED_CHANNELS = 4,
-  B200SEG_CONV_NO_SLIDE = 8 /* tcgen05 streaming kernel even where the sliding-window kernel applies (tests) */
+  B200SEG_CONV_NO_SLIDE = 8, /* tcgen05 streaming kernel even where the sliding-window kernel applies (tests) */
+  /* EXPERIMENTAL: layers with few output tiles (<= 74 CTAs) run on the split-K cluster kernel -- 2 or 4 CTAs of a
+   * thread-block cluster share one output tile and reduce their partial accumulators through distributed shared
+   * memory.  Ignored where the kernel does not apply.  Also switched on for every call by the environment
+   * variable B200SEG_CONV_SPLITK=1. */
+  B200SEG_CONV_SPLIT_K = 16
 };
 
 /*

@@ -5,6 +5,8 @@ fixtures produced by the reference's own in-tree functions (tests/golden).  Tole
 BASELINE.json north_star: 1e-4 relative (fp32 check mode), 1e-2 relative (bf16); integer / label
 outputs bit-exact.
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -252,6 +254,69 @@ def test_tcgen05_conv_vs_torch_and_generic(dims, cin, cout, k, s, tr, n, sp):
     gw2, _ = ops.conv_wgrad(g, x_cl, dy_cl, flags=_lib.CONV_FORCE_GENERIC)
     assert rel(gw, gw2) < 1e-4, "tc vs generic wgrad"
     assert rel(gb, dy.sum(dim=[0] + list(range(2, 2 + dims)))) < 1e-2
+
+
+SPLITK_CASES = [
+    # cin, cout, stride, transposed, n, input spatial -- layers of the 8^3 levels (<= 74 CTAs on the streaming kernel)
+    (256, 256, 1, False, 2, (8, 8, 8)),     # 8 tiles x 8 channel tiles -> clusters of 2
+    (128, 128, 1, False, 2, (8, 8, 8)),     # 8 x 4 -> clusters of 4
+    (64, 128, 2, False, 2, (16, 16, 16)),   # stride 2 into 8^3 (parity maps)
+    (128, 256, 1, False, 1, (6, 6, 6)),     # ragged tiles
+    (384, 64, 2, True, 1, (4, 4, 4)),       # ConvTranspose: 8 parity classes with 1..8 taps each
+]
+
+
+@pytest.mark.skipif(os.environ.get("B200SEG_TEST_SPLITK", "0") != "1",
+                    reason="experimental split-K cluster kernel: not yet validated on a GPU (B200SEG_TEST_SPLITK=1)")
+@pytest.mark.parametrize("cin,cout,s,tr,n,sp", SPLITK_CASES)
+def test_splitk_cluster_conv(cin, cout, s, tr, n, sp):
+    """Split-K cluster kernel (B200SEG_CONV_SPLIT_K) against the streaming kernel it replaces -- same MMAs in
+    another summation order: 2e-3 -- and torch fp32 (1e-2); fprop with statistics partials, dgrad with
+    residual + accumulate."""
+    lib = _lib.load()
+    dtype = torch.bfloat16
+    torch.manual_seed(4711)
+    g = ConvGeom(3, cin, cout, 3, s, tr)
+    w = q(torch.randn((cin, cout, 3, 3, 3) if tr else (cout, cin, 3, 3, 3)) * (2.0 / (cin * 27)) ** 0.5, dtype)
+    w.requires_grad_(True)
+    b = torch.randn(cout)
+    x = q(torch.randn(n, cin, *sp), dtype).requires_grad_(True)
+    y_ref = ref_conv(g, x, w, b)
+    dy = q(torch.randn_like(y_ref), dtype)
+    y_ref.backward(dy)
+
+    def dev(t_nc):
+        out = ops.alloc_activation(t_nc.shape[0], tuple(t_nc.shape[2:]), t_nc.shape[1], dtype, DEV)
+        out.copy_(t_nc.permute(0, 2, 3, 4, 1))
+        return out
+
+    wdev = w.detach().to(DEV)
+    x_cl, dy_cl = dev(x.detach()), dev(dy)
+    wp = ops.pack_weight(g, _lib.W_CONVTR_FPROP if tr else _lib.W_CONV_FPROP, wdev, dtype)
+    y0, y1 = ops.alloc_like(dy_cl), ops.alloc_like(dy_cl)
+    ops.conv_fprop(g, x_cl, wp, b.to(DEV), y0)
+    assert lib.b200seg_last_launch() == b"tc_conv"
+    ops.conv_fprop(g, x_cl, wp, b.to(DEV), y1, flags=_lib.CONV_SPLIT_K)
+    assert lib.b200seg_last_launch() == b"tc_conv_splitk"
+    assert rel(y1, y0) < 2e-3 and rel(nc_cpu(y1, 3), y_ref.detach()) < 1e-2
+    # statistics partials through the split kernel
+    c1, c0 = ops.alloc_like(dy_cl), ops.alloc_like(dy_cl)
+    h1 = ops.conv_fprop_partials(g, x_cl, wp, b.to(DEV), c1, flags=_lib.CONV_SPLIT_K)
+    h0 = ops.conv_fprop_partials(g, x_cl, wp, b.to(DEV), c0)
+    assert (h1 is None) == (h0 is None)
+    if h1 is not None:
+        a1, a0 = ops.alloc_like(c1), ops.alloc_like(c0)
+        alpha = torch.tensor([0.25], device=DEV)
+        m1, r1 = ops.instnorm_prelu_fwd_partials(c1, h1, alpha, a1)
+        m0, r0 = ops.instnorm_prelu_fwd_partials(c0, h0, alpha, a0)
+        assert rel(m1, m0) < 1e-4 and rel(r1, r0) < 1e-4 and rel(a1, a0) < 5e-3
+    # dgrad with residual + accumulate
+    wp_d = ops.pack_weight(g, _lib.W_CONVTR_DGRAD if tr else _lib.W_CONV_DGRAD, wdev, dtype)
+    addend, base = q(torch.randn_like(x.grad), dtype), q(torch.randn_like(x.grad), dtype)
+    dx0, dx1 = dev(base), dev(base)
+    ops.conv_dgrad(g, dy_cl, wp_d, dx0, residual=dev(addend), accumulate=True)
+    ops.conv_dgrad(g, dy_cl, wp_d, dx1, residual=dev(addend), accumulate=True, flags=_lib.CONV_SPLIT_K)
+    assert rel(dx1, dx0) < 4e-3 and rel(nc_cpu(dx1, 3), x.grad + addend + base) < 2e-2
 
 
 CONVTR_SLIDE = [
