@@ -221,5 +221,11 @@ class GraphedTrainStep:
         else:
             loss = self._fwd_bwd()
         if self.optimizer is not None:
+            if not hasattr(self.optimizer, "bind_grad_buffer"):
+                # a stock torch optimiser reads p.grad: keep it pointing at the bucket even after a
+                # zero_grad(set_to_none=True) by the caller
+                for p, v in zip(self.bucket.params, self.bucket.views):
+                    if p.grad is not v:
+                        p.grad = v
             self.optimizer.step()
         return loss

@@ -1,4 +1,5 @@
 #!/bin/bash
+# N-GPU box (gpurun --gpus 2): gradient-exchange check of GraphedTrainStep, then the 2-GPU bench line
 mkdir -p gpurun_out
 timeout 150 python -u -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 \
   scripts/ddp_overlap_check.py > gpurun_out/ddp_check.log 2> gpurun_out/ddp_check.err
