@@ -322,7 +322,7 @@ def roofline_probe(args, dev, dtype, pk):
                     "still takes ~100 us (scripts/ubench/mma_rate.cu, DESIGN.md section 3)",
             "algorithmic_bytes": bytes_alg, "algorithmic_flops": flops,
             "step_share_ncu": "this kernel: 6 launches = 11 % of the step's kernel time, the largest single kernel "
-                              "(profiles/r1_step_launch_summary.txt); InstanceNorm/PReLU passes together 22 % at "
+                              "(profiles/r1_step_launch_summary.txt); InstanceNorm/PReLU passes together 28 % at "
                               "4.3-6 TB/s for the full-resolution ones"}
 
 
