@@ -465,9 +465,9 @@ class UNet(nn.Module):
     def _wgrad(self, geom: ConvGeom, x, g, want_bias: bool = True, weight=None, bias=None):
         sink = self._grad_sink
         out_w = out_b = None
-        if sink is not None:
-            out_w = sink[weight]
-            out_b = sink[bias] if want_bias else None
+        if sink is not None:  # (a frozen parameter is not in the bucket: its gradient goes to a scratch tensor)
+            out_w = sink.get(weight)
+            out_b = sink.get(bias) if want_bias else None
         if not (self.wgrad_stream and x.is_cuda):
             return ops.conv_wgrad(geom, x, g, want_bias=want_bias, out_w=out_w, out_b=out_b)
         side = self._wgrad_side
@@ -511,7 +511,7 @@ class UNet(nn.Module):
             g_c = ops.alloc_like(c)
             sink = self._grad_sink
             dalpha = ops.instnorm_prelu_bwd(c, s["mean"], s["rstd"], m.act.weight.detach(), g_out, g_c, m.norm.eps,
-                                            out_dalpha=None if sink is None else sink[m.act.weight])
+                                            out_dalpha=None if sink is None else sink.get(m.act.weight))
             if sink is None:
                 grads[m.act.weight] = dalpha
         if getattr(self, "_bwd_taps", None) is not None:
