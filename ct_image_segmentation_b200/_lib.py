@@ -59,6 +59,9 @@ SIGNATURES = {
     "b200seg_softmax_loss_workspace_bytes": (C.c_size_t, [_P]),
     "b200seg_softmax_loss_fwd": (C.c_int, [_P, _P, _P, C.c_float, _P, _P, C.c_size_t, _P]),
     "b200seg_softmax_loss_bwd": (C.c_int, [_P, _P, _P, C.c_float, _P, _P, _P, _P, _P, _P]),
+    "b200seg_softmax_boundary_loss_workspace_bytes": (C.c_size_t, [_P]),
+    "b200seg_softmax_boundary_loss_fwd": (C.c_int, [_P, _P, _P, _P, C.c_float, _P, _P, C.c_size_t, _P]),
+    "b200seg_softmax_boundary_loss_bwd": (C.c_int, [_P, _P, _P, _P, C.c_float, _P, _P, _P, _P, _P, _P, _P]),
     "b200seg_adam_step": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int64, _P]),
     "b200seg_dice_loss_epilogue": (C.c_int, [_P, C.c_int32, C.c_int32, C.c_int32, C.c_float, C.c_int32, _P, _P, _P, _P]),
     "b200seg_conv_fprop_partials": (C.c_int, [_P, C.c_int32, _P, _P, _P, _P, _P, C.c_size_t, _P, _P, _P]),

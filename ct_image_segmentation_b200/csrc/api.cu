@@ -551,6 +551,37 @@ int b200seg_softmax_loss_bwd(const b200seg_dice_desc* d, const void* logits, con
   return launch_softmax_loss_bwd(*d, logits, labels, gamma, gI, gP, gF, gN, dlogits, as_stream(stream));
 }
 
+size_t b200seg_softmax_boundary_loss_workspace_bytes(const b200seg_dice_desc* d) {
+  return d ? boundary_workspace_bytes(*d) : 0;
+}
+
+int b200seg_softmax_boundary_loss_fwd(const b200seg_dice_desc* d, const void* logits, const void* labels,
+                                      const float* dist_maps, float gamma, float* sums6, void* workspace,
+                                      size_t workspace_bytes, void* stream) {
+  int rc = check_dice_desc(d);
+  if (rc) return rc;
+  B200SEG_CHECK_ARG(logits && labels && dist_maps && sums6 && workspace && gamma >= 0.f,
+                    "softmax_boundary_loss_fwd: bad argument");
+  if (workspace_bytes < boundary_workspace_bytes(*d)) {
+    set_error("softmax_boundary_loss_fwd: workspace %zu < required %zu", workspace_bytes,
+              boundary_workspace_bytes(*d));
+    return B200SEG_ERR_WORKSPACE;
+  }
+  return launch_softmax_boundary_loss_fwd(*d, logits, labels, dist_maps, gamma, sums6, workspace, as_stream(stream));
+}
+
+int b200seg_softmax_boundary_loss_bwd(const b200seg_dice_desc* d, const void* logits, const void* labels,
+                                      const float* dist_maps, float gamma, const float* gI, const float* gP,
+                                      const float* gF, const float* gN, const float* gB, void* dlogits,
+                                      void* stream) {
+  int rc = check_dice_desc(d);
+  if (rc) return rc;
+  B200SEG_CHECK_ARG(logits && labels && dist_maps && gI && gP && gF && gN && gB && dlogits,
+                    "softmax_boundary_loss_bwd: NULL pointer");
+  return launch_softmax_boundary_loss_bwd(*d, logits, labels, dist_maps, gamma, gI, gP, gF, gN, gB, dlogits,
+                                          as_stream(stream));
+}
+
 int b200seg_dice_loss_epilogue(const float* sums, int32_t n, int32_t c, int32_t include_background, float smooth,
                                int32_t mean, float* loss, float* gI, float* gP, void* stream) {
   B200SEG_CHECK_ARG(sums && loss && gI && gP && n > 0 && c > 0, "dice_loss_epilogue: bad argument");

@@ -219,19 +219,26 @@ softmax_dice_bwd_kernel(const T* __restrict__ logits, const void* __restrict__ l
 //   F = sum t_c (1 - p_c)^gamma (-log p_c)                              (monai FocalLoss, one-hot target)
 //   N = sum t_c (-log p_c)                                              (F.cross_entropy, plain or class-weighted)
 // log p = (z - max) - log sum exp, as log_softmax computes it.
-template <typename T, int CMAX, int LT, int CE = 0>
+// HAS_B: a sixth sum for the Boundary loss (capstone/models/losses.py:127-157),
+//   B = sum p_c * dist_{c-1}  (c >= 1; dist = pre-computed signed distance maps, planar (N, C-1, spatial) fp32)
+// and the row stride of `partial` / sums becomes 6.
+template <typename T, int CMAX, int LT, int CE = 0, bool HAS_B = false>
 __global__ void __launch_bounds__(kDiceThreads)
 softmax_loss_fwd_kernel(const T* __restrict__ logits, const void* __restrict__ labels, int64_t spatial, int C,
-                        int ld, int64_t vox_per_block, float gamma, float* __restrict__ partial, bool vec16) {
+                        int ld, int64_t vox_per_block, float gamma, float* __restrict__ partial, bool vec16,
+                        const float* __restrict__ dist = nullptr) {
   if constexpr (CE > 0) C = CE;
   constexpr int CL = CE > 0 ? CE : CMAX;
-  __shared__ float red[kDiceThreads / 32][CMAX * 5];
+  constexpr int NS = HAS_B ? 6 : 5;
+  __shared__ float red[kDiceThreads / 32][CMAX * NS];
   const int n = blockIdx.y;
   const int64_t v_begin = (int64_t)blockIdx.x * vox_per_block;
   const int64_t v_end = min(v_begin + vox_per_block, spatial);
-  float aI[CMAX], aG[CMAX], aP[CMAX], aF[CMAX], aN[CMAX];
+  float aI[CMAX], aG[CMAX], aP[CMAX], aF[CMAX], aN[CMAX], aB[HAS_B ? CMAX : 1];
 #pragma unroll
   for (int c = 0; c < CMAX; ++c) aI[c] = aG[c] = aP[c] = aF[c] = aN[c] = 0.f;
+#pragma unroll
+  for (int c = 0; c < (HAS_B ? CMAX : 1); ++c) aB[c] = 0.f;
   for (int64_t v = v_begin + threadIdx.x; v < v_end; v += kDiceThreads) {
     const int64_t vox = (int64_t)n * spatial + v;
     float p[CMAX], mx, ls;
@@ -251,6 +258,13 @@ softmax_loss_fwd_kernel(const T* __restrict__ logits, const void* __restrict__ l
       aF[c] += hit ? fw * nll : 0.f;
       aN[c] += hit ? nll : 0.f;
     }
+    if constexpr (HAS_B) {
+      // consecutive threads read consecutive voxels of one distance-map plane: coalesced
+      const float* dv = dist + (int64_t)n * (C - 1) * spatial + v;
+#pragma unroll
+      for (int c = 1; c < CL; ++c)
+        if (c < C) aB[c] = fmaf(p[c], dv[(int64_t)(c - 1) * spatial], aB[c]);
+    }
   }
   const int warp = threadIdx.x / 32, lane = threadIdx.x % 32;
 #pragma unroll
@@ -258,37 +272,44 @@ softmax_loss_fwd_kernel(const T* __restrict__ logits, const void* __restrict__ l
     const float i_ = warp_sum(aI[c]), g_ = warp_sum(aG[c]), p_ = warp_sum(aP[c]), f_ = warp_sum(aF[c]),
                 n_ = warp_sum(aN[c]);
     if (lane == 0) {
-      red[warp][c * 5 + 0] = i_;
-      red[warp][c * 5 + 1] = g_;
-      red[warp][c * 5 + 2] = p_;
-      red[warp][c * 5 + 3] = f_;
-      red[warp][c * 5 + 4] = n_;
+      red[warp][c * NS + 0] = i_;
+      red[warp][c * NS + 1] = g_;
+      red[warp][c * NS + 2] = p_;
+      red[warp][c * NS + 3] = f_;
+      red[warp][c * NS + 4] = n_;
+    }
+    if constexpr (HAS_B) {
+      const float b_ = warp_sum(aB[c]);
+      if (lane == 0) red[warp][c * NS + 5] = b_;
     }
   }
   __syncthreads();
-  if (threadIdx.x < C * 5) {
+  if (threadIdx.x < C * NS) {
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < kDiceThreads / 32; ++w) s += red[w][threadIdx.x];
-    partial[((int64_t)n * gridDim.x + blockIdx.x) * C * 5 + threadIdx.x] = s;
+    partial[((int64_t)n * gridDim.x + blockIdx.x) * C * NS + threadIdx.x] = s;
   }
 }
 
 // dlogits for d(loss)/d(sums5) = (gI, -, gP, gF, gN) per (n, c):
 //   dz_j = p_j (g_j - sum_k g_k p_k) + (delta_{lab,j} - p_j) * A,   g_c = gI_c t_c + gP_c,
 //   A = gF_lab * u f'(u) - gN_lab,  u = p_lab,  u f'(u) = -gamma (1-u)^(gamma-1) u nll - (1-u)^gamma
-template <typename T, int CMAX, int LT, int CE = 0>
+// HAS_B: g_c additionally carries gB_c * dist_{c-1}(v) (Boundary loss, see the forward kernel)
+template <typename T, int CMAX, int LT, int CE = 0, bool HAS_B = false>
 __global__ void __launch_bounds__(kDiceThreads)
 softmax_loss_bwd_kernel(const T* __restrict__ logits, const void* __restrict__ labels, const float* __restrict__ gI,
                         const float* __restrict__ gP, const float* __restrict__ gF, const float* __restrict__ gN,
-                        T* __restrict__ dlogits, int64_t spatial, int C, int ld, float gamma, bool vec16) {
+                        T* __restrict__ dlogits, int64_t spatial, int C, int ld, float gamma, bool vec16,
+                        const float* __restrict__ gB = nullptr, const float* __restrict__ dist = nullptr) {
   if constexpr (CE > 0) C = CE;
   constexpr int CL = CE > 0 ? CE : CMAX;
-  __shared__ float sF[CMAX], sN[CMAX];
+  __shared__ float sF[CMAX], sN[CMAX], sB[CMAX];
   const int n = blockIdx.y;
   if (threadIdx.x < CMAX) {
     sF[threadIdx.x] = threadIdx.x < C ? gF[n * C + threadIdx.x] : 0.f;
     sN[threadIdx.x] = threadIdx.x < C ? gN[n * C + threadIdx.x] : 0.f;
+    if constexpr (HAS_B) sB[threadIdx.x] = (threadIdx.x < C && threadIdx.x > 0) ? gB[n * C + threadIdx.x] : 0.f;
   }
   float cI[CMAX], cP[CMAX];
 #pragma unroll
@@ -320,6 +341,10 @@ softmax_loss_bwd_kernel(const T* __restrict__ logits, const void* __restrict__ l
     for (int c = 0; c < CMAX; ++c) {
       if (c < CL) {
         g[c] = (lab == c ? cI[c] : 0.f) + cP[c];
+        if constexpr (HAS_B) {
+          if (c >= 1 && c < C)
+            g[c] = fmaf(sB[c], dist[((int64_t)n * (C - 1) + (c - 1)) * spatial + v], g[c]);
+        }
         dot = fmaf(g[c], p[c], dot);
       } else {
         g[c] = 0.f;
@@ -713,6 +738,56 @@ int launch_softmax_loss_fwd(const b200seg_dice_desc& d, const void* logits, cons
   int total = d.n * d.c * 5;
   dice_sums_final_kernel<<<(total * 32 + 255) / 256, 256, 0, st>>>(partial, nb, d.c * 5, total, sums5);
   B200SEG_CHECK_LAUNCH("dice_sums_final");
+  return B200SEG_OK;
+}
+
+size_t boundary_workspace_bytes(const b200seg_dice_desc& d) {
+  return (size_t)d.n * dice_blocks(d.spatial, d.n) * d.c * 6 * sizeof(float) + 256;
+}
+
+int launch_softmax_boundary_loss_fwd(const b200seg_dice_desc& d, const void* logits, const void* labels,
+                                     const float* dist, float gamma, float* sums6, void* ws, cudaStream_t st) {
+  int nb = dice_blocks(d.spatial, d.n);
+  int64_t per = cdiv64(d.spatial, nb);
+  dim3 grid(nb, d.n);
+  float* partial = (float*)ws;
+  if (d.c > 16 || d.c < 2) { set_error("softmax_boundary_loss: 2..16 classes, got %d", d.c); return B200SEG_ERR_UNSUPPORTED; }
+  if (d.c == 10) {
+    DISPATCH_DICE10(d, (softmax_loss_fwd_kernel<T, 16, LT, 10, true><<<grid, kDiceThreads, 0, st>>>(
+                           (const T*)logits, labels, d.spatial, d.c, d.ld, per, gamma, partial,
+                           vec16_ok(d, logits, nullptr), dist)));
+  } else {
+    DISPATCH_DICE10(d, (softmax_loss_fwd_kernel<T, 16, LT, 0, true><<<grid, kDiceThreads, 0, st>>>(
+                           (const T*)logits, labels, d.spatial, d.c, d.ld, per, gamma, partial,
+                           vec16_ok(d, logits, nullptr), dist)));
+  }
+  B200SEG_CHECK_LAUNCH("softmax_boundary_loss_fwd");
+  int total = d.n * d.c * 6;
+  dice_sums_final_kernel<<<(total * 32 + 255) / 256, 256, 0, st>>>(partial, nb, d.c * 6, total, sums6);
+  B200SEG_CHECK_LAUNCH("dice_sums_final");
+  return B200SEG_OK;
+}
+
+int launch_softmax_boundary_loss_bwd(const b200seg_dice_desc& d, const void* logits, const void* labels,
+                                     const float* dist, float gamma, const float* gI, const float* gP,
+                                     const float* gF, const float* gN, const float* gB, void* dlogits,
+                                     cudaStream_t st) {
+  int64_t nb = cdiv64(d.spatial, kDiceThreads * 2);
+  int64_t cap = 4736 / (d.n > 0 ? d.n : 1);
+  if (cap < 1) cap = 1;
+  if (nb > cap) nb = cap;
+  dim3 grid((unsigned)nb, d.n);
+  if (d.c > 16 || d.c < 2) { set_error("softmax_boundary_loss: 2..16 classes, got %d", d.c); return B200SEG_ERR_UNSUPPORTED; }
+  if (d.c == 10) {
+    DISPATCH_DICE10(d, (softmax_loss_bwd_kernel<T, 16, LT, 10, true><<<grid, kDiceThreads, 0, st>>>(
+                           (const T*)logits, labels, gI, gP, gF, gN, (T*)dlogits, d.spatial, d.c, d.ld, gamma,
+                           vec16_ok(d, logits, dlogits), gB, dist)));
+  } else {
+    DISPATCH_DICE10(d, (softmax_loss_bwd_kernel<T, 16, LT, 0, true><<<grid, kDiceThreads, 0, st>>>(
+                           (const T*)logits, labels, gI, gP, gF, gN, (T*)dlogits, d.spatial, d.c, d.ld, gamma,
+                           vec16_ok(d, logits, dlogits), gB, dist)));
+  }
+  B200SEG_CHECK_LAUNCH("softmax_boundary_loss_bwd");
   return B200SEG_OK;
 }
 

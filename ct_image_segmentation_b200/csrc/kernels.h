@@ -89,6 +89,13 @@ int launch_softmax_loss_fwd(const b200seg_dice_desc& d, const void* logits, cons
 int launch_softmax_loss_bwd(const b200seg_dice_desc& d, const void* logits, const void* labels, float gamma,
                             const float* gI, const float* gP, const float* gF, const float* gN, void* dlogits,
                             cudaStream_t st);
+size_t boundary_workspace_bytes(const b200seg_dice_desc& d);
+int launch_softmax_boundary_loss_fwd(const b200seg_dice_desc& d, const void* logits, const void* labels,
+                                     const float* dist, float gamma, float* sums6, void* ws, cudaStream_t st);
+int launch_softmax_boundary_loss_bwd(const b200seg_dice_desc& d, const void* logits, const void* labels,
+                                     const float* dist, float gamma, const float* gI, const float* gP,
+                                     const float* gF, const float* gN, const float* gB, void* dlogits,
+                                     cudaStream_t st);
 int launch_dice_loss_epilogue(const float* sums, int n, int c, int c0, float smooth, float inv_count, float* loss,
                               float* gI, float* gP, cudaStream_t st);
 int launch_argmax_dice_counts(const b200seg_dice_desc& d, const void* logits, const void* target,

@@ -2,7 +2,7 @@
 
 * Pre-processed patients: the ``.npz`` files the reference writes with ``np.savez(image=..., masks=...,
   mask_indicator=...)`` (``capstone/data/process_miccai.py:96-131``): ``image`` (1, D, H, W) HU volume
-  (or (H, W) for a 2-D slice, ``:60-93``), ``masks`` (9, D, H, W) / (9, H, W) uint8 -- one binary mask per
+  (or (1, H, W) for a 2-D slice, ``:60-93``), ``masks`` (9, D, H, W) / (9, H, W) uint8 -- one binary mask per
   structure in ``STRUCTURES`` order -- and ``mask_indicator`` (9,) with 0 for structures that were not
   annotated.  ``PatientVolume.sampler`` puts the volume in HBM (int16 HU + squashed uint8 label map, fused
   ``b200seg_squash_masks``) behind the GPU patch sampler.
@@ -52,10 +52,16 @@ def load_patient_npz(path: Union[str, Path]) -> PatientVolume:
         if missing:
             raise KeyError(f"{path}: not a reference .npz (missing {sorted(missing)})")
         image, masks, ind = z["image"], z["masks"], z["mask_indicator"]
-    if image.ndim == 4 and image.shape[0] == 1:
-        image = image[0]
-    if image.ndim == 2:  # 2-D slice files
+    if masks.ndim == 3:
+        # 2-D slice files (``_patient_to_2d``, ``capstone/data/process_miccai.py:60-93``): ``image`` is
+        # ``vol[:, index]`` = (1, H, W) -- the leading axis is the CHANNEL, not a depth -- and ``masks`` (9, H, W)
+        if image.ndim == 3 and image.shape[0] == 1:
+            image = image[0]
+        if image.ndim != 2:
+            raise ValueError(f"{path}: 2-D masks {masks.shape} need an (H, W) or (1, H, W) image, got {image.shape}")
         image, masks = image[None], masks[:, None]
+    elif image.ndim == 4 and image.shape[0] == 1:
+        image = image[0]
     if image.ndim != 3 or masks.ndim != 4 or masks.shape[1:] != image.shape:
         raise ValueError(f"{path}: image {image.shape} / masks {masks.shape} are not (D, H, W) / (S, D, H, W)")
     if masks.shape[0] != len(STRUCTURES) or ind.shape != (len(STRUCTURES),):
@@ -76,11 +82,24 @@ def save_patient_npz(path: Union[str, Path], image: np.ndarray, masks: np.ndarra
     np.savez(str(path), image=image, masks=np.asarray(masks), mask_indicator=np.asarray(mask_indicator))
 
 
-def unet_state_dict_from_checkpoint(ckpt: Union[str, Path, Dict]) -> Dict[str, torch.Tensor]:
+def _load_checkpoint_file(path: Union[str, Path], allow_pickle: bool = False) -> Dict:
+    """``torch.load`` restricted to tensors and plain containers (``weights_only=True``).  Lightning checkpoints
+    whose ``hyper_parameters`` hold arbitrary pickled objects need the explicit opt-in ``allow_pickle=True``
+    (arbitrary code execution on load: only for files you trust)."""
+    try:
+        return torch.load(str(path), map_location="cpu", weights_only=True)
+    except Exception as e:  # noqa: BLE001
+        if not allow_pickle:
+            raise RuntimeError(f"{path}: not loadable with weights_only=True ({e}); pass allow_pickle=True "
+                               f"if the file is trusted") from e
+        return torch.load(str(path), map_location="cpu", weights_only=False)
+
+
+def unet_state_dict_from_checkpoint(ckpt: Union[str, Path, Dict], allow_pickle: bool = False) -> Dict[str, torch.Tensor]:
     """The U-Net's ``state_dict`` out of a reference Lightning checkpoint (file or already-loaded dict):
     keys ``unet.model...`` -> ``model...``; a plain U-Net state dict passes through."""
     if not isinstance(ckpt, dict):
-        ckpt = torch.load(str(ckpt), map_location="cpu", weights_only=False)
+        ckpt = _load_checkpoint_file(ckpt, allow_pickle)
     sd = ckpt.get("state_dict", ckpt)
     out = {k[len("unet."):]: v for k, v in sd.items() if k.startswith("unet.")}
     if not out:
@@ -90,9 +109,9 @@ def unet_state_dict_from_checkpoint(ckpt: Union[str, Path, Dict]) -> Dict[str, t
     return out
 
 
-def load_lightning_checkpoint(ckpt: Union[str, Path, Dict], net: torch.nn.Module) -> Dict:
+def load_lightning_checkpoint(ckpt: Union[str, Path, Dict], net: torch.nn.Module, allow_pickle: bool = False) -> Dict:
     """Load the reference's released weights (``model_large.ckpt`` / ``model_mixup.ckpt``) into a b200seg
     ``UNet`` built with the same hyper-parameters; returns the checkpoint's ``hyper_parameters``."""
-    loaded = ckpt if isinstance(ckpt, dict) else torch.load(str(ckpt), map_location="cpu", weights_only=False)
+    loaded = ckpt if isinstance(ckpt, dict) else _load_checkpoint_file(ckpt, allow_pickle)
     net.load_state_dict(unet_state_dict_from_checkpoint(loaded), strict=True)
     return dict(loaded.get("hyper_parameters", {})) if isinstance(loaded, dict) else {}

@@ -83,11 +83,32 @@ class _SoftmaxLossSums(torch.autograd.Function):
         return ops.softmax_loss_bwd(logits_cl, labels, ctx.gamma, g[..., 0], g[..., 2], g[..., 3], g[..., 4]), None, None
 
 
-def softmax_loss_sums(input: torch.Tensor, target: torch.Tensor, gamma: float = 2.0) -> torch.Tensor:
-    """One softmax pass for every voxel-wise loss of the reference: (B, C, 5) = [I, G, P, F, N]."""
+class _SoftmaxBoundaryLossSums(torch.autograd.Function):
+    """(B, C, 6) = [I, G, P, F, N, B] of ``b200seg_softmax_boundary_loss_fwd``: the shared pass with the Boundary
+    loss's ``sum p_c * dist_{c-1}`` as a sixth accumulated sum."""
+
+    @staticmethod
+    def forward(ctx, logits_cl, labels, dist_maps, gamma):
+        ctx.save_for_backward(logits_cl, labels, dist_maps)
+        ctx.gamma = gamma
+        return ops.softmax_boundary_loss_sums(logits_cl, labels, dist_maps, gamma)
+
+    @staticmethod
+    def backward(ctx, g):
+        logits_cl, labels, dist_maps = ctx.saved_tensors
+        return ops.softmax_boundary_loss_bwd(logits_cl, labels, dist_maps, ctx.gamma, g[..., 0], g[..., 2],
+                                             g[..., 3], g[..., 4], g[..., 5]), None, None, None
+
+
+def softmax_loss_sums(input: torch.Tensor, target: torch.Tensor, gamma: float = 2.0,
+                      dist_maps: torch.Tensor = None) -> torch.Tensor:
+    """One softmax pass for every voxel-wise loss of the reference: (B, C, 5) = [I, G, P, F, N]; with
+    ``dist_maps`` (B, C-1, *S) a sixth column B = sum p_c * dist_{c-1} (Boundary loss)."""
     cl = _as_cl(input)
     if target.dim() == cl.dim() and target.shape[1] == 1:
         target = target[:, 0]
+    if dist_maps is not None:
+        return _SoftmaxBoundaryLossSums.apply(cl, target, dist_maps, float(gamma))
     return _SoftmaxLossSums.apply(cl, target, float(gamma))
 
 
@@ -201,6 +222,28 @@ class FocalLoss(nn.Module):
         return f
 
 
+class BoundaryLoss(nn.Module):
+    """The reference's ``BoundaryLossWrapper`` arithmetic (``capstone/models/losses.py:127-157``):
+    ``softmax(input, 1)[:, 1:] * dist_maps`` averaged over everything (``mean``) or over the spatial axes
+    (``none`` -> (B, C-1)); ``dist_maps`` (B, C-1, *S) are the dataset's pre-computed signed distance maps
+    (``capstone/data/utils.py:10-26``).  Needs no labels; when it shares the softmax pass with other losses the
+    sums come in through ``sums`` (column 5)."""
+
+    def __init__(self, reduction: str = "mean"):
+        super().__init__()
+        if reduction not in ("none", "mean"):
+            raise AssertionError("reduction must be 'none' or 'mean'")
+        self.reduction = reduction
+
+    def forward(self, input, dist_maps, sums=None):
+        if sums is None:
+            b = input.shape[0]
+            dummy = torch.zeros((b, 1) + tuple(input.shape[2:]), dtype=torch.uint8, device=input.device)
+            sums = softmax_loss_sums(input, dummy, dist_maps=dist_maps)
+        per = sums[:, 1:, 5] / float(_n_voxels(input))  # (B, C-1): spatial mean per sample and class
+        return per if self.reduction == "none" else per.mean()
+
+
 class CrossEntropyLoss(nn.Module):
     """``F.cross_entropy(input, target[, weight])`` (mean reduction) as the reference's
     ``CrossEntropyWrapper`` / ``WeightedCrossEntropyWrapper`` call it (``capstone/models/losses.py:45-68``)."""
@@ -276,6 +319,20 @@ class WeightedCrossEntropyWrapper(CrossEntropyWrapper):
         self.loss_fx = CrossEntropyLoss(weight=list(WEIGHT.values()))
 
 
+class BoundaryLossWrapper(nn.Module):
+    """``BoundaryLossWrapper(reduction)(input, dist_maps)`` (reference ``capstone/models/losses.py:127-157``; the
+    2-D ndim asserts are dropped as in the 3-D twins of the other wrappers)."""
+
+    def __init__(self, reduction="mean"):
+        super().__init__()
+        assert reduction in ["none", "mean"]
+        self.reduction = reduction
+        self.loss_fx = BoundaryLoss(reduction=reduction)
+
+    def forward(self, input, dist_maps):
+        return self.loss_fx(input, dist_maps)
+
+
 DiceLossWrapper3D = DiceLossWrapper
 GeneralizedDiceLossWrapper3D = GeneralizedDiceLossWrapper
 FocalLossWrapper3D = FocalLossWrapper
@@ -283,7 +340,8 @@ CrossEntropyWrapper3D = CrossEntropyWrapper
 WeightedCrossEntropyWrapper3D = WeightedCrossEntropyWrapper
 
 LOSSES = {"CrossEntropy": CrossEntropyWrapper, "WeightedCrossEntropy": WeightedCrossEntropyWrapper,
-          "Focal": FocalLossWrapper, "Dice": DiceLossWrapper, "GeneralizedDice": GeneralizedDiceLossWrapper}
+          "Focal": FocalLossWrapper, "Dice": DiceLossWrapper, "GeneralizedDice": GeneralizedDiceLossWrapper,
+          "Boundary": BoundaryLossWrapper}
 
 
 def apply_missing_mask(name, loss, mask_indicator):
@@ -318,14 +376,19 @@ class MultipleLossWrapper(nn.Module):
         values = {}
         if mask_indicator is not None:
             mask_indicator = mask_indicator.float()
-        # Focal / CrossEntropy present: ONE softmax pass feeds every requested loss (the reference runs a
+        if "Boundary" in self.losses:
+            assert dist_maps is not None, "Distance maps are required for using boundary loss"
+        # Focal / CrossEntropy / Boundary present: ONE softmax pass feeds every requested loss (the reference runs a
         # softmax / log_softmax per loss); Dice alone keeps its 3-sum kernel and one-launch epilogue
         shared = None
-        if any(n in ("Focal", "CrossEntropy", "WeightedCrossEntropy") for n in self.losses):
-            shared = softmax_loss_sums(input, target.unsqueeze(1))
+        if any(n in ("Focal", "CrossEntropy", "WeightedCrossEntropy", "Boundary") for n in self.losses):
+            shared = softmax_loss_sums(input, target.unsqueeze(1),
+                                       dist_maps=dist_maps if "Boundary" in self.losses else None)
         for name, fx in self.losses.items():
             if shared is None:
                 loss = fx(input, target)
+            elif name == "Boundary":
+                loss = fx.loss_fx(input, dist_maps, sums=shared)
             elif name in ("CrossEntropy", "WeightedCrossEntropy"):
                 loss = fx.loss_fx(input, target, sums=shared)
             else:

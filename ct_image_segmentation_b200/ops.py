@@ -576,6 +576,51 @@ def softmax_loss_bwd(logits, labels, gamma, g_i, g_p, g_f, g_n) -> torch.Tensor:
     return dlogits
 
 
+def _dist_maps(dist: torch.Tensor, n: int, c: int, spatial: int) -> torch.Tensor:
+    """Planar (N, C-1, spatial) fp32 distance maps as the dataset delivers them ((N, C-1, *S), any float dtype)."""
+    if not dist.is_cuda:
+        raise RuntimeError("b200seg ops run on CUDA tensors only (no CPU fallback)")
+    if dist.shape[0] != n or dist.shape[1] != c - 1 or dist[0, 0].numel() != spatial:
+        raise ValueError(f"distance maps {tuple(dist.shape)} do not match logits (N={n}, C-1={c - 1}, {spatial} voxels)")
+    return dist.reshape(n, c - 1, spatial).float().contiguous()
+
+
+def softmax_boundary_loss_sums(logits, labels, dist, gamma: float = 2.0) -> torch.Tensor:
+    """(N, C, 6) fp32: softmax_loss_sums plus B = sum_v p_c * dist_{c-1} (Boundary loss; B[:, 0] = 0)."""
+    lib = _lib.load()
+    n, d, h, w, c, ld = cl_info(logits)
+    labels, code = _labels(labels, n, d * h * w)
+    dist = _dist_maps(dist, n, c, d * h * w)
+    desc = _dice_desc(logits, code)
+    sums = torch.empty(n, c, 6, dtype=torch.float32, device=logits.device)
+    ws = workspace(lib.b200seg_softmax_boundary_loss_workspace_bytes(C.byref(desc)), logits.device)
+    _lib.check(lib.b200seg_softmax_boundary_loss_fwd(C.byref(desc), logits.data_ptr(), labels.data_ptr(),
+                                                     dist.data_ptr(), float(gamma), sums.data_ptr(), ws.data_ptr(),
+                                                     ws.numel(), _stream()), "b200seg_softmax_boundary_loss_fwd")
+    return sums
+
+
+def softmax_boundary_loss_bwd(logits, labels, dist, gamma, g_i, g_p, g_f, g_n, g_b) -> torch.Tensor:
+    lib = _lib.load()
+    n, d, h, w, c, ld = cl_info(logits)
+    labels, code = _labels(labels, n, d * h * w)
+    dist = _dist_maps(dist, n, c, d * h * w)
+    if ld > c:  # keep the (zero) channel padding of the logits buffer
+        dlogits = alloc_activation(n, (d, h, w), c, logits.dtype, logits.device)
+        if cl_info(dlogits)[5] != ld:
+            dlogits = torch.zeros((n, d, h, w, ld), dtype=logits.dtype, device=logits.device)[..., :c]
+    else:
+        dlogits = torch.empty(logits.shape, dtype=logits.dtype, device=logits.device)
+    gs = [g.contiguous().float() for g in (g_i, g_p, g_f, g_n, g_b)]
+    desc = _dice_desc(logits, code)
+    _lib.check(lib.b200seg_softmax_boundary_loss_bwd(C.byref(desc), logits.data_ptr(), labels.data_ptr(),
+                                                     dist.data_ptr(), float(gamma), gs[0].data_ptr(),
+                                                     gs[1].data_ptr(), gs[2].data_ptr(), gs[3].data_ptr(),
+                                                     gs[4].data_ptr(), dlogits.data_ptr(), _stream()),
+               "b200seg_softmax_boundary_loss_bwd")
+    return dlogits
+
+
 def dice_loss_epilogue(sums: torch.Tensor, include_background: bool, smooth: float, mean: bool):
     """(loss scalar, gI (N, C), gP (N, C)) from the (N, C, 3) Dice sums -- one launch."""
     lib = _lib.load()

@@ -265,6 +265,20 @@ int b200seg_softmax_loss_bwd(const b200seg_dice_desc* d, const void* logits, con
                              const float* gI, const float* gP, const float* gF, const float* gN, void* dlogits,
                              void* stream);
 
+/* The same pass with the Boundary loss added (capstone/models/losses.py:127-157: BoundaryLossWrapper =
+ * mean(softmax(x)[:, 1:] * dist_maps); dispatched at :186-191 with the batch's pre-computed signed distance maps,
+ * capstone/data/utils.py:10-26): sums6[n][c][6] = {I, G, P, F, N, B},  B = sum_v p_c(v) * dist_maps[n][c-1][v]
+ * for c >= 1 (B[.,0] = 0).  dist_maps is PLANAR (n, c-1, spatial) fp32 as the dataset delivers it.  bwd takes the
+ * extra coefficient gB = d loss / d B (n*c floats; entry 0 of every row ignored). */
+size_t b200seg_softmax_boundary_loss_workspace_bytes(const b200seg_dice_desc* d);
+int b200seg_softmax_boundary_loss_fwd(const b200seg_dice_desc* d, const void* logits, const void* labels,
+                                      const float* dist_maps, float gamma, float* sums6, void* workspace,
+                                      size_t workspace_bytes, void* stream);
+int b200seg_softmax_boundary_loss_bwd(const b200seg_dice_desc* d, const void* logits, const void* labels,
+                                      const float* dist_maps, float gamma, const float* gI, const float* gP,
+                                      const float* gF, const float* gN, const float* gB, void* dlogits,
+                                      void* stream);
+
 /* Dice loss value and gradient coefficients from the (n, c, 3) sums of b200seg_softmax_dice_fwd, in one
  * launch: the arithmetic of monai.losses.DiceLoss.forward after the spatial sums
  * (capstone/models/losses.py:80-85 configures it; formula in SURVEY.md A.6):

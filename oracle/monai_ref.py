@@ -26,6 +26,8 @@ Pinning status
   importing that file (``tests/golden/make_golden.py``).
 * Dice metric / reductions / mask squashing / missing-annotation masking /
   HU windowing: pinned against the reference's own functions the same way.
+* ``GeneralizedDiceLoss`` ("square" / "simple" weights incl. the inf -> max rule) and ``BoundaryLoss``: pinned
+  against the reference's own ``capstone/models/temp.py`` / ``capstone/models/losses.py`` classes the same way.
 """
 from __future__ import annotations
 
@@ -221,6 +223,55 @@ class DiceLoss(nn.Module):
         raise ValueError(self.reduction)
 
 
+class GeneralizedDiceLoss(nn.Module):
+    """The reference's in-tree ``GeneralizedDiceLoss`` (``capstone/models/temp.py:17-170``; softmax, one-hot target,
+    ``batch=False``): per (n, c) ``1 - (2 I w + s) / ((G + P) w + s)`` with ``w = 1/G^2`` ("square"), ``1/G``
+    ("simple") or 1 ("uniform"); infinite weights (class absent from the sample) become the largest finite weight
+    of that sample (``:146-152``).  Pinned by fixtures made from that file (``tests/golden/make_golden.py``)."""
+
+    def __init__(self, include_background=True, to_onehot_y=False, softmax=False, w_type="square",
+                 reduction="mean", smooth_nr=1e-5, smooth_dr=1e-5):
+        super().__init__()
+        self.include_background, self.to_onehot_y, self.softmax = include_background, to_onehot_y, softmax
+        self.w_type, self.reduction, self.smooth_nr, self.smooth_dr = w_type, reduction, smooth_nr, smooth_dr
+
+    def forward(self, input, target):
+        c = input.shape[1]
+        p = torch.softmax(input, 1) if (self.softmax and c > 1) else input
+        t = one_hot(target, c) if (self.to_onehot_y and c > 1) else target
+        if not self.include_background and c > 1:
+            p, t = p[:, 1:], t[:, 1:]
+        axes = list(range(2, p.ndim))
+        inter, ground, pred = (t * p).sum(axes), t.sum(axes), p.sum(axes)
+        g = ground.float()
+        w = {"simple": torch.reciprocal(g), "square": torch.reciprocal(g * g)}.get(self.w_type, torch.ones_like(g))
+        for row in w:
+            infs = torch.isinf(row)
+            row[infs] = 0.0
+            row[infs] = torch.max(row)
+        f = 1.0 - (2.0 * (inter * w) + self.smooth_nr) / ((ground + pred) * w + self.smooth_dr)
+        if self.reduction == "mean":
+            return f.mean()
+        if self.reduction == "sum":
+            return f.sum()
+        return f
+
+
+class BoundaryLoss(nn.Module):
+    """``BoundaryLossWrapper`` of the reference (``capstone/models/losses.py:127-157``): ``softmax(input)[:, 1:] *
+    dist_maps``, mean over everything or over the spatial axes.  Pinned by fixtures made from that class."""
+
+    def __init__(self, reduction="mean"):
+        super().__init__()
+        self.reduction = reduction
+
+    def forward(self, input, dist_maps):
+        loss = torch.softmax(input, dim=1)[:, 1:] * dist_maps.type_as(input)
+        if self.reduction == "none":
+            return loss.mean(dim=tuple(range(2, loss.ndim)))
+        return loss.mean()
+
+
 class FocalLoss(nn.Module):
     """``monai.losses.FocalLoss`` (0.3), gamma=2, one-hot target path
     (reference ``capstone/models/losses.py:105-124``).  **parity unpinned**."""
@@ -272,12 +323,18 @@ class MultipleLossWrapper(nn.Module):
         self.exclude_missing = exclude_missing
         self.reduction = "none" if exclude_missing else "mean"
 
-    def forward(self, input, target, mask_indicator=None):
+    def forward(self, input, target, mask_indicator=None, dist_maps=None):
         out = {}
         if mask_indicator is not None:
             mask_indicator = mask_indicator.type_as(input)
         for name in self.names:
-            if name == "Dice":
+            if name == "Boundary":
+                assert dist_maps is not None, "Distance maps are required for using boundary loss"
+                v = BoundaryLoss(reduction=self.reduction)(input, dist_maps)
+            elif name == "GeneralizedDice":
+                v = GeneralizedDiceLoss(include_background=False, to_onehot_y=True, softmax=True,
+                                        reduction=self.reduction)(input, target.unsqueeze(1))
+            elif name == "Dice":
                 v = DiceLoss(include_background=False, to_onehot_y=True, softmax=True,
                              reduction=self.reduction)(input, target.unsqueeze(1))
             elif name == "Focal":
@@ -389,10 +446,32 @@ def _scan_starts(size, roi, overlap):
     return [min(k * interval, size - roi) for k in range(n)]
 
 
-def sliding_window_inference(inputs, roi_size, sw_batch_size, predictor, overlap=0.25):
-    """Constant-importance sliding window; batch 1; **parity unpinned** (absent from the
+def importance_map(roi_size, mode="constant", sigma_scale=0.125):
+    """MONAI ``compute_importance_map``: ones, or a Gaussian centred on the window (sigma = sigma_scale * roi per
+    axis), normalised to max 1 with its zeros lifted to the smallest positive value.
+    **parity unpinned** (MONAI semantics from memory)."""
+    if mode == "constant":
+        return torch.ones(tuple(roi_size), dtype=torch.float32)
+    if mode != "gaussian":
+        raise ValueError(mode)
+    imp = torch.ones((), dtype=torch.float64)
+    for k, r in enumerate(roi_size):
+        x = torch.arange(r, dtype=torch.float64) - (r // 2)  # a unit impulse at r // 2, Gaussian-filtered
+        g = torch.exp(-0.5 * (x / (sigma_scale * r)) ** 2)
+        shape = [1] * len(roi_size)
+        shape[k] = r
+        imp = imp * g.reshape(shape)
+    imp = imp / imp.max()
+    imp = imp.float()
+    pos = imp[imp > 0]
+    return torch.clamp(imp, min=float(pos.min()))
+
+
+def sliding_window_inference(inputs, roi_size, sw_batch_size, predictor, overlap=0.25, mode="constant"):
+    """Sliding window with constant or Gaussian importance; batch 1; **parity unpinned** (absent from the
     reference, F6)."""
     assert inputs.shape[0] == 1
+    imp = importance_map(roi_size, mode)
     dims = inputs.shape[2:]
     pad = []
     for sz, r in zip(reversed(dims), reversed(roi_size)):
@@ -412,8 +491,8 @@ def sliding_window_inference(inputs, roi_size, sw_batch_size, predictor, overlap
         if out is None:
             out = torch.zeros((1, pred.shape[1]) + tuple(pdims), dtype=torch.float32)
         for j, (a, b, c) in enumerate(chunk):
-            out[:, :, a:a + roi_size[0], b:b + roi_size[1], c:c + roi_size[2]] += pred[j:j + 1]
-            cnt[:, :, a:a + roi_size[0], b:b + roi_size[1], c:c + roi_size[2]] += 1
+            out[:, :, a:a + roi_size[0], b:b + roi_size[1], c:c + roi_size[2]] += pred[j:j + 1] * imp
+            cnt[:, :, a:a + roi_size[0], b:b + roi_size[1], c:c + roi_size[2]] += imp
     out = out / cnt
     sl = [slice(None), slice(None)]
     for k, (sz, r) in enumerate(zip(dims, roi_size)):

@@ -12,7 +12,8 @@ OUTPUT is recorded is the reference's own code, executed unmodified from
 * ``capstone/models/temp.py``: ``GeneralizedDiceLoss`` (with ``w_type="uniform"``
   it is exactly the MONAI-0.3 DiceLoss formula), ``compute_meandice``,
   ``do_metric_reduction``
-* ``capstone/models/losses.py``: ``apply_missing_mask``
+* ``capstone/models/losses.py``: ``apply_missing_mask``, ``BoundaryLossWrapper``, ``MultipleLossWrapper``
+  (with the Boundary loss, the only entry of its table that needs no monai class)
 * ``capstone/models/metrics.py``: ``DiceMetricWrapper`` (via the 3D subclass)
 * ``capstone/volumetric/utils.py``: ``_squash_masks_3D``;
   ``capstone/training/utils.py``: ``_squash_masks``, ``_squash_predictions``
@@ -227,6 +228,55 @@ def main():
         out[f"window_{name}"] = apply_window(hu, w, l)
         out[f"window_{name}_cfg"] = np.asarray([w, l])
     out["window_soft_noshift"] = apply_window(hu, *WINDOWING_CONFIG["soft_tissue"], shift=False)
+
+    # --- round 2 additions (appended so that the RNG stream of everything above is unchanged) ---------------
+    # GeneralizedDiceLoss with the reference's own default weighting ("square") and "simple", incl. the inf -> max
+    # rule (capstone/models/temp.py:146-152): the sparse labels have classes with no voxel in sample 1
+    for wt in ("square", "simple"):
+        for tag, lab in (("dense", lab_dense), ("sparse", lab_sparse)):
+            for red in ("mean", "none"):
+                fx = ref_temp.GeneralizedDiceLoss(include_background=False, to_onehot_y=True,
+                                                  softmax=True, w_type=wt, reduction=red)
+                lg = logits.clone().requires_grad_(True)
+                v = fx(lg, lab.unsqueeze(1))
+                out[f"gdl_{wt}_{tag}_{red}"] = v.detach().numpy()
+                if red == "mean":
+                    v.backward()
+                    out[f"gdl_{wt}_{tag}_grad"] = lg.grad.numpy()
+
+    # Boundary loss (capstone/models/losses.py:127-157) on 2-D logits with signed distance maps.  The maps are
+    # INPUTS: built here with scipy the way capstone/data/utils.py:10-26 does (that file itself uses np.bool,
+    # removed from current numpy, and cannot run).
+    from capstone.models.losses import BoundaryLossWrapper as RefBoundary
+    from capstone.models.losses import MultipleLossWrapper as RefMultiple
+    from scipy.ndimage import distance_transform_edt as edt
+    mb = m2.numpy().astype(bool)                      # (2, 9, 24, 20)
+    dist = np.zeros(mb.shape, dtype=np.float32)
+    for i in range(mb.shape[0]):
+        for c in range(mb.shape[1]):
+            pos = mb[i, c]
+            if pos.any():
+                neg = ~pos
+                dist[i, c] = edt(neg) * neg - (edt(pos) - 1) * pos
+    dist /= 255.0
+    dist_t = torch.from_numpy(dist)
+    logits_b = torch.randn(2, C, 24, 20) * 2.0
+    out["boundary_logits"] = logits_b.numpy()
+    out["boundary_dist"] = dist
+    for red in ("mean", "none"):
+        lg = logits_b.clone().requires_grad_(True)
+        v = RefBoundary(reduction=red)(lg, dist_t)
+        out[f"boundary_{red}"] = v.detach().numpy()
+        if red == "mean":
+            v.backward()
+            out["boundary_grad"] = lg.grad.numpy()
+    lab_b = _squash_masks(m2, C, "cpu")
+    out["boundary_lab"] = lab_b.numpy().astype(np.uint8)
+    lg = logits_b.clone().requires_grad_(True)
+    vals = RefMultiple(["Boundary"], exclude_missing=True)(lg, lab_b, ind.clone(), dist_t)
+    out["boundary_missing"] = vals["Boundary"].detach().numpy()
+    vals["Boundary"].backward()
+    out["boundary_missing_grad"] = lg.grad.numpy()
 
     path = os.path.join(HERE, "ref_intree.npz")
     np.savez_compressed(path, **out)

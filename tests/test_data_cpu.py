@@ -26,9 +26,16 @@ def test_patient_npz_roundtrip(tmp_path):
     q = data.load_patient_npz(tmp_path / "again.npz")
     assert np.array_equal(q.image, p.image) and np.array_equal(q.masks, p.masks)
     # 2-D slice layout of _patient_to_2d
-    np.savez(tmp_path / "s.npz", image=vol[0, 2], masks=masks[:, 2], mask_indicator=ind)
+    # (capstone/data/process_miccai.py:64: slide = vol[:, index] keeps the channel axis: (1, H, W))
+    np.savez(tmp_path / "s.npz", image=vol[:, 2], masks=masks[:, 2], mask_indicator=ind)
     s = data.load_patient_npz(tmp_path / "s.npz")
     assert s.image.shape == (1, 10, 12) and s.masks.shape == (9, 1, 10, 12)
+    assert np.array_equal(s.image[0], vol[0, 2].astype(np.int16)) and np.array_equal(s.masks[:, 0], masks[:, 2])
+    np.savez(tmp_path / "s2.npz", image=vol[0, 2], masks=masks[:, 2], mask_indicator=ind)  # bare (H, W) also accepted
+    assert np.array_equal(data.load_patient_npz(tmp_path / "s2.npz").image, s.image)
+    np.savez(tmp_path / "s3.npz", image=vol[0, :2], masks=masks[:, 2], mask_indicator=ind)  # 2 "channels": refuse
+    with pytest.raises(ValueError):
+        data.load_patient_npz(tmp_path / "s3.npz")
     np.savez(tmp_path / "bad.npz", image=vol)
     with pytest.raises(KeyError):
         data.load_patient_npz(tmp_path / "bad.npz")

@@ -678,6 +678,70 @@ def test_dice_loss_2d_and_missing_mask(golden):
         assert abs(out["Dice"].item() - float(golden[out_key])) < 1e-5
 
 
+@pytest.mark.parametrize("wt", ["square", "simple", "uniform"])
+@pytest.mark.parametrize("tag", ["dense", "sparse"])
+def test_generalized_dice_golden(golden, wt, tag):
+    """losses.GeneralizedDiceLoss vs the reference's own capstone/models/temp.py class: default "square" weights,
+    "simple", and the inf -> max rule (sparse labels: classes absent from a sample), value / (B, 9) matrix / gradient."""
+    logits = torch.from_numpy(golden["dice_logits"]).to(DEV).requires_grad_(True)
+    lab = torch.from_numpy(golden[f"dice_lab_{tag}"]).to(DEV).unsqueeze(1)
+    key = f"gdl_{wt}_{tag}" if wt != "uniform" else f"dice_{tag}"
+    v = losses.GeneralizedDiceLoss(include_background=False, to_onehot_y=True, softmax=True, w_type=wt)(logits, lab)
+    v.backward()
+    assert abs(v.item() - float(golden[f"{key}_mean"])) < 1e-5
+    assert rel(logits.grad, torch.from_numpy(golden[f"{key}_grad"])) < 1e-4
+    fxn = losses.GeneralizedDiceLoss(include_background=False, to_onehot_y=True, softmax=True, w_type=wt,
+                                     reduction="none")
+    np.testing.assert_allclose(fxn(logits.detach(), lab).cpu().numpy(), golden[f"{key}_none"], rtol=1e-4, atol=2e-6)
+    if wt == "square":  # the wrapper the LOSSES table builds (reference default w_type)
+        w = losses.MultipleLossWrapper(["GeneralizedDice"])(logits.detach(), lab[:, 0])
+        assert abs(w["GeneralizedDice"].item() - float(golden[f"{key}_mean"])) < 1e-5
+
+
+def test_boundary_loss_golden(golden):
+    """Boundary loss (sixth sum of the shared softmax pass) vs the reference's own BoundaryLossWrapper /
+    MultipleLossWrapper(["Boundary"], exclude_missing=True): values, (B, 9) matrix, logit gradients."""
+    logits = torch.from_numpy(golden["boundary_logits"]).to(DEV).requires_grad_(True)
+    dist = torch.from_numpy(golden["boundary_dist"]).to(DEV)
+    v = losses.BoundaryLossWrapper("mean")(logits, dist)
+    v.backward()
+    assert abs(v.item() - float(golden["boundary_mean"])) < 1e-7
+    assert rel(logits.grad, torch.from_numpy(golden["boundary_grad"])) < 1e-4
+    none = losses.BoundaryLossWrapper("none")(logits.detach(), dist)
+    np.testing.assert_allclose(none.cpu().numpy(), golden["boundary_none"], rtol=1e-4, atol=1e-9)
+    lab = torch.from_numpy(golden["boundary_lab"]).to(DEV)
+    ind = torch.from_numpy(golden["indicator"]).to(DEV)
+    logits.grad = None
+    out = losses.MultipleLossWrapper(["Boundary"], exclude_missing=True)(logits, lab, ind, dist)
+    out["Boundary"].backward()
+    assert abs(out["Boundary"].item() - float(golden["boundary_missing"])) < 1e-7
+    assert rel(logits.grad, torch.from_numpy(golden["boundary_missing_grad"])) < 1e-4
+    with pytest.raises(AssertionError):
+        losses.MultipleLossWrapper(["Boundary"])(logits, lab, ind)  # reference: distance maps are required
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_boundary_shares_the_softmax_pass(dtype):
+    """Boundary + Dice + Focal + GeneralizedDice + CrossEntropy through ONE fused pass (3-D, with the 16-channel
+    padded bf16 layout) == the oracle's separate losses, values and the gradient of their sum."""
+    torch.manual_seed(21)
+    n, c, sp = 2, 10, (8, 16, 12)
+    z = q(torch.randn(n, c, *sp) * 1.5, dtype).requires_grad_(True)
+    lab = torch.randint(0, c, (n, *sp))
+    dist = torch.randn(n, c - 1, *sp) * 0.05
+    names = ["Boundary", "CrossEntropy", "Dice", "Focal", "GeneralizedDice"]
+    ref = O.MultipleLossWrapper(names)(z, lab, None, dist)
+    torch.stack(list(ref.values())).sum().backward()
+    zd = cl_dev(z.detach(), dtype, pad_c=6 if dtype == torch.bfloat16 else 0, c_off=0)
+    zin = zd.permute(0, 4, 1, 2, 3).requires_grad_(True)
+    got = losses.MultipleLossWrapper(names)(zin, lab.to(DEV), None, dist.to(DEV))
+    torch.stack(list(got.values())).sum().backward()
+    tol = 1e-4 if dtype == torch.float32 else 2e-3
+    for k in names:
+        assert abs(got[k].item() - ref[k].item()) < tol * max(1.0, abs(ref[k].item())), (k, got[k].item(), ref[k].item())
+    assert rel(zin.grad.float().cpu(), z.grad) < (1e-4 if dtype == torch.float32 else 1e-2)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("n,sp,pad", [(2, (16, 24, 20), 0), (1, (40, 48, 32), 6), (3, (1, 64, 96), 0)])
 def test_dice_loss_vs_oracle(n, sp, pad, dtype):

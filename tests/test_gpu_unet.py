@@ -343,6 +343,84 @@ def test_flat_adam_matches_torch_adam():
     assert all(y.data_ptr() >= ob.flat.data_ptr() for y in pb)  # parameters live in the flat buffer
 
 
+def test_flat_adam_state_dict_roundtrip():
+    """the flat moments and the step count survive state_dict()/load_state_dict(), in torch.optim.Adam's
+    own layout (a checkpoint resumes under either optimiser); unsupported options raise instead of being ignored."""
+    torch.manual_seed(0)
+    shapes = [(8, 2, 3, 3), (8,), (1,)]
+    pa = [torch.nn.Parameter(torch.randn(s, device=DEV)) for s in shapes]
+    pb = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    pc = [torch.nn.Parameter(p.detach().clone()) for p in pa]
+    oa, ob = torch.optim.Adam(pa, lr=1e-2), B.FlatAdam(pb, lr=1e-2)
+    gs = [[torch.randn(s, device=DEV) for s in shapes] for _ in range(5)]
+    for k in range(3):
+        for x, y, g in zip(pa, pb, gs[k]):
+            x.grad, y.grad = g.clone(), g.clone()
+        oa.step()
+        ob.step()
+    sd = ob.state_dict()
+    assert len(sd["state"]) == 3 and float(sd["state"][0]["step"]) == 3.0
+    # resume: FlatAdam <- FlatAdam state, torch Adam <- FlatAdam state
+    with torch.no_grad():
+        for y, z in zip(pb, pc):
+            z.copy_(y)
+    oc = B.FlatAdam(pc, lr=1.0)
+    oc.load_state_dict(sd)
+    assert oc.steps == 3 and oc.param_groups[0]["lr"] == 1e-2
+    od = torch.optim.Adam([torch.nn.Parameter(y.detach().clone()) for y in pb], lr=1e-2)
+    od.load_state_dict(sd)
+    pd_ = od.param_groups[0]["params"]
+    for k in range(3, 5):
+        for x, y, z, w, g in zip(pa, pb, pc, pd_, gs[k]):
+            x.grad, y.grad, z.grad, w.grad = g.clone(), g.clone(), g.clone(), g.clone()
+        for o in (oa, ob, oc, od):
+            o.step()
+    for x, y, z, w in zip(pa, pb, pc, pd_):
+        assert rel(y.detach(), x.detach()) < 1e-6 and torch.equal(y.detach(), z.detach())
+        assert rel(w.detach(), x.detach()) < 1e-6
+    with pytest.raises(NotImplementedError):
+        B.FlatAdam(pb, weight_decay=0.1)
+    with pytest.raises(NotImplementedError):
+        ob.add_param_group({"params": [torch.nn.Parameter(torch.zeros(1, device=DEV))]})
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_flat_adam_eager_steps_refresh_packed_weights(dtype):
+    """FlatAdam writes the parameters through a raw pointer; the packed-weight caches key on
+    ``_version``, so every step must bump it.  Eager (no graph) training with FlatAdam must follow torch.optim.Adam
+    on the oracle: the loss changes from step to step and the parameters / logits stay together."""
+    ref, net = make_pair(3, 1, [8, 16, 16], [2, 2], 2, dtype)
+    torch.manual_seed(5)
+    x = torch.randn(1, 1, 16, 16, 16)
+    lab = torch.randint(0, 10, (1, 1, 16, 16, 16))
+    fr = O.DiceLoss(include_background=False, to_onehot_y=True, softmax=True)
+    fx = B.DiceLoss(include_background=False, to_onehot_y=True, softmax=True)
+    oa = torch.optim.Adam(ref.parameters(), lr=1e-2)
+    ob = B.FlatAdam(net.parameters(), lr=1e-2)
+    v0 = [p._version for p in net.parameters()]
+    losses, losses_ref = [], []
+    for _ in range(4):
+        oa.zero_grad()
+        lr_ = fr(ref(x), lab)
+        lr_.backward()
+        oa.step()
+        losses_ref.append(lr_.item())
+        for p in net.parameters():
+            p.grad = None
+        lb = fx(net(x.to(DEV)), lab.to(DEV))
+        lb.backward()
+        ob.step()
+        losses.append(lb.item())
+    assert all(p._version > v for p, v in zip(net.parameters(), v0))
+    assert len({round(l, 6) for l in losses}) == 4, losses  # stale packed weights would repeat the first loss
+    tol = 1e-3 if dtype == torch.float32 else 2e-2
+    for a, b in zip(losses, losses_ref):
+        assert abs(a - b) < tol, (losses, losses_ref)
+    with torch.no_grad():
+        y, y_ref = net(x.to(DEV)), ref(x)
+    assert rel(y, y_ref) < (5e-3 if dtype == torch.float32 else 8e-2)
+
+
 @pytest.mark.parametrize("use_graph", [False, True])
 def test_graphed_train_step_matches_autograd(use_graph):
     """GraphedTrainStep (weight gradients written straight into the flat bucket, CUDA-graph replay) gives the

@@ -58,6 +58,34 @@ def test_dice_loss_vs_reference_intree(golden, tag):
                                rtol=1e-6, atol=1e-7)
 
 
+@pytest.mark.parametrize("wt", ["square", "simple"])
+@pytest.mark.parametrize("tag", ["dense", "sparse"])
+def test_generalized_dice_vs_reference_intree(golden, wt, tag):
+    """capstone/models/temp.py GeneralizedDiceLoss, its default weighting incl. inf -> max (sparse: absent classes)."""
+    logits = torch.from_numpy(golden["dice_logits"]).requires_grad_(True)
+    lab = torch.from_numpy(golden[f"dice_lab_{tag}"]).long().unsqueeze(1)
+    v = O.GeneralizedDiceLoss(include_background=False, to_onehot_y=True, softmax=True, w_type=wt)(logits, lab)
+    v.backward()
+    np.testing.assert_allclose(v.item(), golden[f"gdl_{wt}_{tag}_mean"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(logits.grad.numpy(), golden[f"gdl_{wt}_{tag}_grad"], rtol=1e-5, atol=1e-9)
+    fxn = O.GeneralizedDiceLoss(include_background=False, to_onehot_y=True, softmax=True, w_type=wt, reduction="none")
+    np.testing.assert_allclose(fxn(logits.detach(), lab).numpy(), golden[f"gdl_{wt}_{tag}_none"], rtol=1e-6, atol=1e-7)
+
+
+def test_boundary_loss_vs_reference(golden):
+    """capstone/models/losses.py BoundaryLossWrapper / MultipleLossWrapper(["Boundary"], exclude_missing=True)."""
+    logits = torch.from_numpy(golden["boundary_logits"]).requires_grad_(True)
+    dist = torch.from_numpy(golden["boundary_dist"])
+    v = O.BoundaryLoss("mean")(logits, dist)
+    v.backward()
+    np.testing.assert_allclose(v.item(), golden["boundary_mean"], rtol=1e-6)
+    np.testing.assert_allclose(logits.grad.numpy(), golden["boundary_grad"], rtol=1e-5, atol=1e-10)
+    np.testing.assert_allclose(O.BoundaryLoss("none")(logits.detach(), dist).numpy(), golden["boundary_none"], rtol=1e-6)
+    out = O.MultipleLossWrapper(["Boundary"], exclude_missing=True)(
+        logits.detach(), torch.from_numpy(golden["boundary_lab"]).long(), torch.from_numpy(golden["indicator"]), dist)
+    np.testing.assert_allclose(out["Boundary"].item(), golden["boundary_missing"], rtol=1e-6)
+
+
 def test_dice_loss_2d(golden):
     fx = O.DiceLoss(include_background=False, to_onehot_y=True, softmax=True, reduction="none")
     v = fx(torch.from_numpy(golden["dice2d_logits"]),
