@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "lib", "libb200seg.so")
 F32, BF16 = 0, 1
 LABEL_U8, LABEL_I64 = 0, 1
 W_CONV_FPROP, W_CONV_DGRAD, W_CONVTR_FPROP, W_CONVTR_DGRAD = 0, 1, 2, 3
-CONV_ACCUMULATE, CONV_FORCE_GENERIC, CONV_PADDED_CHANNELS, CONV_NO_SLIDE, CONV_SPLIT_K = 1, 2, 4, 8, 16
+CONV_ACCUMULATE, CONV_FORCE_GENERIC, CONV_PADDED_CHANNELS, CONV_NO_SLIDE, CONV_SPLIT_K, CONV_NO_SPLIT_K = 1, 2, 4, 8, 16, 32
 PACK_TC_ONLY = 0x100
 
 
@@ -86,6 +86,8 @@ SIGNATURES = {
     "b200seg_instnorm_prelu_bwd": (C.c_int, [_ND, _P, _P, _P, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "b200seg_softmax_dice_workspace_bytes": (C.c_size_t, [_DD]),
     "b200seg_softmax_dice_fwd": (C.c_int, [_DD, _P, _P, _P, _P, C.c_size_t, _P]),
+    "b200seg_softmax_dice_metric_workspace_bytes": (C.c_size_t, [_DD]),
+    "b200seg_softmax_dice_metric_fwd": (C.c_int, [_DD, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "b200seg_softmax_dice_bwd": (C.c_int, [_DD, _P, _P, _P, _P, _P, _P]),
     "b200seg_argmax_dice_counts": (C.c_int, [_DD, _P, _P, _P, _P, _P]),
     "b200seg_label_dice_counts": (C.c_int, [C.c_int32, C.c_int64, C.c_int32, _P, _P, C.c_int32, _P, _P]),
@@ -93,6 +95,7 @@ SIGNATURES = {
     "b200seg_hu_window_norm": (C.c_int, [C.c_int64, C.c_int32, _P, _P, _P, _P, _P, _P, C.c_int32,
                                          C.c_int32, _P]),
     "b200seg_window_accumulate": (C.c_int, [C.c_int32, _P, C.c_int32, _P, _P] + [C.c_int32] * 10 + [_P]),
+    "b200seg_window_accumulate_weighted": (C.c_int, [C.c_int32, _P, C.c_int32, _P, _P, _P] + [C.c_int32] * 10 + [_P]),
     "b200seg_accum_argmax": (C.c_int, [_P, _P, _P, _P, C.c_int64, C.c_int32, _P]),
     "b200seg_crop_window_norm": (C.c_int, [C.c_int32, _P, _P, _P, C.c_int32, _P, _P] + [C.c_int32] * 6 +
                                  [C.c_float] * 4 + [C.c_int32, _P]),

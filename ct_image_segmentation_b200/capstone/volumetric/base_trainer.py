@@ -39,6 +39,10 @@ class BaseUNet3D(LightningModule):
         self.unet = self._construct_model()
         self.loss_func = MultipleLossWrapper3D(losses=loss_fx, exclude_missing=exclude_missing)
         self.dice_score = DiceMetricWrapper3D()
+        # the per-step Dice metric (reference :116-132) rides on the Dice loss's own pass over the logits when Dice
+        # is among the losses and takes the shared multi-loss pass otherwise (then: one fused argmax + count launch)
+        self._fused_metric = ("Dice" in loss_fx and len(loss_fx) == 1 and not exclude_missing
+                              and self.loss_func.enable_metric_counts())
 
     @property
     def _n_classes(self):
@@ -79,7 +83,12 @@ class BaseUNet3D(LightningModule):
     def _log_dice_scores(self, prediction, masks, mask_indicator, prefix):
         self.eval()
         with torch.no_grad():
-            dice_mean, dice_per_class = self.dice_score.from_logits(prediction.detach(), masks)
+            counts = self.loss_func.metric_counts if self._fused_metric else None
+            if counts is not None:
+                from ...metrics import dice_from_counts
+                dice_mean, dice_per_class = dice_from_counts(counts)
+            else:
+                dice_mean, dice_per_class = self.dice_score.from_logits(prediction.detach(), masks)
             for structure, score in zip(STRUCTURES, dice_per_class):
                 self.log(f"{structure} Dice ({prefix})", score, on_step=False, on_epoch=True)
             self.log(f"Mean Dice Score ({prefix})", dice_mean, on_step=False, on_epoch=True)

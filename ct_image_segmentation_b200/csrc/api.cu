@@ -520,6 +520,23 @@ int b200seg_softmax_dice_fwd(const b200seg_dice_desc* d, const void* logits, con
   return launch_softmax_dice_fwd(*d, logits, labels, sums, workspace, as_stream(stream));
 }
 
+size_t b200seg_softmax_dice_metric_workspace_bytes(const b200seg_dice_desc* d) {
+  return d ? dice_metric_workspace_bytes(*d) : 0;
+}
+
+int b200seg_softmax_dice_metric_fwd(const b200seg_dice_desc* d, const void* logits, const void* labels, float* sums,
+                                    int64_t* counts, void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_dice_desc(d);
+  if (rc) return rc;
+  B200SEG_CHECK_ARG(logits && labels && sums && counts && workspace, "softmax_dice_metric_fwd: NULL pointer");
+  if (workspace_bytes < dice_metric_workspace_bytes(*d)) {
+    set_error("softmax_dice_metric_fwd: workspace %zu < required %zu", workspace_bytes,
+              dice_metric_workspace_bytes(*d));
+    return B200SEG_ERR_WORKSPACE;
+  }
+  return launch_softmax_dice_metric_fwd(*d, logits, labels, sums, counts, workspace, as_stream(stream));
+}
+
 int b200seg_softmax_dice_bwd(const b200seg_dice_desc* d, const void* logits, const void* labels,
                              const float* gI, const float* gP, void* dlogits, void* stream) {
   int rc = check_dice_desc(d);
@@ -629,8 +646,20 @@ int b200seg_window_accumulate(int32_t dtype, const void* window_logits, int32_t 
   B200SEG_CHECK_ARG(window_logits && acc && cnt && c > 0 && src_ld >= c && wd > 0 && wh > 0 && ww > 0,
                     "window_accumulate: bad argument");
   B200SEG_CHECK_ARG(d0 >= 0 && h0 >= 0 && w0 >= 0 && d0 < D && h0 < H && w0 < W, "window_accumulate: origin outside");
-  return launch_window_accumulate(dtype, window_logits, src_ld, acc, cnt, c, wd, wh, ww, D, H, W, d0, h0, w0,
+  return launch_window_accumulate(dtype, window_logits, src_ld, nullptr, acc, cnt, c, wd, wh, ww, D, H, W, d0, h0, w0,
                                   as_stream(stream));
+}
+
+int b200seg_window_accumulate_weighted(int32_t dtype, const void* window_logits, int32_t src_ld,
+                                       const float* importance, float* acc, float* cnt, int32_t c, int32_t wd,
+                                       int32_t wh, int32_t ww, int32_t D, int32_t H, int32_t W, int32_t d0, int32_t h0,
+                                       int32_t w0, void* stream) {
+  B200SEG_CHECK_ARG(window_logits && acc && cnt && c > 0 && src_ld >= c && wd > 0 && wh > 0 && ww > 0,
+                    "window_accumulate_weighted: bad argument");
+  B200SEG_CHECK_ARG(d0 >= 0 && h0 >= 0 && w0 >= 0 && d0 < D && h0 < H && w0 < W,
+                    "window_accumulate_weighted: origin outside");
+  return launch_window_accumulate(dtype, window_logits, src_ld, importance, acc, cnt, c, wd, wh, ww, D, H, W, d0, h0,
+                                  w0, as_stream(stream));
 }
 
 int b200seg_accum_argmax(const float* acc, const float* cnt, uint8_t* labels, float* mean_logits, int64_t n_vox,

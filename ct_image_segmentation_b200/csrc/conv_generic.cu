@@ -240,7 +240,10 @@ conv_wgrad_kernel(WgradParams p, const T* __restrict__ S, const T* __restrict__ 
 
   const int lv = tid >> 3, lc = (tid & 7) * 4;  // loader: voxel in chunk, first of 4 channels
   const int ca = tid >> 4, cb = tid & 15;       // compute: rows ca*2.., cols cb*2..
-  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  // a weight gradient sums up to millions of voxel products: a plain fp32 running sum is off by a few 1e-4 at
+  // 2 x 128^3 (r2: 1.6e-4 against a float64 reference).  Products of one 32-voxel chunk are summed in fp32, the
+  // chunks in double (4 DADD per thread and chunk: nothing next to the 128 FMAs).
+  double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
 
   for (int64_t v0 = v_begin; v0 < v_end; v0 += BV) {
     int64_t o = v0 + lv;
@@ -274,15 +277,20 @@ conv_wgrad_kernel(WgradParams p, const T* __restrict__ S, const T* __restrict__ 
       Ss[lv][lc + i] = sv[i];
     }
     __syncthreads();
+    float c00 = 0.f, c01 = 0.f, c10 = 0.f, c11 = 0.f;
 #pragma unroll
     for (int v = 0; v < BV; ++v) {
       float s0 = Ss[v][ca * 2], s1 = Ss[v][ca * 2 + 1];
       float t0 = Ts[v][cb * 2], t1 = Ts[v][cb * 2 + 1];
-      acc[0][0] = fmaf(s0, t0, acc[0][0]);
-      acc[0][1] = fmaf(s0, t1, acc[0][1]);
-      acc[1][0] = fmaf(s1, t0, acc[1][0]);
-      acc[1][1] = fmaf(s1, t1, acc[1][1]);
+      c00 = fmaf(s0, t0, c00);
+      c01 = fmaf(s0, t1, c01);
+      c10 = fmaf(s1, t0, c10);
+      c11 = fmaf(s1, t1, c11);
     }
+    acc[0][0] += (double)c00;
+    acc[0][1] += (double)c01;
+    acc[1][0] += (double)c10;
+    acc[1][1] += (double)c11;
     __syncthreads();
   }
   float* out = partial + ((int64_t)split * p.taps + tap) * p.a_c * p.b_c;
@@ -291,7 +299,7 @@ conv_wgrad_kernel(WgradParams p, const T* __restrict__ S, const T* __restrict__ 
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       int a = a0 + ca * 2 + i, b = b0 + cb * 2 + j;
-      if (a < p.a_c && b < p.b_c) out[(int64_t)a * p.b_c + b] = acc[i][j];
+      if (a < p.a_c && b < p.b_c) out[(int64_t)a * p.b_c + b] = (float)acc[i][j];
     }
 }
 
@@ -305,9 +313,9 @@ __global__ void wgrad_reduce_unpack_kernel(const float* __restrict__ partial, fl
   int64_t r = idx / b_c;
   int a = (int)(r % a_c);
   int tap = (int)(r / a_c);
-  float s = 0.f;
-  for (int i = 0; i < splits; ++i) s += partial[(int64_t)i * total + idx];
-  gw[((int64_t)b * a_c + a) * taps + tap] = s;
+  double s = 0.0;
+  for (int i = 0; i < splits; ++i) s += (double)partial[(int64_t)i * total + idx];
+  gw[((int64_t)b * a_c + a) * taps + tap] = (float)s;
 }
 
 void wgrad_plan(WgradParams& p) {

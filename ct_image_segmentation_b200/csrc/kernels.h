@@ -81,6 +81,9 @@ int launch_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, fl
 size_t dice_workspace_bytes(const b200seg_dice_desc& d);
 int launch_softmax_dice_fwd(const b200seg_dice_desc& d, const void* logits, const void* labels,
                             float* sums, void* ws, cudaStream_t st);
+size_t dice_metric_workspace_bytes(const b200seg_dice_desc& d);
+int launch_softmax_dice_metric_fwd(const b200seg_dice_desc& d, const void* logits, const void* labels, float* sums,
+                                   int64_t* counts, void* ws, cudaStream_t st);
 int launch_softmax_dice_bwd(const b200seg_dice_desc& d, const void* logits, const void* labels,
                             const float* gI, const float* gP, void* dlogits, cudaStream_t st);
 size_t loss_workspace_bytes(const b200seg_dice_desc& d);
@@ -104,8 +107,8 @@ int launch_label_dice_counts(int n, int64_t spatial, int c, const uint8_t* pred,
                              int target_dtype, int64_t* counts, cudaStream_t st);
 int launch_squash_masks(int n, int n_struct, int64_t spatial, const uint8_t* masks, uint8_t* labels,
                         cudaStream_t st);
-int launch_window_accumulate(int dtype, const void* src, int src_ld, float* acc, float* cnt, int C, int wd,
-                             int wh, int ww, int D, int H, int W, int d0, int h0, int w0, cudaStream_t st);
+int launch_window_accumulate(int dtype, const void* src, int src_ld, const float* imp, float* acc, float* cnt, int C,
+                             int wd, int wh, int ww, int D, int H, int W, int d0, int h0, int w0, cudaStream_t st);
 int launch_accum_argmax(const float* acc, const float* cnt, uint8_t* labels, float* mean_out, int64_t nvox, int C,
                         cudaStream_t st);
 int launch_crop_window_norm(int dtype, const int16_t* hu, const uint8_t* lab, const int* origins, int nb_patches,

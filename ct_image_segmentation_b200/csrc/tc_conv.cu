@@ -247,8 +247,7 @@ tc_conv_kernel(const __grid_constant__ TcConvParams p) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Split-K variant for the deep layers (EXPERIMENTAL: opt-in with the B200SEG_CONV_SPLIT_K flag or
-// B200SEG_CONV_SPLITK=1; compiled and SASS-checked, NOT yet run on a GPU -- see DESIGN.md section 7).  The 8^3 layers have 8 output tiles x 4..8 channel tiles = 32..64 CTAs,
+// Split-K variant for the deep layers (default on; B200SEG_CONV_SPLITK=0 / B200SEG_CONV_NO_SPLIT_K switch it off).  The 8^3 layers have 8 output tiles x 4..8 channel tiles = 32..64 CTAs,
 // each streaming 27 taps x Cin of A and B tiles through ONE SM's L2 port (2.2 MB per CTA for 256 -> 256:
 // ~16 us at ~70 B/clk, whatever the tensor core does).  Here a thread-block cluster of `ksplit` CTAs
 // (cluster dims (1, 1, ksplit), blockIdx.z = rank) shares one output tile: every CTA runs the same
@@ -938,11 +937,13 @@ int tc_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void*
   if (gx > 0x7fffffffLL) { set_error("tc_conv: grid too large"); return B200SEG_ERR_ARG; }
   dim3 grid((unsigned)gx, (unsigned)(dst_pad / BN));
 
-  // ---- EXPERIMENTAL (flag B200SEG_CONV_SPLIT_K or B200SEG_CONV_SPLITK=1): deep layers with <= 74 CTAs share an output tile between the 2 or
+  // ---- deep layers with <= 74 CTAs share an output tile between the 2 or
   // 4 CTAs of a cluster, each taking a share of the (tap, K-block) iterations (tc_conv_splitk_kernel)
   {
-    static const int splitk_env = getenv("B200SEG_CONV_SPLITK") ? atoi(getenv("B200SEG_CONV_SPLITK")) : 0;
-    const bool splitk = splitk_env || (d->flags & B200SEG_CONV_SPLIT_K);
+    // default ON since round 2 (parity-tested on a B200: tests/test_gpu_kernels.py::test_splitk_cluster_conv; per layer
+    // 20 -> 14 us (128->128 @8^3), 31 -> 25 us (256->256 @8^3)); B200SEG_CONV_SPLITK=0 or the NO_SPLIT_K flag switch it off
+    static const int splitk_env = getenv("B200SEG_CONV_SPLITK") ? atoi(getenv("B200SEG_CONV_SPLITK")) : 1;
+    const bool splitk = (splitk_env || (d->flags & B200SEG_CONV_SPLIT_K)) && !(d->flags & B200SEG_CONV_NO_SPLIT_K);
     const int64_t ctas = gx * (dst_pad / BN);
     const int iters = (ns / (ncls_total > 0 ? ncls_total : 1)) * p.kblocks;  // smallest class has >= this / 8
     if (splitk && ctas * 2 <= 148 && iters >= 16 && (BN == 32 || BN == 64) && KC == 64) {

@@ -36,8 +36,19 @@ class GraphedTrainStep:
 
     def __init__(self, net: UNet, loss_fn: Callable, optimizer: Optional[torch.optim.Optimizer],
                  images: torch.Tensor, labels: torch.Tensor, warmup: int = 2, use_graph: bool = True,
-                 overlap_allreduce: Optional[bool] = None):
+                 overlap_allreduce: Optional[bool] = None, metric: Optional[Callable] = None):
+        """``metric`` (optional): the reference runs its Dice METRIC on every training step (``_log_dice_scores``,
+        ``capstone/volumetric/base_trainer.py:116-132``: clone, softmax, argmax, two one-hots, sums).  Either
+        ``"fused"`` -- ``loss_fn`` is a ``DiceLoss(with_metric=True)`` whose forward kernel counts {tp, |pred|,
+        |target|} in the SAME pass over the logits (no extra HBM traffic); only the (B, 9) epilogue
+        ``dice_from_counts`` is added, on a second stream -- or a callable ``metric(logits, labels) -> tensors``
+        (e.g. ``DiceMetricWrapper().from_logits``: one fused argmax + integer-count launch) issued on that second
+        stream, a branch BESIDE the backward pass in the captured graph.  The result is in ``self.metric_out``."""
+        if metric == "fused" and not getattr(loss_fn, "with_metric", False):
+            raise ValueError('metric="fused" needs loss_fn = DiceLoss(..., with_metric=True)')
         self.net, self.loss_fn, self.optimizer = net, loss_fn, optimizer
+        self.metric, self.metric_out = metric, None
+        self._metric_stream = None
         dev = next(net.parameters()).device
         self.static_images = torch.empty(images.shape, dtype=images.dtype, device=dev)
         self.static_labels = torch.empty(labels.shape, dtype=labels.dtype, device=dev)
@@ -133,25 +144,84 @@ class GraphedTrainStep:
         else:
             self._allreduce_mean(self.bucket.flat)
 
-    def _fwd_bwd(self):
+    def _loss_and_metric(self):
+        logits = self.net(self.static_images)
+        if self.metric == "fused":
+            from .metrics import dice_from_counts
+            loss = self.loss_fn(logits, self.static_labels.unsqueeze(1))
+            counts = self.loss_fn.metric_counts
+            if self._metric_stream is None:
+                self._metric_stream = torch.cuda.Stream(device=logits.device)
+            self._metric_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._metric_stream), torch.no_grad():
+                self.metric_out = dice_from_counts(counts)
+            self._metric_logits = counts
+            return loss
+        if self.metric is not None:
+            # the metric only reads the logits: a side branch, joined at the end of the step
+            if self._metric_stream is None:
+                self._metric_stream = torch.cuda.Stream(device=logits.device)
+            cur = torch.cuda.current_stream()
+            self._metric_stream.wait_stream(cur)
+            with torch.cuda.stream(self._metric_stream), torch.no_grad():
+                self.metric_out = self.metric(logits.detach(), self.static_labels)
+            self._metric_logits = logits  # stays referenced until the join (caching allocator)
+        return self.loss_fn(logits, self.static_labels.unsqueeze(1))
+
+    def _fwd_bwd(self, exchange: bool = True):
         from . import ops
         self._deep_issued = False
-        self.net.bind_grad_sink(self._sink, self._on_level_done if self._deep is not None else None)
+        self.net.bind_grad_sink(self._sink, self._on_level_done if (self._deep is not None and exchange) else None)
         try:
             if self.use_graph:
                 # zero-padded 10-class buffers are allocated (and zeroed) once and reused by every replay:
                 # a replayed step's activations are dead before the next replay starts
                 with ops.padded_buffer_pool(self._pad_pool):
-                    loss = self.loss_fn(self.net(self.static_images), self.static_labels.unsqueeze(1))
+                    loss = self._loss_and_metric()
                     loss.backward()
             else:
-                loss = self.loss_fn(self.net(self.static_images), self.static_labels.unsqueeze(1))
+                loss = self._loss_and_metric()
                 loss.backward()
         finally:
             self.net.bind_grad_sink(None)
-        if not (self.use_graph and not self._exchange_in_graph and torch.cuda.is_current_stream_capturing()):
+        if self.metric is not None:
+            torch.cuda.current_stream().wait_stream(self._metric_stream)
+            self._metric_logits = None
+        if exchange and not (self.use_graph and not self._exchange_in_graph and torch.cuda.is_current_stream_capturing()):
             self._exchange_rest()
         return loss
+
+    def local_gradients(self) -> torch.Tensor:
+        """This rank's OWN gradient (no exchange) for the current inputs and parameters, as a copy of the flat bucket:
+        one eager forward + backward.  With ``check_exchange`` it is the evidence that the in-graph, overlapped
+        exchange leaves the mean of the ranks' local gradients in the bucket."""
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):  # (not on the default stream: keeps autograd's stream bookkeeping off it)
+            self._fwd_bwd(exchange=False)
+            out = self.bucket.flat.clone()
+        torch.cuda.current_stream().wait_stream(side)
+        return out
+
+    def check_exchange(self) -> dict:
+        """Data-parallel proof, outside any timed region: (1) local gradients without exchange, averaged over the
+        ranks with ONE plain all-reduce; (2) the step as it is timed (graph replay incl. the overlapped in-graph
+        exchange), no optimiser update in between.  Returns the largest deviation between the two buckets."""
+        opt, self.optimizer = self.optimizer, None
+        try:
+            want = self.local_gradients()
+            if self._world > 1:
+                self._allreduce_mean(want)
+            self.__call__(None, None)
+            torch.cuda.synchronize()
+            got = self.bucket.flat
+            diff = (got - want).abs().max()
+            scale = want.abs().max().clamp_min(1e-30)
+            return {"world": self._world, "max_abs_diff": float(diff), "max_abs_grad": float(scale),
+                    "max_rel_to_largest": float(diff / scale), "bitwise_equal": bool(torch.equal(got, want)),
+                    "n_params": int(got.numel())}
+        finally:
+            self.optimizer = opt
 
     def _capture(self, warmup: int):
         side = torch.cuda.Stream()

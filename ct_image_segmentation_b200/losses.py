@@ -56,8 +56,12 @@ class _FusedDiceLoss(torch.autograd.Function):
     epilogue with the gradient coefficients) and one backward kernel (+ a scalar scale)."""
 
     @staticmethod
-    def forward(ctx, logits_cl, labels, include_background, smooth, mean):
-        sums = ops.softmax_dice_sums(logits_cl, labels)
+    def forward(ctx, logits_cl, labels, include_background, smooth, mean, counts_out=None):
+        if counts_out is not None:  # the Dice METRIC counts of the same step, from the same pass over the logits
+            sums, counts = ops.softmax_dice_metric_sums(logits_cl, labels)
+            counts_out.append(counts)
+        else:
+            sums = ops.softmax_dice_sums(logits_cl, labels)
         loss, g_i, g_p = ops.dice_loss_epilogue(sums, include_background, smooth, mean)
         ctx.save_for_backward(logits_cl, labels, g_i, g_p)
         return loss
@@ -65,7 +69,7 @@ class _FusedDiceLoss(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         logits_cl, labels, g_i, g_p = ctx.saved_tensors
-        return ops.softmax_dice_bwd(logits_cl, labels, g_i * g, g_p * g), None, None, None, None
+        return ops.softmax_dice_bwd(logits_cl, labels, g_i * g, g_p * g), None, None, None, None, None
 
 
 class _SoftmaxLossSums(torch.autograd.Function):
@@ -133,8 +137,14 @@ class DiceLoss(nn.Module):
     configuration the reference uses is implemented: ``softmax=True, to_onehot_y=True``."""
 
     def __init__(self, include_background: bool = True, to_onehot_y: bool = False,
-                 softmax: bool = False, reduction: str = "mean", smooth: float = 1e-5, **kwargs):
+                 softmax: bool = False, reduction: str = "mean", smooth: float = 1e-5, with_metric: bool = False,
+                 **kwargs):
+        """``with_metric`` (build-specific): also produce the Dice-metric counts {tp, |pred|, |target|} per (sample,
+        class) of the same logits/labels in the SAME kernel pass (``self.metric_counts``, (B, C, 3) int64; feed
+        ``metrics.dice_from_counts``) -- the reference evaluates that metric on every training step."""
         super().__init__()
+        self.with_metric = bool(with_metric)
+        self.metric_counts = None
         if not (softmax and to_onehot_y):
             raise NotImplementedError("b200seg DiceLoss implements softmax=True, to_onehot_y=True")
         if kwargs.get("sigmoid") or kwargs.get("squared_pred") or kwargs.get("jaccard"):
@@ -150,9 +160,16 @@ class DiceLoss(nn.Module):
             raise AssertionError("labels must have a singleton channel dim (to_onehot_y=True)")
         if sums is None and self.reduction in ("mean", "sum"):
             cl = _as_cl(input)
-            return _FusedDiceLoss.apply(cl, target[:, 0], self.include_background, self.smooth,
-                                        self.reduction == "mean")
+            box = [] if self.with_metric else None
+            loss = _FusedDiceLoss.apply(cl, target[:, 0], self.include_background, self.smooth,
+                                        self.reduction == "mean", box)
+            if box:
+                self.metric_counts = box[0]
+            return loss
         if sums is None:
+            if self.with_metric:
+                with torch.no_grad():
+                    _, self.metric_counts = ops.softmax_dice_metric_sums(_as_cl(input.detach()), target[:, 0])
             sums = softmax_dice_sums(input, target)
         if not self.include_background:
             sums = sums[:, 1:]
@@ -371,6 +388,21 @@ class MultipleLossWrapper(nn.Module):
                     f"loss {name!r} is outside the B200 hot path (implemented: {sorted(LOSSES)})")
         reduction = "none" if exclude_missing else "mean"
         self.losses = nn.ModuleDict({name: LOSSES[name](reduction=reduction) for name in losses})
+
+    def enable_metric_counts(self, on: bool = True) -> bool:
+        """Ask the Dice loss (if it is one of the losses) to produce the Dice-METRIC counts of the same logits in its
+        own kernel pass; ``metric_counts`` then holds them after every ``forward``.  Returns whether it applies."""
+        fx = self.losses["Dice"].loss_fx if "Dice" in self.losses else None
+        if fx is None:
+            return False
+        fx.with_metric = bool(on)
+        fx.metric_counts = None
+        return True
+
+    @property
+    def metric_counts(self):
+        fx = self.losses["Dice"].loss_fx if "Dice" in self.losses else None
+        return None if fx is None else fx.metric_counts
 
     def forward(self, input, target, mask_indicator=None, dist_maps=None):
         values = {}

@@ -544,6 +544,21 @@ def softmax_dice_sums(logits, labels) -> torch.Tensor:
     return sums
 
 
+def softmax_dice_metric_sums(logits, labels):
+    """((N, C, 3) fp32 Dice sums, (N, C, 3) int64 metric counts {tp, |pred|, |target|}) from ONE pass over the logits."""
+    lib = _lib.load()
+    n, d, h, w, c, ld = cl_info(logits)
+    labels, code = _labels(labels, n, d * h * w)
+    desc = _dice_desc(logits, code)
+    sums = torch.empty(n, c, 3, dtype=torch.float32, device=logits.device)
+    counts = torch.empty(n, c, 3, dtype=torch.int64, device=logits.device)
+    ws = workspace(lib.b200seg_softmax_dice_metric_workspace_bytes(C.byref(desc)), logits.device)
+    _lib.check(lib.b200seg_softmax_dice_metric_fwd(C.byref(desc), logits.data_ptr(), labels.data_ptr(), sums.data_ptr(),
+                                                   counts.data_ptr(), ws.data_ptr(), ws.numel(), _stream()),
+               "b200seg_softmax_dice_metric_fwd")
+    return sums, counts
+
+
 def softmax_loss_sums(logits, labels, gamma: float = 2.0) -> torch.Tensor:
     """(N, C, 5) fp32: I, G, P (Dice), F = sum t (1-p)^gamma (-log p) (Focal), N = sum t (-log p) (CE)."""
     lib = _lib.load()

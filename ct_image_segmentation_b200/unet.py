@@ -201,7 +201,7 @@ class UNet(nn.Module):
             if isinstance(m, Convolution):
                 if s.get("c") is not None:
                     taps[names[m] + ".conv"] = ops.from_channels_last(s["c"], self.dimensions).float()
-                if s.get("out") is not None:
+                if s.get("out") is not None and s.get("res") is None:  # (fused residual: not the module's own output)
                     taps[names[m]] = ops.from_channels_last(s["out"], self.dimensions).float()
         return taps
 
@@ -371,7 +371,8 @@ class UNet(nn.Module):
             y = dst if dst is not None else self._new(x, sp, g.cout)
             ops.conv_fprop(g, x, wp, bias, y, residual)
             # with a fused residual the module's own output is never materialised: no tap
-            saved[m] = {"x": x, "c": None, "out": y if (keep and residual is None) else None, "col_geom": g1}
+            saved[m] = {"x": x, "c": None, "out": y if keep else None, "res": residual if keep else None,
+                        "col_geom": g1}
             return y
         c = self._new(x, sp, g.cout)
         a = dst if dst is not None else self._new(x, sp, g.cout)
@@ -389,8 +390,9 @@ class UNet(nn.Module):
             else:
                 mean, rstd = ops.conv_fprop_stats(g, x, wp, bias, c, m.norm.eps)
             ops.instnorm_prelu_fwd(c, mean, rstd, alpha, a, residual, m.norm.eps)
-        saved[m] = {"x": x, "c": c, "mean": mean, "rstd": rstd,
-                    "out": a if (keep and residual is None) else None, "col_geom": g1}
+        # tests (keep): "out" is what the kernel wrote -- with a fused residual that is module output + "res"
+        saved[m] = {"x": x, "c": c, "mean": mean, "rstd": rstd, "out": a if keep else None,
+                    "res": residual if keep else None, "col_geom": g1}
         return a
 
     def _fwd_resunit(self, ru: ResidualUnit, x, saved, dst, keep):
@@ -420,7 +422,7 @@ class UNet(nn.Module):
             if last and side is not None:
                 torch.cuda.current_stream().wait_stream(side)  # join before r is read
             h = self._fwd_convolution(u, h, saved, dst if last else None, r if last else None, keep)
-        saved[ru] = {"x": x, "col_geom": rg1, "col": rcol}
+        saved[ru] = {"x": x, "col_geom": rg1, "col": rcol, "r": r if (keep and ru.res_geom is not None) else None}
         return h
 
     # ---- backward plan -------------------------------------------------------------------------
@@ -548,6 +550,9 @@ class UNet(nn.Module):
             return self._bwd_convolution(units[0], g, saved, grads, need_gx, gx_dst, gx_accum, g_out)
         gx = self._bwd_convolution(units[0], g, saved, grads, need_gx, gx_dst, gx_accum, None)
         rg = ru.res_geom
+        if getattr(self, "_bwd_taps", None) is not None:
+            self._bwd_taps[ru] = {"g_out": g_out, "x": x, "col": sru.get("col"), "col_geom": sru.get("col_geom"),
+                                  "r": sru.get("r")}
         if sru.get("col_geom") is not None:
             gw, gb = self._wgrad(sru["col_geom"], sru["col"], g_out, True, ru.residual.weight, ru.residual.bias)
             gw = gw.view(ru.residual.weight.shape)

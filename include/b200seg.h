@@ -64,11 +64,12 @@ enum b200seg_conv_flags {
    * padding and rewrite it with zeros.  Lets the tcgen05 kernels take the 10-class layers. */
   B200SEG_CONV_PADDED_CHANNELS = 4,
   B200SEG_CONV_NO_SLIDE = 8, /* tcgen05 streaming kernel even where the sliding-window kernel applies (tests) */
-  /* EXPERIMENTAL: layers with few output tiles (<= 74 CTAs) run on the split-K cluster kernel -- 2 or 4 CTAs of a
-   * thread-block cluster share one output tile and reduce their partial accumulators through distributed shared
-   * memory.  Ignored where the kernel does not apply.  Also switched on for every call by the environment
-   * variable B200SEG_CONV_SPLITK=1. */
-  B200SEG_CONV_SPLIT_K = 16
+  /* Layers with few output tiles (<= 74 CTAs) run on the split-K cluster kernel -- 2 or 4 CTAs of a thread-block
+   * cluster share one output tile and reduce their partial accumulators through distributed shared memory.
+   * Ignored where the kernel does not apply.  Default behaviour since 0.2 (environment B200SEG_CONV_SPLITK=0
+   * switches the default off; the flag then opts a call in). */
+  B200SEG_CONV_SPLIT_K = 16,
+  B200SEG_CONV_NO_SPLIT_K = 32 /* streaming kernel even where the split-K kernel applies (tests, A/B timing) */
 };
 
 /*
@@ -242,6 +243,13 @@ int b200seg_instnorm_prelu_bwd(const b200seg_norm_desc* d, const void* x, const 
 size_t b200seg_softmax_dice_workspace_bytes(const b200seg_dice_desc* d);
 int b200seg_softmax_dice_fwd(const b200seg_dice_desc* d, const void* logits, const void* labels,
                              float* sums, void* workspace, size_t workspace_bytes, void* stream);
+/* Loss sums AND the Dice-metric counts of the same step in one pass over the logits: the reference runs its metric on
+ * every training step (`_log_dice_scores`, capstone/volumetric/base_trainer.py:116-132 -> `_squash_predictions`
+ * capstone/training/utils.py:19-20 -> `compute_meandice` capstone/models/temp.py:173-214).  sums as
+ * b200seg_softmax_dice_fwd; counts[n][c][3] = {tp, |pred|, |target|} (int64) as b200seg_argmax_dice_counts. */
+size_t b200seg_softmax_dice_metric_workspace_bytes(const b200seg_dice_desc* d);
+int b200seg_softmax_dice_metric_fwd(const b200seg_dice_desc* d, const void* logits, const void* labels, float* sums,
+                                    int64_t* counts, void* workspace, size_t workspace_bytes, void* stream);
 int b200seg_softmax_dice_bwd(const b200seg_dice_desc* d, const void* logits, const void* labels,
                              const float* gI, const float* gP, void* dlogits, void* stream);
 
@@ -328,6 +336,14 @@ int b200seg_hu_window_norm(int64_t n_vox, int32_t n_windows, const int16_t* hu, 
 int b200seg_window_accumulate(int32_t dtype, const void* window_logits, int32_t src_ld, float* acc, float* cnt,
                               int32_t c, int32_t wd, int32_t wh, int32_t ww, int32_t D, int32_t H, int32_t W,
                               int32_t d0, int32_t h0, int32_t w0, void* stream);
+/* ... with an importance map: acc += importance[(d,h,w)] * logits, cnt += importance[(d,h,w)] (fp32, one value per
+ * window voxel, MONAI mode="gaussian"; NULL = constant 1).  `window_logits` / `importance` may point INTO a window
+ * (a run of its d-slices: wd = the run's depth), which is how a window is split between the d-slabs owned by
+ * different ranks (inference.py). */
+int b200seg_window_accumulate_weighted(int32_t dtype, const void* window_logits, int32_t src_ld,
+                                       const float* importance, float* acc, float* cnt, int32_t c, int32_t wd,
+                                       int32_t wh, int32_t ww, int32_t D, int32_t H, int32_t W, int32_t d0, int32_t h0,
+                                       int32_t w0, void* stream);
 int b200seg_accum_argmax(const float* acc, const float* cnt, uint8_t* labels, float* mean_logits, int64_t n_vox,
                          int32_t c, void* stream);
 

@@ -1,53 +1,105 @@
 """cfg4 (BASELINE.json configs[3]): sliding-window inference on a synthetic 512x512x160 CT volume, ROI 128^3,
-overlap 0.25 (50 windows), bf16, to a uint8 label map.  One GPU here (`--world N` under torchrun shards the
-windows round-robin and all-reduces the accumulators).  Prints one JSON line: volume voxels/s and latency,
-eager predictor vs. CUDA-graph predictor."""
+overlap 0.25 (50 windows), bf16, to a uint8 label map, windows + output slabs sharded over the GPUs of one box.
+
+    python scripts/infer_bench.py                                             # 1 GPU
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29511 scripts/infer_bench.py --gpus 8                   # 8 GPUs
+
+One JSON line (rank 0): latency from "volume resident on rank 0" to "whole uint8 label map on every rank"
+(broadcast of the volume included when N > 1), volume voxels/s, and -- outside the timed region -- whether the label
+map equals the single-GPU one bit for bit.  Timed on the device (CUDA events), barrier on both sides, max over ranks.
+"""
+import argparse
 import json
 import os
 import sys
 
 import torch
+import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import ct_image_segmentation_b200 as B  # noqa: E402
-from ct_image_segmentation_b200.inference import GraphedPredictor, sliding_window_inference, window_list  # noqa: E402
+from ct_image_segmentation_b200.inference import (GraphedPredictor, make_plan,  # noqa: E402
+                                                   sliding_window_inference)
 from ct_image_segmentation_b200.parallel import init_distributed  # noqa: E402
 
 
 def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--reps", type=int, default=5)
+    ap.add_argument("--sw-batch", type=int, default=2)
+    ap.add_argument("--mode", default="constant", choices=["constant", "gaussian"])
+    ap.add_argument("--roi", type=int, default=128)
+    ap.add_argument("--eager", action="store_true", help="also time the eager (non-graph) predictor")
+    args = ap.parse_args()
     rank, world, local = init_distributed()
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     torch.manual_seed(12342)
     net = B.UNet(3, 1, 10, [16, 32, 64, 128, 256], [2, 2, 2, 2], num_res_units=2, dtype=torch.bfloat16).to(dev).eval()
-    vol = torch.randn(1, 1, 160, 512, 512, device=dev)
-    roi, swb = (128, 128, 128), 2
-    nwin = len(window_list(vol.shape[2:], roi, 0.25))
+    g = torch.Generator(device="cpu").manual_seed(12342)
+    vol0 = torch.randn(1, 1, 512, 512, 160, generator=g).to(dev)     # the volume (identical on every rank)
+    vol = vol0.clone() if rank == 0 else torch.zeros_like(vol0)      # ... but only rank 0 "has" it
+    roi, swb = (args.roi,) * 3, args.sw_batch
+    plan = make_plan(vol.shape[2:], roi, 0.25, world)
     graphed = GraphedPredictor(net, torch.zeros(swb, 1, *roi, device=dev))
 
-    def timed(pred, reps=3):
+    def run(pred):
+        if world > 1:
+            dist.broadcast(vol, 0)
+        return sliding_window_inference(vol, roi, swb, pred, overlap=0.25, mode=args.mode)
+
+    def timed(pred, reps):
         best, lab = 1e30, None
-        for _ in range(reps + 1):  # first pass = warm-up
+        for i in range(reps + 2):  # two warm-up passes (graph capture of ragged batches, NCCL channels)
+            if world > 1:
+                dist.barrier()
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            lab = sliding_window_inference(vol, roi, swb, pred, overlap=0.25)
+            lab = run(pred)
             e1.record()
             torch.cuda.synchronize()
-            best = min(best, e0.elapsed_time(e1))
+            ms = e0.elapsed_time(e1)
+            if world > 1:
+                t = torch.tensor([ms], device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = t.item()
+            if i >= 2:
+                best = min(best, ms)
         return best, lab
 
-    ms_e, lab_e = timed(net)
-    ms_g, lab_g = timed(graphed)
+    ms_g, lab_g = timed(graphed, args.reps)
+    ms_e = None
+    if args.eager:
+        ms_e, lab_e = timed(net, 2)
+        assert torch.equal(lab_e, lab_g)
+    # parity outside the timed region: the sharded label map is the single-GPU label map, bit for bit
+    single = sliding_window_inference(vol0, roi, swb, graphed, overlap=0.25, mode=args.mode, rank=0, world=1)
+    equal = bool(torch.equal(single, lab_g))
+    if world > 1:
+        t = torch.tensor([1 if equal else 0], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        equal = bool(t.item())
     vox = vol.numel()
+    moved = sum(v for (s, d), v in plan.pair_voxels.items() if s != d) * 10 * 2
     if rank == 0:
         print(json.dumps({
-            "workload": "sliding-window inference, 512x512x160 volume, roi 128^3, overlap 0.25, sw_batch 2, bf16",
-            "windows": nwin, "n_gpus": world,
-            "eager_ms": ms_e, "eager_voxels_per_s": vox / (ms_e * 1e-3),
-            "graph_ms": ms_g, "graph_voxels_per_s": vox / (ms_g * 1e-3),
-            "labels_equal": bool(torch.equal(lab_e, lab_g)), "label_dtype": str(lab_g.dtype),
-            "label_shape": list(lab_g.shape)}))
+            "metric": "sliding-window inference volume voxels/s (latency to a uint8 label map)",
+            "workload": f"512x512x160 volume, roi {args.roi}^3, overlap 0.25, sw_batch {swb}, bf16, importance "
+                        f"{args.mode} (BASELINE.json configs[3])",
+            "windows": len(plan.wins), "n_gpus": world, "windows_per_rank_max": max(
+                plan.runs[r + 1] - plan.runs[r] for r in range(world)),
+            "latency_ms": ms_g, "value": vox / (ms_g * 1e-3), "unit": "voxels/s",
+            "eager_latency_ms": ms_e,
+            "exchange": "bf16 row runs to slab owners (batch_isend_irecv) + uint8 label all-gather" if world > 1 else "none",
+            "p2p_bytes_total": moved if world > 1 else 0, "label_allgather_bytes": vox if world > 1 else 0,
+            "includes_volume_broadcast": world > 1,
+            "labels_equal_single_gpu": equal, "label_dtype": str(lab_g.dtype), "label_shape": list(lab_g.shape)}))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

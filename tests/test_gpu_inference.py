@@ -34,26 +34,45 @@ def test_sliding_window_matches_oracle_fp32():
         assert float((top2[:, 0] - top2[:, 1])[mism].max()) < 1e-5
 
 
-def test_sliding_window_sharded_equals_single():
-    """Two 'ranks' emulated in one process: each accumulates its share of the windows; the summed
-    accumulators give the same label map as the single-rank run (the all-reduce is a sum)."""
+@pytest.mark.parametrize("mode", ["constant", "gaussian"])
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sliding_window_sharded_is_bit_identical(world, mode):
+    """The world-rank algorithm (windows in contiguous runs, output slabs owned by ranks, row runs of the bf16
+    predictions handed to the slab owners, accumulation in global window order) emulated rank after rank on one GPU:
+    the label map AND the averaged logits equal the single-rank run bit for bit, for every world size."""
+    from ct_image_segmentation_b200.inference import emulate_ranks
     torch.manual_seed(1)
     net = B.UNet(3, 1, 10, [8, 16, 16], [2, 2], num_res_units=1, dtype=torch.bfloat16).to(DEV)
-    x = torch.randn(1, 1, 24, 40, 40, device=DEV)
+    x = torch.randn(1, 1, 40, 40, 24, device=DEV)
     roi = (16, 16, 16)
-    from ct_image_segmentation_b200.inference import _finalize
-    full, full_logits = sliding_window_inference(x, roi, 4, net, 0.25, return_logits=True, rank=0, world=1)
-    parts = [sliding_window_inference(x, roi, 4, net, 0.25, rank=r, world=2, partial_only=True) for r in range(2)]
-    acc, cnt = parts[0][0] + parts[1][0], parts[0][1] + parts[1][1]      # what the all-reduce computes
-    lab2, logits2 = _finalize(acc, cnt, tuple(x.shape[2:]), roi, True)
-    assert float(cnt.min()) >= 1.0
-    assert ((logits2 - full_logits).norm() / full_logits.norm()).item() < 1e-5
-    assert (lab2 != full).float().mean().item() < 1e-4
-    # windows of both shards together are exactly the full window list
-    wins = window_list(x.shape[2:], roi, 0.25)
-    assert len(wins) == len(set(wins)) and len(wins) == 2 * 3 * 3
+    full, full_logits = sliding_window_inference(x, roi, 4, net, 0.25, mode=mode, return_logits=True, rank=0, world=1)
+    lab, logits, plan = emulate_ranks(x, roi, 4, net, world, 0.25, mode=mode)
+    assert torch.equal(lab, full) and torch.equal(logits, full_logits)
+    # geometry: every window is computed exactly once, its rows go to exactly the slabs they fall in
+    assert plan.runs[0] == 0 and plan.runs[-1] == len(plan.wins) == 3 * 3 * 2
+    assert sum(p.e - p.s for p in plan.pieces) == len(plan.wins) * roi[0]
+    assert all(plan.bounds[p.dst] <= p.s < p.e <= plan.bounds[p.dst + 1] for p in plan.pieces)
     assert scan_starts(512, 128, 0.25) == [0, 96, 192, 288, 384] and scan_starts(160, 128, 0.25) == [0, 32]
     assert full.dtype == torch.uint8 and int(full.max()) <= 9
+
+
+def test_sliding_window_gaussian_matches_oracle():
+    torch.manual_seed(7)
+    ch = [8, 16, 16]
+    ref = O.UNet(3, 1, 10, ch, [2, 2], num_res_units=1)
+    net = B.UNet(3, 1, 10, ch, [2, 2], num_res_units=1, dtype=torch.float32)
+    net.load_state_dict(ref.state_dict())
+    net = net.to(DEV)
+    x = torch.randn(1, 1, 24, 40, 28)
+    roi = (16, 16, 16)
+    with torch.no_grad():
+        want = O.sliding_window_inference(x, roi, 3, ref, overlap=0.25, mode="gaussian")
+        const = O.sliding_window_inference(x, roi, 3, ref, overlap=0.25)
+    labels, logits = sliding_window_inference(x.to(DEV), roi, 3, net, overlap=0.25, mode="gaussian",
+                                              return_logits=True)
+    assert ((logits.cpu() - want).norm() / want.norm()).item() < 1e-4
+    assert ((const - want).norm() / want.norm()).item() > 1e-3  # the importance map does change the blend
+    assert (labels.cpu().long() != O.squash_predictions(want)).float().mean().item() < 1e-3
 
 
 def test_graphed_predictor_equals_eager():

@@ -266,8 +266,6 @@ SPLITK_CASES = [
 ]
 
 
-@pytest.mark.skipif(os.environ.get("B200SEG_TEST_SPLITK", "0") != "1",
-                    reason="experimental split-K cluster kernel: not yet validated on a GPU (B200SEG_TEST_SPLITK=1)")
 @pytest.mark.parametrize("cin,cout,s,tr,n,sp", SPLITK_CASES)
 def test_splitk_cluster_conv(cin, cout, s, tr, n, sp):
     """Split-K cluster kernel (B200SEG_CONV_SPLIT_K) against the streaming kernel it replaces -- same MMAs in
@@ -294,7 +292,7 @@ def test_splitk_cluster_conv(cin, cout, s, tr, n, sp):
     x_cl, dy_cl = dev(x.detach()), dev(dy)
     wp = ops.pack_weight(g, _lib.W_CONVTR_FPROP if tr else _lib.W_CONV_FPROP, wdev, dtype)
     y0, y1 = ops.alloc_like(dy_cl), ops.alloc_like(dy_cl)
-    ops.conv_fprop(g, x_cl, wp, b.to(DEV), y0)
+    ops.conv_fprop(g, x_cl, wp, b.to(DEV), y0, flags=_lib.CONV_NO_SPLIT_K)
     assert lib.b200seg_last_launch() == b"tc_conv"
     ops.conv_fprop(g, x_cl, wp, b.to(DEV), y1, flags=_lib.CONV_SPLIT_K)
     assert lib.b200seg_last_launch() == b"tc_conv_splitk"
@@ -302,7 +300,7 @@ def test_splitk_cluster_conv(cin, cout, s, tr, n, sp):
     # statistics partials through the split kernel
     c1, c0 = ops.alloc_like(dy_cl), ops.alloc_like(dy_cl)
     h1 = ops.conv_fprop_partials(g, x_cl, wp, b.to(DEV), c1, flags=_lib.CONV_SPLIT_K)
-    h0 = ops.conv_fprop_partials(g, x_cl, wp, b.to(DEV), c0)
+    h0 = ops.conv_fprop_partials(g, x_cl, wp, b.to(DEV), c0, flags=_lib.CONV_NO_SPLIT_K)
     assert (h1 is None) == (h0 is None)
     if h1 is not None:
         a1, a0 = ops.alloc_like(c1), ops.alloc_like(c0)
@@ -314,8 +312,10 @@ def test_splitk_cluster_conv(cin, cout, s, tr, n, sp):
     wp_d = ops.pack_weight(g, _lib.W_CONVTR_DGRAD if tr else _lib.W_CONV_DGRAD, wdev, dtype)
     addend, base = q(torch.randn_like(x.grad), dtype), q(torch.randn_like(x.grad), dtype)
     dx0, dx1 = dev(base), dev(base)
-    ops.conv_dgrad(g, dy_cl, wp_d, dx0, residual=dev(addend), accumulate=True)
+    ops.conv_dgrad(g, dy_cl, wp_d, dx0, residual=dev(addend), accumulate=True, flags=_lib.CONV_NO_SPLIT_K)
     ops.conv_dgrad(g, dy_cl, wp_d, dx1, residual=dev(addend), accumulate=True, flags=_lib.CONV_SPLIT_K)
+    ops.conv_dgrad(g, dy_cl, wp_d, dx0, residual=dev(addend), accumulate=False)   # the default dispatch is the split kernel
+    assert lib.b200seg_last_launch() == b"tc_conv_splitk"
     assert rel(dx1, dx0) < 4e-3 and rel(nc_cpu(dx1, 3), x.grad + addend + base) < 2e-2
 
 
@@ -766,6 +766,72 @@ def test_dice_loss_vs_oracle(n, sp, pad, dtype):
     v.backward()
     assert abs(v.item() - ref.item()) < 1e-3
     assert rel(inp.grad.float(), logits.grad) < (1e-4 if dtype == torch.float32 else 1e-2)
+
+
+@pytest.mark.parametrize("label_dtype", [torch.uint8, torch.int64])
+@pytest.mark.parametrize("n,sp", [(2, (16, 24, 20)), (1, (5, 7, 6)), (3, (1, 33, 47)), (2, (40, 64, 64))])
+def test_dice_ring_kernels_and_fused_metric(n, sp, label_dtype):
+    """Production layout (bf16, 16-channel rows, 10 classes): the bulk-copy staged forward / backward kernels equal
+    the direct-load kernels (B200SEG_DICE_NO_RING=1) and the oracle, for ragged voxel counts too; the metric counts
+    that ride on the forward pass equal the stand-alone argmax + count kernel exactly."""
+    torch.manual_seed(17)
+    c = 10
+    logits = q(torch.randn(n, c, *sp) * 3, torch.bfloat16).requires_grad_(True)
+    lab = torch.randint(0, c, (n, *sp))
+    lab[0][lab[0] == 7] = 0
+    ref = O.DiceLoss(include_background=False, to_onehot_y=True, softmax=True)(logits, lab.unsqueeze(1))
+    ref.backward()
+    cl = cl_dev(logits.detach(), torch.bfloat16, pad_c=6, c_off=0)       # ld = 16
+    assert ops.cl_info(cl)[5] == 16
+    labd = lab.to(DEV, label_dtype)
+    lib = _lib.load()
+    sums = ops.softmax_dice_sums(cl, labd)
+    assert lib.b200seg_last_launch() in (b"dice_sums_final",)
+    sums_m, counts = ops.softmax_dice_metric_sums(cl, labd)
+    assert lib.b200seg_last_launch() == b"dice_metric_final"            # the one-pass kernel ran
+    gi, gp = torch.rand(n, c, device=DEV) - 0.5, torch.rand(n, c, device=DEV) - 0.5
+    dz = ops.softmax_dice_bwd(cl, labd, gi, gp)
+    os.environ["B200SEG_DICE_NO_RING"] = "1"
+    try:
+        sums_d = ops.softmax_dice_sums(cl, labd)
+        dz_d = ops.softmax_dice_bwd(cl, labd, gi, gp)
+    finally:
+        del os.environ["B200SEG_DICE_NO_RING"]
+    torch.testing.assert_close(sums, sums_d, rtol=1e-5, atol=1e-4)
+    assert torch.equal(sums_m, sums)
+    assert torch.equal(dz, dz_d)                                         # same arithmetic, same order
+    full = dz.as_strided(dz.shape[:-1] + (16,), dz.stride())
+    assert float(full[..., c:].abs().max()) == 0.0                       # channel padding stays zero
+    _, counts_ref = ops.argmax_dice_counts(cl, labd, want_pred=False)
+    assert torch.equal(counts, counts_ref)
+    s = sums[:, 1:]
+    f = 1.0 - (2.0 * s[..., 0] + 1e-5) / (s[..., 1] + s[..., 2] + 1e-5)
+    assert abs(f.mean().item() - ref.item()) < 1e-3
+    # public module: loss + metric from one pass, gradient through the ring backward
+    fx = losses.DiceLoss(include_background=False, to_onehot_y=True, softmax=True, with_metric=True)
+    inp = cl.permute(0, 4, 1, 2, 3).requires_grad_(True)
+    v = fx(inp, labd.unsqueeze(1))
+    v.backward()
+    assert abs(v.item() - ref.item()) < 1e-3
+    assert rel(inp.grad.float(), logits.grad) < 1e-2
+    dm, dpc = metrics.dice_from_counts(fx.metric_counts)
+    dm_ref, dpc_ref = O.dice_metric(O.squash_predictions(logits.detach()), lab)
+    mism = (metrics.squash_predictions(inp.detach()).cpu() != O.squash_predictions(logits.detach())).sum().item()
+    if mism == 0:
+        np.testing.assert_allclose(dpc.cpu().numpy(), dpc_ref.numpy(), rtol=1e-6, atol=1e-7)
+
+
+def test_dice_metric_fused_other_layouts(golden):
+    """fp32 check mode / unpadded rows: b200seg_softmax_dice_metric_fwd falls back to loss kernel + metric kernel and
+    gives the reference's metric (golden, bit-exact argmax) and loss."""
+    logits = torch.from_numpy(golden["dice_logits"]).to(DEV)
+    lab = torch.from_numpy(golden["dice_lab_sparse"]).to(DEV)
+    fx = losses.DiceLoss(include_background=False, to_onehot_y=True, softmax=True, with_metric=True)
+    v = fx(logits, lab.unsqueeze(1))
+    assert abs(v.item() - float(golden["dice_sparse_mean"])) < 1e-5
+    dm, dpc = metrics.dice_from_counts(fx.metric_counts)
+    np.testing.assert_allclose(dpc.cpu().numpy(), golden["metric_sparse_per_class"], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(dm.item(), golden["metric_sparse_mean"], rtol=1e-6, atol=1e-7)
 
 
 def test_label_maps_golden(golden):
