@@ -452,11 +452,13 @@ def roofline_families(args, dev, dtype, pk):
     z = rand_act(n, (p, p, p), 10)
     lab = torch.randint(0, 10, (n, p, p, p), device=dev, dtype=torch.uint8)
     vox = n * p ** 3
-    us = _graph_time_us(lambda: ops.softmax_dice_sums(z, lab))
-    entry(f"softmax+Dice fwd @{p}^3 x{n}", "softmax_dice_fwd", us, vox * (10 * esz + 1), 0, "hbm", key=f"dice_fwd_{p}_{n}")
+    us = _graph_time_us(lambda: ops.softmax_dice_metric_sums(z, lab))
+    entry(f"softmax+Dice fwd incl. Dice-metric counts @{p}^3 x{n}", "softmax_dice_fwd_ring + dice_metric_final", us,
+          vox * (10 * esz + 1), 0, "hbm", key=f"dice_fwd_{p}_{n}")
     gi = torch.rand(n, 10, device=dev)
-    us = _graph_time_us(lambda: ops.softmax_dice_bwd(z, lab, gi, gi))
-    entry(f"softmax+Dice bwd @{p}^3 x{n}", "softmax_dice_bwd", us, vox * (20 * esz + 1), 0, "hbm", key=f"dice_bwd_{p}_{n}")
+    dz = ops.alloc_like(z)  # (the output buffer is the caller's: no allocation / zero fill inside the timed launches)
+    us = _graph_time_us(lambda: ops.softmax_dice_bwd(z, lab, gi, gi, dlogits=dz))
+    entry(f"softmax+Dice bwd @{p}^3 x{n}", "softmax_dice_bwd_ring", us, vox * (20 * esz + 1), 0, "hbm", key=f"dice_bwd_{p}_{n}")
     fams[0]["note"] = ("dominant kernel: head conv fprop (its dgrad is the same kernel with mirrored taps); HBM is the bound "
                        "by arithmetic intensity (135 FLOP/B < ridge 211); algorithmic bytes = 10 + 10 channels x 2 B per "
                        "voxel (unpadded)")

@@ -305,8 +305,6 @@ softmax_dice_fwd_ring_kernel(const __nv_bfloat16* __restrict__ logits, const voi
       r0 = rp[0];
       r1 = rp[1];
     }
-    __syncthreads();  // every row of this stage is in registers: the stage can be refilled
-    if (tid == 0 && k + RING_STAGES < nchunks) issue(k + RING_STAGES);
     if (live) {
       float p[16];
       row_softmax<CE>(r0, r1, p);
@@ -329,6 +327,14 @@ softmax_dice_fwd_ring_kernel(const __nv_bfloat16* __restrict__ logits, const voi
         }
       }
     }
+    // Hand the stage back to the bulk-copy engine only AFTER the rows have been consumed: the shared-memory loads
+    // above are then complete (their values were used), every thread orders its generic-proxy reads before the
+    // async-proxy refill (fence.proxy.async), and the CTA barrier publishes that to the issuing thread.  (With the
+    // refill issued right after the loads were merely ISSUED, the copy could overtake them: r2 found the backward
+    // kernel non-deterministic at 4 x 160^3, 7 CTAs per SM.)
+    tc::fence_proxy_async();
+    __syncthreads();
+    if (tid == 0 && k + RING_STAGES < nchunks) issue(k + RING_STAGES);
   }
   const int warp = tid / 32, lane = tid % 32;
 #pragma unroll
@@ -417,8 +423,6 @@ softmax_dice_bwd_ring_kernel(const __nv_bfloat16* __restrict__ logits, const voi
       r0 = rp[0];
       r1 = rp[1];
     }
-    __syncthreads();
-    if (tid == 0 && k + RING_STAGES < nchunks) issue(k + RING_STAGES);
     if (live) {
       float p[16];
       row_softmax<CE>(r0, r1, p);
@@ -443,6 +447,9 @@ softmax_dice_bwd_ring_kernel(const __nv_bfloat16* __restrict__ logits, const voi
       op[0] = o0;
       op[1] = o1;
     }
+    tc::fence_proxy_async();  // see the forward kernel: rows consumed, reads ordered before the async refill
+    __syncthreads();
+    if (tid == 0 && k + RING_STAGES < nchunks) issue(k + RING_STAGES);
   }
 }
 
@@ -782,9 +789,32 @@ __global__ void window_accumulate_kernel(const T* __restrict__ src, int src_ld, 
     const T* sp = src + sv * src_ld;
     const int64_t o = ((int64_t)(d0 + d) * H + (h0 + h)) * W + (w0 + w);
     float* ap = acc + o * C;
+    if constexpr (sizeof(T) == 2) {
+      // the reference's 10 classes, bf16 rows starting on 4-byte boundaries (padded 16-channel rows of the network
+      // output as well as the compact 10-channel rows of the exchange buffers): five 32-bit loads of the prediction,
+      // five 64-bit read-modify-writes of the fp32 accumulator row (40 bytes, 8-byte aligned)
+      if (C == 10 && (src_ld % 2) == 0 && ((uintptr_t)src % 4) == 0 && ((uintptr_t)acc % 8) == 0) {
+        const float m = imp ? imp[sv] : 1.f;
+        const uint32_t* rp = reinterpret_cast<const uint32_t*>(sp);
+        uint32_t r[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) r[i] = rp[i];
+        float2* a2 = reinterpret_cast<float2*>(ap);
+#pragma unroll
+        for (int i = 0; i < 5; ++i) {
+          const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r[i]));
+          float2 a = a2[i];
+          if (imp) { a.x = fmaf(m, f.x, a.x); a.y = fmaf(m, f.y, a.y); }
+          else { a.x += f.x; a.y += f.y; }
+          a2[i] = a;
+        }
+        cnt[o] += m;
+        continue;
+      }
+    }
     if (imp) {
       const float m = imp[sv];
-      for (int c = 0; c < C; ++c) ap[c] += m * to_f<T>(sp[c]);
+      for (int c = 0; c < C; ++c) ap[c] = fmaf(m, to_f<T>(sp[c]), ap[c]);
       cnt[o] += m;
     } else {
       for (int c = 0; c < C; ++c) ap[c] += to_f<T>(sp[c]);

@@ -111,8 +111,23 @@ def window_list(dims: Sequence[int], roi: Sequence[int], overlap: float) -> List
     return [(a, b, c) for a in st[0] for b in st[1] for c in st[2]]
 
 
+_IMPORTANCE_CACHE: Dict[tuple, torch.Tensor] = {}
+
+
 def importance_map(roi_size: Sequence[int], mode: str = "constant", sigma_scale: float = 0.125,
                    device="cpu") -> Optional[torch.Tensor]:
+    """Cached per (roi, mode, sigma, device): building the 128^3 Gaussian on the host costs ~50 ms."""
+    if mode == "constant":
+        return None
+    key = (tuple(int(r) for r in roi_size), mode, float(sigma_scale), str(device))
+    hit = _IMPORTANCE_CACHE.get(key)
+    if hit is None:
+        hit = _IMPORTANCE_CACHE[key] = _importance_map(roi_size, mode, sigma_scale, device)
+    return hit
+
+
+def _importance_map(roi_size: Sequence[int], mode: str = "constant", sigma_scale: float = 0.125,
+                    device="cpu") -> Optional[torch.Tensor]:
     """MONAI ``compute_importance_map``: ``None`` for "constant" (a weight of 1), else the product of per-axis
     Gaussians centred at ``roi // 2`` with sigma = ``sigma_scale * roi``, normalised to a maximum of 1 and with
     its zeros lifted to the smallest positive value (fp32, shape = roi)."""
@@ -269,8 +284,13 @@ class _RankState:
                 by_win.setdefault(p.win, []).append(p)
         for i in range(0, len(mine), self.swb):
             chunk = mine[i:i + self.swb]
+            # a ragged last batch is filled up with repeats of its last window (their predictions are dropped): every
+            # window is then computed at the SAME batch size whatever the sharding -- kernel grids and the grouping
+            # of the InstanceNorm partial sums depend on the batch size, and bit-identical label maps across world
+            # sizes need bit-identical window predictions
+            padded = chunk + [chunk[-1]] * (self.swb - len(chunk))
             batch = torch.cat([self.x[:, :, a:a + roi[0], b:b + roi[1], c:c + roi[2]]
-                               for a, b, c in (plan.wins[k] for k in chunk)], 0)
+                               for a, b, c in (plan.wins[k] for k in padded)], 0)
             with torch.no_grad():
                 pred = self.predictor(batch)
             cl = ops.to_channels_last(pred) if pred.is_cuda else pred.permute(0, 2, 3, 4, 1)

@@ -56,6 +56,25 @@ def test_sliding_window_sharded_is_bit_identical(world, mode):
     assert full.dtype == torch.uint8 and int(full.max()) <= 9
 
 
+def test_sliding_window_sharded_bit_identical_on_sliding_kernels():
+    """The same property at a ROI large enough for the sliding-window tcgen05 kernels and the deferred InstanceNorm
+    statistics (their grids depend on the batch size): ragged per-rank batches are padded to the full batch size, so
+    windows computed in another batch slot / on another rank are bit-identical and so is the label map."""
+    from ct_image_segmentation_b200.inference import GraphedPredictor, emulate_ranks
+    torch.manual_seed(3)
+    net = B.UNet(3, 1, 10, [16, 32, 64], [2, 2], num_res_units=2, dtype=torch.bfloat16).to(DEV)
+    x = torch.randn(1, 1, 80, 96, 64, device=DEV)
+    roi = (32, 64, 64)
+    pred = GraphedPredictor(net, torch.zeros(2, 1, *roi, device=DEV))
+    full, full_logits = sliding_window_inference(x, roi, 2, pred, 0.25, return_logits=True, rank=0, world=1)
+    eager = sliding_window_inference(x, roi, 2, net, 0.25, rank=0, world=1)
+    assert torch.equal(eager, full)
+    for world in (2, 4):
+        lab, logits, plan = emulate_ranks(x, roi, 2, pred, world, 0.25)
+        assert len(plan.wins) == 6
+        assert torch.equal(logits, full_logits) and torch.equal(lab, full), world
+
+
 def test_sliding_window_gaussian_matches_oracle():
     torch.manual_seed(7)
     ch = [8, 16, 16]
