@@ -65,7 +65,9 @@ class BaseUNet2D(LightningModule):
         masks = squash_masks(masks, self._n_classes)
         mask_indicator = mask_indicator.type_as(images)
         prediction = self.forward(images)
-        loss_dict = self.loss_func(input=prediction, target=masks, mask_indicator=mask_indicator)
+        dist_maps = None if (len(dist_maps) == 0) else dist_maps[0]  # reference :101 (Boundary loss input)
+        loss_dict = self.loss_func(input=prediction, target=masks, mask_indicator=mask_indicator,
+                                   dist_maps=dist_maps)
         total_loss = torch.stack(list(loss_dict.values())).sum()
         for name, loss_value in loss_dict.items():
             self.log(f"{name} Loss ({prefix})", loss_value, on_step=False, on_epoch=True)
@@ -93,7 +95,7 @@ class BaseUNet2D(LightningModule):
     @staticmethod
     def add_model_specific_args(parent_parser):
         parser = ArgumentParser(parents=[parent_parser], add_help=False)
-        parser.add_argument("--batch_size", type=int, default=64)
+        parser.add_argument("--batch_size", type=int, default=128)  # reference capstone/training/base_trainer.py:155
         parser.add_argument("--transform_degree", type=int, default=0)
         parser.add_argument("--filters", nargs=5, type=int, default=[64, 128, 256, 512, 1024])
         parser.add_argument("--use_res_units", action="store_true", default=False)

@@ -308,6 +308,40 @@ def test_lightning_module_2d_step():
     assert torch.isfinite(loss) and all(p.grad is not None for p in mod.unet.parameters())
 
 
+def test_lightning_module_2d_downsample_and_boundary_vs_oracle():
+    """BaseUNet2D as the reference's default recipe uses it (capstone/training/base_trainer.py:22-118): 3 windowed
+    channels -> `conv1x1` (downsample=True) -> UNet, losses Boundary + Dice + Focal with the batch's distance maps
+    (4-tuple batch), Dice metric -- against the oracle with the same weights: total loss, every logged loss, the
+    metric, and the gradient that reaches the 1x1 convolution through the network's input gradient."""
+    torch.manual_seed(4)
+    mod = BaseUNet2D(filters=[8, 16, 16, 32, 32], use_res_units=True, downsample=True,
+                     loss_fx=["Focal", "Dice", "Boundary"], transform_degree=1, dtype=torch.float32).to(DEV)
+    assert mod.unet.in_channels == 1 and list(mod.loss_func.losses) == ["Boundary", "Dice", "Focal"]  # sorted
+    ref = O.UNet(2, 1, 10, [8, 16, 16, 32, 32], [2, 2, 2, 2], num_res_units=2)
+    ref.load_state_dict(mod.unet.state_dict())
+    c11 = torch.nn.Conv2d(3, 1, 1)
+    c11.load_state_dict(mod.conv1x1.state_dict())
+    n, sp = 2, (64, 48)
+    images = torch.randn(n, 3, *sp)
+    lab = sparse_labels(n, sp, seed=5)
+    masks = torch.stack([(lab == c) for c in range(1, 10)], dim=1).to(torch.uint8)
+    dist = torch.randn(n, 9, *sp) * 0.02
+    ind = torch.ones(n, 9)
+    loss = mod.training_step((images.to(DEV), masks.to(DEV), ind.to(DEV), dist.to(DEV)), 0)
+    loss.backward()
+    y_ref = ref(c11(images))
+    want = O.MultipleLossWrapper(["Boundary", "Dice", "Focal"])(y_ref, O.squash_masks(masks), ind, dist)
+    total = torch.stack(list(want.values())).sum()
+    total.backward()
+    assert abs(loss.item() - total.item()) < 1e-5 * max(1.0, abs(total.item()))
+    for k, v in want.items():
+        assert abs(mod.logged[f"{k} Loss (train)"].item() - v.item()) < 1e-5, k
+    dm, _ = O.dice_metric(O.squash_predictions(y_ref.detach()), O.squash_masks(masks))
+    assert abs(mod.logged["Mean Dice Score (train)"].item() - dm.item()) < 1e-6
+    assert rel(mod.conv1x1.weight.grad, c11.weight.grad) < 5e-3 and rel(mod.conv1x1.bias.grad, c11.bias.grad) < 5e-3
+    assert BaseUNet2D.add_model_specific_args(__import__("argparse").ArgumentParser()).parse_args([]).batch_size == 128
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_wgrad_side_stream_is_bitwise_identical(dtype):
     """Weight gradients launched on the second stream (parallel graph branch) == single-stream backward."""
