@@ -74,6 +74,11 @@ SIGNATURES = {
     "b200seg_conv_fprop_stats": (C.c_int, [_CD, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_float, _P, C.c_size_t, _P]),
     "b200seg_convtr_fprop_stats": (C.c_int, [_CD, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_float, _P, C.c_size_t, _P]),
     "b200seg_conv_dgrad": (C.c_int, [_CD, _P, _P, _P, _P, _P]),
+    "b200seg_conv_dgrad_instnorm_partials_bytes": (C.c_size_t, [_CD]),
+    "b200seg_conv_dgrad_instnorm_partials": (C.c_int, [_CD, _P, _P, _P, _P, _P, C.c_int32, _P, _P, C.c_int32, _P, _P,
+                                                       C.c_size_t, _P, _P]),
+    "b200seg_instnorm_prelu_bwd_from_partials": (C.c_int, [_ND, _P, _P, _P, _P, _P, _P, C.c_int64, _P, _P, _P,
+                                                           C.c_size_t, _P]),
     "b200seg_conv_wgrad_workspace_bytes": (C.c_size_t, [_CD]),
     "b200seg_conv_wgrad": (C.c_int, [_CD, _P, _P, _P, _P, _P, C.c_size_t, _P]),
     "b200seg_convtr_fprop": (C.c_int, [_CD, _P, _P, _P, _P, _P, _P]),

@@ -484,6 +484,53 @@ int b200seg_instnorm_prelu_bwd(const b200seg_norm_desc* d, const void* x, const 
   return launch_instnorm_prelu_bwd(*d, x, mean, rstd, alpha, dy, dx, dalpha, workspace, as_stream(stream));
 }
 
+// ---- dgrad fused with the reduction pass of the InstanceNorm + PReLU backward it feeds -------------------------
+size_t b200seg_conv_dgrad_instnorm_partials_bytes(const b200seg_conv_desc* d) {
+  if (!d || !tc_slide_conv_bwdstats_supported(d, TC_CONV_DGRAD)) return 0;
+  return (size_t)tc_slide_conv_grid(d, TC_CONV_DGRAD) * 16 * 3 * sizeof(float);
+}
+
+int b200seg_conv_dgrad_instnorm_partials(const b200seg_conv_desc* d, const void* dy, const void* w_packed,
+                                         const void* residual, void* dx, const void* norm_x, int32_t norm_x_ld,
+                                         const float* mean, const float* rstd, int32_t stat_ld, const float* alpha,
+                                         float* partials, size_t partials_bytes, int64_t* rows_per_sample,
+                                         void* stream) {
+  int rc = check_conv_desc(d, false);
+  if (rc) return rc;
+  B200SEG_CHECK_ARG(dy && w_packed && dx && norm_x && mean && rstd && alpha && partials && rows_per_sample,
+                    "conv_dgrad_instnorm_partials: NULL pointer");
+  if (!tc_conv_supported(d, TC_CONV_DGRAD, dy, dx, residual) || !tc_slide_conv_bwdstats_supported(d, TC_CONV_DGRAD) ||
+      norm_x_ld < 16 || (norm_x_ld % 8) || ((uintptr_t)norm_x % 16) || stat_ld < 16)
+    return B200SEG_STATS_NOT_FUSED;  // nothing was launched: the caller runs the two plain entry points
+  const size_t need = b200seg_conv_dgrad_instnorm_partials_bytes(d);
+  if (partials_bytes < need) {
+    set_error("conv_dgrad_instnorm_partials: partials %zu < required %zu", partials_bytes, need);
+    return B200SEG_ERR_WORKSPACE;
+  }
+  TcBwdStats bst{norm_x, norm_x_ld, stat_ld, mean, rstd, alpha, partials};
+  *rows_per_sample = tc_slide_conv_grid(d, TC_CONV_DGRAD) / d->n;
+  return tc_slide_conv_run(d, TC_CONV_DGRAD, dy, tc_weights(d, w_packed), nullptr, residual, dx, nullptr,
+                           as_stream(stream), &bst);
+}
+
+int b200seg_instnorm_prelu_bwd_from_partials(const b200seg_norm_desc* d, const void* x, const float* mean,
+                                             const float* rstd, const float* alpha, const void* dy,
+                                             const float* partials, int64_t rows_per_sample, void* dx, float* dalpha,
+                                             void* workspace, size_t workspace_bytes, void* stream) {
+  int rc = check_norm_desc(d);
+  if (rc) return rc;
+  B200SEG_CHECK_ARG(x && mean && rstd && alpha && dy && partials && dx && dalpha && workspace,
+                    "instnorm_prelu_bwd_from_partials: NULL pointer");
+  B200SEG_CHECK_ARG(d->c == 16 && rows_per_sample > 0, "instnorm_prelu_bwd_from_partials: partial rows hold 16 channels");
+  B200SEG_CHECK_ARG(d->y_ld >= d->c && d->r_ld >= d->c, "instnorm_prelu_bwd_from_partials: y_ld (dy) / r_ld (dx) too small");
+  if (workspace_bytes < norm_workspace_bytes(*d)) {
+    set_error("instnorm_prelu_bwd_from_partials: workspace %zu < required %zu", workspace_bytes, norm_workspace_bytes(*d));
+    return B200SEG_ERR_WORKSPACE;
+  }
+  return launch_instnorm_prelu_bwd_from_partials(*d, x, mean, rstd, alpha, dy, partials, rows_per_sample, dx, dalpha,
+                                                 workspace, as_stream(stream));
+}
+
 // ---- optimiser --------------------------------------------------------------------------------------
 int b200seg_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                       float beta1, float beta2, float eps, int64_t step, void* stream) {

@@ -73,6 +73,10 @@ int launch_instnorm_prelu_fwd_partials(const b200seg_norm_desc& d, const void* x
 int launch_instnorm_prelu_bwd(const b200seg_norm_desc& d, const void* x, const float* mean,
                               const float* rstd, const float* alpha, const void* dy, void* dx,
                               float* dalpha, void* ws, cudaStream_t st);
+int launch_instnorm_prelu_bwd_from_partials(const b200seg_norm_desc& d, const void* x, const float* mean,
+                                            const float* rstd, const float* alpha, const void* dy,
+                                            const float* partial, int64_t rows, void* dx, float* dalpha, void* ws,
+                                            cudaStream_t st);
 
 int launch_adam_flat(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
                      float eps, int64_t step, cudaStream_t st);

@@ -650,6 +650,30 @@ int launch_instnorm_prelu_bwd(const b200seg_norm_desc& d, const void* x, const f
   return B200SEG_OK;
 }
 
+// InstanceNorm + PReLU backward whose REDUCTION pass already happened in the epilogue of the dgrad that produced
+// dy (tc_slide_conv_kernel<.., BST>): partial[n][rows][c][3] per-CTA sums -> sums (fixed order, double) -> apply.
+int launch_instnorm_prelu_bwd_from_partials(const b200seg_norm_desc& d, const void* x, const float* mean,
+                                            const float* rstd, const float* alpha, const void* dy,
+                                            const float* partial, int64_t rows, void* dx, float* dalpha, void* ws,
+                                            cudaStream_t st) {
+  NormGeom g;
+  int V = pick_vec(d, {x, dy, dx}, {d.x_ld, d.y_ld, d.r_ld});
+  int rc = make_geom(d, V, g);
+  if (rc) return rc;
+  float* sums = (float*)ws;
+  int nc = d.n * d.c;
+  instnorm_bwd_final_kernel<<<(nc * 32 + 255) / 256, 256, 0, st>>>(partial, (int)rows, d.c, nc, d.spatial, sums);
+  B200SEG_CHECK_LAUNCH("instnorm_bwd_final");
+  int64_t per2 = cdiv64(d.spatial, g.nblk_apply);
+  dim3 grid2(g.nblk_apply, d.n);
+  DISPATCH_TV(d.dtype, V,
+              (instnorm_prelu_bwd_apply_kernel<T, VV><<<grid2, 256, 0, st>>>(
+                  (const T*)x, (const T*)dy, mean, rstd, alpha, sums, (T*)dx, d.spatial, d.c,
+                  d.x_ld, d.y_ld, d.r_ld, g.L, g.VB, per2, nc, dalpha)));
+  B200SEG_CHECK_LAUNCH("instnorm_prelu_bwd_apply");
+  return B200SEG_OK;
+}
+
 // mean / rstd from per-(n, c) sum and sum of squares accumulated by a convolution epilogue
 // mean / rstd from the per-CTA partial sums a convolution epilogue produced.  partial index of
 // (class o, sample n, tile t) = (o * N + n) * T + t;  one warp per (n, channel), fixed order, double.

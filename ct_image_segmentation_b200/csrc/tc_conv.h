@@ -20,8 +20,21 @@ int tc_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void*
                 const void* residual, void* dst, float* stats, cudaStream_t st);
 // sliding-window variant for small-channel, high-resolution 3x3x3 stride-1 layers (tc_slide.cu)
 bool tc_slide_conv_supported(const b200seg_conv_desc* d, int op);
+// optional fusion of a dgrad with the reduction pass of the InstanceNorm + PReLU backward its result feeds:
+// nx = that layer's pre-norm tensor (voxel stride nx_ld), mean / rstd with nstat_ld entries per sample, alpha its
+// slope; partials [CTA][16][3] (CTAs of one sample contiguous: tc_slide_conv_grid(d, op) / n rows per sample)
+struct TcBwdStats {
+  const void* nx;
+  int nx_ld, nstat_ld;
+  const float* mean;
+  const float* rstd;
+  const float* alpha;
+  float* partials;
+};
+bool tc_slide_conv_bwdstats_supported(const b200seg_conv_desc* d, int op);
 int tc_slide_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,
-                      const void* residual, void* dst, float* stats, cudaStream_t st);
+                      const void* residual, void* dst, float* stats, cudaStream_t st,
+                      const TcBwdStats* bst = nullptr);
 // sliding-window kernels for the high-resolution stride-2 layers, ConvTranspose and Conv (tc_convtr.cu)
 bool tc_convtr_slide_supported(const b200seg_conv_desc* d, int op, const void* residual);
 int64_t tc_convtr_slide_grid(const b200seg_conv_desc* d, int op);

@@ -45,10 +45,19 @@ struct alignas(64) TcSlideConvParams {
   const bf16* res;
   bf16* dst;
   float* stats;  // optional [CTA][cout][2]: per-CTA sum / sum of squares of its outputs (InstanceNorm)
+  // BST variant (dgrad fused with the reduction pass of the InstanceNorm+PReLU backward of the layer whose output
+  // gradient this kernel writes): nx = that layer's pre-norm tensor (same voxels as dst), its statistics and slope;
+  // bstats [CTA][BN][3] = per-CTA { sum g~, sum g~ xhat, sum dy xhat [xhat <= 0] },  g~ = dy * prelu'(xhat)
+  const bf16* nx;
+  int nx_ld, nstat_ld;
+  const float* nmean;
+  const float* nrstd;
+  const float* nalpha;
+  float* bstats;
 };
 
-template <int BN, int KC>
-__global__ void __launch_bounds__(192)
+template <int BN, int KC, bool BST = false>
+__global__ void __launch_bounds__(192, BST ? 2 : 1)
 tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
   constexpr int PITCH = KC * 2;                          // bytes per voxel row
   constexpr int COPY_BYTES = (TH + 2) * TWV * PITCH;     // one w-shifted halo tile
@@ -93,6 +102,14 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
     tc::prefetch_tmap(&p.tmB);
   }
   if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
+  if constexpr (BST) {  // the consumer InstanceNorm's statistics of this CTA's sample, read per use from shared memory
+    float* nsm = reinterpret_cast<float*>(tmem_slot + 4) + 4 * BN * 3;
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) {
+      const int c = threadIdx.x - 64;
+      nsm[c] = p.nmean[n * p.nstat_ld + c];
+      nsm[BN + c] = p.nrstd[n * p.nstat_ld + c];
+    }
+  }
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
@@ -182,14 +199,42 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
     const int oh = h0 + row / TWV, ow = w0 + row % TWV;
     const bool valid = oh < p.H && ow < p.W;
     float ssum[BN], ssq[BN];  // per-thread partial statistics over this CTA's slabs (same sample n)
+    float sb2[BST ? BN : 1];  // BST: (ssum, ssq, sb2) hold the three InstanceNorm-backward sums instead
     float bias[BN];           // hoisted: the epilogue runs once per slab
 #pragma unroll
     for (int c = 0; c < BN; ++c) {
       ssum[c] = ssq[c] = 0.f;
       bias[c] = (p.bias && c < p.cout) ? p.bias[c] : 0.f;
     }
+#pragma unroll
+    for (int c = 0; c < (BST ? BN : 1); ++c) sb2[c] = 0.f;
+    const float* nsm = reinterpret_cast<const float*>(tmem_slot + 4) + 4 * BN * 3;
+    const float nslope = BST ? p.nalpha[0] : 0.f;
+    // BST: the rows the epilogue READS from global memory (residual addend, the consumer InstanceNorm's pre-norm
+    // tensor) are fetched one slab ahead, before the wait for that slab's accumulator: otherwise every slab pays a
+    // global-load round trip inside the epilogue's serial per-slab loop (r2: 263 us with the loads issued after the
+    // wait, 150 us with the prefetch).  The plain variants keep their code (and 96 registers = 3 CTAs per SM): the
+    // same prefetch there cost more in registers / spills than it hid (dgrad + residual 115 -> 138 us).
+    constexpr bool PF = BST;
+    uint4 pr0 = make_uint4(0, 0, 0, 0), pr1 = pr0, px0 = pr0, px1 = pr0;
+    auto prefetch = [&](int j) {
+      const int64_t l = (((int64_t)n * p.D + d_begin + j) * p.H + oh) * p.W + ow;
+      if (p.res) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + l * p.res_ld);
+        pr0 = rp[0];
+        pr1 = rp[1];
+      }
+      if constexpr (BST) {
+        const uint4* xp = reinterpret_cast<const uint4*>(p.nx + l * p.nx_ld);
+        px0 = xp[0];
+        px1 = xp[1];
+      }
+    };
+    if (PF && valid && nd > 0) prefetch(0);
     for (int j = 0; j < nd; ++j) {
       const int buf = j % ACCR;
+      const uint4 cr0 = pr0, cr1 = pr1, cx0 = px0, cx1 = px1;  // this slab's rows
+      if (PF && valid && j + 1 < nd) prefetch(j + 1);
       tc::mbar_wait(&acc_full[buf], ((uint32_t)(j / ACCR)) & 1u);
       tc::tc_fence_after();
       const int od = d_begin + j;
@@ -207,8 +252,12 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) f[i] += bias[ch * 16 + i];
           if (p.res) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.res + lin * p.res_ld + c0);
-            uint4 r0 = rp[0], r1 = rp[1];
+            uint4 r0 = cr0, r1 = cr1;
+            if constexpr (!PF) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.res + lin * p.res_ld + c0);
+              r0 = rp[0];
+              r1 = rp[1];
+            }
             const __nv_bfloat162* g0 = reinterpret_cast<const __nv_bfloat162*>(&r0);
             const __nv_bfloat162* g1 = reinterpret_cast<const __nv_bfloat162*>(&r1);
 #pragma unroll
@@ -247,6 +296,34 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
           }
           op[0] = o0;
           op[1] = o1;
+          if constexpr (BST) {
+            // the sums of the InstanceNorm + PReLU backward this gradient feeds, from the value AS STORED (bf16)
+            uint4 x0 = cx0, x1 = cx1;
+            if constexpr (!PF) {
+              const uint4* xp = reinterpret_cast<const uint4*>(p.nx + lin * p.nx_ld + c0);
+              x0 = xp[0];
+              x1 = xp[1];
+            }
+            const __nv_bfloat162* h0 = reinterpret_cast<const __nv_bfloat162*>(&x0);
+            const __nv_bfloat162* h1 = reinterpret_cast<const __nv_bfloat162*>(&x1);
+            float xv[16], gv[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              float2 a = __bfloat1622float2(h0[i]), b = __bfloat1622float2(h1[i]);
+              xv[2 * i] = a.x; xv[2 * i + 1] = a.y; xv[8 + 2 * i] = b.x; xv[8 + 2 * i + 1] = b.y;
+              float2 ga = __bfloat1622float2(q0[i]), gb = __bfloat1622float2(q1[i]);
+              gv[2 * i] = ga.x; gv[2 * i + 1] = ga.y; gv[8 + 2 * i] = gb.x; gv[8 + 2 * i + 1] = gb.y;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const float h = (xv[i] - nsm[c0 + i]) * nsm[BN + c0 + i];
+              const bool pos = h > 0.f;
+              const float g = pos ? gv[i] : nslope * gv[i];
+              ssum[c0 + i] += g;
+              ssq[c0 + i] = fmaf(g, h, ssq[c0 + i]);
+              sb2[c0 + i] += pos ? 0.f : gv[i] * h;
+            }
+          }
         }
       }
       // hand the chunk back zeroed
@@ -257,7 +334,18 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
     }
-    if (p.stats) {
+    if constexpr (BST) {
+      float* sred = reinterpret_cast<float*>(tmem_slot + 4);  // [4 warps][BN][3]
+#pragma unroll
+      for (int c = 0; c < BN; ++c) {
+        const float a = warp_sum(ssum[c]), b = warp_sum(ssq[c]), d3 = warp_sum(sb2[c]);
+        if (lane == 0) {
+          sred[(q * BN + c) * 3] = a;
+          sred[(q * BN + c) * 3 + 1] = b;
+          sred[(q * BN + c) * 3 + 2] = d3;
+        }
+      }
+    } else if (p.stats) {
       // warp tree per channel -> shared memory; the CTA's partial is written after the final barrier
       float* sred = reinterpret_cast<float*>(tmem_slot + 4);  // [4 warps][BN][2], after the barriers
 #pragma unroll
@@ -272,7 +360,15 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (p.stats && threadIdx.x < 2 * BN) {
+  if constexpr (BST) {
+    if (threadIdx.x < 3 * BN) {  // every one of the BN (padded) channels: the InstanceNorm kernels see them too
+      const float* sred = reinterpret_cast<const float*>(tmem_slot + 4);
+      const int c = threadIdx.x / 3, m = threadIdx.x % 3;
+      p.bstats[((int64_t)blockIdx.x * BN + c) * 3 + m] =
+          sred[(0 * BN + c) * 3 + m] + sred[(1 * BN + c) * 3 + m] + sred[(2 * BN + c) * 3 + m] +
+          sred[(3 * BN + c) * 3 + m];
+    }
+  } else if (p.stats && threadIdx.x < 2 * BN) {
     const float* sred = reinterpret_cast<const float*>(tmem_slot + 4);
     const int c = threadIdx.x >> 1, m = threadIdx.x & 1;
     if (c < p.cout)
@@ -299,19 +395,20 @@ bool slide_geom(const b200seg_conv_desc* d, int op, SlideGeom& g) {
   return true;
 }
 
-template <int BN, int KC>
+template <int BN, int KC, bool BST = false>
 int launch_slide(const TcSlideConvParams& p, unsigned grid, cudaStream_t st) {
   constexpr int PITCH = KC * 2;
   constexpr int SLAB = 3 * (TH + 2) * TWV * PITCH;
   constexpr int WB = (27 * BN * PITCH + 1023) / 1024 * 1024;
-  const size_t smem = 1024 + WB + RING * SLAB + 8 * PITCH * 8 + 16 * 8 + 64 + 4 * BN * 2 * 4;
+  // ... + reduction scratch [4 warps][BN][3] + the consumer InstanceNorm's mean / rstd [2][BN] (BST)
+  const size_t smem = 1024 + WB + RING * SLAB + 8 * PITCH * 8 + 16 * 8 + 64 + 4 * BN * 3 * 4 + 2 * BN * 4;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(tc_slide_conv_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(tc_slide_conv_kernel<BN, KC, BST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     attr_set = true;
   }
-  tc_slide_conv_kernel<BN, KC><<<grid, 192, smem, st>>>(p);
-  B200SEG_CHECK_LAUNCH("tc_slide_conv");
+  tc_slide_conv_kernel<BN, KC, BST><<<grid, 192, smem, st>>>(p);
+  B200SEG_CHECK_LAUNCH(BST ? "tc_slide_conv_bwdstats" : "tc_slide_conv");
   count_tc_launch();
   return B200SEG_OK;
 }
@@ -343,12 +440,24 @@ int64_t tc_slide_conv_grid(const b200seg_conv_desc* d, int op) {
   return cols * ((g.D + dseg - 1) / dseg);
 }
 
+// dgrad whose output gradient feeds an InstanceNorm + PReLU backward: the fused variant exists for 16 (padded)
+// destination channels -- the head layer 10->10 and the 16->16 layers, where that reduction pass is a full-resolution
+// bandwidth pass of its own
+bool tc_slide_conv_bwdstats_supported(const b200seg_conv_desc* d, int op) {
+  if (op != TC_CONV_DGRAD || (d->flags & B200SEG_CONV_NO_SLIDE) || !tc_slide_conv_supported(d, op)) return false;
+  return round16(d->cin) == 16 && round16(d->cout) == 16;
+}
+
 int tc_slide_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,
-                      const void* residual, void* dst, float* stats, cudaStream_t st) {
+                      const void* residual, void* dst, float* stats, cudaStream_t st, const TcBwdStats* bst) {
   SlideGeom g;
   slide_geom(d, op, g);
   TcSlideConvParams p;
   memset(&p, 0, sizeof(p));
+  if (bst) {
+    p.nx = (const bf16*)bst->nx; p.nx_ld = bst->nx_ld; p.nstat_ld = bst->nstat_ld;
+    p.nmean = bst->mean; p.nrstd = bst->rstd; p.nalpha = bst->alpha; p.bstats = bst->partials;
+  }
   const int KC = round16(g.src_c), BN = round16(g.dst_c);
   p.n = g.n; p.D = g.D; p.H = g.H; p.W = g.W;
   p.tilesH = (g.H + TH - 1) / TH; p.tilesW = (g.W + TWV - 1) / TWV;
@@ -381,6 +490,11 @@ int tc_slide_conv_run(const b200seg_conv_desc* d, int op, const void* src, const
   }
   const int64_t grid = cols * p.nseg;
   if (grid > 0x7fffffffLL) { set_error("tc_slide_conv: grid too large"); return B200SEG_ERR_ARG; }
+  if (bst) {
+    if (BN == 16 && KC == 16) return launch_slide<16, 16, true>(p, (unsigned)grid, st);
+    set_error("tc_slide_conv: no fused InstanceNorm-backward variant for BN=%d KC=%d", BN, KC);
+    return B200SEG_ERR_UNSUPPORTED;
+  }
   if (BN == 16 && KC == 16) return launch_slide<16, 16>(p, (unsigned)grid, st);
   if (BN == 16 && KC == 32) return launch_slide<16, 32>(p, (unsigned)grid, st);
   if (BN == 32 && KC == 16) return launch_slide<32, 16>(p, (unsigned)grid, st);

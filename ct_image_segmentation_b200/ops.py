@@ -378,6 +378,65 @@ def conv_dgrad(geom, dy, wp, dx, residual=None, accumulate=False, flags=0):
     return _conv_call(geom, dy, wp, None, residual, dx, True, flags)
 
 
+def conv_dgrad_instnorm_partials(geom, dy, wp, dx, norm_x, mean, rstd, alpha, residual=None, flags=0):
+    """dx = dgrad(dy) [+ residual] AND the per-CTA partial sums of the InstanceNorm + PReLU backward that consumes dx
+    as its output gradient (``norm_x`` = that layer's pre-norm tensor, ``mean`` / ``rstd`` / ``alpha`` its statistics
+    and slope).  Returns a handle for ``instnorm_prelu_bwd_from_partials`` -- or None WITHOUT having launched anything
+    where the fused kernel does not apply (the caller then runs ``conv_dgrad`` + ``instnorm_prelu_bwd``)."""
+    lib = _lib.load()
+    if geom.transposed or norm_x.shape != dx.shape:
+        return None
+    n, sd_, sh_, sw_, sc, s_ld = cl_info(dy)
+    n2, dd_, dh_, dw_, dc, d_ld = cl_info(dx)
+    if n != n2 or (sc, dc) != (geom.cout, geom.cin) or dy.dtype != torch.bfloat16 or dx.dtype != dy.dtype:
+        return None
+    r_ld = 0
+    if residual is not None:
+        if residual.shape != dx.shape or residual.dtype != dx.dtype:
+            return None
+        r_ld = cl_info(residual)[5]
+    if not (_pad_safe(dy) and _pad_safe(dx) and _pad_safe(residual) and _pad_safe(norm_x)):
+        return None
+    stat_ld = mean.numel() // n
+    if mean.numel() != n * stat_ld or rstd.numel() != mean.numel() or stat_ld < 16:
+        return None
+    flags |= _lib.CONV_PADDED_CHANNELS
+    d = geom.desc(n, (dd_, dh_, dw_), (sd_, sh_, sw_), d_ld, s_ld, r_ld, dy.dtype, flags)
+    nbytes = lib.b200seg_conv_dgrad_instnorm_partials_bytes(C.byref(d))
+    if nbytes == 0:
+        return None
+    part = torch.empty(nbytes // 4, dtype=torch.float32, device=dy.device)
+    rows = C.c_int64(0)
+    rc = lib.b200seg_conv_dgrad_instnorm_partials(C.byref(d), dy.data_ptr(), wp.data_ptr(), _ptr(residual), dx.data_ptr(),
+                                                  norm_x.data_ptr(), cl_info(norm_x)[5], mean.data_ptr(),
+                                                  rstd.data_ptr(), stat_ld, alpha.data_ptr(), part.data_ptr(),
+                                                  part.numel() * 4, C.byref(rows), _stream())
+    if rc == 1:  # B200SEG_STATS_NOT_FUSED: nothing ran
+        return None
+    _lib.check(rc, "b200seg_conv_dgrad_instnorm_partials")
+    return part, rows.value
+
+
+def instnorm_prelu_bwd_from_partials(x, mean, rstd, alpha, dy, dx, handle, eps: float = 1e-5, out_dalpha=None):
+    """The rest of the InstanceNorm + PReLU backward (final reduction + apply) after
+    ``conv_dgrad_instnorm_partials``; same contract as ``instnorm_prelu_bwd``."""
+    lib = _lib.load()
+    part, rows = handle
+    if dy.shape != x.shape or dx.shape != x.shape:
+        raise ValueError("instnorm_prelu_bwd_from_partials: shape mismatch")
+    mean, rstd, x, dy, dx = _match_stats(mean, rstd, "instnorm_prelu_bwd_from_partials", x, dy, dx)
+    d, _ = _norm_desc(x, cl_info(dy)[5], cl_info(dx)[5], eps)
+    dalpha = (torch.empty(1, dtype=torch.float32, device=x.device) if out_dalpha is None
+              else _grad_out(out_dalpha, (1,), "instnorm_prelu_bwd dalpha"))
+    ws = workspace(lib.b200seg_instnorm_workspace_bytes(C.byref(d)), x.device)
+    _lib.check(lib.b200seg_instnorm_prelu_bwd_from_partials(C.byref(d), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                                            alpha.data_ptr(), dy.data_ptr(), part.data_ptr(), rows,
+                                                            dx.data_ptr(), dalpha.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                            _stream()),
+               "b200seg_instnorm_prelu_bwd_from_partials")
+    return dalpha
+
+
 def _grad_out(out, shape, what):
     if out.dtype != torch.float32 or not out.is_contiguous() or out.numel() != math.prod(shape):
         raise ValueError(f"{what}: destination must be a contiguous fp32 tensor of {math.prod(shape)} elements")

@@ -30,6 +30,9 @@ from .ops import ConvGeom
 # (measured on cfg3, ms/step: never 2.291, <= 16^3 2.301, <= 32^3 2.312, <= 64^3 2.288, always 2.330)
 _DEFER_STATS_MAX_VOX = int(os.environ.get("B200SEG_DEFER_STATS_MAX_VOX", str(64 ** 3)))
 
+# dgrad fused with the reduction pass of the InstanceNorm + PReLU backward it feeds (ops.conv_dgrad_instnorm_partials)
+_FUSE_IN_BWD = os.environ.get("B200SEG_FUSE_IN_BWD", "1") == "1"
+
 _CONV = {2: nn.Conv2d, 3: nn.Conv3d}
 _CONVT = {2: nn.ConvTranspose2d, 3: nn.ConvTranspose3d}
 _INORM = {2: nn.InstanceNorm2d, 3: nn.InstanceNorm3d}
@@ -432,6 +435,7 @@ class UNet(nn.Module):
         grads: Dict[torch.Tensor, torch.Tensor] = {}
         self._bwd_taps = taps
         self._wgrad_keep = []
+        self._in_partials = {}  # Convolution -> (handle, g_out): InstanceNorm-backward sums left by the producing dgrad
         gx = self._bwd_level(self.model, g_out, saved, grads, need_gx, None, False, 0)
         side = self._wgrad_side if self.wgrad_stream else None
         if side is not None and g_out.is_cuda:
@@ -499,11 +503,16 @@ class UNet(nn.Module):
             return self._bwd_resunit(layer, g_out, saved, grads, need_gx, gx_dst, gx_accum)
         if isinstance(layer, Convolution):
             return self._bwd_convolution(layer, g_out, saved, grads, need_gx, gx_dst, gx_accum, None)
-        g_h = self._bwd_resunit(layer[1], g_out, saved, grads, True, None, False)
+        # up layer = (ConvTranspose block, residual unit): the unit's input gradient is the block's output gradient
+        g_h = self._bwd_resunit(layer[1], g_out, saved, grads, True, None, False, next_m=layer[0])
         return self._bwd_convolution(layer[0], g_h, saved, grads, need_gx, gx_dst, gx_accum, None)
 
     def _bwd_convolution(self, m: Convolution, g_out, saved, grads, need_gx, gx_dst, gx_accum,
-                         gx_residual):
+                         gx_residual, next_m: Optional[Convolution] = None):
+        """``next_m``: the Convolution (conv -> InstanceNorm -> PReLU) whose OUTPUT gradient this layer's input
+        gradient is, when nothing else is added to it afterwards: its InstanceNorm backward starts with sums over
+        exactly the tensor the dgrad epilogue holds in registers, so the dgrad leaves them as per-CTA partials
+        (``ops.conv_dgrad_instnorm_partials``) and ``next_m``'s backward skips its reduction pass."""
         s = saved.pop(m)
         g, x = m.geom, s["x"]
         if m.conv_only:
@@ -512,8 +521,14 @@ class UNet(nn.Module):
             c = s["c"]
             g_c = ops.alloc_like(c)
             sink = self._grad_sink
-            dalpha = ops.instnorm_prelu_bwd(c, s["mean"], s["rstd"], m.act.weight.detach(), g_out, g_c, m.norm.eps,
-                                            out_dalpha=None if sink is None else sink.get(m.act.weight))
+            out_da = None if sink is None else sink.get(m.act.weight)
+            fused = getattr(self, "_in_partials", {}).pop(m, None)
+            if fused is not None and fused[1] is g_out:
+                dalpha = ops.instnorm_prelu_bwd_from_partials(c, s["mean"], s["rstd"], m.act.weight.detach(), g_out, g_c,
+                                                              fused[0], m.norm.eps, out_dalpha=out_da)
+            else:
+                dalpha = ops.instnorm_prelu_bwd(c, s["mean"], s["rstd"], m.act.weight.detach(), g_out, g_c, m.norm.eps,
+                                                out_dalpha=out_da)
             if sink is None:
                 grads[m.act.weight] = dalpha
         if getattr(self, "_bwd_taps", None) is not None:
@@ -535,19 +550,33 @@ class UNet(nn.Module):
         if not need_gx:
             return None
         gx = gx_dst if gx_dst is not None else ops.alloc_like(x)
-        ops.conv_dgrad(g, g_c, self._w_dgrad(m.conv, g), gx, residual=gx_residual, accumulate=gx_accum)
+        handle = None
+        if next_m is not None and _FUSE_IN_BWD and not next_m.conv_only and x.is_cuda:
+            sn = saved.get(next_m)
+            if sn is not None and sn.get("c") is not None and tuple(sn["c"].shape) == tuple(gx.shape):
+                handle = ops.conv_dgrad_instnorm_partials(
+                    g, g_c, self._w_dgrad(m.conv, g), gx, sn["c"], sn["mean"], sn["rstd"], next_m.act.weight.detach(),
+                    residual=gx_residual, flags=_lib.CONV_ACCUMULATE if gx_accum else 0)
+        if handle is None:
+            ops.conv_dgrad(g, g_c, self._w_dgrad(m.conv, g), gx, residual=gx_residual, accumulate=gx_accum)
+        else:
+            self._in_partials[next_m] = (handle, gx)
         return gx
 
-    def _bwd_resunit(self, ru: ResidualUnit, g_out, saved, grads, need_gx, gx_dst, gx_accum):
+    def _bwd_resunit(self, ru: ResidualUnit, g_out, saved, grads, need_gx, gx_dst, gx_accum,
+                     next_m: Optional[Convolution] = None):
         units = list(ru.conv.children())
         sru = saved.pop(ru)
         x = sru["x"]
         g = g_out
         for i in range(len(units) - 1, 0, -1):
-            g = self._bwd_convolution(units[i], g, saved, grads, True, None, False, None)
+            # unit i's input gradient is unit i-1's output gradient, and nothing else is added to it
+            g = self._bwd_convolution(units[i], g, saved, grads, True, None, False, None, next_m=units[i - 1])
         if ru.res_geom is None:
-            # identity residual: d/dx = dgrad(unit0) + g_out, fused as the dgrad epilogue addend
-            return self._bwd_convolution(units[0], g, saved, grads, need_gx, gx_dst, gx_accum, g_out)
+            # identity residual: d/dx = dgrad(unit0) + g_out, fused as the dgrad epilogue addend (the sum is final
+            # there: a following block's InstanceNorm backward can take its sums from that epilogue)
+            return self._bwd_convolution(units[0], g, saved, grads, need_gx, gx_dst, gx_accum, g_out,
+                                         next_m=next_m if (gx_dst is None and not gx_accum) else None)
         gx = self._bwd_convolution(units[0], g, saved, grads, need_gx, gx_dst, gx_accum, None)
         rg = ru.res_geom
         if getattr(self, "_bwd_taps", None) is not None:

@@ -253,6 +253,28 @@ int b200seg_softmax_dice_metric_fwd(const b200seg_dice_desc* d, const void* logi
 int b200seg_softmax_dice_bwd(const b200seg_dice_desc* d, const void* logits, const void* labels,
                              const float* gI, const float* gP, void* dlogits, void* stream);
 
+/* dgrad of a 3x3x3 stride-1 layer FUSED with the reduction pass of the InstanceNorm + PReLU backward that consumes
+ * its result (the mirror of b200seg_conv_fprop_partials): monai Convolution = conv -> InstanceNorm -> PReLU, so the
+ * input gradient dx of layer L+1 is the output gradient of layer L's PReLU/InstanceNorm, whose backward starts with
+ * three per-(sample, channel) sums over all voxels (sum g~, sum g~ xhat, sum dy xhat [xhat <= 0], g~ = dy prelu'(xhat)).
+ * The dgrad epilogue has dx in registers: it loads layer L's pre-norm tensor `norm_x` (same voxels), forms the sums
+ * from the value AS STORED and leaves per-CTA partials; b200seg_instnorm_prelu_bwd_from_partials reduces them (fixed
+ * order, double) and runs the apply pass.  One full read of dy and norm_x (a bandwidth pass over the layer) is gone.
+ * Returns B200SEG_STATS_NOT_FUSED (1) WITHOUT launching anything where the fused kernel does not apply (it exists for
+ * the sliding-window tcgen05 kernel with 16 padded channels on both sides: the head layer and the 16->16 layers):
+ * the caller then runs b200seg_conv_dgrad + b200seg_instnorm_prelu_bwd.  mean / rstd hold `stat_ld` (>= 16) entries
+ * per sample; partials: b200seg_conv_dgrad_instnorm_partials_bytes(d) (0 = not fusable). */
+size_t b200seg_conv_dgrad_instnorm_partials_bytes(const b200seg_conv_desc* d);
+int b200seg_conv_dgrad_instnorm_partials(const b200seg_conv_desc* d, const void* dy, const void* w_packed,
+                                         const void* residual, void* dx, const void* norm_x, int32_t norm_x_ld,
+                                         const float* mean, const float* rstd, int32_t stat_ld, const float* alpha,
+                                         float* partials, size_t partials_bytes, int64_t* rows_per_sample,
+                                         void* stream);
+int b200seg_instnorm_prelu_bwd_from_partials(const b200seg_norm_desc* d, const void* x, const float* mean,
+                                             const float* rstd, const float* alpha, const void* dy,
+                                             const float* partials, int64_t rows_per_sample, void* dx, float* dalpha,
+                                             void* workspace, size_t workspace_bytes, void* stream);
+
 /* torch.optim.Adam step (the reference's configure_optimizers, capstone/volumetric/base_trainer.py:178-182:
  * Adam(lr), default betas / eps, no weight decay, no amsgrad) on ONE flat fp32 parameter buffer whose
  * gradient is the flat all-reduce bucket; `step` is the 1-based update count (bias correction). */

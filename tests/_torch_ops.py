@@ -126,3 +126,7 @@ def instnorm_prelu_bwd(x, mean, rstd, alpha, dy, dx, eps=1e-5, out_dalpha=None):
         out_dalpha.copy_(dalpha)
         return out_dalpha
     return dalpha
+
+
+def conv_dgrad_instnorm_partials(*args, **kwargs):
+    return None  # (the emulation has no fused kernel: the plan falls back to conv_dgrad + instnorm_prelu_bwd)

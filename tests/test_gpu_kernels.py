@@ -319,6 +319,64 @@ def test_splitk_cluster_conv(cin, cout, s, tr, n, sp):
     assert lib.b200seg_last_launch() == b"tc_conv_splitk"
 
 
+@pytest.mark.parametrize("cin,cout,n,sp,with_res", [(16, 16, 2, (12, 40, 24), False), (10, 10, 1, (9, 32, 40), True),
+                                                     (16, 16, 1, (8, 64, 64), True), (10, 10, 2, (16, 32, 32), False)])
+def test_dgrad_fused_with_instnorm_backward_sums(cin, cout, n, sp, with_res):
+    """b200seg_conv_dgrad_instnorm_partials + b200seg_instnorm_prelu_bwd_from_partials (the dgrad epilogue leaves the
+    three per-(sample, channel) sums of the InstanceNorm + PReLU backward its result feeds) against the two separate
+    entry points: the input gradient is bit-identical, the InstanceNorm-backward result and the PReLU-slope gradient
+    agree to summation order, and both match torch autograd on the same rounded inputs."""
+    dtype = torch.bfloat16
+    torch.manual_seed(77)
+    g = ConvGeom(3, cin, cout, 3, 1, False)
+    w = q(torch.randn(cout, cin, 3, 3, 3) * 0.1, dtype)
+    # layer L (consumer of the gradient): c_prev -> InstanceNorm -> PReLU -> x ; layer L+1: conv(x)
+    c_prev = q(torch.randn(n, cin, *sp) * 1.5 + 0.3, dtype).requires_grad_(True)
+    alpha = torch.tensor([0.2], requires_grad=True)
+    dy = q(torch.randn(n, cout, *sp), dtype)
+    addend = q(torch.randn(n, cin, *sp), dtype) if with_res else None
+    xh = F.prelu(F.instance_norm(c_prev, eps=1e-5), alpha)
+    y = ref_conv(g, xh, w) + (0 if addend is None else 0)
+    go = torch.autograd.grad(y, xh, dy, retain_graph=True)[0]
+    go_total = q(go + (addend if with_res else 0), dtype)          # what the dgrad epilogue stores (bf16)
+    (gc_ref, da_ref) = torch.autograd.grad(xh, (c_prev, alpha), go_total)
+
+    def dev(t_nc):
+        out = ops.alloc_activation(t_nc.shape[0], tuple(t_nc.shape[2:]), t_nc.shape[1], dtype, DEV)
+        out.copy_(t_nc.permute(0, 2, 3, 4, 1))
+        return out
+
+    c_d, dy_d = dev(c_prev.detach()), dev(dy)
+    res_d = dev(addend) if with_res else None
+    wd = ops.pack_weight(g, _lib.W_CONV_DGRAD, w.to(DEV), dtype)
+    mean, rstd = ops.instnorm_stats(c_d)
+    a_d = alpha.detach().to(DEV)
+    lib = _lib.load()
+    # separate path
+    dx0, gc0 = ops.alloc_like(c_d), ops.alloc_like(c_d)
+    ops.conv_dgrad(g, dy_d, wd, dx0, residual=res_d)
+    da0 = ops.instnorm_prelu_bwd(c_d, mean, rstd, a_d, dx0, gc0)
+    # fused path
+    dx1, gc1 = ops.alloc_like(c_d), ops.alloc_like(c_d)
+    h = ops.conv_dgrad_instnorm_partials(g, dy_d, wd, dx1, c_d, mean, rstd, a_d, residual=res_d)
+    assert h is not None and lib.b200seg_last_launch() == b"tc_slide_conv_bwdstats"
+    da1 = ops.instnorm_prelu_bwd_from_partials(c_d, mean, rstd, a_d, dx1, gc1, h)
+    assert lib.b200seg_last_launch() == b"instnorm_prelu_bwd_apply"
+    assert torch.equal(dx1, dx0)
+    assert rel(nc_cpu(dx1, 3), go_total) < 1e-2
+    assert rel(gc1, gc0) < 2e-3 and rel(nc_cpu(gc1, 3), gc_ref) < 1e-2
+    assert abs(da1.item() - da0.item()) <= 1e-3 * abs(da0.item()) + 1e-4
+    assert abs(da1.item() - da_ref.item()) <= 2e-2 * abs(da_ref.item()) + 1e-2
+    # a layer the fused kernel does not take: nothing is launched, None comes back
+    g32 = ConvGeom(3, 32, 32, 3, 1, False)
+    x32 = ops.alloc_activation(1, (8, 32, 32), 32, dtype, DEV)
+    m32, r32 = ops.instnorm_stats(x32)
+    before = lib.b200seg_launch_count()
+    assert ops.conv_dgrad_instnorm_partials(g32, x32, ops.pack_weight(g32, _lib.W_CONV_DGRAD, torch.zeros(32, 32, 3, 3, 3, device=DEV), dtype),
+                                            ops.alloc_like(x32), x32, m32, r32, a_d) is None
+    assert lib.b200seg_launch_count() == before + 1   # (only the weight pack)
+
+
 CONVTR_SLIDE = [
     # cin, cout, n, input spatial -- ConvTranspose k3 s2 layers the sliding-window kernels take
     (32, 10, 1, (8, 24, 40)),     # top layer: 10 classes padded to 16, ragged h tile
