@@ -56,7 +56,9 @@ struct alignas(64) TcSlideConvParams {
   float* bstats;
 };
 
-template <int BN, int KC, bool BST = false>
+// CS (BST only): channels that really exist (10 for the head layer's 16-wide rows): the sums of the padding channels
+// are identically zero and are neither computed nor kept in registers
+template <int BN, int KC, bool BST = false, int CS = BN>
 __global__ void __launch_bounds__(192, BST ? 2 : 1)
 tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
   constexpr int PITCH = KC * 2;                          // bytes per voxel row
@@ -104,10 +106,11 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
   if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
   if constexpr (BST) {  // the consumer InstanceNorm's statistics of this CTA's sample, read per use from shared memory
     float* nsm = reinterpret_cast<float*>(tmem_slot + 4) + 4 * BN * 3;
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) {
+    if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) {  // xhat = x * rstd + (-mean * rstd): one FMA per element
       const int c = threadIdx.x - 64;
-      nsm[c] = p.nmean[n * p.nstat_ld + c];
-      nsm[BN + c] = p.nrstd[n * p.nstat_ld + c];
+      const float r = p.nrstd[n * p.nstat_ld + c];
+      nsm[2 * c] = r;
+      nsm[2 * c + 1] = -p.nmean[n * p.nstat_ld + c] * r;
     }
   }
   tc::tc_fence_before();
@@ -199,7 +202,7 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
     const int oh = h0 + row / TWV, ow = w0 + row % TWV;
     const bool valid = oh < p.H && ow < p.W;
     float ssum[BN], ssq[BN];  // per-thread partial statistics over this CTA's slabs (same sample n)
-    float sb2[BST ? BN : 1];  // BST: (ssum, ssq, sb2) hold the three InstanceNorm-backward sums instead
+    float sb0[BST ? CS : 1], sb1[BST ? CS : 1], sb2[BST ? CS : 1];  // BST: the three InstanceNorm-backward sums
     float bias[BN];           // hoisted: the epilogue runs once per slab
 #pragma unroll
     for (int c = 0; c < BN; ++c) {
@@ -207,8 +210,8 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
       bias[c] = (p.bias && c < p.cout) ? p.bias[c] : 0.f;
     }
 #pragma unroll
-    for (int c = 0; c < (BST ? BN : 1); ++c) sb2[c] = 0.f;
-    const float* nsm = reinterpret_cast<const float*>(tmem_slot + 4) + 4 * BN * 3;
+    for (int c = 0; c < (BST ? CS : 1); ++c) sb0[c] = sb1[c] = sb2[c] = 0.f;
+    const float2* nsm = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(tmem_slot + 4) + 4 * BN * 3);
     const float nslope = BST ? p.nalpha[0] : 0.f;
     // BST: the rows the epilogue READS from global memory (residual addend, the consumer InstanceNorm's pre-norm
     // tensor) are fetched one slab ahead, before the wait for that slab's accumulator: otherwise every slab pays a
@@ -279,7 +282,7 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
               f[8 + 2 * i] += b.x; f[8 + 2 * i + 1] += b.y;
             }
           }
-          if (p.stats) {
+          if (!BST && p.stats) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
               ssum[ch * 16 + i] += f[i];
@@ -316,12 +319,15 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
             }
 #pragma unroll
             for (int i = 0; i < 16; ++i) {
-              const float h = (xv[i] - nsm[c0 + i]) * nsm[BN + c0 + i];
-              const bool pos = h > 0.f;
-              const float g = pos ? gv[i] : nslope * gv[i];
-              ssum[c0 + i] += g;
-              ssq[c0 + i] = fmaf(g, h, ssq[c0 + i]);
-              sb2[c0 + i] += pos ? 0.f : gv[i] * h;
+              if (c0 + i < CS) {  // (compile time)
+                const float2 ab = nsm[c0 + i];
+                const float h = fmaf(xv[i], ab.x, ab.y);
+                const bool pos = h > 0.f;
+                const float g = pos ? gv[i] : nslope * gv[i];
+                sb0[c0 + i] += g;
+                sb1[c0 + i] = fmaf(g, h, sb1[c0 + i]);
+                sb2[c0 + i] += pos ? 0.f : gv[i] * h;
+              }
             }
           }
         }
@@ -338,7 +344,12 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
       float* sred = reinterpret_cast<float*>(tmem_slot + 4);  // [4 warps][BN][3]
 #pragma unroll
       for (int c = 0; c < BN; ++c) {
-        const float a = warp_sum(ssum[c]), b = warp_sum(ssq[c]), d3 = warp_sum(sb2[c]);
+        float a = 0.f, b = 0.f, d3 = 0.f;
+        if (c < CS) {  // (compile time; padding channels: exact zeros)
+          a = warp_sum(sb0[c < CS ? c : 0]);
+          b = warp_sum(sb1[c < CS ? c : 0]);
+          d3 = warp_sum(sb2[c < CS ? c : 0]);
+        }
         if (lane == 0) {
           sred[(q * BN + c) * 3] = a;
           sred[(q * BN + c) * 3 + 1] = b;
@@ -395,7 +406,7 @@ bool slide_geom(const b200seg_conv_desc* d, int op, SlideGeom& g) {
   return true;
 }
 
-template <int BN, int KC, bool BST = false>
+template <int BN, int KC, bool BST = false, int CS = BN>
 int launch_slide(const TcSlideConvParams& p, unsigned grid, cudaStream_t st) {
   constexpr int PITCH = KC * 2;
   constexpr int SLAB = 3 * (TH + 2) * TWV * PITCH;
@@ -404,10 +415,10 @@ int launch_slide(const TcSlideConvParams& p, unsigned grid, cudaStream_t st) {
   const size_t smem = 1024 + WB + RING * SLAB + 8 * PITCH * 8 + 16 * 8 + 64 + 4 * BN * 3 * 4 + 2 * BN * 4;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(tc_slide_conv_kernel<BN, KC, BST>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(tc_slide_conv_kernel<BN, KC, BST, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     attr_set = true;
   }
-  tc_slide_conv_kernel<BN, KC, BST><<<grid, 192, smem, st>>>(p);
+  tc_slide_conv_kernel<BN, KC, BST, CS><<<grid, 192, smem, st>>>(p);
   B200SEG_CHECK_LAUNCH(BST ? "tc_slide_conv_bwdstats" : "tc_slide_conv");
   count_tc_launch();
   return B200SEG_OK;
@@ -491,6 +502,7 @@ int tc_slide_conv_run(const b200seg_conv_desc* d, int op, const void* src, const
   const int64_t grid = cols * p.nseg;
   if (grid > 0x7fffffffLL) { set_error("tc_slide_conv: grid too large"); return B200SEG_ERR_ARG; }
   if (bst) {
+    if (BN == 16 && KC == 16 && g.dst_c == 10) return launch_slide<16, 16, true, 10>(p, (unsigned)grid, st);
     if (BN == 16 && KC == 16) return launch_slide<16, 16, true>(p, (unsigned)grid, st);
     set_error("tc_slide_conv: no fused InstanceNorm-backward variant for BN=%d KC=%d", BN, KC);
     return B200SEG_ERR_UNSUPPORTED;
