@@ -448,6 +448,28 @@ def roofline_families(args, dev, dtype, pk):
         entry(f"InstanceNorm+PReLU bwd (reduce + apply) {tag} x{n}", lib.b200seg_last_launch().decode(), us,
               5 * esz * elems, 0, "hbm", key=f"in_bwd_{cc}_{p}_{n}",
               note="two passes: reductions (reads dy, x) then dx (reads dy, x, writes dx) = 5 e per element")
+    # the pair the step actually runs for the head layer and the c0 = 16 layers: dgrad with the InstanceNorm-backward
+    # sums in its epilogue, then final reduction + apply
+    if dtype == torch.bfloat16:
+        for cc, sp, tag in ((10, (p, p, p), f"head 10->10 @{p}^3"), (c0, (p // 2,) * 3, f"{c0}->{c0} @{p // 2}^3")):
+            g = ops.ConvGeom(3, cc, cc, 3, 1, False)
+            cprev, dy, res = rand_act(n, sp, cc), rand_act(n, sp, cc), rand_act(n, sp, cc)
+            dx, gc = ops.alloc_like(cprev), ops.alloc_like(cprev)
+            wd = ops.pack_weight(g, _lib.W_CONV_DGRAD, torch.randn(cc, cc, 3, 3, 3, device=dev) * 0.1, dtype)
+            mean, rstd = ops.instnorm_stats(cprev)
+            alpha = torch.full((1,), 0.25, device=dev)
+            h = ops.conv_dgrad_instnorm_partials(g, dy, wd, dx, cprev, mean, rstd, alpha, residual=res)
+            if h is None:
+                continue
+            vox_l = n * sp[0] * sp[1] * sp[2]
+            us = _graph_time_us(lambda: ops.conv_dgrad_instnorm_partials(g, dy, wd, dx, cprev, mean, rstd, alpha,
+                                                                         residual=res))
+            entry(f"{tag} x{n} dgrad + residual + InstanceNorm-backward sums (fused epilogue)", "tc_slide_conv_bwdstats",
+                  us, vox_l * cc * 4 * esz, 2.0 * 27 * cc * cc * vox_l, "hbm",
+                  note="reads dy, the residual addend and the consumer layer's pre-norm tensor, writes dx: 4 e per element")
+            us = _graph_time_us(lambda: ops.instnorm_prelu_bwd_from_partials(cprev, mean, rstd, alpha, dx, gc, h))
+            entry(f"InstanceNorm+PReLU bwd after the fused sums (final + apply) {cc}ch x{n}",
+                  "instnorm_bwd_final + instnorm_prelu_bwd_apply", us, vox_l * cc * 3 * esz, 0, "hbm")
     # softmax + Dice, forward sums and backward
     z = rand_act(n, (p, p, p), 10)
     lab = torch.randint(0, 10, (n, p, p, p), device=dev, dtype=torch.uint8)
