@@ -84,6 +84,21 @@ __device__ __forceinline__ uint32_t swizzle_offset(uint32_t off) {
   return off ^ ((off >> 3) & mask);
 }
 
+// A value every lane of the (converged) warp holds, handed to the compiler as warp-uniform: REDUX writes a
+// uniform register, so everything derived from it (TMEM addresses, shared-memory descriptors, instruction
+// descriptors of the MMA issue loops) is computed once per warp in the uniform datapath and feeds UTCHMMA
+// directly.  With the TMEM base address read from shared memory (a per-lane register as far as ptxas knows)
+// every MMA cost ~17 dependent instructions in the single issuing warp -- 6 R2UR moves, two 64-bit vector adds,
+// ELECT / VOTEU -- and that instruction stream, not the tensor pipe, bounded the small-N kernels (ncu r2: the
+// issuing warp of tc_slide_conv spent 70 % of its samples there with the pipe's operand fetch 53 % busy).
+__device__ __forceinline__ uint32_t warp_uniform(uint32_t v) { return __reduce_or_sync(0xffffffffu, v); }
+// Warp index the compiler KNOWS to be warp-uniform (REDUX result = a uniform register; a shuffle from lane 0 is only
+// sometimes recognised): role branches on it are uniform
+// branches, so the issue loops inside them are not compiled as potentially divergent regions.  Call at kernel
+// entry (all lanes converged).  The issue branch must hang off the producer's `if (warp == 0)` as an `else if`:
+// as a separate `if` after the producer's divergent `if (lane == 0)` region ptxas falls back to per-lane registers.
+__device__ __forceinline__ int warp_index() { return (int)__reduce_or_sync(0xffffffffu, threadIdx.x >> 5); }
+
 // ---- TMEM / tcgen05 ------------------------------------------------------------------------------
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {  // one full warp

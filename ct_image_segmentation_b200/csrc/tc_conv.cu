@@ -78,7 +78,7 @@ tc_conv_kernel(const __grid_constant__ TcConvParams p) {
   uint64_t* acc_full = empty + stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc::warp_index(), lane = threadIdx.x & 31;
 
   // ---- tile coordinates (block-uniform)
   int bx = blockIdx.x;
@@ -129,6 +129,7 @@ tc_conv_kernel(const __grid_constant__ TcConvParams p) {
     }
   } else if (warp == 1) {
     {  // warp-uniform issue loop, one elected lane issues (see umma_bf16_warp)
+      const uint32_t tmem_acc = tc::warp_uniform(*tmem_slot);  // uniform register: see tc::warp_uniform
       constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN, false, false);
       constexpr uint64_t layout = tc::layout_for_row_bytes(Cfg::ROW_BYTES);
       int st = 0;
@@ -291,7 +292,7 @@ tc_conv_splitk_kernel(const __grid_constant__ TcConvParams p) {
   float* sred = reinterpret_cast<float*>(tmem_slot + 4);  // [4 warps][BN][2]
   float* staging = sred + 4 * BN * 2;                     // [ksplit - 1][BN][128]: partial tiles of ranks 1..
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc::warp_index(), lane = threadIdx.x & 31;
   const int nsplit = p.ksplit;
   const int z = (int)tcx::cluster_ctarank();  // == blockIdx.z (cluster dims (1, 1, ksplit), gridDim.z == ksplit)
 
@@ -345,6 +346,7 @@ tc_conv_splitk_kernel(const __grid_constant__ TcConvParams p) {
     }
     __syncwarp();
   } else if (warp == 1) {
+    const uint32_t tmem_acc = tc::warp_uniform(*tmem_slot);  // uniform register: see tc::warp_uniform
     constexpr uint32_t idesc = tc::make_idesc_bf16(128, BN, false, false);
     constexpr uint64_t layout = tc::layout_for_row_bytes(Cfg::ROW_BYTES);
     int st = 0;

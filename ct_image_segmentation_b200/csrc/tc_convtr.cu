@@ -81,7 +81,7 @@ tc_convtr_fprop_kernel(const __grid_constant__ TcConvTrFpropParams p) {
   uint64_t* wbar = acc_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc::warp_index(), lane = threadIdx.x & 31;
   int bx = blockIdx.x;
   const int seg = bx % p.nseg; bx /= p.nseg;
   const int tw_i = bx % p.tilesW; bx /= p.tilesW;
@@ -135,6 +135,7 @@ tc_convtr_fprop_kernel(const __grid_constant__ TcConvTrFpropParams p) {
     }
   } else if (warp == 1) {
     {  // warp-uniform issue loop, one elected lane issues
+      const uint32_t tmem_acc = tc::warp_uniform(*tmem_slot);  // uniform register: see tc::warp_uniform
       constexpr uint64_t layout = tc::layout_for_row_bytes(PITCH);
       const uint32_t w_addr = tc::smem_u32(wsm), r_addr = tc::smem_u32(ring);
       const uint64_t tmpl = tc::make_smem_desc(0, 16, 8 * PITCH, layout);
@@ -331,7 +332,7 @@ tc_convtr_dgrad_kernel(const __grid_constant__ TcConvTrDgradParams p) {
   uint64_t* wbar = acc_empty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc::warp_index(), lane = threadIdx.x & 31;
   int bx = blockIdx.x;
   const int seg = bx % p.nseg; bx /= p.nseg;
   const int tw_i = bx % p.tilesW; bx /= p.tilesW;
@@ -377,6 +378,7 @@ tc_convtr_dgrad_kernel(const __grid_constant__ TcConvTrDgradParams p) {
     }
   } else if (warp == 1) {
     {  // warp-uniform issue loop, one elected lane issues
+      const uint32_t tmem_acc = tc::warp_uniform(*tmem_slot);  // uniform register: see tc::warp_uniform
       constexpr uint32_t idesc = tc::make_idesc_bf16(128, CI, false, false);
       const uint32_t w_addr = tc::smem_u32(wsm), r_addr = tc::smem_u32(ring);
       const uint64_t tmpl = tc::make_smem_desc(0, 16, 8 * DY_PITCH, tc::LAYOUT_SW32);
@@ -516,7 +518,7 @@ tc_convtr_wgrad_kernel(const __grid_constant__ TcConvTrWgradParams p) {
   uint64_t* acc_full = emptyX + XR;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc::warp_index(), lane = threadIdx.x & 31;
   int bx = blockIdx.x;
   const int seg = bx % p.nseg; bx /= p.nseg;
   const int tw_i = bx % p.tilesW; bx /= p.tilesW;
@@ -557,11 +559,11 @@ tc_convtr_wgrad_kernel(const __grid_constant__ TcConvTrWgradParams p) {
         }
       }
     }
-  }
-  if (warp >= 1 && warp <= 3) {  // warp-uniform issue loop, one elected lane issues
+  } else if (warp <= 3) {  // warp-uniform issue loop, one elected lane issues (`else`: see tc::warp_index)
     constexpr uint32_t idesc = tc::make_idesc_bf16(64, CI, true, true);
     constexpr uint64_t layB = tc::layout_for_row_bytes(PX);
-    const int kd = warp - 1;
+    const uint32_t tmem_acc = tc::warp_uniform(*tmem_slot);  // uniform registers: see tc::warp_uniform
+    const int kd = (int)tc::warp_uniform((uint32_t)warp) - 1;
     const uint32_t r_addr = tc::smem_u32(ring), x_addr = tc::smem_u32(xring);
     // A (MN-major): LBO = stride between 16-channel slots = the copy stride of the section, SBO = one line (8 voxels)
     const uint64_t a_tmpl0 = tc::make_smem_desc(0, TH * DY_LINE, DY_LINE, tc::LAYOUT_SW32);        // section ph=0

@@ -15,6 +15,7 @@
 //     adjacent columns except at the wrap, where the MMA is split); a chunk is complete after source
 //     slab j+2 and is drained by the epilogue warps while later slabs accumulate.
 //   wgrad: see tc_slide_wgrad_kernel below.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -33,6 +34,16 @@ constexpr int TH = 16;      // lines per tile
 constexpr int TWV = 8;      // voxels per line (one swizzle atom of rows)
 constexpr int RING = 4;     // source slabs in flight
 inline int round16(int c) { return (c + 15) / 16 * 16; }
+// d segments per column: enough CTAs for ~`oversub` per SM (3 are co-resident), at least 8 slabs each.
+// B200SEG_SLIDE_OVERSUB overrides the default of 4 (tuning / A-B runs).
+inline int slide_oversub() {
+  static const int v = [] {
+    const char* e = getenv("B200SEG_SLIDE_OVERSUB");
+    const int x = e ? atoi(e) : 4;
+    return x >= 1 && x <= 64 ? x : 4;
+  }();
+  return v;
+}
 }  // namespace
 
 struct alignas(64) TcSlideConvParams {
@@ -79,7 +90,7 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
   uint64_t* wbar = acc_empty + ACCR;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc::warp_index(), lane = threadIdx.x & 31;
   int bx = blockIdx.x;
   const int seg = bx % p.nseg; bx /= p.nseg;
   const int tw_i = bx % p.tilesW; bx /= p.tilesW;
@@ -157,6 +168,7 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
     }
   } else if (warp == 1) {
     {  // the whole warp runs the (warp-uniform) issue loop; one elected lane issues each MMA / commit
+      const uint32_t tmem_acc = tc::warp_uniform(*tmem_slot);  // (shadows the per-lane copy: see warp_uniform)
       constexpr uint64_t layout = tc::layout_for_row_bytes(PITCH);
       const uint32_t w_addr = tc::smem_u32(wsm), r_addr = tc::smem_u32(ring);
       const uint64_t tmpl = tc::make_smem_desc(0, 16, 8 * PITCH, layout);
@@ -443,7 +455,7 @@ int64_t tc_slide_conv_grid(const b200seg_conv_desc* d, int op) {
   slide_geom(d, op, g);
   const int tilesH = (g.H + TH - 1) / TH, tilesW = (g.W + TWV - 1) / TWV;
   const int64_t cols = (int64_t)g.n * tilesH * tilesW;
-  int nseg = (int)((148 * 4 + cols - 1) / cols);
+  int nseg = (int)((148 * slide_oversub() + cols - 1) / cols);
   if (nseg < 1) nseg = 1;
   int dseg = (g.D + nseg - 1) / nseg;
   if (dseg < 8) dseg = 8;
@@ -472,9 +484,8 @@ int tc_slide_conv_run(const b200seg_conv_desc* d, int op, const void* src, const
   const int KC = round16(g.src_c), BN = round16(g.dst_c);
   p.n = g.n; p.D = g.D; p.H = g.H; p.W = g.W;
   p.tilesH = (g.H + TH - 1) / TH; p.tilesW = (g.W + TWV - 1) / TWV;
-  // d segments: enough CTAs for ~4 per SM, at least 8 slabs each
   const int64_t cols = (int64_t)g.n * p.tilesH * p.tilesW;
-  int nseg = (int)((148 * 4 + cols - 1) / cols);
+  int nseg = (int)((148 * slide_oversub() + cols - 1) / cols);
   if (nseg < 1) nseg = 1;
   int dseg = (g.D + nseg - 1) / nseg;
   if (dseg < 8) dseg = 8;

@@ -65,7 +65,7 @@ tc_slide_wgrad_kernel(const __grid_constant__ TcSlideWgradParams p) {
   uint64_t* acc_full = emptyT + RT;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc::warp_index(), lane = threadIdx.x & 31;
   int bx = blockIdx.x;
   const int seg = bx % p.nseg; bx /= p.nseg;
   const int tw_i = bx % p.tilesW; bx /= p.tilesW;
@@ -123,9 +123,10 @@ tc_slide_wgrad_kernel(const __grid_constant__ TcSlideWgradParams p) {
   }
   // ---- MMA issue: warps 1, 2, 3 each own one kw (one accumulator of 3*CB columns); warp-uniform loop,
   // one elected lane issues
-  if (warp >= 1 && warp <= 3) {
+  else if (warp <= 3) {  // (`else`, not a second `if`: see tc::warp_index)
     constexpr uint64_t layA = tc::layout_for_row_bytes(PA), layB = tc::layout_for_row_bytes(PB);
-    const int iw = warp - 1;
+    const uint32_t tmem_acc = tc::warp_uniform(*tmem_slot);  // uniform registers: see tc::warp_uniform
+    const int iw = (int)tc::warp_uniform((uint32_t)warp) - 1;
     const uint32_t r_addr = tc::smem_u32(ring), t_addr = tc::smem_u32(tring);
     const uint64_t a_tmpl = tc::make_smem_desc(0, TWV * PA, TWV * PA, layA);    // slots one line apart
     const uint64_t b_tmpl = tc::make_smem_desc(0, TSLAB_BYTES, TWV * PB, layB); // N chunks one T slab apart

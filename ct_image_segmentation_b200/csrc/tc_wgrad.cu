@@ -78,7 +78,7 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
   uint64_t* acc_full = empty + stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_full + 1);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = tc::warp_index(), lane = threadIdx.x & 31;
   const int pass = blockIdx.z;
   const int n0 = blockIdx.y * p.N;
   const int slot_begin = pass * slots_pass_cap;
@@ -133,8 +133,9 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
           if (++st == stages) { st = 0; ph ^= 1u; }
         }
       }
-    }
-    if (warp >= 1 && warp <= nissue) {  // warp-uniform issue loop, one elected lane issues
+    } else if (warp <= nissue) {  // warp-uniform issue loop, one elected lane issues (`else`: see tc::warp_index)
+      const uint32_t tmem_acc = tc::warp_uniform(*tmem_slot);  // uniform registers: see tc::warp_uniform
+      const int warp_u = (int)tc::warp_uniform((uint32_t)warp);
       const uint32_t idesc = tc::make_idesc_bf16(128, p.N, true, true);
       const uint64_t layA = tc::layout_for_row_bytes(pitchA), layB = tc::layout_for_row_bytes(pitchB);
       const uint64_t a_tmpl = tc::make_smem_desc(0, tileA, 8 * pitchA, layA);
@@ -148,7 +149,7 @@ tc_wgrad_kernel(const __grid_constant__ TcWgradParams p) {
         tc::tc_fence_after();
         const uint32_t b_addr = tc::smem_u32(smem + (size_t)st * stage_bytes);
         const uint64_t bd0 = b_tmpl + (b_addr >> 4);
-        for (int mt = warp - 1; mt < mtiles; mt += nissue) {
+        for (int mt = warp_u - 1; mt < mtiles; mt += nissue) {
           const uint64_t ad0 = a_tmpl + ((b_addr + p.nb * tileB + mt * p.spm * tileA) >> 4);
           const uint32_t acc = tmem_acc + mt * p.N;
           for (int j = 0; j < ksteps; ++j)
