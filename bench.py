@@ -464,8 +464,8 @@ def roofline_families(args, dev, dtype, pk):
             vox_l = n * sp[0] * sp[1] * sp[2]
             us = _graph_time_us(lambda: ops.conv_dgrad_instnorm_partials(g, dy, wd, dx, cprev, mean, rstd, alpha,
                                                                          residual=res))
-            entry(f"{tag} x{n} dgrad + residual + InstanceNorm-backward sums (fused epilogue)", "tc_slide_conv_bwdstats",
-                  us, vox_l * cc * 4 * esz, 2.0 * 27 * cc * cc * vox_l, "hbm",
+            entry(f"{tag} x{n} dgrad + residual + InstanceNorm-backward sums (fused epilogue)",
+                  lib.b200seg_last_launch().decode(), us, vox_l * cc * 4 * esz, 2.0 * 27 * cc * cc * vox_l, "hbm",
                   note="reads dy, the residual addend and the consumer layer's pre-norm tensor, writes dx: 4 e per element")
             us = _graph_time_us(lambda: ops.instnorm_prelu_bwd_from_partials(cprev, mean, rstd, alpha, dx, gc, h))
             entry(f"InstanceNorm+PReLU bwd after the fused sums (final + apply) {cc}ch x{n}",

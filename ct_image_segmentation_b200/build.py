@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIBDIR, "libb200seg.so")
-SOURCES = ["api.cu", "conv_generic.cu", "norm.cu", "dice.cu", "tc_conv.cu", "tc_wgrad.cu", "tc_slide.cu", "tc_slide_wgrad.cu", "tc_convtr.cu", "conv_small_cin.cu"]
+SOURCES = ["api.cu", "conv_generic.cu", "norm.cu", "dice.cu", "tc_conv.cu", "tc_wgrad.cu", "tc_slide.cu", "tc_line.cu", "tc_slide_wgrad.cu", "tc_convtr.cu", "conv_small_cin.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

@@ -35,6 +35,12 @@ bool tc_slide_conv_bwdstats_supported(const b200seg_conv_desc* d, int op);
 int tc_slide_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,
                       const void* residual, void* dst, float* stats, cudaStream_t st,
                       const TcBwdStats* bst = nullptr);
+// line-tiled variant of the sliding kernel (tc_line.cu): 16 -> 16 (padded) channels, row length 32 / 64 / 128, source
+// voxel stride exactly 16 elements; tc_slide_conv_supported / _grid / _run route to it where it applies
+bool tc_line_conv_supported(const b200seg_conv_desc* d, int op);
+int64_t tc_line_conv_rows(const b200seg_conv_desc* d, int op);
+int tc_line_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,
+                     const void* residual, void* dst, float* stats, cudaStream_t st, const TcBwdStats* bst);
 // sliding-window kernels for the high-resolution stride-2 layers, ConvTranspose and Conv (tc_convtr.cu)
 bool tc_convtr_slide_supported(const b200seg_conv_desc* d, int op, const void* residual);
 int64_t tc_convtr_slide_grid(const b200seg_conv_desc* d, int op);

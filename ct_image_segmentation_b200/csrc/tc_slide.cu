@@ -441,6 +441,7 @@ int launch_slide(const TcSlideConvParams& p, unsigned grid, cudaStream_t st) {
 // Layers the sliding kernel takes (on top of tc_conv_supported): 3-D, 3x3x3, stride 1, source and
 // destination channel counts (padded) in {16, 32}, and a volume large enough to amortise the sweep.
 bool tc_slide_conv_supported(const b200seg_conv_desc* d, int op) {
+  if (tc_line_conv_supported(d, op)) return true;
   SlideGeom g;
   if (!slide_geom(d, op, g)) return false;
   const int sp = round16(g.src_c), dp = round16(g.dst_c);
@@ -451,6 +452,7 @@ bool tc_slide_conv_supported(const b200seg_conv_desc* d, int op) {
 
 // number of CTAs (= per-CTA statistic partials); CTAs of one sample are contiguous
 int64_t tc_slide_conv_grid(const b200seg_conv_desc* d, int op) {
+  if (tc_line_conv_supported(d, op)) return tc_line_conv_rows(d, op);
   SlideGeom g;
   slide_geom(d, op, g);
   const int tilesH = (g.H + TH - 1) / TH, tilesW = (g.W + TWV - 1) / TWV;
@@ -473,6 +475,7 @@ bool tc_slide_conv_bwdstats_supported(const b200seg_conv_desc* d, int op) {
 
 int tc_slide_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,
                       const void* residual, void* dst, float* stats, cudaStream_t st, const TcBwdStats* bst) {
+  if (tc_line_conv_supported(d, op)) return tc_line_conv_run(d, op, src, w_tc, bias, residual, dst, stats, st, bst);
   SlideGeom g;
   slide_geom(d, op, g);
   TcSlideConvParams p;

@@ -185,6 +185,12 @@ TC_GEOMS = [
     (3, 16, 32, 3, 1, False, 1, (9, 48, 16)),
     (3, 32, 16, 3, 1, False, 1, (16, 24, 32)),
     (3, 16, 16, 3, 1, False, 2, (40, 128, 128)),   # long sweeps: the TMEM accumulator ring wraps
+    # line-tiled kernel (tc_line.cu: rows of 32 / 64 / 128 voxels, 16 padded channels): ragged line tiles, several
+    # items per persistent CTA, rows 31|32 of a 128-voxel line exchanged through shared memory
+    (3, 16, 16, 3, 1, False, 2, (9, 19, 32)),
+    (3, 10, 10, 3, 1, False, 1, (13, 10, 64)),
+    (3, 16, 10, 3, 1, False, 1, (6, 5, 128)),
+    (3, 10, 16, 3, 1, False, 3, (5, 3, 128)),
 ]
 
 
@@ -320,7 +326,8 @@ def test_splitk_cluster_conv(cin, cout, s, tr, n, sp):
 
 
 @pytest.mark.parametrize("cin,cout,n,sp,with_res", [(16, 16, 2, (12, 40, 24), False), (10, 10, 1, (9, 32, 40), True),
-                                                     (16, 16, 1, (8, 64, 64), True), (10, 10, 2, (16, 32, 32), False)])
+                                                     (16, 16, 1, (8, 64, 64), True), (10, 10, 2, (16, 32, 32), False),
+                                                     (10, 10, 2, (7, 5, 128), True), (16, 16, 1, (20, 9, 64), False)])
 def test_dgrad_fused_with_instnorm_backward_sums(cin, cout, n, sp, with_res):
     """b200seg_conv_dgrad_instnorm_partials + b200seg_instnorm_prelu_bwd_from_partials (the dgrad epilogue leaves the
     three per-(sample, channel) sums of the InstanceNorm + PReLU backward its result feeds) against the two separate
@@ -359,7 +366,7 @@ def test_dgrad_fused_with_instnorm_backward_sums(cin, cout, n, sp, with_res):
     # fused path
     dx1, gc1 = ops.alloc_like(c_d), ops.alloc_like(c_d)
     h = ops.conv_dgrad_instnorm_partials(g, dy_d, wd, dx1, c_d, mean, rstd, a_d, residual=res_d)
-    assert h is not None and lib.b200seg_last_launch() == b"tc_slide_conv_bwdstats"
+    assert h is not None and lib.b200seg_last_launch() in (b"tc_slide_conv_bwdstats", b"tc_line_conv_bwdstats")
     da1 = ops.instnorm_prelu_bwd_from_partials(c_d, mean, rstd, a_d, dx1, gc1, h)
     assert lib.b200seg_last_launch() == b"instnorm_prelu_bwd_apply"
     assert torch.equal(dx1, dx0)
@@ -594,6 +601,8 @@ def test_instnorm_prelu(n, c, sp, dtype):
 PARTIALS_CASES = [
     # cin, cout, stride, transposed, n, input spatial
     (16, 16, 1, False, 2, (12, 40, 24)),    # stride-1 sliding kernel
+    (16, 16, 1, False, 2, (10, 21, 64)),    # line-tiled kernel: per-warp partial statistics per item
+    (10, 10, 1, False, 1, (7, 6, 128)),
     (32, 32, 1, False, 1, (8, 32, 32)),
     (32, 10, 2, True, 2, (8, 24, 40)),      # ConvTranspose lo->hi, 10 classes padded to 16
     (16, 32, 2, False, 1, (16, 48, 64)),    # stride-2 conv hi->lo
