@@ -487,7 +487,7 @@ int b200seg_instnorm_prelu_bwd(const b200seg_norm_desc* d, const void* x, const 
 // ---- dgrad fused with the reduction pass of the InstanceNorm + PReLU backward it feeds -------------------------
 size_t b200seg_conv_dgrad_instnorm_partials_bytes(const b200seg_conv_desc* d) {
   if (!d || !tc_slide_conv_bwdstats_supported(d, TC_CONV_DGRAD)) return 0;
-  return (size_t)tc_slide_conv_grid(d, TC_CONV_DGRAD) * 16 * 3 * sizeof(float);
+  return (size_t)tc_slide_conv_grid(d, TC_CONV_DGRAD, true) * 16 * 3 * sizeof(float);
 }
 
 int b200seg_conv_dgrad_instnorm_partials(const b200seg_conv_desc* d, const void* dy, const void* w_packed,
@@ -508,7 +508,7 @@ int b200seg_conv_dgrad_instnorm_partials(const b200seg_conv_desc* d, const void*
     return B200SEG_ERR_WORKSPACE;
   }
   TcBwdStats bst{norm_x, norm_x_ld, stat_ld, mean, rstd, alpha, partials};
-  *rows_per_sample = tc_slide_conv_grid(d, TC_CONV_DGRAD) / d->n;
+  *rows_per_sample = tc_slide_conv_grid(d, TC_CONV_DGRAD, true) / d->n;
   return tc_slide_conv_run(d, TC_CONV_DGRAD, dy, tc_weights(d, w_packed), nullptr, residual, dx, nullptr,
                            as_stream(stream), &bst);
 }

@@ -15,7 +15,7 @@ bool tc_conv_supported(const b200seg_conv_desc* d, int op, const void* src, cons
 // stats (optional, fprop without residual only): [blockIdx.x][cout][2] fp32 per-CTA sum / sum of squares;
 // blockIdx.x = (class * n + sample) * tiles + tile (tc_conv_grid) or sample-major (tc_slide_conv_grid)
 void tc_conv_grid(const b200seg_conv_desc* d, int op, int* ncls_out, int64_t* tiles_out);
-int64_t tc_slide_conv_grid(const b200seg_conv_desc* d, int op);
+int64_t tc_slide_conv_grid(const b200seg_conv_desc* d, int op, bool bst = false);  // rows of statistic partials
 int tc_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,
                 const void* residual, void* dst, float* stats, cudaStream_t st);
 // sliding-window variant for small-channel, high-resolution 3x3x3 stride-1 layers (tc_slide.cu)

@@ -34,15 +34,46 @@ constexpr int TH = 16;      // lines per tile
 constexpr int TWV = 8;      // voxels per line (one swizzle atom of rows)
 constexpr int RING = 4;     // source slabs in flight
 inline int round16(int c) { return (c + 15) / 16 * 16; }
-// d segments per column: enough CTAs for ~`oversub` per SM (3 are co-resident), at least 8 slabs each.
-// B200SEG_SLIDE_OVERSUB overrides the default of 4 (tuning / A-B runs).
-inline int slide_oversub() {
+inline int env_int(const char* name, int dflt, int lo, int hi) {
+  const char* e = getenv(name);
+  if (!e) return dflt;
+  const int x = atoi(e);
+  return x >= lo && x <= hi ? x : dflt;
+}
+// B200SEG_SLIDE_PERSIST=0: one CTA per item with the r1 segmentation (A/B runs)
+inline int slide_persist() { static const int v = env_int("B200SEG_SLIDE_PERSIST", 1, 0, 1); return v; }
+inline int sm_count() {
   static const int v = [] {
-    const char* e = getenv("B200SEG_SLIDE_OVERSUB");
-    const int x = e ? atoi(e) : 4;
-    return x >= 1 && x <= 64 ? x : 4;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+    return n;
   }();
   return v;
+}
+// Work decomposition shared by the run / grid / workspace queries.  Persistent mode: `slots` CTAs stay resident
+// (3 per SM; 2 for the fused InstanceNorm-backward variant) and walk the items round-robin; the number of d segments
+// per column minimises rounds x (slabs per item + 2 halo slabs), fewest segments on ties.
+inline void slide_segments(int64_t cols, int D, int slots_per_sm, int& dseg, int& nseg) {
+  if (!slide_persist()) {
+    nseg = (int)((148 * 4 + cols - 1) / cols);
+    if (nseg < 1) nseg = 1;
+    dseg = (D + nseg - 1) / nseg;
+    if (dseg < 8) dseg = 8;
+    if (dseg > D) dseg = D;
+    nseg = (D + dseg - 1) / dseg;
+    return;
+  }
+  const int64_t slots = (int64_t)sm_count() * slots_per_sm;
+  int64_t best = -1;
+  nseg = 1;
+  for (int ns = 1; ns <= D / 4 && ns <= 64; ++ns) {
+    const int ds = (D + ns - 1) / ns;
+    if ((D + ds - 1) / ds != ns) continue;
+    const int64_t cost = ((cols * ns + slots - 1) / slots) * (ds + 2);
+    if (best < 0 || cost < best) { best = cost; nseg = ns; }
+  }
+  dseg = (D + nseg - 1) / nseg;
 }
 }  // namespace
 
@@ -51,14 +82,15 @@ struct alignas(64) TcSlideConvParams {
   CUtensorMap tmB;
   int n, D, H, W;
   int tilesH, tilesW, dseg, nseg;
+  int items;     // (sample, line tile, voxel tile, d segment) columns: CTA b works on items b, b + gridDim.x, ...
   int cout, dst_ld, res_ld, accumulate, flip;
   const float* bias;
   const bf16* res;
   bf16* dst;
-  float* stats;  // optional [CTA][cout][2]: per-CTA sum / sum of squares of its outputs (InstanceNorm)
+  float* stats;  // optional [item][epilogue warp][cout][2]: sum / sum of squares of the outputs (InstanceNorm)
   // BST variant (dgrad fused with the reduction pass of the InstanceNorm+PReLU backward of the layer whose output
   // gradient this kernel writes): nx = that layer's pre-norm tensor (same voxels as dst), its statistics and slope;
-  // bstats [CTA][BN][3] = per-CTA { sum g~, sum g~ xhat, sum dy xhat [xhat <= 0] },  g~ = dy * prelu'(xhat)
+  // bstats [item][epilogue warp][BN][3] = { sum g~, sum g~ xhat, sum dy xhat [xhat <= 0] },  g~ = dy * prelu'(xhat)
   const bf16* nx;
   int nx_ld, nstat_ld;
   const float* nmean;
@@ -70,7 +102,7 @@ struct alignas(64) TcSlideConvParams {
 // CS (BST only): channels that really exist (10 for the head layer's 16-wide rows): the sums of the padding channels
 // are identically zero and are neither computed nor kept in registers
 template <int BN, int KC, bool BST = false, int CS = BN>
-__global__ void __launch_bounds__(192, BST ? 2 : 1)
+__global__ void __launch_bounds__(192, BST ? 2 : ((BN == 16 && KC == 16) ? 3 : 1))
 tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
   constexpr int PITCH = KC * 2;                          // bytes per voxel row
   constexpr int COPY_BYTES = (TH + 2) * TWV * PITCH;     // one w-shifted halo tile
@@ -91,14 +123,23 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
 
   const int warp = tc::warp_index(), lane = threadIdx.x & 31;
-  int bx = blockIdx.x;
-  const int seg = bx % p.nseg; bx /= p.nseg;
-  const int tw_i = bx % p.tilesW; bx /= p.tilesW;
-  const int th_i = bx % p.tilesH; bx /= p.tilesH;
-  const int n = bx;
-  const int h0 = th_i * TH, w0 = tw_i * TWV;
-  const int d_begin = seg * p.dseg;
-  const int nd = min(p.dseg, p.D - d_begin);  // output slabs of this CTA
+  // Persistent CTAs: the grid is min(items, resident CTAs) and a CTA walks its items without re-allocating TMEM,
+  // re-loading the weights or draining its pipelines: the source ring (counter g) and the accumulator ring
+  // (counter ob) run on across item borders.  (r2: with one item per CTA the set-up was ~8 % of a CTA's life
+  // and 768 CTAs on 444 slots left the last 0.27 wave half empty.)
+  struct Item { int n, h0, w0, d_begin, nd; };
+  auto decode = [&](int item) {
+    Item it;
+    int bx = item;
+    const int seg = bx % p.nseg; bx /= p.nseg;
+    const int tw_i = bx % p.tilesW; bx /= p.tilesW;
+    const int th_i = bx % p.tilesH; bx /= p.tilesH;
+    it.n = bx;
+    it.h0 = th_i * TH; it.w0 = tw_i * TWV;
+    it.d_begin = seg * p.dseg;
+    it.nd = min(p.dseg, p.D - it.d_begin);  // output slabs of this item
+    return it;
+  };
 
   if (warp == 0 && lane == 0) {
     for (int i = 0; i < RING; ++i) {
@@ -115,13 +156,13 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
     tc::prefetch_tmap(&p.tmB);
   }
   if (warp == 1) tc::tmem_alloc<TMEM_COLS>(tmem_slot);
-  if constexpr (BST) {  // the consumer InstanceNorm's statistics of this CTA's sample, read per use from shared memory
+  if constexpr (BST) {  // the consumer InstanceNorm's statistics of every sample (n <= 16), read per use from shared memory
     float* nsm = reinterpret_cast<float*>(tmem_slot + 4) + 4 * BN * 3;
-    if (threadIdx.x >= 64 && threadIdx.x < 64 + BN) {  // xhat = x * rstd + (-mean * rstd): one FMA per element
-      const int c = threadIdx.x - 64;
-      const float r = p.nrstd[n * p.nstat_ld + c];
-      nsm[2 * c] = r;
-      nsm[2 * c + 1] = -p.nmean[n * p.nstat_ld + c] * r;
+    for (int idx = threadIdx.x; idx < p.n * BN; idx += blockDim.x) {  // xhat = x * rstd + (-mean * rstd): one FMA
+      const int c = idx % BN, nn = idx / BN;
+      const float r = p.nrstd[nn * p.nstat_ld + c];
+      nsm[2 * idx] = r;
+      nsm[2 * idx + 1] = -p.nmean[nn * p.nstat_ld + c] * r;
     }
   }
   tc::tc_fence_before();
@@ -153,17 +194,19 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
           const int tap = p.flip ? ((2 - id) * 3 + (2 - ih)) * 3 + (2 - iw) : (id * 3 + ih) * 3 + iw;
           tc::tma_load_2d(wsm + (hw * 3 + i) * WT_BYTES, &p.tmB, wbar, 0, tap * BN);
         }
-      uint32_t ph = 0;
-      for (int s = 0; s < nd + 2; ++s) {
-        const int slot = s % RING;
-        if (s > 0 && slot == 0) ph ^= 1u;
-        tc::mbar_wait(&empty[slot], ph ^ 1u);
-        uint8_t* dst = ring + slot * SLAB_BYTES;
-        tc::mbar_expect_tx(&full[slot], SLAB_BYTES);
-        const int ds = d_begin - 1 + s;
+      uint32_t g = 0;  // source slabs issued by this CTA
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+        const Item it = decode(item);
+        for (int s = 0; s < it.nd + 2; ++s, ++g) {
+          const uint32_t slot = g % RING;
+          tc::mbar_wait(&empty[slot], ((g / RING) & 1u) ^ 1u);
+          uint8_t* dst = ring + slot * SLAB_BYTES;
+          tc::mbar_expect_tx(&full[slot], SLAB_BYTES);
+          const int ds = it.d_begin - 1 + s;
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw)
-          tc::tma_load_5d(dst + kw * COPY_BYTES, &p.tmA, &full[slot], 0, w0 + kw - 1, h0 - 1, ds, n);
+          for (int kw = 0; kw < 3; ++kw)
+            tc::tma_load_5d(dst + kw * COPY_BYTES, &p.tmA, &full[slot], 0, it.w0 + kw - 1, it.h0 - 1, ds, it.n);
+        }
       }
     }
   } else if (warp == 1) {
@@ -174,24 +217,29 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
       const uint64_t tmpl = tc::make_smem_desc(0, 16, 8 * PITCH, layout);
       const uint64_t w_desc = tmpl + (w_addr >> 4);
       tc::mbar_wait(wbar, 0);
-      for (int s = 0; s < nd + 2; ++s) {
+      uint32_t g = 0, ob = 0;  // source slabs consumed / output slabs started before this item
+      for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+      const int nd = decode(item).nd;
+      for (int s = 0; s < nd + 2; ++s, ++g) {
         // source slab s (absolute d = d_begin - 1 + s) feeds output slabs s-2, s-1, s (clipped to [0, nd))
         const int lo = max(s - 2, 0), hi = min(s, nd - 1);
-        const bool fresh = s < nd;  // output slab s receives its first contribution: overwrite
-        if (fresh) tc::mbar_wait(&acc_empty[s % ACCR], (((uint32_t)(s / ACCR)) & 1u) ^ 1u);
-        tc::mbar_wait(&full[s % RING], ((uint32_t)(s / RING)) & 1u);
+        if (s < nd) {  // output slab s receives its first contribution: its chunk must have been drained (zeroed)
+          const uint32_t o = ob + (uint32_t)s;
+          tc::mbar_wait(&acc_empty[o % ACCR], ((o / ACCR) & 1u) ^ 1u);
+        }
+        const uint32_t slot = g % RING;
+        tc::mbar_wait(&full[slot], (g / RING) & 1u);
         tc::tc_fence_after();
         // The accumulating range [lo, hi] is one MMA (adjacent TMEM chunks) or two where the
-        // accumulator ring wraps.  Everything below is registers + constants: one thread feeds the
-        // tensor pipe, every instruction on its path counts.
-        const int c_lo = lo % ACCR;
+        // accumulator ring wraps.
+        const int c_lo = (int)((ob + (uint32_t)lo) % ACCR);
         const int len0 = min(hi - lo + 1, ACCR - c_lo), len1 = hi - lo + 1 - len0;
         const uint32_t d0 = tmem_acc + c_lo * BN, d1 = tmem_acc;  // a wrapped part starts at chunk 0
         const uint32_t i0 = tc::make_idesc_bf16(128, len0 * BN, false, false);
         const uint32_t i1 = tc::make_idesc_bf16(128, (len1 > 0 ? len1 : 1) * BN, false, false);
         const uint64_t b0 = w_desc + (((lo - (s - 2)) * WT_BYTES) >> 4);
         const uint64_t b1 = b0 + ((len0 * WT_BYTES) >> 4);
-        const uint64_t slab = tmpl + ((r_addr + (s % RING) * SLAB_BYTES) >> 4);
+        const uint64_t slab = tmpl + ((r_addr + slot * SLAB_BYTES) >> 4);
         tc::umma_bf16_warp(d0, slab, b0, i0, 1u);
         if (len1 > 0) tc::umma_bf16_warp(d1, slab, b1, i1, 1u);
 #pragma unroll
@@ -204,27 +252,33 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
             tc::umma_bf16_warp(d0, a, b0 + bo, i0, 1u);
             if (len1 > 0) tc::umma_bf16_warp(d1, a, b1 + bo, i1, 1u);
           }
-        tc::umma_commit_warp(&empty[s % RING]);
-        if (s >= 2) tc::umma_commit_warp(&acc_full[(s - 2) % ACCR]);
+        tc::umma_commit_warp(&empty[slot]);
+        if (s >= 2) tc::umma_commit_warp(&acc_full[(ob + (uint32_t)(s - 2)) % ACCR]);
+      }
+      ob += (uint32_t)nd;
       }
     }
   } else {
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    const int oh = h0 + row / TWV, ow = w0 + row % TWV;
-    const bool valid = oh < p.H && ow < p.W;
-    float ssum[BN], ssq[BN];  // per-thread partial statistics over this CTA's slabs (same sample n)
-    float sb0[BST ? CS : 1], sb1[BST ? CS : 1], sb2[BST ? CS : 1];  // BST: the three InstanceNorm-backward sums
     float bias[BN];           // hoisted: the epilogue runs once per slab
 #pragma unroll
-    for (int c = 0; c < BN; ++c) {
-      ssum[c] = ssq[c] = 0.f;
-      bias[c] = (p.bias && c < p.cout) ? p.bias[c] : 0.f;
-    }
+    for (int c = 0; c < BN; ++c) bias[c] = (p.bias && c < p.cout) ? p.bias[c] : 0.f;
+    const float nslope = BST ? p.nalpha[0] : 0.f;
+    float* sred = reinterpret_cast<float*>(tmem_slot + 4);  // [4 warps][BN][3]: the item's statistics, warp by warp
+    uint32_t ob = 0;  // output slabs of the items before this one
+    for (int item = blockIdx.x; item < p.items; item += gridDim.x) {
+    const Item it = decode(item);
+    const int n = it.n, d_begin = it.d_begin, nd = it.nd;
+    const int oh = it.h0 + row / TWV, ow = it.w0 + row % TWV;
+    const bool valid = oh < p.H && ow < p.W;
+    float ssum[BN], ssq[BN];  // per-thread partial statistics over this item's slabs (same sample n)
+    float sb0[BST ? CS : 1], sb1[BST ? CS : 1], sb2[BST ? CS : 1];  // BST: the three InstanceNorm-backward sums
+#pragma unroll
+    for (int c = 0; c < BN; ++c) ssum[c] = ssq[c] = 0.f;
 #pragma unroll
     for (int c = 0; c < (BST ? CS : 1); ++c) sb0[c] = sb1[c] = sb2[c] = 0.f;
-    const float2* nsm = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(tmem_slot + 4) + 4 * BN * 3);
-    const float nslope = BST ? p.nalpha[0] : 0.f;
+    const float2* nsm = reinterpret_cast<const float2*>(reinterpret_cast<const float*>(tmem_slot + 4) + 4 * BN * 3) + n * BN;
     // BST: the rows the epilogue READS from global memory (residual addend, the consumer InstanceNorm's pre-norm
     // tensor) are fetched one slab ahead, before the wait for that slab's accumulator: otherwise every slab pays a
     // global-load round trip inside the epilogue's serial per-slab loop (r2: 263 us with the loads issued after the
@@ -247,10 +301,11 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
     };
     if (PF && valid && nd > 0) prefetch(0);
     for (int j = 0; j < nd; ++j) {
-      const int buf = j % ACCR;
+      const uint32_t o = ob + (uint32_t)j;
+      const int buf = (int)(o % ACCR);
       const uint4 cr0 = pr0, cr1 = pr1, cx0 = px0, cx1 = px1;  // this slab's rows
       if (PF && valid && j + 1 < nd) prefetch(j + 1);
-      tc::mbar_wait(&acc_full[buf], ((uint32_t)(j / ACCR)) & 1u);
+      tc::mbar_wait(&acc_full[buf], (o / ACCR) & 1u);
       tc::tc_fence_after();
       const int od = d_begin + j;
       const int64_t lin = (((int64_t)n * p.D + od) * p.H + oh) * p.W + ow;
@@ -352,8 +407,10 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
     }
+    // the item's statistics: warp tree per channel -> shared memory -> one row per item (the four epilogue warps
+    // meet at a named barrier: the producer and the MMA warp are already working on the next items)
+    const int et = threadIdx.x - 64;
     if constexpr (BST) {
-      float* sred = reinterpret_cast<float*>(tmem_slot + 4);  // [4 warps][BN][3]
 #pragma unroll
       for (int c = 0; c < BN; ++c) {
         float a = 0.f, b = 0.f, d3 = 0.f;
@@ -368,9 +425,15 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
           sred[(q * BN + c) * 3 + 2] = d3;
         }
       }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et < 3 * BN) {  // every one of the BN (padded) channels: the InstanceNorm kernels see them too
+        const int c = et / 3, m = et % 3;
+        p.bstats[((int64_t)item * BN + c) * 3 + m] =
+            sred[(0 * BN + c) * 3 + m] + sred[(1 * BN + c) * 3 + m] + sred[(2 * BN + c) * 3 + m] +
+            sred[(3 * BN + c) * 3 + m];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
     } else if (p.stats) {
-      // warp tree per channel -> shared memory; the CTA's partial is written after the final barrier
-      float* sred = reinterpret_cast<float*>(tmem_slot + 4);  // [4 warps][BN][2], after the barriers
 #pragma unroll
       for (int c = 0; c < BN; ++c) {
         const float a = warp_sum(ssum[c]), b = warp_sum(ssq[c]);
@@ -379,26 +442,21 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
           sred[(q * BN + c) * 2 + 1] = b;
         }
       }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (et < 2 * BN) {
+        const int c = et >> 1, m = et & 1;
+        if (c < p.cout)
+          p.stats[((int64_t)item * p.cout + c) * 2 + m] =
+              sred[(0 * BN + c) * 2 + m] + sred[(1 * BN + c) * 2 + m] + sred[(2 * BN + c) * 2 + m] +
+              sred[(3 * BN + c) * 2 + m];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    ob += (uint32_t)nd;
     }
   }
   tc::tc_fence_before();
   __syncthreads();
-  if constexpr (BST) {
-    if (threadIdx.x < 3 * BN) {  // every one of the BN (padded) channels: the InstanceNorm kernels see them too
-      const float* sred = reinterpret_cast<const float*>(tmem_slot + 4);
-      const int c = threadIdx.x / 3, m = threadIdx.x % 3;
-      p.bstats[((int64_t)blockIdx.x * BN + c) * 3 + m] =
-          sred[(0 * BN + c) * 3 + m] + sred[(1 * BN + c) * 3 + m] + sred[(2 * BN + c) * 3 + m] +
-          sred[(3 * BN + c) * 3 + m];
-    }
-  } else if (p.stats && threadIdx.x < 2 * BN) {
-    const float* sred = reinterpret_cast<const float*>(tmem_slot + 4);
-    const int c = threadIdx.x >> 1, m = threadIdx.x & 1;
-    if (c < p.cout)
-      p.stats[((int64_t)blockIdx.x * p.cout + c) * 2 + m] =
-          sred[(0 * BN + c) * 2 + m] + sred[(1 * BN + c) * 2 + m] + sred[(2 * BN + c) * 2 + m] +
-          sred[(3 * BN + c) * 2 + m];
-  }
   if (warp == 1) tc::tmem_dealloc<TMEM_COLS>(tmem_acc);
 }
 
@@ -418,18 +476,34 @@ bool slide_geom(const b200seg_conv_desc* d, int op, SlideGeom& g) {
   return true;
 }
 
-template <int BN, int KC, bool BST = false, int CS = BN>
-int launch_slide(const TcSlideConvParams& p, unsigned grid, cudaStream_t st) {
+template <int BN, int KC, bool BST>
+constexpr size_t slide_smem() {
   constexpr int PITCH = KC * 2;
   constexpr int SLAB = 3 * (TH + 2) * TWV * PITCH;
   constexpr int WB = (27 * BN * PITCH + 1023) / 1024 * 1024;
-  // ... + reduction scratch [4 warps][BN][3] + the consumer InstanceNorm's mean / rstd [2][BN] (BST)
-  const size_t smem = 1024 + WB + RING * SLAB + 8 * PITCH * 8 + 16 * 8 + 64 + 4 * BN * 3 * 4 + 2 * BN * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // ... + reduction scratch [4 warps][BN][3] + the consumer InstanceNorm's rstd / -mean * rstd of up to 16 samples (BST)
+  return 1024 + WB + RING * SLAB + 8 * PITCH * 8 + 16 * 8 + 64 + 4 * BN * 3 * 4 + (BST ? 16 * BN * 8 : 0);
+}
+
+// co-resident CTAs per SM of one variant (registers, shared memory, TMEM columns), asked once from the runtime
+template <int BN, int KC, bool BST, int CS>
+int slide_ctas_per_sm() {
+  static const int v = [] {
     cudaFuncSetAttribute(tc_slide_conv_kernel<BN, KC, BST, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-    attr_set = true;
-  }
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tc_slide_conv_kernel<BN, KC, BST, CS>, 192,
+                                                      slide_smem<BN, KC, BST>()) != cudaSuccess || nb < 1)
+      nb = 1;
+    const int by_tmem = 512 / (8 * BN);
+    return nb < by_tmem ? nb : by_tmem;
+  }();
+  return v;
+}
+
+template <int BN, int KC, bool BST = false, int CS = BN>
+int launch_slide(const TcSlideConvParams& p, unsigned grid, cudaStream_t st) {
+  const size_t smem = slide_smem<BN, KC, BST>();
+  slide_ctas_per_sm<BN, KC, BST, CS>();  // (sets the shared-memory attribute)
   tc_slide_conv_kernel<BN, KC, BST, CS><<<grid, 192, smem, st>>>(p);
   B200SEG_CHECK_LAUNCH(BST ? "tc_slide_conv_bwdstats" : "tc_slide_conv");
   count_tc_launch();
@@ -450,19 +524,26 @@ bool tc_slide_conv_supported(const b200seg_conv_desc* d, int op) {
   return true;
 }
 
-// number of CTAs (= per-CTA statistic partials); CTAs of one sample are contiguous
-int64_t tc_slide_conv_grid(const b200seg_conv_desc* d, int op) {
+// co-resident CTAs per SM of the variant this layer / op runs on (the segmentation must be the same in the workspace
+// queries and in the run)
+static int slide_slots_per_sm(int KC, int BN, bool bst, int dst_c) {
+  if (bst) return dst_c == 10 ? slide_ctas_per_sm<16, 16, true, 10>() : slide_ctas_per_sm<16, 16, true, 16>();
+  if (BN == 16 && KC == 16) return slide_ctas_per_sm<16, 16, false, 16>();
+  if (BN == 16 && KC == 32) return slide_ctas_per_sm<16, 32, false, 16>();
+  if (BN == 32 && KC == 16) return slide_ctas_per_sm<32, 16, false, 32>();
+  return slide_ctas_per_sm<32, 32, false, 32>();
+}
+
+// number of items (= statistic partial rows); items of one sample are contiguous
+int64_t tc_slide_conv_grid(const b200seg_conv_desc* d, int op, bool bst) {
   if (tc_line_conv_supported(d, op)) return tc_line_conv_rows(d, op);
   SlideGeom g;
   slide_geom(d, op, g);
   const int tilesH = (g.H + TH - 1) / TH, tilesW = (g.W + TWV - 1) / TWV;
   const int64_t cols = (int64_t)g.n * tilesH * tilesW;
-  int nseg = (int)((148 * slide_oversub() + cols - 1) / cols);
-  if (nseg < 1) nseg = 1;
-  int dseg = (g.D + nseg - 1) / nseg;
-  if (dseg < 8) dseg = 8;
-  if (dseg > g.D) dseg = g.D;
-  return cols * ((g.D + dseg - 1) / dseg);
+  int dseg, nseg;
+  slide_segments(cols, g.D, slide_slots_per_sm(round16(g.src_c), round16(g.dst_c), bst, g.dst_c), dseg, nseg);
+  return cols * nseg;
 }
 
 // dgrad whose output gradient feeds an InstanceNorm + PReLU backward: the fused variant exists for 16 (padded)
@@ -470,7 +551,7 @@ int64_t tc_slide_conv_grid(const b200seg_conv_desc* d, int op) {
 // bandwidth pass of its own
 bool tc_slide_conv_bwdstats_supported(const b200seg_conv_desc* d, int op) {
   if (op != TC_CONV_DGRAD || (d->flags & B200SEG_CONV_NO_SLIDE) || !tc_slide_conv_supported(d, op)) return false;
-  return round16(d->cin) == 16 && round16(d->cout) == 16;
+  return round16(d->cin) == 16 && round16(d->cout) == 16 && d->n <= 16;
 }
 
 int tc_slide_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,
@@ -488,12 +569,8 @@ int tc_slide_conv_run(const b200seg_conv_desc* d, int op, const void* src, const
   p.n = g.n; p.D = g.D; p.H = g.H; p.W = g.W;
   p.tilesH = (g.H + TH - 1) / TH; p.tilesW = (g.W + TWV - 1) / TWV;
   const int64_t cols = (int64_t)g.n * p.tilesH * p.tilesW;
-  int nseg = (int)((148 * slide_oversub() + cols - 1) / cols);
-  if (nseg < 1) nseg = 1;
-  int dseg = (g.D + nseg - 1) / nseg;
-  if (dseg < 8) dseg = 8;
-  if (dseg > g.D) dseg = g.D;
-  p.dseg = dseg; p.nseg = (g.D + dseg - 1) / dseg;
+  const int slots_per_sm = slide_slots_per_sm(KC, BN, bst != nullptr, g.dst_c);
+  slide_segments(cols, g.D, slots_per_sm, p.dseg, p.nseg);
   p.cout = g.dst_c; p.dst_ld = g.dst_ld; p.res_ld = d->r_ld;
   p.accumulate = (d->flags & B200SEG_CONV_ACCUMULATE) ? 1 : 0;
   p.flip = (op == TC_CONV_DGRAD) ? 1 : 0;
@@ -513,8 +590,11 @@ int tc_slide_conv_run(const b200seg_conv_desc* d, int op, const void* src, const
     int rc = tc_make_map(&p.tmB, w_tc, 2, dims, strides, box, KC * 2);
     if (rc) return rc;
   }
-  const int64_t grid = cols * p.nseg;
-  if (grid > 0x7fffffffLL) { set_error("tc_slide_conv: grid too large"); return B200SEG_ERR_ARG; }
+  const int64_t items = cols * p.nseg;
+  if (items > 0x3fffffffLL) { set_error("tc_slide_conv: grid too large"); return B200SEG_ERR_ARG; }
+  p.items = (int)items;
+  const int64_t slots = (int64_t)sm_count() * slots_per_sm;
+  const int64_t grid = (slide_persist() && items > slots) ? slots : items;
   if (bst) {
     if (BN == 16 && KC == 16 && g.dst_c == 10) return launch_slide<16, 16, true, 10>(p, (unsigned)grid, st);
     if (BN == 16 && KC == 16) return launch_slide<16, 16, true>(p, (unsigned)grid, st);

@@ -327,7 +327,7 @@ def test_splitk_cluster_conv(cin, cout, s, tr, n, sp):
 
 @pytest.mark.parametrize("cin,cout,n,sp,with_res", [(16, 16, 2, (12, 40, 24), False), (10, 10, 1, (9, 32, 40), True),
                                                      (16, 16, 1, (8, 64, 64), True), (10, 10, 2, (16, 32, 32), False),
-                                                     (10, 10, 2, (7, 5, 128), True), (16, 16, 1, (20, 9, 64), False)])
+                                                     (10, 10, 2, (9, 8, 128), True), (16, 16, 1, (20, 9, 64), False)])
 def test_dgrad_fused_with_instnorm_backward_sums(cin, cout, n, sp, with_res):
     """b200seg_conv_dgrad_instnorm_partials + b200seg_instnorm_prelu_bwd_from_partials (the dgrad epilogue leaves the
     three per-(sample, channel) sums of the InstanceNorm + PReLU backward its result feeds) against the two separate
