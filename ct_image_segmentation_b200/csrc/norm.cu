@@ -2,8 +2,14 @@
 // alpha) and the residual sum of the enclosing ResidualUnit.  Channels-last, bandwidth-bound:
 // vectorised coalesced access (up to 16 B per thread), fp32 statistics, deterministic two-stage
 // reductions (per-block partials, then a fixed-order finalisation in double).
+#include <cooperative_groups.h>
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 #include "kernels.h"
+
+namespace cg = cooperative_groups;
 
 namespace b200seg {
 
@@ -507,6 +513,127 @@ instnorm_prelu_bwd_small_kernel(const T* __restrict__ x, const T* __restrict__ d
   }
 }
 
+// Mid-size instances (up to 32^3 voxels per sample) in ONE launch on a thread-block CLUSTER: the CL CTAs of a cluster
+// own the same V channels of one sample and 1/CL of its voxels each.  Pass 1 leaves a CTA's three partial sums in its
+// shared memory, after the cluster barrier every CTA adds up the CL partials through distributed shared memory in rank
+// order (so all of them hold bit-identical totals), pass 2 re-reads the CTA's own voxels (L2 hits) and writes dx.
+// Replaces, for 16^3 instances, the single-CTA-per-channel-group kernel above (16 CTAs walking 4096 voxels each:
+// 20 us in the r2 launch list for a 1 MB tensor, pure load latency) and, for 32^3 instances, the three launches
+// partial + final + apply (22 us).  Loads of two iterations are issued before the arithmetic.
+template <typename T, int V>
+__global__ void __launch_bounds__(512)
+instnorm_prelu_bwd_cluster_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean,
+                                  const float* __restrict__ rstd, const float* __restrict__ alpha, T* __restrict__ dx,
+                                  int64_t spatial, int c, int x_ld, int dy_ld, int dx_ld, int CL,
+                                  float* __restrict__ sums) {
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ float red[16][3 * V];
+  __shared__ float part[3 * V];  // this CTA's partial sums: read by the whole cluster
+  __shared__ float tot[3 * V];
+  const int t = threadIdx.x, n = blockIdx.y;
+  const int rank = (int)cluster.block_rank();
+  const int c0 = (blockIdx.x / CL) * V;
+  const int64_t per = (spatial + CL - 1) / CL;
+  const int64_t v_begin = (int64_t)rank * per, v_end = min(spatial, v_begin + per);
+  float m[V], r[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    m[i] = mean[n * c + c0 + i];
+    r[i] = rstd[n * c + c0 + i];
+  }
+  const float a = alpha[0];
+  const int64_t vox0 = (int64_t)n * spatial;
+  float acc[3][V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) acc[0][i] = acc[1][i] = acc[2][i] = 0.f;
+  auto reduce = [&](const Vec<T, V>& xv, const Vec<T, V>& gv) {
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float h = (xv.v[i] - m[i]) * r[i];
+      const bool pos = h > 0.f;
+      const float g = pos ? gv.v[i] : a * gv.v[i];
+      acc[0][i] += g;
+      acc[1][i] = fmaf(g, h, acc[1][i]);
+      acc[2][i] += pos ? 0.f : gv.v[i] * h;
+    }
+  };
+  {
+    int64_t v = v_begin + t;
+    for (; v + 512 < v_end; v += 1024) {
+      Vec<T, V> x0, g0, x1, g1;
+      x0.load(x + (vox0 + v) * x_ld + c0);
+      g0.load(dy + (vox0 + v) * dy_ld + c0);
+      x1.load(x + (vox0 + v + 512) * x_ld + c0);
+      g1.load(dy + (vox0 + v + 512) * dy_ld + c0);
+      reduce(x0, g0);
+      reduce(x1, g1);
+    }
+    if (v < v_end) {
+      Vec<T, V> x0, g0;
+      x0.load(x + (vox0 + v) * x_ld + c0);
+      g0.load(dy + (vox0 + v) * dy_ld + c0);
+      reduce(x0, g0);
+    }
+  }
+  const int warp = t >> 5, lane = t & 31;
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float w = warp_sum(acc[k][i]);
+      if (lane == 0) red[warp][k * V + i] = w;
+    }
+  __syncthreads();
+  if (t < 3 * V) {
+    float s_ = 0.f;
+#pragma unroll
+    for (int w = 0; w < 16; ++w) s_ += red[w][t];  // fixed order
+    part[t] = s_;
+  }
+  cluster.sync();
+  if (t < 3 * V) {
+    float s_ = 0.f;
+    for (int rk = 0; rk < CL; ++rk) s_ += *cluster.map_shared_rank(&part[t], rk);  // rank order: same bits in every CTA
+    const int k = t / V, i = t % V;
+    const float o = k < 2 ? s_ / (float)spatial : s_;
+    tot[t] = o;
+    if (rank == 0) sums[(n * c + c0 + i) * 3 + k] = o;
+  }
+  cluster.sync();  // totals visible to the block; no CTA leaves while a peer may still read its partials
+  float s1[V], s2[V];
+#pragma unroll
+  for (int i = 0; i < V; ++i) {
+    s1[i] = tot[i];
+    s2[i] = tot[V + i];
+  }
+  auto apply = [&](const Vec<T, V>& xv, const Vec<T, V>& gv, int64_t v) {
+    Vec<T, V> ov;
+#pragma unroll
+    for (int i = 0; i < V; ++i) {
+      const float h = (xv.v[i] - m[i]) * r[i];
+      const float g = h > 0.f ? gv.v[i] : a * gv.v[i];
+      ov.v[i] = r[i] * (g - s1[i] - h * s2[i]);
+    }
+    ov.store(dx + (vox0 + v) * dx_ld + c0);
+  };
+  int64_t v = v_begin + t;
+  for (; v + 512 < v_end; v += 1024) {
+    Vec<T, V> x0, g0, x1, g1;
+    x0.load(x + (vox0 + v) * x_ld + c0);
+    g0.load(dy + (vox0 + v) * dy_ld + c0);
+    x1.load(x + (vox0 + v + 512) * x_ld + c0);
+    g1.load(dy + (vox0 + v + 512) * dy_ld + c0);
+    apply(x0, g0, v);
+    apply(x1, g1, v + 512);
+  }
+  if (v < v_end) {
+    Vec<T, V> x0, g0;
+    x0.load(x + (vox0 + v) * x_ld + c0);
+    g0.load(dy + (vox0 + v) * dy_ld + c0);
+    apply(x0, g0, v);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 namespace {
 
@@ -617,6 +744,36 @@ int launch_instnorm_prelu_bwd(const b200seg_norm_desc& d, const void* x, const f
   if (rc) return rc;
   float* partial = (float*)ws;
   float* sums = partial + (size_t)d.n * g.nblk * d.c * 3;
+  // B200SEG_NORM_CLUSTER=0: the r1 / r2 paths (A/B runs)
+  static const bool use_cluster = [] { const char* e = getenv("B200SEG_NORM_CLUSTER"); return !(e && e[0] == '0'); }();
+  if (use_cluster && d.spatial > 1024 && d.spatial <= 32768 && V >= 4) {  // 16^3 .. 32^3: one launch on clusters
+    int CL = 2;
+    while (CL < 8 && (int64_t)CL * 1024 < d.spatial) CL *= 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)(d.c / V * CL), (unsigned)d.n);
+    cfg.blockDim = dim3(512);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaSuccess;
+    DISPATCH_TV(d.dtype, V,
+                (e = cudaLaunchKernelEx(&cfg, instnorm_prelu_bwd_cluster_kernel<T, VV>, (const T*)x, (const T*)dy, mean,
+                                        rstd, alpha, (T*)dx, d.spatial, d.c, d.x_ld, d.y_ld, d.r_ld, CL, sums)));
+    if (e != cudaSuccess) {
+      set_error("instnorm_prelu_bwd_cluster launch failed: %s", cudaGetErrorString(e));
+      return B200SEG_ERR_CUDA;
+    }
+    B200SEG_CHECK_LAUNCH("instnorm_prelu_bwd_cluster");
+    dalpha_final_kernel<<<1, 256, 0, st>>>(sums, d.n * d.c, dalpha);
+    B200SEG_CHECK_LAUNCH("dalpha_final");
+    return B200SEG_OK;
+  }
   if (d.spatial <= 4096 && V >= 4) {  // deep layers: one launch, sums stay in the block
     dim3 gs(d.c / V, d.n);
     DISPATCH_TV(d.dtype, V,

@@ -458,6 +458,7 @@ int env_int(const char* name, int dflt, int lo, int hi) {
 // B200SEG_LINE_CONV=0 sends every layer back to tc_slide_conv (A/B runs); B200SEG_LINE_EG = epilogue warp groups
 int line_enabled() { static const int v = env_int("B200SEG_LINE_CONV", 1, 0, 1); return v; }
 int line_eg() { static const int v = env_int("B200SEG_LINE_EG", 2, 1, 2); return v; }
+int line_w128() { static const int v = env_int("B200SEG_LINE_W128", 0, 0, 1); return v; }
 
 struct LineGeom {
   int n, D, H, W, src_c, dst_c, src_ld, dst_ld;
@@ -470,7 +471,9 @@ bool line_geom(const b200seg_conv_desc* d, int op, LineGeom& g) {
   g.n = d->n; g.D = d->in_d; g.H = d->in_h; g.W = d->in_w;
   if (op == TC_CONV_FPROP) { g.src_c = d->cin; g.dst_c = d->cout; g.src_ld = d->x_ld; g.dst_ld = d->y_ld; }
   else { g.src_c = d->cout; g.dst_c = d->cin; g.src_ld = d->y_ld; g.dst_ld = d->x_ld; }
-  if (g.W != 32 && g.W != 64 && g.W != 128) return false;
+  // rows of 128 voxels run (B200SEG_LINE_W128=1, tests) but are slower than tc_slide_conv there: draining three kw
+  // accumulators per voxel through tcgen05.ld costs more than the folded MMAs save
+  if (g.W != 32 && g.W != 64 && !(g.W == 128 && line_w128())) return false;
   if (g.src_c > 16 || g.dst_c > 16 || g.src_ld != 16) return false;
   if (g.D < 4 || (int64_t)g.D * g.H < 64) return false;
   g.lpt = 256 / g.W;

@@ -40,8 +40,11 @@ inline int env_int(const char* name, int dflt, int lo, int hi) {
   const int x = atoi(e);
   return x >= lo && x <= hi ? x : dflt;
 }
-// B200SEG_SLIDE_PERSIST=0: one CTA per item with the r1 segmentation (A/B runs)
-inline int slide_persist() { static const int v = env_int("B200SEG_SLIDE_PERSIST", 1, 0, 1); return v; }
+// B200SEG_SLIDE_PERSIST=1: at most `resident CTAs` CTAs that walk several items each.  Measured (r2, head layer
+// 2 x 128^3): fprop 118 -> 111 us, but the variants whose epilogue reads global rows (residual addend, fused
+// InstanceNorm-backward sums) 118 -> 203 and 145 -> 198 us, whole step 2.116 -> 2.167 ms: off by default, one CTA per
+// item; the kernel is the same code either way (grid == items).
+inline int slide_persist() { static const int v = env_int("B200SEG_SLIDE_PERSIST", 0, 0, 1); return v; }
 inline int sm_count() {
   static const int v = [] {
     int dev = 0, n = 0;
@@ -51,29 +54,41 @@ inline int sm_count() {
   }();
   return v;
 }
-// Work decomposition shared by the run / grid / workspace queries.  Persistent mode: `slots` CTAs stay resident
-// (3 per SM; 2 for the fused InstanceNorm-backward variant) and walk the items round-robin; the number of d segments
-// per column minimises rounds x (slabs per item + 2 halo slabs), fewest segments on ties.
+// Work decomposition shared by the run / grid / workspace queries.  One CTA per item: enough d segments per column
+// for ~4 CTAs per SM, at least 8 slabs each (r1) -- except where that lands between one and two waves of the `slots`
+// CTAs resident at a time and a nearly full SINGLE wave exists: then the largest segment count that still fits one
+// wave (16 -> 16 at 64^3 x 2: 384 CTAs in one wave instead of 512 in 1.15, dgrad + residual 24.7 -> 20.2 us; the
+// set-up of a CTA -- TMEM allocation, 27 weight tiles, ring fill -- is worth several slabs).  Persistent mode
+// (experiments): the split that minimises rounds x (slabs + 2 halo slabs) over the resident CTAs.
 inline void slide_segments(int64_t cols, int D, int slots_per_sm, int& dseg, int& nseg) {
-  if (!slide_persist()) {
-    nseg = (int)((148 * 4 + cols - 1) / cols);
-    if (nseg < 1) nseg = 1;
+  const int64_t slots = (int64_t)sm_count() * slots_per_sm;
+  if (slide_persist()) {
+    int64_t best = -1;
+    nseg = 1;
+    for (int ns = 1; ns <= (D + 3) / 4 && ns <= 64; ++ns) {
+      const int ds = (D + ns - 1) / ns;
+      if ((D + ds - 1) / ds != ns) continue;
+      const int64_t cost = ((cols * ns + slots - 1) / slots) * (ds + 2);
+      if (best < 0 || cost < best) { best = cost; nseg = ns; }
+    }
     dseg = (D + nseg - 1) / nseg;
-    if (dseg < 8) dseg = 8;
-    if (dseg > D) dseg = D;
-    nseg = (D + dseg - 1) / dseg;
     return;
   }
-  const int64_t slots = (int64_t)sm_count() * slots_per_sm;
-  int64_t best = -1;
-  nseg = 1;
-  for (int ns = 1; ns <= D / 4 && ns <= 64; ++ns) {
-    const int ds = (D + ns - 1) / ns;
-    if ((D + ds - 1) / ds != ns) continue;
-    const int64_t cost = ((cols * ns + slots - 1) / slots) * (ds + 2);
-    if (best < 0 || cost < best) { best = cost; nseg = ns; }
-  }
+  nseg = (int)((148 * 4 + cols - 1) / cols);
+  if (nseg < 1) nseg = 1;
   dseg = (D + nseg - 1) / nseg;
+  if (dseg < 8) dseg = 8;
+  if (dseg > D) dseg = D;
+  nseg = (D + dseg - 1) / dseg;
+  const int64_t items = cols * nseg;
+  if (items > slots && items <= 2 * slots) {
+    for (int ns = nseg - 1; ns >= 1; --ns) {
+      const int ds = (D + ns - 1) / ns;
+      if ((D + ds - 1) / ds != ns || cols * ns > slots) continue;
+      if (4 * cols * ns >= 3 * slots) { nseg = ns; dseg = ds; }
+      break;
+    }
+  }
 }
 }  // namespace
 

@@ -567,7 +567,9 @@ def test_first_layer_im2col(dims, cin, cout, s, n, sp):
 
 
 NORM_CASES = [(2, 16, (6, 8, 10)), (1, 10, (8, 8, 12)), (2, 64, (4, 4, 4)), (3, 32, (1, 12, 20)),
-              (1, 256, (2, 3, 4)), (2, 7, (3, 5, 7)), (1, 16, (20, 16, 16)), (2, 32, (18, 16, 16))]
+              (1, 256, (2, 3, 4)), (2, 7, (3, 5, 7)), (1, 16, (20, 16, 16)), (2, 32, (18, 16, 16)),
+              # cluster backward (1024 < voxels <= 32768): 2 / 4 / 8 CTAs per channel group, ragged split
+              (2, 64, (16, 16, 16)), (1, 32, (32, 32, 32)), (1, 24, (9, 11, 13)), (2, 128, (8, 8, 8))]
 
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
