@@ -356,21 +356,6 @@ __global__ void instnorm_bwd_final_kernel(const float* __restrict__ partial, int
   }
 }
 
-// dalpha = sum over (n,c) of sums[.][2], one block, fixed order
-__global__ void dalpha_final_kernel(const float* __restrict__ sums, int nc_total,
-                                    float* __restrict__ dalpha) {
-  __shared__ double red[256];
-  double s = 0.0;
-  for (int i = threadIdx.x; i < nc_total; i += 256) s += (double)sums[i * 3 + 2];
-  red[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) dalpha[0] = (float)red[0];
-}
-
 template <typename T, int V>
 __global__ void __launch_bounds__(256)
 instnorm_prelu_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ dy,
@@ -436,6 +421,37 @@ instnorm_prelu_bwd_apply_kernel(const T* __restrict__ x, const T* __restrict__ d
   }
 }
 
+// d loss / d alpha = sum over (n, c) of sums[.][2], finished INSIDE the kernel that produced the sums: every producer
+// CTA takes a ticket after its sums are visible (fence + atomicInc, which wraps back to 0 for the next launch), the
+// CTA that draws the last ticket adds all nc terms in a fixed order (strided per thread, then a shared-memory tree in
+// double), so the result does not depend on which CTA comes last.  Saves the one-block dalpha_final launch that sat
+// on the serial backward chain after each of these kernels (12 per step of the 16-256 net) although nothing on
+// that chain reads dalpha.  Call with the whole block; `writer` = this CTA wrote sums and takes a ticket.
+__device__ unsigned int g_dalpha_ticket = 0;
+
+template <int NT>
+__device__ __forceinline__ void dalpha_last_block(bool writer, unsigned int total, const float* sums, int nc_total,
+                                                  float* dalpha) {
+  __shared__ double dred[NT];
+  __shared__ unsigned int is_last;
+  if (!writer) return;  // (block-uniform)
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) is_last = atomicInc(&g_dalpha_ticket, total - 1) == total - 1 ? 1u : 0u;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double s = 0.0;
+  for (int i = threadIdx.x; i < nc_total; i += NT) s += (double)__ldcg(sums + i * 3 + 2);
+  dred[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = NT / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) dred[threadIdx.x] += dred[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) dalpha[0] = (float)dred[0];
+}
+
 // Small-instance backward in ONE launch (deep layers: <= 4096 voxels per sample, tensors of a MB that
 // live in L2): a CTA owns V channels of one sample for ALL voxels, so the three spatial sums never
 // leave the block -- pass 1 accumulates them, a shared-memory tree makes them block-wide, pass 2
@@ -445,7 +461,8 @@ template <typename T, int V>
 __global__ void __launch_bounds__(512)
 instnorm_prelu_bwd_small_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean,
                                 const float* __restrict__ rstd, const float* __restrict__ alpha, T* __restrict__ dx,
-                                int64_t spatial, int c, int x_ld, int dy_ld, int dx_ld, float* __restrict__ sums) {
+                                int64_t spatial, int c, int x_ld, int dy_ld, int dx_ld, float* __restrict__ sums,
+                                float* __restrict__ dalpha) {
   __shared__ float red[16][3 * V];
   __shared__ float tot[3 * V];
   const int t = threadIdx.x, n = blockIdx.y, c0 = blockIdx.x * V;
@@ -511,6 +528,7 @@ instnorm_prelu_bwd_small_kernel(const T* __restrict__ x, const T* __restrict__ d
     }
     ov.store(dx + (vox0 + v) * dx_ld + c0);
   }
+  dalpha_last_block<512>(true, gridDim.x * gridDim.y, sums, (int)gridDim.y * c, dalpha);
 }
 
 // Mid-size instances (up to 32^3 voxels per sample) in ONE launch on a thread-block CLUSTER: the CL CTAs of a cluster
@@ -525,7 +543,7 @@ __global__ void __launch_bounds__(512)
 instnorm_prelu_bwd_cluster_kernel(const T* __restrict__ x, const T* __restrict__ dy, const float* __restrict__ mean,
                                   const float* __restrict__ rstd, const float* __restrict__ alpha, T* __restrict__ dx,
                                   int64_t spatial, int c, int x_ld, int dy_ld, int dx_ld, int CL,
-                                  float* __restrict__ sums) {
+                                  float* __restrict__ sums, float* __restrict__ dalpha) {
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ float red[16][3 * V];
   __shared__ float part[3 * V];  // this CTA's partial sums: read by the whole cluster
@@ -632,6 +650,7 @@ instnorm_prelu_bwd_cluster_kernel(const T* __restrict__ x, const T* __restrict__
     g0.load(dy + (vox0 + v) * dy_ld + c0);
     apply(x0, g0, v);
   }
+  dalpha_last_block<512>(rank == 0, (gridDim.x / CL) * gridDim.y, sums, (int)gridDim.y * c, dalpha);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -764,14 +783,12 @@ int launch_instnorm_prelu_bwd(const b200seg_norm_desc& d, const void* x, const f
     cudaError_t e = cudaSuccess;
     DISPATCH_TV(d.dtype, V,
                 (e = cudaLaunchKernelEx(&cfg, instnorm_prelu_bwd_cluster_kernel<T, VV>, (const T*)x, (const T*)dy, mean,
-                                        rstd, alpha, (T*)dx, d.spatial, d.c, d.x_ld, d.y_ld, d.r_ld, CL, sums)));
+                                        rstd, alpha, (T*)dx, d.spatial, d.c, d.x_ld, d.y_ld, d.r_ld, CL, sums, dalpha)));
     if (e != cudaSuccess) {
       set_error("instnorm_prelu_bwd_cluster launch failed: %s", cudaGetErrorString(e));
       return B200SEG_ERR_CUDA;
     }
     B200SEG_CHECK_LAUNCH("instnorm_prelu_bwd_cluster");
-    dalpha_final_kernel<<<1, 256, 0, st>>>(sums, d.n * d.c, dalpha);
-    B200SEG_CHECK_LAUNCH("dalpha_final");
     return B200SEG_OK;
   }
   if (d.spatial <= 4096 && V >= 4) {  // deep layers: one launch, sums stay in the block
@@ -779,10 +796,8 @@ int launch_instnorm_prelu_bwd(const b200seg_norm_desc& d, const void* x, const f
     DISPATCH_TV(d.dtype, V,
                 (instnorm_prelu_bwd_small_kernel<T, VV><<<gs, 512, 0, st>>>(
                     (const T*)x, (const T*)dy, mean, rstd, alpha, (T*)dx, d.spatial, d.c, d.x_ld, d.y_ld,
-                    d.r_ld, sums)));
+                    d.r_ld, sums, dalpha)));
     B200SEG_CHECK_LAUNCH("instnorm_prelu_bwd_small");
-    dalpha_final_kernel<<<1, 256, 0, st>>>(sums, d.n * d.c, dalpha);
-    B200SEG_CHECK_LAUNCH("dalpha_final");
     return B200SEG_OK;
   }
   int64_t per = cdiv64(d.spatial, g.nblk);

@@ -455,8 +455,14 @@ int env_int(const char* name, int dflt, int lo, int hi) {
   return x >= lo && x <= hi ? x : dflt;
 }
 
-// B200SEG_LINE_CONV=0 sends every layer back to tc_slide_conv (A/B runs); B200SEG_LINE_EG = epilogue warp groups
-int line_enabled() { static const int v = env_int("B200SEG_LINE_CONV", 1, 0, 1); return v; }
+// OFF by default (B200SEG_LINE_CONV=1 enables it): validated on the GPU (the -m gpu suite passes with it on, rows
+// of 32 / 64 / 128 voxels), but measured no better than tc_slide_conv where it counts -- r2, graph-replayed:
+//   head 10->10 @128^3 x2      fprop 118 -> 124 us, dgrad + residual 118 -> 132, fused sums 145 -> 185
+//   16->16 @64^3 x2            dgrad + residual 20.2 -> 17.5 us, fused sums 26.9 -> 25.0, whole step 2.094 -> 2.096 ms
+// The tensor pipe and the TMEM read path of tcgen05.ld are one serial resource (ncu sm__pipe_tc_cycles_active): the
+// three kw accumulators per voxel cost 3x the drain (192 B per voxel at 64 B/clk/SM) and that eats what the 3x fewer,
+// 3x wider MMAs save.  B200SEG_LINE_EG = epilogue warp groups.
+int line_enabled() { static const int v = env_int("B200SEG_LINE_CONV", 0, 0, 1); return v; }
 int line_eg() { static const int v = env_int("B200SEG_LINE_EG", 2, 1, 2); return v; }
 int line_w128() { static const int v = env_int("B200SEG_LINE_W128", 0, 0, 1); return v; }
 
