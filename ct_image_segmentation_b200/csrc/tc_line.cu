@@ -55,6 +55,8 @@ struct alignas(64) TcLineConvParams {
   int n, D, H, W;
   int tilesH, dseg, nseg, items;  // item = (sample * nseg + segment) * tilesH + line tile
   int cout, dst_ld, res_ld, accumulate, flip;
+  int debug;      // B200SEG_LINE_DEBUG (timing experiments, results are wrong): 1 = epilogue drains and hands back the
+                  // accumulators only, 2 = no MMAs, 4 = no TMA loads of the source
   const float* bias;
   const bf16* res;
   bf16* dst;
@@ -68,10 +70,10 @@ struct alignas(64) TcLineConvParams {
   float* bstats;  // [item][epilogue warp][16][3]
 };
 
-// PPL = voxel pairs per line (W / 2: 16, 32 or 64); EG = epilogue warp groups (4 warps each, alternating slabs);
+// PPL = voxel pairs per line (W / 2: 16, 32 or 64); EG = sets of 8 epilogue warps (alternating slabs);
 // BST / CS as in tc_slide_conv_kernel
 template <int PPL, int EG, bool BST, int CS>
-__global__ void __launch_bounds__(64 + 128 * EG, 1)
+__global__ void __launch_bounds__(64 + 256 * EG, 1)
 tc_line_conv_kernel(const __grid_constant__ TcLineConvParams p) {
   constexpr int LPT = 128 / PPL;                         // lines per tile
   constexpr int LINE_BYTES = PPL * 64;
@@ -86,8 +88,8 @@ tc_line_conv_kernel(const __grid_constant__ TcLineConvParams p) {
   uint64_t* acc_empty = acc_full + LACCR;    // [LACCR]
   uint64_t* wbar = acc_empty + LACCR;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(wbar + 1);
-  float* xch = reinterpret_cast<float*>(tmem_slot + 4);   // [2 slab parities][EG][4 warps][2][16] row exchange
-  float* bias_s = xch + 2 * EG * 4 * 32;                   // [16]
+  float* xch = reinterpret_cast<float*>(tmem_slot + 4);   // [2 slab parities][2 EG groups][4 warps][16] row exchange
+  float* bias_s = xch + 2 * (2 * EG) * 4 * 16;             // [16]
 
   const int warp = tc::warp_index(), lane = threadIdx.x & 31;
 
@@ -98,7 +100,7 @@ tc_line_conv_kernel(const __grid_constant__ TcLineConvParams p) {
     }
     for (int i = 0; i < LACCR; ++i) {
       tc::mbar_init(&acc_full[i], 1);
-      tc::mbar_init(&acc_empty[i], 4);
+      tc::mbar_init(&acc_empty[i], 8);
     }
     tc::mbar_init(wbar, 1);
     tc::fence_barrier_init();
@@ -148,6 +150,7 @@ tc_line_conv_kernel(const __grid_constant__ TcLineConvParams p) {
         for (int s = 0; s < nd + 2; ++s, ++g) {
           const uint32_t slot = g % LRING;
           tc::mbar_wait(&empty[slot], ((g / LRING) & 1u) ^ 1u);
+          if (p.debug & 4) { tc::mbar_arrive(&full[slot]); continue; }
           tc::mbar_expect_tx(&full[slot], SLAB_BYTES);
           tc::tma_load_5d(ring + slot * SLAB_BYTES, &p.tmA, &full[slot], 0, 0, h0 - 1, d_begin - 1 + s, n);
         }
@@ -184,6 +187,7 @@ tc_line_conv_kernel(const __grid_constant__ TcLineConvParams p) {
         const uint64_t b0 = w_desc + (((lo - (s - 2)) * 3 * LWT_BYTES) >> 4);
         const uint64_t b1 = b0 + ((len0 * 3 * LWT_BYTES) >> 4);
         const uint64_t slab = a_tmpl + ((r_addr + slot * SLAB_BYTES) >> 4);
+        if (!(p.debug & 2))
 #pragma unroll
         for (int kh = 0; kh < 3; ++kh)
 #pragma unroll
@@ -200,14 +204,20 @@ tc_line_conv_kernel(const __grid_constant__ TcLineConvParams p) {
       ob += (uint32_t)nd;
     }
   } else {
-    // ---- epilogue: group eg of EG takes every EG-th output slab; warp q owns TMEM lanes [32 q, 32 q + 32)
-    const int eg = (warp - 2) >> 2;
+    // ---- epilogue: 8 * EG warps.  Warp group (eg, half) = four warps, one per TMEM lane quadrant q; group eg of EG
+    // takes every EG-th output slab and, inside it, `half` = 0 the even voxel of every pair, 1 the odd one: a thread
+    // produces ONE voxel (16 channels) from three of the six 16-column blocks of the slab's two accumulators --
+    //   out[even] = odd.kw0 of the previous pair + even.kw1 + odd.kw2
+    //   out[odd]  = even.kw0 + odd.kw1 + even.kw2 of the next pair
+    // -- so the per-slab instruction stream, which bounds this kernel (B200SEG_LINE_DEBUG: 120 us with it, 61 us with
+    // the accumulators only drained and handed back), is split over twice the warps at half the registers.
+    const int sub = (warp - 2) >> 2;
+    const int half = sub & 1, eg = sub >> 1;
     const int q = warp & 3;
     const int row = q * 32 + lane;          // pair index inside the tile
     const int l = row / PPL, pp = row % PPL;
-    const bool first = pp == 0, last = pp == PPL - 1;
-    const uint32_t tmem_acc = *tmem_slot;
-    const uint32_t lane_base = tmem_acc + ((uint32_t)(q * 32) << 16);
+    const bool edge = half == 0 ? pp == 0 : pp == PPL - 1;  // no neighbour on that side: zero padding
+    const uint32_t lane_base = *tmem_slot + ((uint32_t)(q * 32) << 16);
     float nslope = 0.f;
     if constexpr (BST) nslope = p.nalpha[0];
     uint32_t ob = 0;
@@ -236,91 +246,75 @@ tc_line_conv_kernel(const __grid_constant__ TcLineConvParams p) {
       // are fetched one slab of this group ahead -- right after the previous slab consumed its rows, so that they
       // travel during the wait for the accumulator (see tc_slide.cu: a global-load round trip inside the serial
       // per-slab loop otherwise)
-      uint4 pr[4], px[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) pr[i] = px[i] = make_uint4(0, 0, 0, 0);
-      auto row_index = [&](int j) { return (((int64_t)n * p.D + d_begin + j) * p.H + oh) * p.W + 2 * pp; };
+      uint4 pr0 = make_uint4(0, 0, 0, 0), pr1 = pr0, px0 = pr0, px1 = pr0;
+      const int64_t lin0 = (((int64_t)n * p.D + d_begin) * p.H + oh) * p.W + 2 * pp + half;  // this thread's voxel, slab 0
+      const int64_t slab_vox = (int64_t)p.H * p.W;
       auto prefetch = [&](int j) {
-        const int64_t lin = row_index(j);
+        const int64_t lin = lin0 + j * slab_vox;
         if (p.res) {
           const uint4* r0 = reinterpret_cast<const uint4*>(p.res + lin * p.res_ld);
-          const uint4* r1 = reinterpret_cast<const uint4*>(p.res + (lin + 1) * p.res_ld);
-          pr[0] = r0[0]; pr[1] = r0[1]; pr[2] = r1[0]; pr[3] = r1[1];
+          pr0 = r0[0]; pr1 = r0[1];
         }
         if constexpr (BST) {
           const uint4* x0 = reinterpret_cast<const uint4*>(p.nx + lin * p.nx_ld);
-          const uint4* x1 = reinterpret_cast<const uint4*>(p.nx + (lin + 1) * p.nx_ld);
-          px[0] = x0[0]; px[1] = x0[1]; px[2] = x1[0]; px[3] = x1[1];
+          px0 = x0[0]; px1 = x0[1];
         }
       };
-      // first slab of this group inside the item
-      int j0 = (int)((EG - (ob % EG) + eg) % EG);
+      int j0 = (int)((EG - (ob % EG) + eg) % EG);  // first slab of this group inside the item
       if (valid && j0 < nd) prefetch(j0);
       for (int j = j0; j < nd; j += EG) {
         const uint32_t o = ob + (uint32_t)j;
         const uint32_t chunk = o % LACCR;
         tc::mbar_wait(&acc_full[chunk], (o / LACCR) & 1u);
         tc::tc_fence_after();
-        // even-voxel accumulator e*, odd-voxel accumulator o*: 3 kw blocks of 16 channels each
-        uint32_t e0[16], e1[16], e2[16], o0[16], o1[16], o2[16];
+        // ctr = own voxel's kw1 block, same = the pair partner's block, nbr = the block of the neighbouring pair
         const uint32_t ce = lane_base + chunk * LCHUNK, co = ce + LRSTRIDE;
-        tc::tmem_ld16(ce, e0);
-        tc::tmem_ld16(ce + 16, e1);
-        tc::tmem_ld16(ce + 32, e2);
-        tc::tmem_ld16(co, o0);
-        tc::tmem_ld16(co + 16, o1);
-        tc::tmem_ld16(co + 32, o2);
+        const uint32_t a_ctr = (half ? co : ce) + 16;
+        const uint32_t a_same = half ? ce : co + 32;        // odd: even.kw0      even: odd.kw2
+        const uint32_t a_nbr = half ? ce + 32 : co;         // odd: even.kw2 (next pair)   even: odd.kw0 (previous pair)
+        uint32_t vc[16], vs[16], vn[16];
+        tc::tmem_ld16(a_ctr, vc);
+        tc::tmem_ld16(a_same, vs);
+        tc::tmem_ld16(a_nbr, vn);
         tc::tmem_ld_wait();
-        // hand the chunk back zeroed before anything else: the MMA warp is three slabs ahead at most
-#pragma unroll
-        for (int c = 0; c < LCHUNK; c += 16) {
-          tc::tmem_st16_zero(ce + c);
-          tc::tmem_st16_zero(co + c);
-        }
+        // hand the blocks back zeroed before anything else (the chunk is free again after all 8 warps did)
+        tc::tmem_st16_zero(a_ctr);
+        tc::tmem_st16_zero(a_same);
+        tc::tmem_st16_zero(a_nbr);
         tc::tmem_st_wait();
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&acc_empty[chunk]);
-        // out[even] = odd.kw0 of the previous pair + even.kw1 + odd.kw2
-        // out[odd]  = even.kw0 + odd.kw1 + even.kw2 of the next pair
-        float up[16], dn[16];
+        if (p.debug & 1) continue;
+        float nb16[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          up[i] = __shfl_up_sync(0xffffffffu, __uint_as_float(o0[i]), 1);
-          dn[i] = __shfl_down_sync(0xffffffffu, __uint_as_float(e2[i]), 1);
+          const float v = __uint_as_float(vn[i]);
+          const float u = __shfl_up_sync(0xffffffffu, v, 1), d2 = __shfl_down_sync(0xffffffffu, v, 1);
+          nb16[i] = half ? d2 : u;
         }
         if constexpr (PPL > 32) {  // a line spans two warps: rows 31 | 32 exchange through shared memory
           // double buffered by the parity of the GROUP's slab count: a warp that is one slab ahead of its group
           // writes the other buffer, and cannot be two ahead (the barrier of the slab in between)
-          float* xb = xch + ((((o / EG) & 1u) * EG + eg) * 4) * 32;
-          if (lane == 31) {
+          float* xb = xch + ((((o / EG) & 1u) * (2 * EG) + sub) * 4) * 16;
+          if (lane == (half ? 0 : 31)) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) xb[q * 32 + i] = __uint_as_float(o0[i]);
+            for (int i = 0; i < 16; ++i) xb[q * 16 + i] = __uint_as_float(vn[i]);
           }
-          if (lane == 0) {
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + sub) : "memory");
+          if (lane == (half ? 31 : 0) && !edge) {
+            const int qq = half ? q + 1 : q - 1;
 #pragma unroll
-            for (int i = 0; i < 16; ++i) xb[q * 32 + 16 + i] = __uint_as_float(e2[i]);
-          }
-          asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
-          if (lane == 0 && !first) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) up[i] = xb[(q - 1) * 32 + i];
-          }
-          if (lane == 31 && !last) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) dn[i] = xb[(q + 1) * 32 + 16 + i];
+            for (int i = 0; i < 16; ++i) nb16[i] = xb[qq * 16 + i];
           }
         }
         if (valid) {
-          float f0[16], f1[16];
+          float f[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float b = bias_s[i];
-            f0[i] = (first ? 0.f : up[i]) + __uint_as_float(e1[i]) + __uint_as_float(o2[i]) + b;
-            f1[i] = __uint_as_float(e0[i]) + __uint_as_float(o1[i]) + (last ? 0.f : dn[i]) + b;
-          }
-          const int64_t lin = row_index(j);
-          auto add_rows = [&](const uint4& a0, const uint4& a1, float (&f)[16]) {
+          for (int i = 0; i < 16; ++i)
+            f[i] = (edge ? 0.f : nb16[i]) + __uint_as_float(vc[i]) + __uint_as_float(vs[i]) + bias_s[i];
+          const int64_t lin = lin0 + j * slab_vox;
+          auto add_rows = [&](const uint4& a0, const uint4& a1) {
             const __nv_bfloat162* g0 = reinterpret_cast<const __nv_bfloat162*>(&a0);
             const __nv_bfloat162* g1 = reinterpret_cast<const __nv_bfloat162*>(&a1);
 #pragma unroll
@@ -330,78 +324,61 @@ tc_line_conv_kernel(const __grid_constant__ TcLineConvParams p) {
               f[8 + 2 * i] += b.x; f[8 + 2 * i + 1] += b.y;
             }
           };
-          if (p.res) {
-            add_rows(pr[0], pr[1], f0);
-            add_rows(pr[2], pr[3], f1);
-          }
-          uint4* op0 = reinterpret_cast<uint4*>(p.dst + lin * p.dst_ld);
-          uint4* op1 = reinterpret_cast<uint4*>(p.dst + (lin + 1) * p.dst_ld);
+          if (p.res) add_rows(pr0, pr1);
+          uint4* op = reinterpret_cast<uint4*>(p.dst + lin * p.dst_ld);
           if (p.accumulate) {
-            const uint4 a0 = op0[0], a1 = op0[1], b0 = op1[0], b1 = op1[1];
-            add_rows(a0, a1, f0);
-            add_rows(b0, b1, f1);
+            const uint4 a0 = op[0], a1 = op[1];
+            add_rows(a0, a1);
           }
           if constexpr (!BST) {
             if (p.stats) {
 #pragma unroll
               for (int i = 0; i < 16; ++i) {
-                ssum[i] += f0[i] + f1[i];
-                ssq[i] = fmaf(f0[i], f0[i], fmaf(f1[i], f1[i], ssq[i]));
+                ssum[i] += f[i];
+                ssq[i] = fmaf(f[i], f[i], ssq[i]);
               }
             }
           }
-          uint4 s0, s1, s2, s3;
+          uint4 s0, s1;
           __nv_bfloat162* q0 = reinterpret_cast<__nv_bfloat162*>(&s0);
           __nv_bfloat162* q1 = reinterpret_cast<__nv_bfloat162*>(&s1);
-          __nv_bfloat162* q2 = reinterpret_cast<__nv_bfloat162*>(&s2);
-          __nv_bfloat162* q3 = reinterpret_cast<__nv_bfloat162*>(&s3);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            q0[i] = __floats2bfloat162_rn(f0[2 * i], f0[2 * i + 1]);
-            q1[i] = __floats2bfloat162_rn(f0[8 + 2 * i], f0[8 + 2 * i + 1]);
-            q2[i] = __floats2bfloat162_rn(f1[2 * i], f1[2 * i + 1]);
-            q3[i] = __floats2bfloat162_rn(f1[8 + 2 * i], f1[8 + 2 * i + 1]);
+            q0[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+            q1[i] = __floats2bfloat162_rn(f[8 + 2 * i], f[8 + 2 * i + 1]);
           }
-          op0[0] = s0;
-          op0[1] = s1;
-          op1[0] = s2;
-          op1[1] = s3;
+          op[0] = s0;
+          op[1] = s1;
           if constexpr (BST) {
             // the sums of the InstanceNorm + PReLU backward this gradient feeds, from the values AS STORED (bf16)
-            auto bst_rows = [&](const uint4& x0, const uint4& x1, const uint4& g0, const uint4& g1) {
-              const __nv_bfloat162* hx0 = reinterpret_cast<const __nv_bfloat162*>(&x0);
-              const __nv_bfloat162* hx1 = reinterpret_cast<const __nv_bfloat162*>(&x1);
-              const __nv_bfloat162* hg0 = reinterpret_cast<const __nv_bfloat162*>(&g0);
-              const __nv_bfloat162* hg1 = reinterpret_cast<const __nv_bfloat162*>(&g1);
-              float xv[16], gv[16];
+            const __nv_bfloat162* hx0 = reinterpret_cast<const __nv_bfloat162*>(&px0);
+            const __nv_bfloat162* hx1 = reinterpret_cast<const __nv_bfloat162*>(&px1);
+            float xv[16], gv[16];
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 a = __bfloat1622float2(hx0[i]), b = __bfloat1622float2(hx1[i]);
-                xv[2 * i] = a.x; xv[2 * i + 1] = a.y; xv[8 + 2 * i] = b.x; xv[8 + 2 * i + 1] = b.y;
-                const float2 ga = __bfloat1622float2(hg0[i]), gb = __bfloat1622float2(hg1[i]);
-                gv[2 * i] = ga.x; gv[2 * i + 1] = ga.y; gv[8 + 2 * i] = gb.x; gv[8 + 2 * i + 1] = gb.y;
-              }
+            for (int i = 0; i < 4; ++i) {
+              const float2 a = __bfloat1622float2(hx0[i]), b = __bfloat1622float2(hx1[i]);
+              xv[2 * i] = a.x; xv[2 * i + 1] = a.y; xv[8 + 2 * i] = b.x; xv[8 + 2 * i + 1] = b.y;
+              const float2 ga = __bfloat1622float2(q0[i]), gb = __bfloat1622float2(q1[i]);
+              gv[2 * i] = ga.x; gv[2 * i + 1] = ga.y; gv[8 + 2 * i] = gb.x; gv[8 + 2 * i + 1] = gb.y;
+            }
 #pragma unroll
-              for (int i = 0; i < 16; ++i) {
-                if (i < CS) {  // (compile time)
-                  const float h = fmaf(xv[i], nr[i < CS ? i : 0], nb[i < CS ? i : 0]);
-                  const bool pos = h > 0.f;
-                  const float g = pos ? gv[i] : nslope * gv[i];
-                  sb0[i < CS ? i : 0] += g;
-                  sb1[i < CS ? i : 0] = fmaf(g, h, sb1[i < CS ? i : 0]);
-                  sb2[i < CS ? i : 0] += pos ? 0.f : gv[i] * h;
-                }
+            for (int i = 0; i < 16; ++i) {
+              if (i < CS) {  // (compile time)
+                const float h = fmaf(xv[i], nr[i < CS ? i : 0], nb[i < CS ? i : 0]);
+                const bool pos = h > 0.f;
+                const float g = pos ? gv[i] : nslope * gv[i];
+                sb0[i < CS ? i : 0] += g;
+                sb1[i < CS ? i : 0] = fmaf(g, h, sb1[i < CS ? i : 0]);
+                sb2[i < CS ? i : 0] += pos ? 0.f : gv[i] * h;
               }
-            };
-            bst_rows(px[0], px[1], s0, s1);
-            bst_rows(px[2], px[3], s2, s3);
+            }
           }
           if (j + EG < nd) prefetch(j + EG);
         }
       }
       // per-warp partial statistics of this item (rows of one sample are contiguous: item order is sample-major)
       if constexpr (BST) {
-        float* out = p.bstats + (((int64_t)item * EG + eg) * 4 + q) * 16 * 3;
+        float* out = p.bstats + (((int64_t)item * (2 * EG) + sub) * 4 + q) * 16 * 3;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           float a = 0.f, b = 0.f, d3 = 0.f;
@@ -417,7 +394,7 @@ tc_line_conv_kernel(const __grid_constant__ TcLineConvParams p) {
           }
         }
       } else if (p.stats) {
-        float* out = p.stats + (((int64_t)item * EG + eg) * 4 + q) * p.cout * 2;
+        float* out = p.stats + (((int64_t)item * (2 * EG) + sub) * 4 + q) * p.cout * 2;
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           const float a = warp_sum(ssum[c]), b = warp_sum(ssq[c]);
@@ -463,7 +440,7 @@ int env_int(const char* name, int dflt, int lo, int hi) {
 // three kw accumulators per voxel cost 3x the drain (192 B per voxel at 64 B/clk/SM) and that eats what the 3x fewer,
 // 3x wider MMAs save.  B200SEG_LINE_EG = epilogue warp groups.
 int line_enabled() { static const int v = env_int("B200SEG_LINE_CONV", 0, 0, 1); return v; }
-int line_eg() { static const int v = env_int("B200SEG_LINE_EG", 2, 1, 2); return v; }
+int line_eg() { static const int v = env_int("B200SEG_LINE_EG", 1, 1, 2); return v; }
 int line_w128() { static const int v = env_int("B200SEG_LINE_W128", 0, 0, 1); return v; }
 
 struct LineGeom {
@@ -515,7 +492,7 @@ int launch_line(const TcLineConvParams& p, cudaStream_t st) {
     attr_set = true;
   }
   const int grid = p.items < sm_count() ? p.items : sm_count();
-  tc_line_conv_kernel<PPL, EG, BST, CS><<<grid, 64 + 128 * EG, smem, st>>>(p);
+  tc_line_conv_kernel<PPL, EG, BST, CS><<<grid, 64 + 256 * EG, smem, st>>>(p);
   B200SEG_CHECK_LAUNCH(BST ? "tc_line_conv_bwdstats" : "tc_line_conv");
   count_tc_launch();
   return B200SEG_OK;
@@ -539,7 +516,7 @@ bool tc_line_conv_supported(const b200seg_conv_desc* d, int op) {
 int64_t tc_line_conv_rows(const b200seg_conv_desc* d, int op) {
   LineGeom g;
   if (!line_geom(d, op, g)) return 0;
-  return (int64_t)g.items * line_eg() * 4;
+  return (int64_t)g.items * line_eg() * 8;
 }
 
 int tc_line_conv_run(const b200seg_conv_desc* d, int op, const void* src, const void* w_tc, const float* bias,
@@ -558,6 +535,8 @@ int tc_line_conv_run(const b200seg_conv_desc* d, int op, const void* src, const 
   p.accumulate = (d->flags & B200SEG_CONV_ACCUMULATE) ? 1 : 0;
   p.flip = (op == TC_CONV_DGRAD) ? 1 : 0;
   p.bias = bias; p.res = (const bf16*)residual; p.dst = (bf16*)dst; p.stats = stats;
+  static const int dbg = env_int("B200SEG_LINE_DEBUG", 0, 0, 7);
+  p.debug = dbg;
   {
     // the source as (N, D, H, W/2) voxel pairs of 32 bf16 (pairs are contiguous: voxel stride = 16 elements)
     uint64_t dims[5] = {32, (uint64_t)g.W / 2, (uint64_t)g.H, (uint64_t)g.D, (uint64_t)g.n};
