@@ -1,10 +1,11 @@
-// Line-tiled tcgen05 kernel for the 16-channel 3x3x3 stride-1 layers whose row length divides 128 voxels
-// (head 10->10 at 128^3, 16->16 at 64^3 of the cfg3 net): fprop / dgrad, optional fused InstanceNorm statistics
-// (fprop) or InstanceNorm-backward sums (dgrad), same contract as tc_slide_conv_kernel (tc_slide.cu), which stays
-// the kernel for every other shape.
+// EXPERIMENTAL (off by default, see line_enabled() below for the measurements): line-tiled tcgen05 kernel for the
+// 16-channel 3x3x3 stride-1 layers whose row length divides 128 voxels (head 10->10 at 128^3, 16->16 at 64^3 of the
+// cfg3 net): fprop / dgrad, optional fused InstanceNorm statistics (fprop) or InstanceNorm-backward sums (dgrad), same
+// contract as tc_slide_conv_kernel (tc_slide.cu), which is the production kernel.
 //
-// What tc_slide_conv pays for and this kernel does not (ncu r2, head layer: tensor pipe 28 % busy, the TMA engine
-// the longest pole with 432 box rows of 32 bytes per slab, 9-11 N=48 MMAs per slab bound by the 4 KB A-tile fetch):
+// What tc_slide_conv pays for and this kernel does not (ncu r2, head layer: the tensor-core pipe 79 % busy with 9-11
+// N=48 MMAs per slab that cost 46 cycles each for 24 cycles of math -- the 4 KB A-tile fetch -- and 432 TMA box rows
+// of 32 bytes per slab):
 //   * ONE copy of the source per slab instead of three w-shifted ones.  The three kw taps are folded along N: an
 //     MMA multiplies the un-shifted source tile with the weights of all three kw taps (and all three kd taps, as
 //     before), i.e. N = 3 kd x 3 kw x 16 = 144, so an accumulator row holds, for ITS source voxel, the three
@@ -432,13 +433,19 @@ int env_int(const char* name, int dflt, int lo, int hi) {
   return x >= lo && x <= hi ? x : dflt;
 }
 
-// OFF by default (B200SEG_LINE_CONV=1 enables it): validated on the GPU (the -m gpu suite passes with it on, rows
-// of 32 / 64 / 128 voxels), but measured no better than tc_slide_conv where it counts -- r2, graph-replayed:
-//   head 10->10 @128^3 x2      fprop 118 -> 124 us, dgrad + residual 118 -> 132, fused sums 145 -> 185
-//   16->16 @64^3 x2            dgrad + residual 20.2 -> 17.5 us, fused sums 26.9 -> 25.0, whole step 2.094 -> 2.096 ms
-// The tensor pipe and the TMEM read path of tcgen05.ld are one serial resource (ncu sm__pipe_tc_cycles_active): the
-// three kw accumulators per voxel cost 3x the drain (192 B per voxel at 64 B/clk/SM) and that eats what the 3x fewer,
-// 3x wider MMAs save.  B200SEG_LINE_EG = epilogue warp groups.
+// OFF by default (B200SEG_LINE_CONV=1 enables it; B200SEG_LINE_W128=1 adds rows of 128 voxels).  Validated on the GPU
+// (the -m gpu kernel / network / guard tests pass with it on) but not faster than tc_slide_conv where it counts --
+// r2, head layer 10->10 @128^3 x2:  fprop 100-118 us (slide) vs 106 us (line), dgrad + residual 118 vs 202 us, whole
+// step 2.096 ms (slide) vs 2.265 ms (line everywhere) / 2.106 ms (line for rows of 32 / 64 voxels only).
+// Where its time goes (B200SEG_LINE_DEBUG, fprop): everything 106 us; accumulators only drained and handed back 61 us;
+// additionally no MMAs 38 us; additionally no TMA loads 31 us.  So the folded MMAs are cheap (~25 us: N=144 costs
+// 72 cycles against 46 for N=48, scripts/ubench/tmem_drain.cu) and what remains is (a) the hand-back round trip of an
+// accumulator chunk -- commit -> mbarrier -> tcgen05.ld of three blocks (each wait::ld ~90 cycles while MMAs run) ->
+// tcgen05.st zeros -> arrive -- with only 5 chunks of 96 columns fitting the 512 TMEM columns, i.e. two slabs of
+// run-ahead, and (b) ~45 us of per-voxel epilogue instructions on 8 warps.  The residual variant additionally keeps
+// global loads in flight across the releasing mbarrier arrive.  tc_slide_conv hides the same costs behind three
+// co-resident CTAs per SM.  Kept as a tested experiment; the next step would be first-touch MMAs instead of the zero
+// fill and a third TMEM parity-free layout (48 instead of 96 columns per slab).
 int line_enabled() { static const int v = env_int("B200SEG_LINE_CONV", 0, 0, 1); return v; }
 int line_eg() { static const int v = env_int("B200SEG_LINE_EG", 1, 1, 2); return v; }
 int line_w128() { static const int v = env_int("B200SEG_LINE_W128", 0, 0, 1); return v; }
