@@ -45,6 +45,14 @@ inline int env_int(const char* name, int dflt, int lo, int hi) {
 // InstanceNorm-backward sums) 118 -> 203 and 145 -> 198 us, whole step 2.116 -> 2.167 ms: off by default, one CTA per
 // item; the kernel is the same code either way (grid == items).
 inline int slide_persist() { static const int v = env_int("B200SEG_SLIDE_PERSIST", 0, 0, 1); return v; }
+// The plain 16 -> 16 kernel exists twice: two CTAs per SM (115 registers) and three (96 registers, 8 bytes of
+// spill).  Measured (r2, graph-replayed, 2 x 128^3 head layer / 2 x 64^3): without a residual addend two are faster
+// (fprop 99.6 vs 106.6 us, dgrad 101.6 vs 108.4, 22.1 vs 24.0), with one -- its rows are global loads inside the
+// epilogue's per-slab loop -- three hide that latency better (137 vs 118 us).  B200SEG_SLIDE_MINB3 = 0 / 1 forces one.
+inline bool slide_three_ctas(bool has_residual) {
+  static const int v = env_int("B200SEG_SLIDE_MINB3", -1, -1, 1);
+  return v < 0 ? has_residual : v == 1;
+}
 inline int sm_count() {
   static const int v = [] {
     int dev = 0, n = 0;
@@ -116,8 +124,9 @@ struct alignas(64) TcSlideConvParams {
 
 // CS (BST only): channels that really exist (10 for the head layer's 16-wide rows): the sums of the padding channels
 // are identically zero and are neither computed nor kept in registers
-template <int BN, int KC, bool BST = false, int CS = BN>
-__global__ void __launch_bounds__(192, BST ? 2 : ((BN == 16 && KC == 16) ? 3 : 1))
+// MINB = CTAs per SM the register allocation is held to (3 x 6 warps = 5 warps on some SM sub-partitions: 96 registers)
+template <int BN, int KC, bool BST = false, int CS = BN, int MINB = (BST ? 2 : 1)>
+__global__ void __launch_bounds__(192, MINB)
 tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
   constexpr int PITCH = KC * 2;                          // bytes per voxel row
   constexpr int COPY_BYTES = (TH + 2) * TWV * PITCH;     // one w-shifted halo tile
@@ -501,12 +510,12 @@ constexpr size_t slide_smem() {
 }
 
 // co-resident CTAs per SM of one variant (registers, shared memory, TMEM columns), asked once from the runtime
-template <int BN, int KC, bool BST, int CS>
+template <int BN, int KC, bool BST, int CS, int MINB = (BST ? 2 : 1)>
 int slide_ctas_per_sm() {
   static const int v = [] {
-    cudaFuncSetAttribute(tc_slide_conv_kernel<BN, KC, BST, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    cudaFuncSetAttribute(tc_slide_conv_kernel<BN, KC, BST, CS, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
     int nb = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tc_slide_conv_kernel<BN, KC, BST, CS>, 192,
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tc_slide_conv_kernel<BN, KC, BST, CS, MINB>, 192,
                                                       slide_smem<BN, KC, BST>()) != cudaSuccess || nb < 1)
       nb = 1;
     const int by_tmem = 512 / (8 * BN);
@@ -515,11 +524,11 @@ int slide_ctas_per_sm() {
   return v;
 }
 
-template <int BN, int KC, bool BST = false, int CS = BN>
+template <int BN, int KC, bool BST = false, int CS = BN, int MINB = (BST ? 2 : 1)>
 int launch_slide(const TcSlideConvParams& p, unsigned grid, cudaStream_t st) {
   const size_t smem = slide_smem<BN, KC, BST>();
-  slide_ctas_per_sm<BN, KC, BST, CS>();  // (sets the shared-memory attribute)
-  tc_slide_conv_kernel<BN, KC, BST, CS><<<grid, 192, smem, st>>>(p);
+  slide_ctas_per_sm<BN, KC, BST, CS, MINB>();  // (sets the shared-memory attribute)
+  tc_slide_conv_kernel<BN, KC, BST, CS, MINB><<<grid, 192, smem, st>>>(p);
   B200SEG_CHECK_LAUNCH(BST ? "tc_slide_conv_bwdstats" : "tc_slide_conv");
   count_tc_launch();
   return B200SEG_OK;
@@ -541,9 +550,10 @@ bool tc_slide_conv_supported(const b200seg_conv_desc* d, int op) {
 
 // co-resident CTAs per SM of the variant this layer / op runs on (the segmentation must be the same in the workspace
 // queries and in the run)
-static int slide_slots_per_sm(int KC, int BN, bool bst, int dst_c) {
+static int slide_slots_per_sm(int KC, int BN, bool bst, int dst_c, bool has_residual = false) {
   if (bst) return dst_c == 10 ? slide_ctas_per_sm<16, 16, true, 10>() : slide_ctas_per_sm<16, 16, true, 16>();
-  if (BN == 16 && KC == 16) return slide_ctas_per_sm<16, 16, false, 16>();
+  if (BN == 16 && KC == 16)
+    return slide_three_ctas(has_residual) ? slide_ctas_per_sm<16, 16, false, 16, 3>() : slide_ctas_per_sm<16, 16, false, 16>();
   if (BN == 16 && KC == 32) return slide_ctas_per_sm<16, 32, false, 16>();
   if (BN == 32 && KC == 16) return slide_ctas_per_sm<32, 16, false, 32>();
   return slide_ctas_per_sm<32, 32, false, 32>();
@@ -584,7 +594,9 @@ int tc_slide_conv_run(const b200seg_conv_desc* d, int op, const void* src, const
   p.n = g.n; p.D = g.D; p.H = g.H; p.W = g.W;
   p.tilesH = (g.H + TH - 1) / TH; p.tilesW = (g.W + TWV - 1) / TWV;
   const int64_t cols = (int64_t)g.n * p.tilesH * p.tilesW;
-  const int slots_per_sm = slide_slots_per_sm(KC, BN, bst != nullptr, g.dst_c);
+  // (statistics are only fused without a residual addend, so the rows tc_slide_conv_grid reports -- no residual --
+  // are the rows this run writes)
+  const int slots_per_sm = slide_slots_per_sm(KC, BN, bst != nullptr, g.dst_c, residual != nullptr);
   slide_segments(cols, g.D, slots_per_sm, p.dseg, p.nseg);
   p.cout = g.dst_c; p.dst_ld = g.dst_ld; p.res_ld = d->r_ld;
   p.accumulate = (d->flags & B200SEG_CONV_ACCUMULATE) ? 1 : 0;
@@ -616,7 +628,9 @@ int tc_slide_conv_run(const b200seg_conv_desc* d, int op, const void* src, const
     set_error("tc_slide_conv: no fused InstanceNorm-backward variant for BN=%d KC=%d", BN, KC);
     return B200SEG_ERR_UNSUPPORTED;
   }
-  if (BN == 16 && KC == 16) return launch_slide<16, 16>(p, (unsigned)grid, st);
+  if (BN == 16 && KC == 16)
+    return slide_three_ctas(residual != nullptr) ? launch_slide<16, 16, false, 16, 3>(p, (unsigned)grid, st)
+                                                  : launch_slide<16, 16>(p, (unsigned)grid, st);
   if (BN == 16 && KC == 32) return launch_slide<16, 32>(p, (unsigned)grid, st);
   if (BN == 32 && KC == 16) return launch_slide<32, 16>(p, (unsigned)grid, st);
   if (BN == 32 && KC == 32) return launch_slide<32, 32>(p, (unsigned)grid, st);

@@ -215,6 +215,10 @@ int b200seg_convtr_wgrad(const b200seg_conv_desc* d, const void* x, const void* 
  * fwd:    y = prelu((x - mean) * rstd, alpha) [+ residual]
  * bwd:    dx = d loss / d x  given dy = d loss / d y ;  dalpha[0] = d loss / d alpha
  * alpha / dalpha are DEVICE pointers to one float.
+ * Ordering contract of the backward: for instances of up to 32^3 voxels dalpha is finished inside the kernel that
+ * produces the per-(sample, channel) sums (the CTA that draws the last ticket of a per-device counter adds them up in
+ * a fixed order), so two b200seg_instnorm_prelu_bwd calls on ONE device must be stream-ordered with respect to each
+ * other (same stream, or event dependencies) -- as they are in any backward pass.
  */
 size_t b200seg_instnorm_workspace_bytes(const b200seg_norm_desc* d);
 int b200seg_instnorm_stats(const b200seg_norm_desc* d, const void* x, float* mean, float* rstd,
