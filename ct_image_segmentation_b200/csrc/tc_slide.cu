@@ -124,6 +124,9 @@ struct alignas(64) TcSlideConvParams {
 
 // CS (BST only): channels that really exist (10 for the head layer's 16-wide rows): the sums of the padding channels
 // are identically zero and are neither computed nor kept in registers
+template <int BN, int MINB>
+__host__ __device__ constexpr int slide_accr() { return 8; }  // (16 where two CTAs share the 512 columns: measured, no gain)
+
 // MINB = CTAs per SM the register allocation is held to (3 x 6 warps = 5 warps on some SM sub-partitions: 96 registers)
 template <int BN, int KC, bool BST = false, int CS = BN, int MINB = (BST ? 2 : 1)>
 __global__ void __launch_bounds__(192, MINB)
@@ -133,7 +136,10 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
   constexpr int SLAB_BYTES = 3 * COPY_BYTES;
   constexpr int WT_BYTES = BN * PITCH;                   // one weight tile (tap)
   constexpr int W_BYTES = (27 * WT_BYTES + 1023) / 1024 * 1024;
-  constexpr int ACCR = 8;                                // TMEM accumulator ring (output slabs)
+  // TMEM accumulator ring (output slabs).  The folded MMAs are split where the ring wraps (2 of ACCR slabs).  A ring
+  // of 16 chunks in the two-CTAs-per-SM builds (10.1 instead of 11.25 MMAs per slab, deeper run-ahead) changed nothing:
+  // head fprop 99.6 -> 99.8 us (r2b, profiles/r2b_slide_accr16.txt).
+  constexpr int ACCR = slide_accr<BN, MINB>();
   constexpr uint32_t TMEM_COLS = ACCR * BN;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -506,7 +512,7 @@ constexpr size_t slide_smem() {
   constexpr int SLAB = 3 * (TH + 2) * TWV * PITCH;
   constexpr int WB = (27 * BN * PITCH + 1023) / 1024 * 1024;
   // ... + reduction scratch [4 warps][BN][3] + the consumer InstanceNorm's rstd / -mean * rstd of up to 16 samples (BST)
-  return 1024 + WB + RING * SLAB + 8 * PITCH * 8 + 16 * 8 + 64 + 4 * BN * 3 * 4 + (BST ? 16 * BN * 8 : 0);
+  return 1024 + WB + RING * SLAB + 8 * PITCH * 8 + (2 * RING + 2 * 16 + 1) * 8 + 64 + 4 * BN * 3 * 4 + (BST ? 16 * BN * 8 : 0);
 }
 
 // co-resident CTAs per SM of one variant (registers, shared memory, TMEM columns), asked once from the runtime
@@ -518,7 +524,7 @@ int slide_ctas_per_sm() {
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, tc_slide_conv_kernel<BN, KC, BST, CS, MINB>, 192,
                                                       slide_smem<BN, KC, BST>()) != cudaSuccess || nb < 1)
       nb = 1;
-    const int by_tmem = 512 / (8 * BN);
+    const int by_tmem = 512 / (slide_accr<BN, MINB>() * BN);
     return nb < by_tmem ? nb : by_tmem;
   }();
   return v;
