@@ -106,6 +106,8 @@ struct alignas(64) TcSlideConvParams {
   int n, D, H, W;
   int tilesH, tilesW, dseg, nseg;
   int items;     // (sample, line tile, voxel tile, d segment) columns: CTA b works on items b, b + gridDim.x, ...
+  int debug;     // B200SEG_SLIDE_DEBUG (timing experiments, results are wrong): 1 = the epilogue only drains and hands
+                 // back the accumulators, 2 = no MMAs, 4 = no TMA loads of the source
   int cout, dst_ld, res_ld, accumulate, flip;
   const float* bias;
   const bf16* res;
@@ -230,6 +232,7 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
         for (int s = 0; s < it.nd + 2; ++s, ++g) {
           const uint32_t slot = g % RING;
           tc::mbar_wait(&empty[slot], ((g / RING) & 1u) ^ 1u);
+          if (p.debug & 4) { tc::mbar_arrive(&full[slot]); continue; }
           uint8_t* dst = ring + slot * SLAB_BYTES;
           tc::mbar_expect_tx(&full[slot], SLAB_BYTES);
           const int ds = it.d_begin - 1 + s;
@@ -270,6 +273,7 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
         const uint64_t b0 = w_desc + (((lo - (s - 2)) * WT_BYTES) >> 4);
         const uint64_t b1 = b0 + ((len0 * WT_BYTES) >> 4);
         const uint64_t slab = tmpl + ((r_addr + slot * SLAB_BYTES) >> 4);
+        if (!(p.debug & 2)) {
         tc::umma_bf16_warp(d0, slab, b0, i0, 1u);
         if (len1 > 0) tc::umma_bf16_warp(d1, slab, b1, i1, 1u);
 #pragma unroll
@@ -282,6 +286,7 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
             tc::umma_bf16_warp(d0, a, b0 + bo, i0, 1u);
             if (len1 > 0) tc::umma_bf16_warp(d1, a, b1 + bo, i1, 1u);
           }
+        }
         tc::umma_commit_warp(&empty[slot]);
         if (s >= 2) tc::umma_commit_warp(&acc_full[(ob + (uint32_t)(s - 2)) % ACCR]);
       }
@@ -344,7 +349,7 @@ tc_slide_conv_kernel(const __grid_constant__ TcSlideConvParams p) {
         uint32_t v[16];
         tc::tmem_ld16(tmem_acc + ((uint32_t)(q * 32) << 16) + buf * BN + ch * 16, v);
         tc::tmem_ld_wait();
-        if (valid) {
+        if (valid && !(p.debug & 1)) {
           const int c0 = ch * 16;
           float f[16];
 #pragma unroll
@@ -605,6 +610,8 @@ int tc_slide_conv_run(const b200seg_conv_desc* d, int op, const void* src, const
   const int slots_per_sm = slide_slots_per_sm(KC, BN, bst != nullptr, g.dst_c, residual != nullptr);
   slide_segments(cols, g.D, slots_per_sm, p.dseg, p.nseg);
   p.cout = g.dst_c; p.dst_ld = g.dst_ld; p.res_ld = d->r_ld;
+  static const int dbg = env_int("B200SEG_SLIDE_DEBUG", 0, 0, 7);
+  p.debug = dbg;
   p.accumulate = (d->flags & B200SEG_CONV_ACCUMULATE) ? 1 : 0;
   p.flip = (op == TC_CONV_DGRAD) ? 1 : 0;
   p.bias = bias; p.res = (const bf16*)residual; p.dst = (bf16*)dst; p.stats = stats;
