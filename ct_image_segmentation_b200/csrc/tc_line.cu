@@ -542,7 +542,11 @@ int tc_line_conv_run(const b200seg_conv_desc* d, int op, const void* src, const 
   p.accumulate = (d->flags & B200SEG_CONV_ACCUMULATE) ? 1 : 0;
   p.flip = (op == TC_CONV_DGRAD) ? 1 : 0;
   p.bias = bias; p.res = (const bf16*)residual; p.dst = (bf16*)dst; p.stats = stats;
-  static const int dbg = env_int("B200SEG_LINE_DEBUG", 0, 0, 7);
+  static const int dbg = [] {
+    const int v = env_int("B200SEG_LINE_DEBUG", 0, 0, 7);
+    if (v) fprintf(stderr, "b200seg: B200SEG_LINE_DEBUG=%d switches parts of the kernel off: timing experiment, results are WRONG\n", v);
+    return v;
+  }();
   p.debug = dbg;
   {
     // the source as (N, D, H, W/2) voxel pairs of 32 bf16 (pairs are contiguous: voxel stride = 16 elements)

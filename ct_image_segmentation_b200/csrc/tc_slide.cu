@@ -610,7 +610,11 @@ int tc_slide_conv_run(const b200seg_conv_desc* d, int op, const void* src, const
   const int slots_per_sm = slide_slots_per_sm(KC, BN, bst != nullptr, g.dst_c, residual != nullptr);
   slide_segments(cols, g.D, slots_per_sm, p.dseg, p.nseg);
   p.cout = g.dst_c; p.dst_ld = g.dst_ld; p.res_ld = d->r_ld;
-  static const int dbg = env_int("B200SEG_SLIDE_DEBUG", 0, 0, 7);
+  static const int dbg = [] {
+    const int v = env_int("B200SEG_SLIDE_DEBUG", 0, 0, 7);
+    if (v) fprintf(stderr, "b200seg: B200SEG_SLIDE_DEBUG=%d switches parts of the kernel off: timing experiment, results are WRONG\n", v);
+    return v;
+  }();
   p.debug = dbg;
   p.accumulate = (d->flags & B200SEG_CONV_ACCUMULATE) ? 1 : 0;
   p.flip = (op == TC_CONV_DGRAD) ? 1 : 0;
